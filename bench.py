@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- PMC samples/sec for one full iteration (sample + likelihood +
+importance weights + EM update) of the SN Ia configuration (BASELINE.json
+configs[1]: SNLS/Union SN Ia likelihood, 5 parameters, 10-component proposal,
+10^7 samples per iteration), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pmc_samples_per_sec_full_iteration"
+UNIT = "samples/s"
+SEED = 20090903
+
+# algorithmic FLOPs of the SN likelihood (convention SURVEY.md 8d: + - * = 1,
+# FMA = 2, / sqrt exp log pow = 1 each); derivation in DESIGN.md
+FLOP_PER_EVAL = 14.0       # one integrand evaluation 1/sqrt(a^4 E^2(a))
+FLOP_PER_ZSTEP = 58.0      # per (sample, redshift): trapezoid combine 5x3, Neville 34, test 3, D_L + modulus 6
+FLOP_PER_SN = 24.0         # per (sample, supernova): mu_obs 6, sigma^2 14, chi^2 term 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nsamples", type=int, default=10_000_000, help="samples per GPU per iteration")
+    ap.add_argument("--config", default="sn", choices=["sn", "banana", "sn_bao", "cmb_bao_sn"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def make_config(name):
+    from cosmopmc_b200 import targets as T
+    if name == "sn":
+        spec = T.target_sn_demo()
+        w, m, cov = T.proposal_sn(10)
+        label = "SN Ia (Union 307 SNe, flat wCDM): Omega_m w0 M alpha beta, K=10 Gaussian proposal"
+    elif name == "banana":
+        spec = T.target_banana(20)
+        w, m, cov = T.proposal_banana(10, 20)
+        label = "20-D banana (Wraith et al. 2009), K=10"
+    elif name == "sn_bao":
+        spec = T.target_sn_bao_w0wa()
+        w, m, cov = T.proposal_generic(spec, 10, 4, [0.28, 0.72, -1.0, 0.0, 19.31, 1.4, -2.4],
+                                       [0.04, 0.06, 0.2, 0.5, 0.03, 0.1, 0.1])
+        label = "SN Ia + BAO d_z, w0-wa, 7 parameters, K=10"
+    else:
+        spec = T.target_cmb_bao_sn()
+        w, m, cov = T.proposal_generic(spec, 30, 4, [0.045, 0.27, 0.73, 0.71, -1.0, 19.31, 1.4, -2.4],
+                                       [0.003, 0.02, 0.02, 0.02, 0.1, 0.03, 0.1, 0.1])
+        label = "WMAP7 distance priors + BAO + SN Ia, 8 parameters, K=30"
+    ch = np.stack([np.linalg.cholesky(c) for c in cov])
+    return spec, w, m, ch, label
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4)
+                          if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_iteration_rate(spec, w, m, ch, seconds, nthreads):
+    """Times the CPU oracle (kind 'port': restatement of pmclib+nicaea, the
+    reference binary cannot be built here) on a bounded sample of the workload."""
+    from oracle import oracle_lib as O
+    O.build()
+    n0 = 2000
+    t = time.perf_counter()
+    O.iteration(spec, n0, SEED, 0, 1.0, w, m, ch, nthreads=nthreads)
+    dt = max(time.perf_counter() - t, 1e-3)
+    n = int(min(max(n0, n0 * seconds / dt), 2_000_000))
+    t = time.perf_counter()
+    O.iteration(spec, n, SEED, 0, 1.0, w, m, ch, nthreads=nthreads)
+    dt = time.perf_counter() - t
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec, w, m, ch, label = make_config(args.config)
+    cores = os.cpu_count() or 1
+    from oracle import oracle_lib as O
+    O.build()
+    # bounded sample per step, sized so the whole run ends within a few minutes
+    rate, n_cal, _ = cpu_iteration_rate(spec, w, m, ch, 2.0, cores)
+    per_step = int(min(max(2000, rate * min(20.0, 150.0 / max(1, args.steps + args.warmup))), 2_000_000))
+    for i in range(args.warmup):
+        O.iteration(spec, per_step, SEED, i, 1.0, w, m, ch, nthreads=cores)
+    t = time.perf_counter()
+    for i in range(args.steps):
+        O.iteration(spec, per_step, SEED, args.warmup + i, 1.0, w, m, ch, nthreads=cores)
+    dt = time.perf_counter() - t
+    val = per_step * args.steps / dt
+    sample = "%d samples/step of the %s workload (full iteration: sample+likelihood+weights+EM)" % (per_step, args.config)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": label, "samples_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU oracle (C restatement of pmclib+nicaea, OpenMP over samples in the weight stage); "
+                    "the reference binary cannot be built in this image (pmclib/nicaea/GSL/MPI absent)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cosmopmc_b200.pmc import PMC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    spec, w, m, ch, label = make_config(args.config)
+    d, K = len(m[0]), len(w)
+    n_loc = args.nsamples if args.scaling == "weak" else (args.nsamples + world - 1) // world
+    n_glob = n_loc * world
+    off = rank * n_loc
+
+    pmc = PMC(local)
+    pmc.set_target(spec)
+    pmc.set_proposal(w, m, chol=ch)
+    bufs = pmc.alloc(n_loc)
+    blen = pmc.stat_block_len()
+    block = torch.zeros(blen, dtype=torch.float64, device="cuda")
+    allb = torch.zeros((world, blen), dtype=torch.float64, device="cuda")
+    # pinned host buffers for the end-to-end path
+    hX = torch.empty((n_loc, d), dtype=torch.float64).pin_memory()
+    hidx = torch.empty(n_loc, dtype=torch.int32).pin_memory()
+    hflg = torch.empty(n_loc, dtype=torch.int16).pin_memory()
+    hw = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+    w_pin = torch.from_numpy(w.copy()).pin_memory()
+    m_pin = torch.from_numpy(m.copy()).pin_memory()
+    ch_pin = torch.from_numpy(ch.copy()).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(it):
+        """hot path, inputs resident in HBM: the proposal is re-installed every
+        step so that every step does identical work"""
+        pmc.set_proposal(w, m, chol=ch)
+        pmc.iteration_local(n_loc, SEED, it, off, 1.0, block, bufs)
+        if world > 1:
+            dist.all_gather_into_tensor(allb, block)
+            return pmc.update_prop_rb(world, allb, n_glob)
+        return pmc.update_prop_rb(1, block, n_glob)
+
+    def step_e2e(it):
+        """the reference-facing call: host proposal in, host pmc_simu arrays out"""
+        pmc.set_proposal(w_pin.numpy(), m_pin.numpy(), chol=ch_pin.numpy())
+        if world == 1:
+            return pmc.iteration_host(n_loc, SEED, it, 1.0, hX, hidx, hflg, hw)
+        pmc.iteration_local(n_loc, SEED, it, off, 1.0, block, bufs)
+        dist.all_gather_into_tensor(allb, block)
+        hX.copy_(bufs["X"], non_blocking=True)
+        hidx.copy_(bufs["idx"], non_blocking=True)
+        st = pmc.update_prop_rb(world, allb, n_glob)
+        pmc.normalize_importance_weight(bufs["flg"], bufs["logw"], n_loc)
+        hflg.copy_(bufs["flg"], non_blocking=True)
+        hw.copy_(bufs["logw"], non_blocking=True)
+        torch.cuda.synchronize()
+        return st
+
+    def timed(fn, steps, warmup, sampler=None):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        pmc.counters()
+        l0 = pmc.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        e0.record()
+        st = None
+        for i in range(steps):
+            st = fn(warmup + i)
+        e1.record()
+        barrier()
+        if sampler:
+            sampler.stop_flag = True
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), st, pmc.launch_count() - l0, pmc.counters()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, st, launches, cnt = timed(step_device, args.steps, args.warmup, sampler)
+    ms_e2e, st_e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    value = n_glob * args.steps / (ms * 1e-3)
+    e2e = n_glob * args.steps / (ms_e2e * 1e-3)
+
+    # dominant kernel alone (SN likelihood), CUDA events on the launching stream
+    roof = None
+    if args.config == "sn":
+        pmc.set_proposal(w, m, chol=ch)
+        pmc.simulate_mix_mvdens(n_loc, SEED, 0, off, bufs["X"], bufs["idx"], bufs["flg"])
+        for _ in range(2):
+            pmc.posterior_log_pdf(bufs["X"])
+        torch.cuda.synchronize()
+        pmc.counters()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            pmc.posterior_log_pdf(bufs["X"])
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        c = pmc.counters()
+        n_sn = spec.t.like[0].sn_n
+        flops = (c["sn_evals"] * FLOP_PER_EVAL + c["sn_zsteps"] * FLOP_PER_ZSTEP
+                 + reps * n_loc * n_sn * FLOP_PER_SN) / reps
+        peak = pmc.fp64_peak_tflops()
+        ach = flops / (k_ms * 1e-3) * 1e-12
+        roof = {"kernel": "k_like_sn", "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak if peak else None, "traffic": None,
+                "kernel_ms": k_ms, "flop_per_launch": flops,
+                "evals_per_sample": c["sn_evals"] / reps / n_loc,
+                "peak_source": "measured live: DFMA-only kernel (pmcb200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "hbm_algorithmic_GBs": n_loc * (8 * d + 8 + 4) / (k_ms * 1e-3) * 1e-9}
+
+    if rank == 0:
+        clocks = sampler.summary() if sampler else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": label, "samples_per_gpu": n_loc, "samples_global": n_glob,
+                           "ndim": d, "ncomp": K, "seed": SEED,
+                           "l2": "inputs larger than L2 (sample array %.0f MB per GPU)" % (n_loc * d * 8 / 1e6),
+                           "parallelism": "samples sharded over %d GPU(s); one NCCL all-gather of %d doubles per iteration" % (world, blen)},
+                "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(w_pin.numel() + m_pin.numel() + ch_pin.numel()) * 8,
+                        "d2h_bytes_per_step": int(n_loc * (8 * d + 4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d)))},
+                "gpu_launches": launches, "clocks": clocks,
+                "stats": {k: st[k] for k in ("perplexity", "ess", "nok", "enc", "ndead")} if st else None}
+        if roof:
+            line["roofline"] = roof
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            rate, n, dt = cpu_iteration_rate(spec, w, m, ch, args.cpu_seconds, cores)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d samples, one full iteration of the same workload, %.1f s" % (n, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

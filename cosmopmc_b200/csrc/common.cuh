@@ -1,0 +1,210 @@
+// common.cuh -- shared device helpers: Philox4x32-10, warp/block reductions,
+// the packed device layout of the Gaussian/Student-t mixture, and the
+// Romberg quadrature that the distance integrals use.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/pmcb200.h"
+
+#define PMC_BLOCK 256
+#define LN2PI 1.8378770664093454836
+#define R_HUBBLE 2997.92458
+#define C_KMS 299792.458
+#define ROMB_EPS 1.0e-6
+#define ROMB_JMAX 20
+#define SN_H_FID 0.7
+#define FLAT_EPS 1.0e-8
+#define OMEGA_GAMMA_H2 2.469e-5
+#define NEFF_NU 3.04
+
+// ---- packed mixture ---------------------------------------------------------
+// One contiguous device buffer of doubles (mirrors pmclib keeping a mix_mvdens
+// in one lump): for component k at mix + k*stride
+//   [0] wght   [1] lognorm = log-pdf constant (-d/2 ln2pi - log det L, or the
+//   Student-t lgamma form)   [2 .. 2+d) mean   [2+d .. 2+d+T) lower Cholesky
+//   factor packed by rows (row i holds L[i][0..i])   [2+d+T .. 2+2d+T) 1/L[i][i]
+// followed after K*stride by the common EM pivot p[d].
+struct MixHdr {
+  int K, d, df, stride, tri;
+};
+__host__ __device__ inline int mix_tri(int d) { return d * (d + 1) / 2; }
+__host__ __device__ inline int mix_stride(int d) { return 2 + 2 * d + mix_tri(d); }
+
+// ---- per-iteration device scalars --------------------------------------------
+struct DevScal {
+  unsigned long long max_key;   // order-preserving key of max log w (0 = none)
+  unsigned long long nok;       // samples with finite weight
+  unsigned long long nok_box;   // samples inside the box
+  unsigned long long pad;
+};
+// measurement counters (never reset by the iteration itself)
+struct DevCount {
+  unsigned long long sn_evals;  // SN integrand evaluations
+  unsigned long long sn_zsteps; // (sample, redshift) pairs integrated
+  unsigned long long pad[2];
+};
+
+__device__ __forceinline__ unsigned long long dkey(double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+  if (k == 0ull) return -INFINITY;
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011) ---------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // (0,1]
+  unsigned long long b = (((unsigned long long)hi << 32) | lo) >> 11;
+  return ((double)b + 1.0) * (1.0 / 9007199254740992.0);
+}
+
+// ---- reductions ---------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum in a fixed order (warp shuffles, then warp 0 over the warp
+// partials): deterministic for a given block size.  red: >= 32 doubles smem.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  return red[0];
+}
+
+// ---- component selection (bit-exact mirror of the reference's inverse-CDF
+// scan; oracle orc_select_component) ------------------------------------------
+__device__ __forceinline__ int select_component(const double *__restrict__ mix, const MixHdr h,
+                                                double u) {
+  double cw = 0.0;
+  int last = 0;
+  for (int k = 0; k < h.K; k++) {
+    double w = mix[(size_t)k * h.stride];
+    if (w == 0.0) continue;
+    cw = __dadd_rn(cw, w);
+    last = k;
+    if (u < cw) return k;
+  }
+  return last;
+}
+
+// ---- Gaussian / Student-t component log-pdf: forward substitution
+// y = L^-1 (x - mu), m = y.y (the "batched triangular contraction") ------------
+template <int D>
+__device__ __forceinline__ double comp_maha(const double *__restrict__ comp, int d,
+                                            const double (&x)[D], double (&y)[D]) {
+  const double *mean = comp + 2, *L = comp + 2 + d, *rd = comp + 2 + d + mix_tri(d);
+  double m = 0.0;
+  int off = 0;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    if (i < d) {
+      double t = x[i] - mean[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) t = fma(-L[off + k], y[k], t);
+      y[i] = t * rd[i];
+      m = fma(y[i], y[i], m);
+      off += i + 1;
+    }
+  }
+  return m;
+}
+__device__ __forceinline__ double comp_logpdf_from_maha(const double *__restrict__ comp, int d,
+                                                        int df, double m) {
+  if (df <= 0) return fma(-0.5, m, comp[1]);
+  return comp[1] - 0.5 * (double)(df + d) * log1p(m / (double)df);
+}
+
+// log q(x) = log sum_k alpha_k exp(log phi_k(x)), NO max shift (reference
+// semantics)
+template <int D>
+__device__ __forceinline__ double mix_logpdf(const double *__restrict__ mix, const MixHdr h,
+                                             const double (&x)[D]) {
+  double s = 0.0, y[D];
+  for (int k = 0; k < h.K; k++) {
+    const double *comp = mix + (size_t)k * h.stride;
+    double w = comp[0];
+    if (w == 0.0) continue;
+    double m = comp_maha<D>(comp, h.d, x, y);
+    s = fma(w, exp(comp_logpdf_from_maha(comp, h.d, h.df, m)), s);
+  }
+  return log(s);
+}
+
+// ---- Romberg (Numerical Recipes qromb, K = 5) ---------------------------------
+// Window y[0..4] of the last five trapezoid values (step ratio 1/4): Neville at
+// h = 0 with the constant ratios folded in.  Returns ss, sets dss.
+__device__ __forceinline__ double romb_extrap(const double (&y)[5], double &dss) {
+  double c[5], d[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) { c[i] = y[i]; d[i] = y[i]; }
+  double ss = y[4], dy = 0.0;
+  const double r1[4] = {1.0 / 3.0, 1.0 / 15.0, 1.0 / 63.0, 1.0 / 255.0};
+  const double r4[4] = {4.0 / 3.0, 16.0 / 15.0, 64.0 / 63.0, 256.0 / 255.0};
+#pragma unroll
+  for (int m = 1; m < 5; m++) {
+#pragma unroll
+    for (int i = 0; i < 5 - m; i++) {
+      double w = c[i + 1] - d[i];
+      d[i] = w * r1[m - 1];
+      c[i] = w * r4[m - 1];
+    }
+    dy = d[4 - m];
+    ss += dy;
+  }
+  dss = dy;
+  return ss;
+}
+
+// Generic adaptive Romberg of f over [a,b] with on-the-fly nodes (used for the
+// few BAO/CMB integrals per sample; the SN kernel has its own tabulated-node
+// version).  err is set on non-finite result or too many stages.
+template <class F>
+__device__ double romberg(F f, double a, double b, int &err) {
+  double y[5];
+  double st = 0.5 * (b - a) * (f(a) + f(b));
+  y[0] = st;
+  double ss = st, dss;
+  for (int j = 1; j < ROMB_JMAX; j++) {
+    long it = 1L << (j - 1);
+    double tnm = (double)it, del = (b - a) / tnm, sum = 0.0;
+    for (long i = 0; i < it; i++) sum += f(fma((double)i + 0.5, del, a));
+    st = 0.5 * (st + (b - a) * sum / tnm);
+    if (j < 5) y[j] = st;
+    else { y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4]; y[4] = st; }
+    if (j >= 4) {
+      ss = romb_extrap(y, dss);
+      if (!isfinite(ss)) { err = 1; return ss; }
+      if (fabs(dss) <= ROMB_EPS * fabs(ss)) return ss;
+    }
+  }
+  err = 1;
+  return ss;
+}

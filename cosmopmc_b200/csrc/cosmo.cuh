@@ -1,0 +1,411 @@
+// cosmo.cuh -- batched cosmology likelihoods (one sample per thread):
+// SN Ia chi^2 (replaces nicaea SetDl + chi2_SN behind wrappers/src/sn.c:138-281),
+// BAO distance ratios (bao.c:80-184), WMAP distance priors (wmap.c:945-1049).
+// FP64 throughout; the Romberg node sequence and stopping rule of the
+// reference are reproduced exactly.
+#pragma once
+#include "common.cuh"
+
+#define SN_NODES 64      // tabulated Romberg nodes per redshift: stages 1..7
+#define SN_ROW 12        // doubles per supernova row in the device table
+
+// Device-side likelihood descriptor (pointers are device pointers).
+struct DevLike {
+  int kind, npar, special, pad0;
+  int par[PMCB200_MAX_DIM];
+  pmcb200_cosmo_t model;
+  // SN Ia
+  int sn_chi2mode, sn_add_logdetCov, sn_n, sn_nz;
+  double Theta2[4], Theta2_denom[3], sig_int2, pv_fac;
+  const double2 *nodes;   // [sn_nz][SN_NODES] {a, ln a}; entry 0 = a(z), entry i in
+                          // [2^(j-2), 2^(j-1)) = nodes of trapezoid stage j >= 2
+  const int *first;       // [sn_nz+1] ranges of supernovae sharing a redshift
+  const double *sn;       // [sn_n][SN_ROW]: m s c z Vmm Vss Vcc Cms Cmc Csc pv2 -
+  // Gaussian data (BAO, CMB distance priors): packed like a mixture component
+  int bao_method, g_ndim;
+  const double *g_z;
+  const double *g_comp;   // [2 + 2n + tri(n)] = wght, lognorm, mean, L packed, 1/diag
+  // analytic targets
+  MixHdr mixh;
+  const double *mix;
+  double banana_b, banana_sigma1sq;
+};
+
+struct Model {
+  pmcb200_cosmo_t c;
+  double Theta2[4], stretch, color;
+};
+
+// The `switch (like->par[i])` blocks of sn.c:167-224 / bao.c:100-147 /
+// wmap.c:966-1019 followed by set_base_parameters (param.c:1544-1661).
+// Returns non-zero on the reference's error conditions.
+__device__ inline int apply_params(const DevLike &L, const double *__restrict__ x, Model &m) {
+  double Omegam = -1, Omegab = -1, Omegac = -1, Omegade = -1, Omeganumass = -1;
+  double omegam = -1, omegab = -1, omegac = -1, omegade = -1, omeganumass = -1, h100 = -1;
+  double OmegaK = 0, omegaK = 0;
+  int iOmegade = 0, iOmegaK = 0, iomegade = 0, iomegaK = 0, bad = 0;
+  m.c = L.model;
+#pragma unroll
+  for (int i = 0; i < 4; i++) m.Theta2[i] = L.Theta2[i];
+  m.stretch = 1.0; m.color = 0.0;
+  const bool sn = (L.kind == PMCB200_LIKE_SNIa);
+  for (int i = 0; i < L.npar; i++) {
+    double v = x[i];
+    switch (L.par[i]) {
+      case PMCB200_P_Omegam: Omegam = v; break;
+      case PMCB200_P_Omegab: Omegab = v; break;
+      case PMCB200_P_Omegade: Omegade = v; iOmegade = 1; break;
+      case PMCB200_P_Omeganumass: Omeganumass = v; break;
+      case PMCB200_P_Omegac: Omegac = v; break;
+      case PMCB200_P_OmegaK: OmegaK = v; iOmegaK = 1; break;
+      case PMCB200_P_omegam: omegam = v; break;
+      case PMCB200_P_omegab: omegab = v; break;
+      case PMCB200_P_100_omegab: omegab = v / 100.0; break;
+      case PMCB200_P_omegade: omegade = v; iomegade = 1; break;
+      case PMCB200_P_omeganumass: if (!sn) omeganumass = v; break;
+      case PMCB200_P_omegac: omegac = v; break;
+      case PMCB200_P_omegaK: omegaK = v; iomegaK = 1; break;
+      case PMCB200_P_w0de: m.c.w0_de = v; break;
+      case PMCB200_P_w1de: m.c.w1_de = v; break;
+      case PMCB200_P_h100: h100 = v; break;
+      case PMCB200_P_Neffnumass: if (!sn) m.c.Neff_nu_mass = v; break;
+      case PMCB200_P_M: if (sn) m.Theta2[0] = v; break;
+      case PMCB200_P_alpha: if (sn) m.Theta2[1] = v; break;
+      case PMCB200_P_beta: if (sn) m.Theta2[2] = v; break;
+      case PMCB200_P_logbeta: if (sn) m.Theta2[2] = -exp(v); break;
+      case PMCB200_P_beta_z: if (sn) m.Theta2[3] = v; break;
+      case PMCB200_P_stretch: if (sn) m.stretch = v; break;
+      case PMCB200_P_color: if (sn) m.color = v; break;
+      default: break;
+    }
+    if (L.kind == PMCB200_LIKE_CMBDistPrior && !isfinite(v)) bad = 1;
+  }
+  if (h100 < 0) h100 = m.c.h_100; else m.c.h_100 = h100;
+  if (Omegam > 0 || Omegab > 0 || iOmegade == 1 || Omeganumass > 0 || Omegac > 0 || iOmegaK == 1) {
+    if (omegam > 0 || omegab > 0 || iomegade == 1 || omeganumass > 0 || omegac > 0 || iomegaK == 1)
+      bad = 1;
+  } else {
+    if (h100 < 0) bad = 1;
+    double h2 = h100 * h100;
+    Omegam = omegam / h2; Omegab = omegab / h2; Omegade = omegade / h2;
+    Omeganumass = omeganumass / h2; Omegac = omegac / h2; OmegaK = omegaK / h2;
+    iOmegade = iomegade; iOmegaK = iomegaK;
+  }
+  if (Omegam > 0 && iOmegade == 1 && iOmegaK == 1) bad = 1;
+  if (Omegam > 0 && Omegab > 0 && Omegac > 0) bad = 1;
+  if (Omeganumass < 0) Omeganumass = 0;
+  if (Omegam > 0) m.c.Omega_m = Omegam;
+  else if (Omegab > 0 && Omegac > 0) m.c.Omega_m = Omegab + Omegac;
+  else if (Omegade > 0 && iOmegaK == 1) m.c.Omega_m = 1.0 - Omegade - OmegaK - Omeganumass;
+  if (Omegab > 0) m.c.Omega_b = Omegab;
+  else if (Omegam > 0 && Omegac > 0) m.c.Omega_b = Omegam - Omegac;
+  if (Omegade > 0) m.c.Omega_de = Omegade;
+  else if (Omegam > 0) m.c.Omega_de = 1.0 - Omegam - OmegaK - Omeganumass;
+  else if (Omegab > 0 && Omegac > 0) m.c.Omega_de = 1.0 - Omegab - Omegac - OmegaK - Omeganumass;
+  if (Omeganumass > 0) m.c.Omega_nu_mass = Omeganumass;
+  return bad;
+}
+
+// Coefficients of a^4 E^2(a) = a (Om + OK a) + Or + Ode exp(p ln a + q g(a)),
+// g = (1-a) [linder] or (1-a)^2 [jassal].
+struct ECoef {
+  double Om, OK, Ode, Or, p, q;
+  int jassal;
+};
+__device__ __forceinline__ ECoef make_ecoef(const pmcb200_cosmo_t &c, int wOmegar) {
+  ECoef e;
+  e.Om = c.Omega_m + c.Omega_nu_mass;
+  e.OK = 1.0 - c.Omega_m - c.Omega_de - c.Omega_nu_mass;
+  e.Ode = c.Omega_de;
+  e.Or = wOmegar ? OMEGA_GAMMA_H2 * (1.0 + 0.2271 * NEFF_NU) / (c.h_100 * c.h_100) : 0.0;
+  e.jassal = (c.de_param == PMCB200_DE_jassal);
+  if (e.jassal) { e.p = 4.0 - 3.0 * (1.0 + c.w0_de); e.q = 1.5 * c.w1_de; }
+  else { e.p = 4.0 - 3.0 * (1.0 + c.w0_de + c.w1_de); e.q = -3.0 * c.w1_de; }
+  return e;
+}
+__device__ __forceinline__ double a4E2(const ECoef &e, double a, double lna) {
+  double oma = 1.0 - a;
+  double t = e.jassal ? fma(e.q * oma, oma, e.p * lna) : fma(e.q, oma, e.p * lna);
+  double de = (a > 0.0) ? e.Ode * exp(t) : 0.0;
+  return fma(a, fma(e.OK, a, e.Om), e.Or) + de;
+}
+__device__ __forceinline__ double f_K(const pmcb200_cosmo_t &c, double w) {
+  double OK = 1.0 - c.Omega_m - c.Omega_de - c.Omega_nu_mass;
+  if (fabs(OK) < FLAT_EPS) return w;
+  double sk = sqrt(fabs(OK)) / R_HUBBLE;
+  return OK > 0.0 ? sinh(sk * w) / sk : sin(sk * w) / sk;
+}
+// comoving distance [Mpc/h] with on-the-fly nodes
+__device__ inline double w_generic(const pmcb200_cosmo_t &c, double a, int wOmegar, int &err) {
+  ECoef e = make_ecoef(c, wOmegar);
+  int bad = 0;
+  double r = romberg([&](double x) {
+    double dd = a4E2(e, x, log(x));
+    if (!(dd > 0.0)) bad = 1;
+    return rsqrt(dd);
+  }, a, 1.0, err);
+  if (bad) err = 1;
+  return R_HUBBLE * r;
+}
+__device__ inline double r_sound(const pmcb200_cosmo_t &c, double a, int &err) {
+  ECoef e = make_ecoef(c, 1);
+  double Rfac = 0.75 * c.Omega_b * c.h_100 * c.h_100 / OMEGA_GAMMA_H2;
+  int bad = 0;
+  double r = romberg([&](double x) {
+    double dd = a4E2(e, x, x > 0.0 ? log(x) : 0.0) * 3.0 * fma(Rfac, x, 1.0);
+    if (!(dd > 0.0)) bad = 1;
+    return rsqrt(dd);
+  }, 0.0, a, err);
+  if (bad) err = 1;
+  return R_HUBBLE * r;
+}
+__device__ inline double D_V(const pmcb200_cosmo_t &c, double z, int &err) {
+  double a = 1.0 / (1.0 + z);
+  double ww = w_generic(c, a, 0, err);
+  double fK = f_K(c, ww);
+  ECoef e = make_ecoef(c, 0);
+  double a2 = a * a;
+  double EE = a4E2(e, a, log(a)) / (a2 * a2);
+  if (!(EE > 0.0)) { err = 1; return NAN; }
+  return cbrt(fK * fK * R_HUBBLE * z / sqrt(EE));
+}
+__device__ inline double z_drag(const pmcb200_cosmo_t &c) {
+  double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
+  double b1 = 0.313 * pow(omm, -0.419) * (1.0 + 0.607 * pow(omm, 0.674));
+  double b2 = 0.238 * pow(omm, 0.223);
+  return 1291.0 * pow(omm, 0.251) / (1.0 + 0.659 * pow(omm, 0.828)) * (1.0 + b1 * pow(omb, b2));
+}
+__device__ inline double z_star(const pmcb200_cosmo_t &c) {
+  double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
+  double g1 = 0.0783 * pow(omb, -0.238) / (1.0 + 39.5 * pow(omb, 0.763));
+  double g2 = 0.560 / (1.0 + 21.1 * pow(omb, 1.81));
+  return 1048.0 * (1.0 + 0.00124 * pow(omb, -0.738)) * (1.0 + g1 * pow(omm, g2));
+}
+// Gaussian log-pdf of a model vector against data packed as a component
+__device__ inline double gauss_comp_logpdf(const double *__restrict__ comp, int n, const double *model) {
+  const double *mean = comp + 2, *L = comp + 2 + n, *rd = comp + 2 + n + mix_tri(n);
+  double y[4], m = 0.0;
+  int off = 0;
+  for (int i = 0; i < n; i++) {
+    double t = model[i] - mean[i];
+    for (int k = 0; k < i; k++) t = fma(-L[off + k], y[k], t);
+    y[i] = t * rd[i];
+    m = fma(y[i], y[i], m);
+    off += i + 1;
+  }
+  return fma(-0.5, m, comp[1]);
+}
+
+// write/accumulate one likelihood term
+__device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t n, int set,
+                                            double add_const, double res, int e) {
+  if (set) { logpi[n] = res + add_const; if (err) err[n] = e; }
+  else { logpi[n] += res; if (err && e) err[n] = 1; }
+}
+
+// ---- SN Ia: one sample per thread; the whole warp walks the same redshift
+// so node loads are warp-uniform and the adaptive stage count is resolved by
+// a warp vote ---------------------------------------------------------------
+__device__ __forceinline__ double sn_f(const ECoef &e, double2 nd) {
+  return rsqrt(a4E2(e, nd.x, nd.y));
+}
+
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+          const int16_t *__restrict__ flg, double *__restrict__ logpi,
+          int32_t *__restrict__ err, int set, double add_const, DevCount *cnt) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = (n < N) && (!flg || flg[n]);
+  unsigned nev = 0;
+  Model m;
+  int e = 0;
+  if (active) e = apply_params(L, X + n * d, m);
+  if (!active || e) { DevLike const &LL = L; m.c = LL.model; for (int i = 0; i < 4; i++) m.Theta2[i] = LL.Theta2[i]; m.stretch = 1.0; m.color = 0.0; }
+  const ECoef ec = make_ecoef(m.c, 0);
+  const double f1 = rsqrt(ec.Om + ec.OK + ec.Ode);      // integrand at a = 1
+  const bool flat = fabs(ec.OK) < FLAT_EPS;
+  const double sk = sqrt(fabs(ec.OK)) / R_HUBBLE;
+  double t1 = m.Theta2[1], t2base = m.Theta2[2];
+  const int mode = L.sn_chi2mode;
+  double chi2 = 0.0, logdet = 0.0;
+
+  for (int iz = 0; iz < L.sn_nz; iz++) {
+    const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
+    const double2 n0 = __ldg(&nd[0]);
+    const double az = n0.x, h = 1.0 - az;
+    double y[5];
+    // trapezoid stages 1..5 (17 integrand evaluations)
+    double st = 0.5 * h * (sn_f(ec, n0) + f1);
+    y[0] = st;
+    st = 0.5 * (st + h * sn_f(ec, __ldg(&nd[1])));
+    y[1] = st;
+    {
+      double s = sn_f(ec, __ldg(&nd[2]));
+      s += sn_f(ec, __ldg(&nd[3]));
+      st = 0.5 * (st + h * s * 0.5);
+      y[2] = st;
+    }
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 4; i < 8; i++) s += sn_f(ec, __ldg(&nd[i]));
+      st = 0.5 * (st + h * s * 0.25);
+      y[3] = st;
+    }
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 8; i < 16; i++) s += sn_f(ec, __ldg(&nd[i]));
+      st = 0.5 * (st + h * s * 0.125);
+      y[4] = st;
+    }
+    double dss, ss = romb_extrap(y, dss);
+    bool done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
+    nev += 17;
+    int j = 5;                      // stages completed
+    while (!__all_sync(0xffffffffu, done)) {
+      if (j >= ROMB_JMAX) { if (!done) { ss = NAN; done = true; } break; }
+      if (!done) {
+        const int it = 1 << (j - 1);
+        double s = 0.0;
+        if (2 * it <= SN_NODES) {
+#pragma unroll 4
+          for (int i = it; i < 2 * it; i++) s += sn_f(ec, __ldg(&nd[i]));
+        } else {
+          const double del = h / (double)it;
+          for (int i = 0; i < it; i++) {
+            double a = fma((double)i + 0.5, del, az);
+            s += rsqrt(a4E2(ec, a, log(a)));
+          }
+        }
+        nev += it;
+        st = 0.5 * (st + h * s / (double)it);
+        y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4]; y[4] = st;
+        ss = romb_extrap(y, dss);
+        done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
+      }
+      j++;
+    }
+    // luminosity distance [Mpc/h] and distance modulus
+    double ww = R_HUBBLE * ss;
+    double fk = flat ? ww : (ec.OK > 0.0 ? sinh(sk * ww) : sin(sk * ww)) / sk;
+    double dl = fk / az;
+    if (!(dl > 0.0)) e = 1;         // also catches NaN
+    double mu_th = fma(5.0, log10(dl / SN_H_FID), 25.0);
+    const int i0 = __ldg(&L.first[iz]), i1 = __ldg(&L.first[iz + 1]);
+    for (int i = i0; i < i1; i++) {
+      const double *__restrict__ r = L.sn + (size_t)i * SN_ROW;
+      double t2 = t2base;
+      if (mode == PMCB200_CHI2_betaz) t2 = fma(m.Theta2[3], r[3], t2base);
+      double mu_obs, d1, d2;
+      if (mode == PMCB200_CHI2_no_sc) {
+        mu_obs = r[0] + m.Theta2[0]; d1 = 0.0; d2 = 0.0;
+      } else {
+        mu_obs = r[0] + m.Theta2[0] + t1 * (r[1] - m.stretch) + t2 * (r[2] - m.color);
+        d1 = t1; d2 = t2;
+        if (mode == PMCB200_CHI2_Theta2_denom_fixed) { d1 = L.Theta2_denom[1]; d2 = L.Theta2_denom[2]; }
+      }
+      double sig2 = r[4] + d1 * d1 * r[5] + d2 * d2 * r[6]
+                    + 2.0 * (d1 * r[7] + d2 * r[8] + d1 * d2 * r[9]) + r[10];
+      double res = mu_obs - mu_th;
+      chi2 += res * res / sig2;
+      if (L.sn_add_logdetCov) logdet += log(sig2);
+    }
+  }
+  double res = -0.5 * chi2;
+  if (L.sn_add_logdetCov) res -= 0.5 * logdet;
+  if (!isfinite(res)) e = 1;
+  if (active) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  else if (n < N && set) { logpi[n] = 0.0; if (err) err[n] = 0; }
+  if (cnt) {   // measurement only: one atomic pair per warp
+    unsigned tot = active ? nev : 0u, nact = active ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      nact += __shfl_xor_sync(0xffffffffu, nact, o);
+    }
+    if ((threadIdx.x & 31) == 0 && nact) {
+      atomicAdd(&cnt->sn_evals, (unsigned long long)tot);
+      atomicAdd(&cnt->sn_zsteps, (unsigned long long)nact * L.sn_nz);
+    }
+  }
+}
+
+// ---- BAO / CMB distance priors / analytic targets: one sample per thread -----
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_like_bao(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+           const int16_t *__restrict__ flg, double *__restrict__ logpi,
+           int32_t *__restrict__ err, int set, double add_const) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
+  Model m;
+  int e = apply_params(L, X + n * d, m);
+  double res = 0.0;
+  if (!e) {
+    double model[4];
+    const int nd = L.g_ndim;
+    const pmcb200_cosmo_t &c = m.c;
+    if (L.bao_method == PMCB200_BAO_distance_A) {
+      if (!(c.Omega_m > 0.0)) e = 1;
+      else for (int i = 0; i < nd; i++)
+        model[i] = D_V(c, L.g_z[i], e) * sqrt(c.Omega_m) / (L.g_z[i] * R_HUBBLE);
+    } else if (L.bao_method == PMCB200_BAO_distance_d_z) {
+      if (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0)) e = 1;
+      else {
+        double rs = r_sound(c, 1.0 / (1.0 + z_drag(c)), e);
+        for (int i = 0; i < nd; i++) model[i] = rs / D_V(c, L.g_z[i], e);
+      }
+    } else {
+      for (int i = 0; i < nd; i++) model[i] = D_V(c, L.g_z[2 * i], e) / D_V(c, L.g_z[2 * i + 1], e);
+    }
+    if (!e) res = gauss_comp_logpdf(L.g_comp, nd, model);
+    if (!isfinite(res)) e = 1;
+  }
+  put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+}
+
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+             const int16_t *__restrict__ flg, double *__restrict__ logpi,
+             int32_t *__restrict__ err, int set, double add_const) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
+  Model m;
+  int e = apply_params(L, X + n * d, m);
+  double res = 0.0;
+  const pmcb200_cosmo_t &c = m.c;
+  if (!e && (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0))) e = 1;
+  if (!e) {
+    double model[4];
+    double zs = z_star(c), as = 1.0 / (1.0 + zs);
+    double ww = w_generic(c, as, 1, e);
+    double fK = f_K(c, ww);
+    double rs = r_sound(c, as, e);
+    model[0] = M_PI * fK / rs;
+    model[1] = sqrt(c.Omega_m) * fK / R_HUBBLE;
+    model[2] = zs;
+    model[3] = 100.0 * c.Omega_b * c.h_100 * c.h_100;
+    if (!e) res = gauss_comp_logpdf(L.g_comp, L.g_ndim, model);
+    if (!isfinite(res)) e = 1;
+  }
+  put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+}
+
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_like_banana(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+              const int16_t *__restrict__ flg, double *__restrict__ logpi,
+              int32_t *__restrict__ err, int set, double add_const) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
+  const double *x = X + n * d;
+  double s1 = L.banana_sigma1sq, b = L.banana_b;
+  double x0 = x[0], y2 = x[1] + b * (x0 * x0 - s1);
+  double q = x0 * x0 / s1 + y2 * y2;
+  for (int j = 2; j < d; j++) q = fma(x[j], x[j], q);
+  double res = -0.5 * q - 0.5 * (d * LN2PI + log(s1));
+  int e = !isfinite(res);
+  put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+}

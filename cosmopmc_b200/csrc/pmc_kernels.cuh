@@ -1,0 +1,456 @@
+// pmc_kernels.cuh -- sampler, mixture log-pdf, importance weights, EM
+// sufficient statistics and the M-step.  One sample per thread; D (padded
+// dimension) is a template parameter so x/y live in registers.
+#pragma once
+#include "common.cuh"
+
+// ---- K1: mixture sampler (replaces simulate_mix_mvdens, cosmo_pmc.c:320) ------
+// Philox counter = (g_lo, g_hi, call, iter), key = seed; g = global sample
+// index, so a shard's draws are independent of the number of ranks.
+template <int D>
+__device__ __forceinline__ void draw_normals(uint64_t seed, uint32_t iter, uint64_t g, int d, int df,
+                                             double &u, double (&z)[D], double &tscale) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t g0 = (uint32_t)g, g1 = (uint32_t)(g >> 32), r[4];
+  philox4x32_10(g0, g1, 0u, iter, k0, k1, r);
+  u = (double)r[0] * (1.0 / 4294967296.0);
+  const int nz = d + (df > 0 ? df : 0);
+  double chi2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; i++) z[i] = 0.0;
+  for (int p = 0; 2 * p < nz; p++) {
+    philox4x32_10(g0, g1, 1u + p, iter, k0, k1, r);
+    double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
+    double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincos(2.0 * M_PI * u2, &sn, &cs);
+    double zz0 = rad * cs, zz1 = rad * sn;
+    int i0 = 2 * p, i1 = 2 * p + 1;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      if (i == i0 && i < d) z[i] = zz0;
+      if (i == i1 && i < d) z[i] = zz1;
+    }
+    if (i0 >= d && i0 < nz) chi2 = fma(zz0, zz0, chi2);
+    if (i1 >= d && i1 < nz) chi2 = fma(zz1, zz1, chi2);
+  }
+  tscale = (df > 0) ? sqrt((double)df / chi2) : 1.0;
+}
+
+template <int D>
+__device__ __forceinline__ void transform_store(const double *__restrict__ comp, int d,
+                                                const double (&z)[D], double scale,
+                                                const double *__restrict__ bmin,
+                                                const double *__restrict__ bmax,
+                                                double *__restrict__ xout, int &inbox) {
+  const double *mean = comp + 2, *L = comp + 2 + d;
+  int off = 0, ok = 1;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    if (i < d) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k <= i; k++) t = fma(L[off + k], z[k], t);
+      double x = fma(scale, t, mean[i]);
+      xout[i] = x;
+      if (!(x >= bmin[i] && x <= bmax[i])) ok = 0;
+      off += i + 1;
+    }
+  }
+  inbox = ok;
+}
+
+template <int D>
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_simulate(const double *__restrict__ mix, const MixHdr h, const double *__restrict__ box,
+           int64_t N, uint64_t seed, uint32_t iter, int64_t offset,
+           double *__restrict__ X, int32_t *__restrict__ idx, int16_t *__restrict__ flg,
+           DevScal *scal) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int inbox = 0;
+  if (n < N) {
+    double u, z[D], ts;
+    draw_normals<D>(seed, iter, (uint64_t)(offset + n), h.d, h.df, u, z, ts);
+    int k = select_component(mix, h, u);
+    transform_store<D>(mix + (size_t)k * h.stride, h.d, z, ts, box, box + h.d, X + n * h.d, inbox);
+    idx[n] = k;
+    flg[n] = (int16_t)inbox;
+  }
+  unsigned b = __ballot_sync(0xffffffffu, inbox);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&scal->nok_box, (unsigned long long)__popc(b));
+}
+
+template <int D>
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_simulate_from_draws(const double *__restrict__ mix, const MixHdr h,
+                      const double *__restrict__ box, int64_t N,
+                      const double *__restrict__ U, const double *__restrict__ Z,
+                      double *__restrict__ X, int32_t *__restrict__ idx,
+                      int16_t *__restrict__ flg) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double z[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) z[i] = (i < h.d) ? Z[n * h.d + i] : 0.0;
+  int k = select_component(mix, h, U[n]);
+  int inbox;
+  transform_store<D>(mix + (size_t)k * h.stride, h.d, z, 1.0, box, box + h.d, X + n * h.d, inbox);
+  idx[n] = k;
+  flg[n] = (int16_t)inbox;
+}
+
+// ---- K2: batched mixture log-pdf (mix_mvdens_log_pdf_void, cosmo_pmc.c:343) ---
+template <int D>
+__device__ __forceinline__ void load_x(const double *__restrict__ X, int64_t n, int d, double (&x)[D]) {
+#pragma unroll
+  for (int i = 0; i < D; i++) x[i] = (i < d) ? X[n * d + i] : 0.0;
+}
+
+template <int D>
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_logq(const double *__restrict__ mix, const MixHdr h, int64_t N,
+       const double *__restrict__ X, double *__restrict__ logq) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double x[D];
+  load_x<D>(X, n, h.d, x);
+  logq[n] = mix_logpdf<D>(mix, h, x);
+}
+
+// Mixture / Gaussian used as a *target* (likeli_Mvdens / likeli_MixMvdens,
+// param.c:1485-1537) or as the Gaussian prior (param.c:1009-1026, sel = the
+// indprior gather map, nsel = its length).
+template <int D>
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_like_mix(const double *__restrict__ mix, const MixHdr h, int is_mixture, int64_t N,
+           const double *__restrict__ X, int dX, const int *__restrict__ sel,
+           const int16_t *__restrict__ flg, double *__restrict__ logpi,
+           int32_t *__restrict__ err, int set, double add_const) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
+  double x[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) x[i] = (i < h.d) ? X[n * dX + (sel ? sel[i] : i)] : 0.0;
+  double res;
+  if (is_mixture) res = mix_logpdf<D>(mix, h, x);
+  else {
+    double y[D];
+    double m = comp_maha<D>(mix, h.d, x, y);
+    res = comp_logpdf_from_maha(mix, h.d, h.df, m);
+  }
+  if (set) { logpi[n] = res + add_const; if (err) err[n] = 0; }
+  else logpi[n] += res;
+}
+
+// ---- K4: importance weights (generic_get_importance_weight_and_deduced_verb,
+// cosmo_pmc.c:343-345): log w = beta log pi - log q, flag clearing, running
+// max (warp shuffle + one atomic per block) and nok ----------------------------
+template <int D>
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_weights(const double *__restrict__ mix, const MixHdr h, int64_t N,
+          const double *__restrict__ X, const double *__restrict__ logpi,
+          const int32_t *__restrict__ err, double beta, int16_t *__restrict__ flg,
+          double *__restrict__ logw, DevScal *scal) {
+  __shared__ double red[32];
+  __shared__ int cnt[32];
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double lw = -INFINITY;
+  int ok = 0;
+  if (n < N) {
+    if (flg[n]) {
+      double x[D];
+      load_x<D>(X, n, h.d, x);
+      double lq = mix_logpdf<D>(mix, h, x);
+      double v = beta * logpi[n] - lq;
+      ok = (err[n] == 0) && isfinite(lq) && isfinite(v);
+      if (ok) lw = v; else flg[n] = 0;
+    }
+    logw[n] = ok ? lw : 0.0;
+  }
+  double wm = warp_max(lw);
+  unsigned b = __ballot_sync(0xffffffffu, ok);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { red[w] = wm; cnt[w] = __popc(b); }
+  __syncthreads();
+  if (w == 0) {
+    double v = (lane < (blockDim.x >> 5)) ? red[lane] : -INFINITY;
+    int c = (lane < (blockDim.x >> 5)) ? cnt[lane] : 0;
+    v = warp_max(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0 && c > 0) {
+      atomicMax(&scal->max_key, dkey(v));
+      atomicAdd(&scal->nok, (unsigned long long)c);
+    }
+  }
+}
+
+// normalize_importance_weight (cosmo_pmc.c:378): wbar = exp(lw - M)/S
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_normalize(int64_t N, const int16_t *__restrict__ flg, double *__restrict__ w, double M, double invS) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  w[n] = flg[n] ? exp(w[n] - M) * invS : 0.0;
+}
+
+// ---- K5: Rao-Blackwellised EM sufficient statistics (update_prop_rb,
+// cosmo_pmc.c:247).  Stat block layout (doubles):
+//   [0] M = local max log w  [1] S = sum e^(lw-M)  [2] S2 = sum e^2(lw-M)
+//   [3] T = sum e^(lw-M) (lw-M)  [4] nok  [5] nok_box  [6] N_local  [7] -
+//   then per component k at 8 + k*cs, cs = 3 + d + tri(d):
+//   A = sum w rho, G = sum w rho gamma, count (points drawn from k),
+//   B[d] = sum w rho gamma (x - p), C[tri] = sum w rho gamma (x-p)(x-p)^T (lower)
+// with w = e^(lw-M) and p the common pivot (weighted mean of the old means).
+#define STAT_HDR 8
+__host__ __device__ inline int stat_cs(int d) { return 3 + d + mix_tri(d); }
+__host__ __device__ inline int64_t stat_len(int K, int d) { return STAT_HDR + (int64_t)K * stat_cs(d); }
+
+// Phase 1 (per tile of PMC_BLOCK samples): each thread computes its sample's
+// w and responsibilities into shared memory.  Phase 2: the K x M outputs are
+// distributed over the threads, each accumulating over the tile (a K x tile x M
+// contraction) in registers across all tiles of a persistent block.
+#define EM_MAXOUT 20     // max outputs per thread: K*cs <= PMC_BLOCK*EM_MAXOUT
+template <int D>
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
+           const double *__restrict__ X, const int32_t *__restrict__ idx,
+           const int16_t *__restrict__ flg, const double *__restrict__ logw,
+           const DevScal *__restrict__ scal, double *__restrict__ partials) {
+  extern __shared__ double sm[];
+  const int K = h.K, d = h.d, tri = mix_tri(d), cs = stat_cs(d);
+  const int XS = d | 1;                       // padded row stride (bank spread)
+  const bool student = h.df > 0;
+  double *s_wr = sm;                          // [K][PMC_BLOCK]  w*rho
+  double *s_wg = student ? s_wr + (size_t)K * PMC_BLOCK : s_wr;   // w*rho*gamma (Gaussian: gamma = 1)
+  double *s_x = s_wg + (size_t)K * PMC_BLOCK;   // [PMC_BLOCK][XS] x - pivot
+  int *s_idx = (int *)(s_x + (size_t)PMC_BLOCK * XS);   // [PMC_BLOCK] drawn comp or -1
+  __shared__ double red[32];
+  const double *pivot = mix + (size_t)K * h.stride;
+  const double M = dunkey(scal->max_key);
+  const int nout = K * cs;
+  double acc[EM_MAXOUT];
+#pragma unroll
+  for (int o = 0; o < EM_MAXOUT; o++) acc[o] = 0.0;
+  double tS = 0.0, tS2 = 0.0, tT = 0.0;
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t n = tile * PMC_BLOCK + tid;
+    __syncthreads();
+    // ---- phase 1
+    const bool ok = (n < N) && flg[n];
+    double w = 0.0;
+    if (ok) {
+      double x[D], y[D];
+      load_x<D>(X, n, d, x);
+      const double lw = logw[n] - M;
+      w = exp(lw);
+      tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT);
+      double rt = 0.0;
+      for (int k = 0; k < K; k++) {
+        const double *comp = mix + (size_t)k * h.stride;
+        const double a = comp[0];
+        double r = 0.0, gam = 1.0;
+        if (a != 0.0) {
+          double m = comp_maha<D>(comp, d, x, y);
+          r = a * exp(comp_logpdf_from_maha(comp, d, h.df, m));
+          if (h.df > 0) gam = (double)(h.df + d) / ((double)h.df + m);
+        }
+        rt += r;
+        s_wr[k * PMC_BLOCK + tid] = r;
+        if (student) s_wg[k * PMC_BLOCK + tid] = gam;
+      }
+      const double sc = w / rt;
+      for (int k = 0; k < K; k++) {
+        double r = s_wr[k * PMC_BLOCK + tid] * sc;
+        s_wr[k * PMC_BLOCK + tid] = r;
+        if (student) s_wg[k * PMC_BLOCK + tid] *= r;
+      }
+#pragma unroll
+      for (int i = 0; i < D; i++) if (i < d) s_x[tid * XS + i] = x[i] - pivot[i];
+      s_idx[tid] = idx[n];
+    } else {
+      for (int k = 0; k < K; k++) { s_wr[k * PMC_BLOCK + tid] = 0.0; if (student) s_wg[k * PMC_BLOCK + tid] = 0.0; }
+      for (int i = 0; i < d; i++) s_x[tid * XS + i] = 0.0;
+      s_idx[tid] = -1;
+    }
+    __syncthreads();
+    // ---- phase 2: out(k, f) += sum_t weight(k,t) * feature(f,t)
+#pragma unroll
+    for (int o = 0; o < EM_MAXOUT; o++) {
+      const int out = tid + o * PMC_BLOCK;
+      if (out < nout) {
+        const int k = out / cs, f = out - k * cs;
+        double a = acc[o];
+        if (f == 0) {
+          for (int t = 0; t < PMC_BLOCK; t++) a += s_wr[k * PMC_BLOCK + t];
+        } else if (f == 1) {
+          for (int t = 0; t < PMC_BLOCK; t++) a += s_wg[k * PMC_BLOCK + t];
+        } else if (f == 2) {
+          for (int t = 0; t < PMC_BLOCK; t++) a += (s_idx[t] == k) ? 1.0 : 0.0;
+        } else if (f < 3 + d) {
+          const int i = f - 3;
+          for (int t = 0; t < PMC_BLOCK; t++) a = fma(s_wg[k * PMC_BLOCK + t], s_x[t * XS + i], a);
+        } else {
+          int q = f - 3 - d, i = 0;
+          while ((i + 1) * (i + 2) / 2 <= q) i++;
+          const int j = q - i * (i + 1) / 2;
+          for (int t = 0; t < PMC_BLOCK; t++)
+            a = fma(s_wg[k * PMC_BLOCK + t] * s_x[t * XS + i], s_x[t * XS + j], a);
+        }
+        acc[o] = a;
+      }
+    }
+  }
+  // ---- write this block's partial
+  double *P = partials + (size_t)blockIdx.x * stat_len(K, d);
+  double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red);
+  if (tid == 0) { P[0] = M; P[1] = bS; P[2] = bS2; P[3] = bT; P[4] = 0; P[5] = 0; P[6] = 0; P[7] = 0; }
+#pragma unroll
+  for (int o = 0; o < EM_MAXOUT; o++) {
+    const int out = tid + o * PMC_BLOCK;
+    if (out < nout) P[STAT_HDR + out] = acc[o];
+  }
+  (void)tri;
+}
+
+// fixed-order sum of the block partials -> this rank's stat block
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_em_reduce(const double *__restrict__ partials, int nblocks, int64_t len,
+            const DevScal *__restrict__ scal, int64_t N_local, double *__restrict__ block) {
+  for (int64_t o = threadIdx.x; o < len; o += blockDim.x) {
+    double s = 0.0;
+    if (o >= 1 && o != 4 && o != 5 && o != 6 && o != 7)
+      for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * len + o];
+    if (o == 0) s = dunkey(scal->max_key);
+    if (o == 4) s = (double)scal->nok;
+    if (o == 5) s = (double)scal->nok_box;
+    if (o == 6) s = (double)N_local;
+    block[o] = s;
+  }
+}
+
+// ---- M-step: combine the rank blocks in rank order, update alpha/mu/Sigma,
+// dead-component rule (manual.tex:482-490), Cholesky, diagnostics ---------------
+// result layout (doubles): [0..16) stats, then wght[K], mean[K*d], chol[K*d*d]
+#define RES_HDR 16
+__global__ void __launch_bounds__(64)
+k_em_finish(const double *__restrict__ mix, const MixHdr h, int nranks,
+            const double *__restrict__ all, int64_t N_global, double *__restrict__ work,
+            double *__restrict__ result) {
+  const int K = h.K, d = h.d, tri = mix_tri(d), cs = stat_cs(d);
+  const int64_t len = stat_len(K, d);
+  const double *pivot = mix + (size_t)K * h.stride;
+  __shared__ double sh[8];
+  __shared__ double s_scale[64];
+  __shared__ int s_dead[PMCB200_MAX_COMP];
+  __shared__ double s_alpha[PMCB200_MAX_COMP];
+  const int tid = threadIdx.x;
+  // global max and per-rank rescale
+  if (tid == 0) {
+    double M = -INFINITY;
+    for (int g = 0; g < nranks; g++) M = fmax(M, all[g * len]);
+    sh[0] = M;
+  }
+  __syncthreads();
+  const double M = sh[0];
+  for (int g = tid; g < nranks; g += blockDim.x) {
+    double Mg = all[g * len];
+    s_scale[g] = (Mg == -INFINITY) ? 0.0 : exp(Mg - M);
+  }
+  __syncthreads();
+  // combined block into work[len] (fixed rank order)
+  for (int64_t o = tid; o < len; o += blockDim.x) {
+    double s = 0.0;
+    if (o == 0) s = M;
+    else if (o == 1 || o >= STAT_HDR) {
+      bool is_count = (o >= STAT_HDR) && (((o - STAT_HDR) % cs) == 2);
+      for (int g = 0; g < nranks; g++) s += all[g * len + o] * (is_count ? 1.0 : s_scale[g]);
+    } else if (o == 2) {
+      for (int g = 0; g < nranks; g++) s += all[g * len + o] * s_scale[g] * s_scale[g];
+    } else if (o == 3) {   // T_g shifts: sum w_g (lw - M) = e^(Mg-M) [T_g + (Mg-M) S_g]
+      for (int g = 0; g < nranks; g++) {
+        double Mg = all[g * len];
+        if (s_scale[g] > 0.0) s += s_scale[g] * (all[g * len + 3] + (Mg - M) * all[g * len + 1]);
+      }
+    } else {
+      for (int g = 0; g < nranks; g++) s += all[g * len + o];
+    }
+    work[o] = s;
+  }
+  __syncthreads();
+  const double S = work[1], S2 = work[2], T = work[3];
+  // per-component M-step, one thread per component
+  for (int k = tid; k < K; k += blockDim.x) {
+    const double *st = work + STAT_HDR + (size_t)k * cs;
+    const double *comp = mix + (size_t)k * h.stride;
+    double *o_mean = result + RES_HDR + K + (size_t)k * d;
+    double *o_chol = result + RES_HDR + K + (size_t)K * d + (size_t)k * d * d;
+    const double A = st[0], G = st[1], count = st[2];
+    const double alpha = A / S;
+    int was_alive = comp[0] != 0.0;
+    int dead = !was_alive || !(alpha >= 1.0 / (double)N_global) || count < (double)PMCB200_MINCOUNT;
+    if (!dead) {
+      // delta = B/G, mu' = p + delta, Sigma' = (C - G delta delta^T)/A; Cholesky in place
+      const double *B = st + 3, *Cc = st + 3 + d;
+      for (int i = 0; i < d; i++)
+        for (int j = 0; j <= i; j++) {
+          double di = B[i] / G, dj = B[j] / G;
+          o_chol[i * d + j] = (Cc[i * (i + 1) / 2 + j] - G * di * dj) / A;
+        }
+      for (int j = 0; j < d && !dead; j++) {
+        double s = o_chol[j * d + j];
+        for (int q = 0; q < j; q++) s -= o_chol[j * d + q] * o_chol[j * d + q];
+        if (!(s > 0.0) || !isfinite(s)) { dead = 1; break; }
+        double ljj = sqrt(s);
+        o_chol[j * d + j] = ljj;
+        for (int i = j + 1; i < d; i++) {
+          double t = o_chol[i * d + j];
+          for (int q = 0; q < j; q++) t -= o_chol[i * d + q] * o_chol[j * d + q];
+          o_chol[i * d + j] = t / ljj;
+        }
+      }
+      if (!dead) {
+        for (int i = 0; i < d; i++) {
+          o_mean[i] = pivot[i] + B[i] / G;
+          for (int j = i + 1; j < d; j++) o_chol[i * d + j] = 0.0;
+        }
+      }
+    }
+    if (dead) {   // keep the old mean / factor, weight 0
+      const double *mean = comp + 2, *L = comp + 2 + d;
+      for (int i = 0; i < d; i++) {
+        o_mean[i] = mean[i];
+        for (int j = 0; j < d; j++) o_chol[i * d + j] = (j <= i) ? L[i * (i + 1) / 2 + j] : 0.0;
+      }
+    }
+    s_dead[k] = dead && was_alive;
+    s_alpha[k] = dead ? 0.0 : alpha;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double wsum = 0.0, enc = 0.0;
+    int ndead = 0;
+    for (int k = 0; k < K; k++) { wsum += s_alpha[k]; ndead += s_dead[k]; }
+    for (int k = 0; k < K; k++) {
+      double a = (wsum > 0.0) ? s_alpha[k] / wsum : 0.0;
+      result[RES_HDR + k] = a;
+      enc = fma(a, a, enc);
+    }
+    const double Ng = (double)N_global;
+    result[0] = M;                                   // maxW
+    result[1] = S;                                   // sum_shift
+    result[2] = log(S) + M;                          // logSum
+    result[3] = exp(log(S) - T / S) / Ng;            // perplexity = exp(-sum wbar log wbar)/N
+    result[4] = S * S / S2;                          // ESS
+    result[5] = log(S) + M - log(Ng);                // ln evidence
+    result[6] = 1.0 / enc;                           // ENC (updated proposal)
+    result[7] = (double)ndead;
+    result[8] = work[4];                             // nok
+    result[9] = work[5];                             // nok_box
+    result[10] = work[6];                            // N summed over ranks
+  }
+  (void)tri;
+}

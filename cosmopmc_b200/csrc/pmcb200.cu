@@ -1,0 +1,833 @@
+// pmcb200.cu -- C-ABI of the B200-native PMC iteration (include/pmcb200.h).
+// Host side: context, packing of the proposal/target into device layouts,
+// kernel launches.  No CPU compute path: every entry point launches kernels.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+#include "common.cuh"
+#include "cosmo.cuh"
+#include "pmc_kernels.cuh"
+
+// ---- context ----------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct pmcb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  char errmsg[512] = {0};
+  int64_t launches = 0;
+  // proposal
+  bool have_prop = false;
+  MixHdr h{};
+  std::vector<double> wght, mean, chol;   // host mirror: [K], [K*d], [K*d*d]
+  double *d_mix = nullptr;                // packed device mixture (+ pivot)
+  size_t mix_cap = 0;
+  // target
+  bool have_target = false;
+  pmcb200_target_t tgt{};
+  DevLike like[PMCB200_MAX_DATA];
+  std::vector<void *> tgt_allocs;
+  double *d_box = nullptr;                // [2*d]: min, max
+  double logpr_const = 0.0;
+  MixHdr prior_h{};
+  double *d_prior = nullptr;
+  int *d_prior_sel = nullptr;
+  // per-iteration device state
+  DevScal *d_scal = nullptr;
+  DevCount *d_cnt = nullptr;
+  double *d_partials = nullptr; size_t partials_cap = 0;
+  double *d_work = nullptr, *d_result = nullptr; size_t work_cap = 0;
+  double *h_result = nullptr;             // pinned
+  int em_blocks = 0;
+  int sm_count = 148;
+  // scratch for the host-buffer API
+  DevBuf sX, sIdx, sFlg, sLogw, sLogpi, sErr, sBlock;
+};
+
+static int fail(pmcb200_ctx *c, int code, const char *fmt, ...) {
+  if (c) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(c->errmsg, sizeof(c->errmsg), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+#define CUDA_OK(c, call)                                                            \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess)                                                         \
+      return fail(c, PMCB200_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                              \
+  } while (0)
+#define LAUNCH_OK(c)                                                                \
+  do {                                                                              \
+    (c)->launches++;                                                                \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess)                                                         \
+      return fail(c, PMCB200_ERR_CUDA, "kernel launch: %s (%s:%d)",                 \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                     \
+  } while (0)
+
+static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
+
+static int ensure(pmcb200_ctx *c, DevBuf &b, size_t bytes) {
+  if (b.cap >= bytes) return 0;
+  if (b.p) CUDA_OK(c, cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  CUDA_OK(c, cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  return 0;
+}
+
+// dispatch on the padded dimension
+#define DISPATCH_D(d, CALL)                                  \
+  do {                                                       \
+    if ((d) <= 2) { constexpr int DD = 2; CALL; }            \
+    else if ((d) <= 3) { constexpr int DD = 3; CALL; }       \
+    else if ((d) <= 4) { constexpr int DD = 4; CALL; }       \
+    else if ((d) <= 5) { constexpr int DD = 5; CALL; }       \
+    else if ((d) <= 6) { constexpr int DD = 6; CALL; }       \
+    else if ((d) <= 7) { constexpr int DD = 7; CALL; }       \
+    else if ((d) <= 8) { constexpr int DD = 8; CALL; }       \
+    else if ((d) <= 10) { constexpr int DD = 10; CALL; }     \
+    else if ((d) <= 12) { constexpr int DD = 12; CALL; }     \
+    else if ((d) <= 16) { constexpr int DD = 16; CALL; }     \
+    else if ((d) <= 20) { constexpr int DD = 20; CALL; }     \
+    else if ((d) <= 24) { constexpr int DD = 24; CALL; }     \
+    else { constexpr int DD = 32; CALL; }                    \
+  } while (0)
+
+// ---- host-side packing ---------------------------------------------------------
+static int host_cholesky(int d, double *A) {
+  for (int j = 0; j < d; j++) {
+    double s = A[j * d + j];
+    for (int k = 0; k < j; k++) s -= A[j * d + k] * A[j * d + k];
+    if (!(s > 0.0) || !std::isfinite(s)) return -1;
+    double ljj = std::sqrt(s);
+    A[j * d + j] = ljj;
+    for (int i = j + 1; i < d; i++) {
+      double t = A[i * d + j];
+      for (int k = 0; k < j; k++) t -= A[i * d + k] * A[j * d + k];
+      A[i * d + j] = t / ljj;
+    }
+  }
+  for (int i = 0; i < d; i++)
+    for (int j = i + 1; j < d; j++) A[i * d + j] = 0.0;
+  return 0;
+}
+
+// pack one component (wght, mean[d], chol[d*d] lower) at dst[stride]
+static void pack_comp(double *dst, int d, int df, double w, const double *mean, const double *chol) {
+  const int tri = mix_tri(d);
+  double logdet = 0.0;
+  dst[0] = w;
+  for (int i = 0; i < d; i++) {
+    dst[2 + i] = mean[i];
+    for (int j = 0; j <= i; j++) dst[2 + d + i * (i + 1) / 2 + j] = chol[i * d + j];
+    dst[2 + d + tri + i] = 1.0 / chol[i * d + i];
+    logdet += std::log(chol[i * d + i]);
+  }
+  if (df <= 0) dst[1] = -0.5 * d * LN2PI - logdet;
+  else {
+    double nu = (double)df;
+    dst[1] = std::lgamma(0.5 * (nu + d)) - std::lgamma(0.5 * nu) - 0.5 * d * std::log(nu * M_PI) - logdet;
+  }
+}
+
+static int upload_mix(pmcb200_ctx *c, int K, int d, int df, const double *w, const double *mean,
+                      const double *chol, MixHdr &h, double **dbuf, size_t *cap) {
+  h.K = K; h.d = d; h.df = df; h.stride = mix_stride(d); h.tri = mix_tri(d);
+  size_t n = (size_t)K * h.stride + d;
+  std::vector<double> buf(n, 0.0);
+  double wsum = 0.0;
+  for (int k = 0; k < K; k++) {
+    pack_comp(buf.data() + (size_t)k * h.stride, d, df, w[k], mean + (size_t)k * d, chol + (size_t)k * d * d);
+    wsum += w[k];
+  }
+  for (int i = 0; i < d; i++) {   // common EM pivot: weighted mean of component means
+    double p = 0.0;
+    for (int k = 0; k < K; k++) p += w[k] * mean[(size_t)k * d + i];
+    buf[(size_t)K * h.stride + i] = (wsum > 0.0) ? p / wsum : 0.0;
+  }
+  if (!*dbuf || *cap < n) {
+    if (*dbuf) CUDA_OK(c, cudaFree(*dbuf));
+    *dbuf = nullptr;
+    CUDA_OK(c, cudaMalloc((void **)dbuf, n * sizeof(double)));
+    *cap = n;
+  }
+  CUDA_OK(c, cudaMemcpyAsync(*dbuf, buf.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));   // buf is a stack-lifetime staging vector
+  return 0;
+}
+
+template <class T>
+static int dev_copy(pmcb200_ctx *c, const T *src, size_t n, const T **out) {
+  T *p = nullptr;
+  CUDA_OK(c, cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+  c->tgt_allocs.push_back(p);
+  if (n) CUDA_OK(c, cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+
+static void free_target(pmcb200_ctx *c) {
+  for (void *p : c->tgt_allocs) cudaFree(p);
+  c->tgt_allocs.clear();
+  c->have_target = false;
+  c->d_box = nullptr; c->d_prior = nullptr; c->d_prior_sel = nullptr;
+}
+
+// ---- life cycle ------------------------------------------------------------------
+extern "C" int pmcb200_version(void) { return PMCB200_VERSION; }
+
+extern "C" int pmcb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int pmcb200_create(int device, void *stream, pmcb200_ctx **out) {
+  if (!out) return PMCB200_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    fprintf(stderr, "pmcb200_create: no usable CUDA device %d (%s); there is no CPU fallback\n",
+            device, e != cudaSuccess ? cudaGetErrorString(e) : "device count");
+    return PMCB200_ERR_CUDA;
+  }
+  pmcb200_ctx *c = new pmcb200_ctx();
+  c->device = device;
+  CUDA_OK(c, cudaSetDevice(device));
+  // NULL = the legacy default stream (orders with torch's default stream and
+  // with plain cudaMemcpy in C hosts); (void*)-1 = a private non-blocking stream
+  if (stream == (void *)-1) { CUDA_OK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  else c->stream = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  CUDA_OK(c, cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_OK(c, cudaMalloc((void **)&c->d_scal, sizeof(DevScal)));
+  CUDA_OK(c, cudaMemset(c->d_scal, 0, sizeof(DevScal)));
+  CUDA_OK(c, cudaMalloc((void **)&c->d_cnt, sizeof(DevCount)));
+  CUDA_OK(c, cudaMemset(c->d_cnt, 0, sizeof(DevCount)));
+  CUDA_OK(c, cudaMallocHost((void **)&c->h_result, sizeof(double) * (RES_HDR + PMCB200_MAX_COMP * (1 + PMCB200_MAX_DIM + PMCB200_MAX_DIM * PMCB200_MAX_DIM))));
+  *out = c;
+  return 0;
+}
+
+extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_target(c);
+  for (DevBuf *b : {&c->sX, &c->sIdx, &c->sFlg, &c->sLogw, &c->sLogpi, &c->sErr, &c->sBlock})
+    if (b->p) cudaFree(b->p);
+  if (c->d_mix) cudaFree(c->d_mix);
+  if (c->d_scal) cudaFree(c->d_scal);
+  if (c->d_cnt) cudaFree(c->d_cnt);
+  if (c->d_partials) cudaFree(c->d_partials);
+  if (c->d_work) cudaFree(c->d_work);
+  if (c->d_result) cudaFree(c->d_result);
+  if (c->h_result) cudaFreeHost(c->h_result);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char *pmcb200_last_error(const pmcb200_ctx *c) { return c ? c->errmsg : "null context"; }
+extern "C" void *pmcb200_stream(pmcb200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int64_t pmcb200_launch_count(const pmcb200_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int pmcb200_sync(pmcb200_ctx *c) {
+  if (!c) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int pmcb200_dev_alloc(pmcb200_ctx *c, size_t bytes, void **dptr) {
+  if (!c || !dptr) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  CUDA_OK(c, cudaMalloc(dptr, std::max<size_t>(bytes, 1)));
+  return 0;
+}
+extern "C" int pmcb200_dev_free(pmcb200_ctx *c, void *dptr) {
+  if (!c) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaFree(dptr));
+  return 0;
+}
+extern "C" int pmcb200_h2d(pmcb200_ctx *c, void *dptr, const void *hptr, size_t bytes) {
+  if (!c) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int pmcb200_d2h(pmcb200_ctx *c, void *hptr, const void *dptr, size_t bytes) {
+  if (!c) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- proposal ----------------------------------------------------------------------
+static int install_proposal(pmcb200_ctx *c, int K, int d, int df, const double *w, const double *mean,
+                            const double *chol) {
+  if (K < 1 || K > PMCB200_MAX_COMP || d < 1 || d > PMCB200_MAX_DIM)
+    return fail(c, PMCB200_ERR_DIM, "proposal: ncomp=%d (max %d), ndim=%d (max %d)", K, PMCB200_MAX_COMP, d,
+                PMCB200_MAX_DIM);
+  if ((int64_t)K * stat_cs(d) > (int64_t)PMC_BLOCK * EM_MAXOUT)
+    return fail(c, PMCB200_ERR_UNSUP, "proposal: K*(3+d+d(d+1)/2)=%lld exceeds the EM kernel limit %d",
+                (long long)K * stat_cs(d), PMC_BLOCK * EM_MAXOUT);
+  for (int k = 0; k < K; k++) {
+    if (!(w[k] >= 0.0) || !std::isfinite(w[k])) return fail(c, PMCB200_ERR_ARG, "proposal weight %d = %g", k, w[k]);
+    for (int i = 0; i < d; i++)
+      if (!(chol[(size_t)k * d * d + i * d + i] > 0.0))
+        return fail(c, PMCB200_ERR_CHOLESKY, "component %d: Cholesky diagonal %d not positive", k, i);
+  }
+  c->wght.assign(w, w + K);
+  c->mean.assign(mean, mean + (size_t)K * d);
+  c->chol.assign(chol, chol + (size_t)K * d * d);
+  for (int k = 0; k < K; k++)   // strict upper triangle is ignored
+    for (int i = 0; i < d; i++)
+      for (int j = i + 1; j < d; j++) c->chol[(size_t)k * d * d + i * d + j] = 0.0;
+  int rc = upload_mix(c, K, d, df, c->wght.data(), c->mean.data(), c->chol.data(), c->h, &c->d_mix, &c->mix_cap);
+  if (rc) return rc;
+  // EM work buffers
+  int64_t len = stat_len(K, d);
+  c->em_blocks = 2 * c->sm_count;
+  size_t need = (size_t)c->em_blocks * len;
+  if (c->partials_cap < need) {
+    if (c->d_partials) CUDA_OK(c, cudaFree(c->d_partials));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_partials, need * sizeof(double)));
+    c->partials_cap = need;
+  }
+  size_t rlen = RES_HDR + (size_t)K * (1 + d + (size_t)d * d);
+  if (c->work_cap < std::max<size_t>(len, rlen)) {
+    if (c->d_work) CUDA_OK(c, cudaFree(c->d_work));
+    if (c->d_result) CUDA_OK(c, cudaFree(c->d_result));
+    c->work_cap = std::max<size_t>(len, rlen);
+    CUDA_OK(c, cudaMalloc((void **)&c->d_work, c->work_cap * sizeof(double)));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_result, c->work_cap * sizeof(double)));
+  }
+  c->have_prop = true;
+  return 0;
+}
+
+extern "C" int pmcb200_set_proposal(pmcb200_ctx *c, int K, int d, int df, const double *w,
+                                    const double *mean, const double *chol) {
+  if (!c || !w || !mean || !chol) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  return install_proposal(c, K, d, df, w, mean, chol);
+}
+
+extern "C" int pmcb200_set_proposal_cov(pmcb200_ctx *c, int K, int d, int df, const double *w,
+                                        const double *mean, const double *cov) {
+  if (!c || !w || !mean || !cov) return PMCB200_ERR_ARG;
+  if (K < 1 || K > PMCB200_MAX_COMP || d < 1 || d > PMCB200_MAX_DIM)
+    return fail(c, PMCB200_ERR_DIM, "proposal: ncomp=%d, ndim=%d out of range", K, d);
+  std::vector<double> L(cov, cov + (size_t)K * d * d);
+  for (int k = 0; k < K; k++)
+    if (host_cholesky(d, L.data() + (size_t)k * d * d))
+      return fail(c, PMCB200_ERR_CHOLESKY, "component %d: covariance not positive definite", k);
+  CUDA_OK(c, cudaSetDevice(c->device));
+  return install_proposal(c, K, d, df, w, mean, L.data());
+}
+
+extern "C" int pmcb200_get_proposal(pmcb200_ctx *c, double *w, double *mean, double *chol, double *cov) {
+  if (!c) return PMCB200_ERR_ARG;
+  if (!c->have_prop) return fail(c, PMCB200_ERR_STATE, "no proposal set");
+  const int K = c->h.K, d = c->h.d;
+  if (w) memcpy(w, c->wght.data(), K * sizeof(double));
+  if (mean) memcpy(mean, c->mean.data(), (size_t)K * d * sizeof(double));
+  if (chol) memcpy(chol, c->chol.data(), (size_t)K * d * d * sizeof(double));
+  if (cov)
+    for (int k = 0; k < K; k++) {
+      const double *L = c->chol.data() + (size_t)k * d * d;
+      for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) {
+          double s = 0.0;
+          for (int q = 0; q <= std::min(i, j); q++) s += L[i * d + q] * L[j * d + q];
+          cov[(size_t)k * d * d + i * d + j] = s;
+        }
+    }
+  return 0;
+}
+
+// ---- target ------------------------------------------------------------------------
+static int pack_gauss(pmcb200_ctx *c, int n, const double *mean, const double *chol, const double **out) {
+  std::vector<double> buf(mix_stride(n));
+  pack_comp(buf.data(), n, -1, 1.0, mean, chol);
+  return dev_copy<double>(c, buf.data(), buf.size(), out);
+}
+
+static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
+  const int n = L.sn_n;
+  if (n < 1 || !L.sn_z || !L.sn_m || !L.sn_s || !L.sn_c || !L.sn_cov)
+    return fail(c, PMCB200_ERR_ARG, "SNIa: empty sample");
+  if (L.sn_chi2mode < 0 || L.sn_chi2mode > PMCB200_CHI2_betaz)
+    return fail(c, PMCB200_ERR_UNSUP, "SNIa: chi2mode %d not supported (chi2_Theta1 / chi2_dust)", L.sn_chi2mode);
+  // sort by redshift; supernovae sharing a redshift share one distance integral
+  std::vector<int> ord(n);
+  for (int i = 0; i < n; i++) ord[i] = i;
+  std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return L.sn_z[a] < L.sn_z[b]; });
+  std::vector<double> rows((size_t)n * SN_ROW, 0.0);
+  std::vector<int> first;
+  std::vector<double2> nodes;
+  const double pv_fac = 5.0 / M_LN10 * L.sn_v_pec / C_KMS;
+  for (int r = 0; r < n; r++) {
+    int i = ord[r];
+    double z = L.sn_z[i];
+    if (!(z > 0.0)) return fail(c, PMCB200_ERR_ARG, "SNIa: redshift[%d] = %g", i, z);
+    if (r == 0 || z != L.sn_z[ord[r - 1]]) {
+      first.push_back(r);
+      double a = 1.0 / (1.0 + z), hh = 1.0 - a;
+      size_t base = nodes.size();
+      nodes.resize(base + SN_NODES);
+      nodes[base] = make_double2(a, std::log(a));
+      for (int j = 2; j <= 7; j++) {
+        int it = 1 << (j - 2);
+        double del = hh / (double)it, x = a + 0.5 * del;   // NR trapzd: x += del
+        for (int q = 0; q < it; q++, x += del) nodes[base + it + q] = make_double2(x, std::log(x));
+      }
+    }
+    double *row = rows.data() + (size_t)r * SN_ROW;
+    row[0] = L.sn_m[i]; row[1] = L.sn_s[i]; row[2] = L.sn_c[i]; row[3] = z;
+    for (int q = 0; q < 6; q++) row[4 + q] = L.sn_cov[(size_t)i * 6 + q];
+    double spv = pv_fac / z;
+    row[10] = spv * spv + L.sn_sig_int * L.sn_sig_int;
+  }
+  first.push_back(n);
+  D.sn_n = n;
+  D.sn_nz = (int)first.size() - 1;
+  D.sn_chi2mode = L.sn_chi2mode;
+  D.sn_add_logdetCov = L.sn_add_logdetCov;
+  for (int i = 0; i < 4; i++) D.Theta2[i] = L.sn_Theta2[i];
+  for (int i = 0; i < 3; i++) D.Theta2_denom[i] = L.sn_Theta2_denom[i];
+  D.sig_int2 = L.sn_sig_int * L.sn_sig_int;
+  D.pv_fac = pv_fac;
+  int rc;
+  if ((rc = dev_copy<double2>(c, nodes.data(), nodes.size(), &D.nodes))) return rc;
+  if ((rc = dev_copy<int>(c, first.data(), first.size(), &D.first))) return rc;
+  if ((rc = dev_copy<double>(c, rows.data(), rows.size(), &D.sn))) return rc;
+  return 0;
+}
+
+extern "C" int pmcb200_set_target(pmcb200_ctx *c, const pmcb200_target_t *t) {
+  if (!c || !t) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  free_target(c);
+  if (t->npar < 1 || t->npar > PMCB200_MAX_DIM || t->ndata < 1 || t->ndata > PMCB200_MAX_DATA)
+    return fail(c, PMCB200_ERR_DIM, "target: npar=%d ndata=%d out of range", t->npar, t->ndata);
+  c->tgt = *t;
+  const int d = t->npar;
+  int rc;
+  // flat box prior: logpr_default = -sum log(max-min), param.c:124-129
+  double logpr = 0.0;
+  std::vector<double> box(2 * d);
+  for (int j = 0; j < d; j++) {
+    if (!(t->max[j] > t->min[j])) return fail(c, PMCB200_ERR_ARG, "target: max[%d] <= min[%d]", j, j);
+    logpr -= std::log(t->max[j] - t->min[j]);
+    box[j] = t->min[j]; box[d + j] = t->max[j];
+  }
+  // special prior of data set 0 only, param.c:998-1001,1055-1101
+  int special = t->like[0].special;
+  if (special == PMCB200_SPECIAL_unity) for (int j = 0; j < d; j++) logpr += std::log(t->max[j] - t->min[j]);
+  else if (special != PMCB200_SPECIAL_none)
+    return fail(c, PMCB200_ERR_UNSUP, "target: special prior %d not supported", special);
+  c->logpr_const = logpr;
+  const double *dbox;
+  if ((rc = dev_copy<double>(c, box.data(), box.size(), &dbox))) return rc;
+  c->d_box = (double *)dbox;
+
+  for (int i = 0; i < t->ndata; i++) {
+    const pmcb200_like_t &L = t->like[i];
+    DevLike &D = c->like[i];
+    memset(&D, 0, sizeof(D));
+    D.kind = L.kind; D.npar = L.npar; D.special = L.special; D.model = L.model;
+    if (L.npar != d) return fail(c, PMCB200_ERR_DIM, "like %d: npar %d != %d", i, L.npar, d);
+    for (int j = 0; j < d; j++) D.par[j] = L.par[j];
+    switch (L.kind) {
+      case PMCB200_LIKE_SNIa:
+        if ((rc = build_sn(c, L, D))) return rc;
+        break;
+      case PMCB200_LIKE_BAO: {
+        if (L.g_ndim < 1 || L.g_ndim > 4 || !L.g_z || !L.g_mean || !L.g_chol)
+          return fail(c, PMCB200_ERR_ARG, "BAO: bad data (ndim=%d)", L.g_ndim);
+        D.bao_method = L.bao_method; D.g_ndim = L.g_ndim;
+        int nz = L.g_ndim * (L.bao_method == PMCB200_BAO_distance_D_V_ratio ? 2 : 1);
+        if ((rc = dev_copy<double>(c, L.g_z, nz, &D.g_z))) return rc;
+        if ((rc = pack_gauss(c, L.g_ndim, L.g_mean, L.g_chol, &D.g_comp))) return rc;
+        break;
+      }
+      case PMCB200_LIKE_CMBDistPrior:
+        if (L.g_ndim < 3 || L.g_ndim > 4 || !L.g_mean || !L.g_chol)
+          return fail(c, PMCB200_ERR_ARG, "CMBDistPrior: ndim=%d (3 or 4)", L.g_ndim);
+        D.g_ndim = L.g_ndim;
+        if ((rc = pack_gauss(c, L.g_ndim, L.g_mean, L.g_chol, &D.g_comp))) return rc;
+        break;
+      case PMCB200_LIKE_Mvdens:
+      case PMCB200_LIKE_MixMvdens: {
+        int K = L.kind == PMCB200_LIKE_Mvdens ? 1 : L.mix_ncomp;
+        if (K < 1 || K > PMCB200_MAX_COMP || L.mix_ndim != d || !L.mix_mean || !L.mix_chol)
+          return fail(c, PMCB200_ERR_DIM, "Mvdens target: ncomp=%d ndim=%d (npar=%d)", K, L.mix_ndim, d);
+        std::vector<double> w(K, 1.0);
+        if (L.mix_wght) w.assign(L.mix_wght, L.mix_wght + K);
+        double *dm = nullptr; size_t cap = 0;
+        if ((rc = upload_mix(c, K, d, L.mix_df, w.data(), L.mix_mean, L.mix_chol, D.mixh, &dm, &cap))) return rc;
+        c->tgt_allocs.push_back(dm);
+        D.mix = dm;
+        break;
+      }
+      case PMCB200_LIKE_BANANA:
+        if (d < 2) return fail(c, PMCB200_ERR_DIM, "banana target needs d >= 2");
+        D.banana_b = L.banana_b; D.banana_sigma1sq = L.banana_sigma1sq;
+        break;
+      default:
+        return fail(c, PMCB200_ERR_UNSUP, "likelihood kind %d not supported on the device path", L.kind);
+    }
+  }
+  // Gaussian prior, param.c:1009-1026
+  if (t->prior_mean) {
+    int np = t->prior_ndim;
+    if (np < 1 || np > d || !t->prior_chol) return fail(c, PMCB200_ERR_DIM, "prior: ndim=%d", np);
+    std::vector<int> sel;
+    if (t->nprior > 0) { for (int j = 0; j < d; j++) if (t->indprior[j] == 1) sel.push_back(j); }
+    else for (int j = 0; j < np; j++) sel.push_back(j);
+    if ((int)sel.size() != np) return fail(c, PMCB200_ERR_DIM, "prior: %d selected parameters != ndim %d", (int)sel.size(), np);
+    double one = 1.0, *dm = nullptr; size_t cap = 0;
+    if ((rc = upload_mix(c, 1, np, -1, &one, t->prior_mean, t->prior_chol, c->prior_h, &dm, &cap))) return rc;
+    c->tgt_allocs.push_back(dm);
+    c->d_prior = dm;
+    const int *dsel;
+    if ((rc = dev_copy<int>(c, sel.data(), sel.size(), &dsel))) return rc;
+    c->d_prior_sel = (int *)dsel;
+  }
+  c->have_target = true;
+  return 0;
+}
+
+// ---- stage launches ------------------------------------------------------------------
+static int need(pmcb200_ctx *c, bool prop, bool tgt) {
+  if (!c) return PMCB200_ERR_ARG;
+  if (prop && !c->have_prop) return fail(c, PMCB200_ERR_STATE, "proposal not set (pmcb200_set_proposal)");
+  if (tgt && !c->have_target) return fail(c, PMCB200_ERR_STATE, "target not set (pmcb200_set_target)");
+  if (prop && tgt && c->h.d != c->tgt.npar)
+    return fail(c, PMCB200_ERR_DIM, "proposal ndim %d != target npar %d", c->h.d, c->tgt.npar);
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return fail(c, PMCB200_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int reset_scal(pmcb200_ctx *c) {
+  CUDA_OK(c, cudaMemsetAsync(c->d_scal, 0, sizeof(DevScal), c->stream));
+  return 0;
+}
+
+static int launch_simulate(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, int64_t offset,
+                           double *dX, int32_t *didx, int16_t *dflg) {
+  if (N <= 0) return 0;
+  if (!c->d_box) return fail(c, PMCB200_ERR_STATE, "simulate needs the target's box (pmcb200_set_target)");
+  DISPATCH_D(c->h.d, (k_simulate<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
+                         c->d_mix, c->h, c->d_box, N, seed, iter, offset, dX, didx, dflg, c->d_scal)));
+  LAUNCH_OK(c);
+  return 0;
+}
+
+static int launch_posterior(pmcb200_ctx *c, int64_t N, const double *dX, const int16_t *dflg,
+                            double *dlogpi, int32_t *derr) {
+  if (N <= 0) return 0;
+  const int d = c->tgt.npar;
+  for (int i = 0; i < c->tgt.ndata; i++) {
+    const DevLike &L = c->like[i];
+    const int set = (i == 0);
+    const double add = set ? c->logpr_const : 0.0;
+    switch (L.kind) {
+      case PMCB200_LIKE_SNIa:
+        k_like_sn<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
+        break;
+      case PMCB200_LIKE_BAO:
+        k_like_bao<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add);
+        break;
+      case PMCB200_LIKE_CMBDistPrior:
+        k_like_cmbdp<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add);
+        break;
+      case PMCB200_LIKE_BANANA:
+        k_like_banana<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add);
+        break;
+      case PMCB200_LIKE_Mvdens:
+      case PMCB200_LIKE_MixMvdens:
+        DISPATCH_D(d, (k_like_mix<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
+                          L.mix, L.mixh, L.kind == PMCB200_LIKE_MixMvdens, N, dX, d, nullptr, dflg, dlogpi,
+                          derr, set, add)));
+        break;
+      default:
+        return fail(c, PMCB200_ERR_UNSUP, "likelihood kind %d", L.kind);
+    }
+    LAUNCH_OK(c);
+  }
+  if (c->d_prior) {
+    DISPATCH_D(c->prior_h.d, (k_like_mix<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
+                                 c->d_prior, c->prior_h, 0, N, dX, d, c->d_prior_sel, dflg, dlogpi, derr, 0, 0.0)));
+    LAUNCH_OK(c);
+  }
+  return 0;
+}
+
+static int launch_weights(pmcb200_ctx *c, int64_t N, const double *dX, const double *dlogpi,
+                          const int32_t *derr, double beta, int16_t *dflg, double *dlogw) {
+  if (N <= 0) return 0;
+  DISPATCH_D(c->h.d, (k_weights<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
+                         c->d_mix, c->h, N, dX, dlogpi, derr, beta, dflg, dlogw, c->d_scal)));
+  LAUNCH_OK(c);
+  return 0;
+}
+
+template <int DD>
+static cudaError_t em_launch(pmcb200_ctx *c, int blocks, size_t smem, int64_t N, const double *dX,
+                             const int32_t *didx, const int16_t *dflg, const double *dlogw) {
+  cudaError_t e = cudaFuncSetAttribute(k_em_stats<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_em_stats<DD><<<blocks, PMC_BLOCK, smem, c->stream>>>(c->d_mix, c->h, N, dX, didx, dflg, dlogw, c->d_scal,
+                                                         c->d_partials);
+  return cudaSuccess;
+}
+
+static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const int32_t *didx,
+                           const int16_t *dflg, const double *dlogw, double *dblock) {
+  const int K = c->h.K, d = c->h.d;
+  const int64_t len = stat_len(K, d);
+  int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
+  int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->em_blocks, ntiles));
+  size_t smem = ((size_t)K * PMC_BLOCK * (c->h.df > 0 ? 2 : 1) + (size_t)PMC_BLOCK * (d | 1)) * sizeof(double) +
+                PMC_BLOCK * sizeof(int);
+  if (smem > 227 * 1024) return fail(c, PMCB200_ERR_UNSUP, "EM kernel needs %zu B shared memory", smem);
+  cudaError_t e = cudaSuccess;
+  DISPATCH_D(d, (e = em_launch<DD>(c, blocks, smem, N, dX, didx, dflg, dlogw)));
+  if (e != cudaSuccess) return fail(c, PMCB200_ERR_CUDA, "k_em_stats attribute: %s", cudaGetErrorString(e));
+  LAUNCH_OK(c);
+  k_em_reduce<<<1, PMC_BLOCK, 0, c->stream>>>(c->d_partials, blocks, len, c->d_scal, N, dblock);
+  LAUNCH_OK(c);
+  return 0;
+}
+
+// ---- C-ABI stage entry points ------------------------------------------------------------
+extern "C" int pmcb200_simulate(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, int64_t offset,
+                                double *dX, int32_t *didx, int16_t *dflg) {
+  int rc = need(c, true, false);
+  if (rc) return rc;
+  if (N < 0 || !dX || !didx || !dflg) return fail(c, PMCB200_ERR_ARG, "simulate: bad arguments");
+  if ((rc = reset_scal(c))) return rc;
+  return launch_simulate(c, N, seed, iter, offset, dX, didx, dflg);
+}
+
+extern "C" int pmcb200_simulate_from_draws(pmcb200_ctx *c, int64_t N, const double *du, const double *dz,
+                                           double *dX, int32_t *didx, int16_t *dflg) {
+  int rc = need(c, true, false);
+  if (rc) return rc;
+  if (N < 0 || !du || !dz || !dX || !didx || !dflg) return fail(c, PMCB200_ERR_ARG, "simulate_from_draws: bad arguments");
+  if (!c->d_box) return fail(c, PMCB200_ERR_STATE, "simulate needs the target's box (pmcb200_set_target)");
+  if (c->h.df > 0) return fail(c, PMCB200_ERR_UNSUP, "simulate_from_draws: Gaussian proposals only");
+  if (N == 0) return 0;
+  DISPATCH_D(c->h.d, (k_simulate_from_draws<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
+                         c->d_mix, c->h, c->d_box, N, du, dz, dX, didx, dflg)));
+  LAUNCH_OK(c);
+  return 0;
+}
+
+extern "C" int pmcb200_proposal_log_pdf(pmcb200_ctx *c, int64_t N, const double *dX, double *dlogq) {
+  int rc = need(c, true, false);
+  if (rc) return rc;
+  if (N < 0 || !dX || !dlogq) return fail(c, PMCB200_ERR_ARG, "proposal_log_pdf: bad arguments");
+  if (N == 0) return 0;
+  DISPATCH_D(c->h.d, (k_logq<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(c->d_mix, c->h, N, dX, dlogq)));
+  LAUNCH_OK(c);
+  return 0;
+}
+
+extern "C" int pmcb200_posterior_log_pdf(pmcb200_ctx *c, int64_t N, const double *dX, double *dlogpi,
+                                         int32_t *derr) {
+  int rc = need(c, false, true);
+  if (rc) return rc;
+  if (N < 0 || !dX || !dlogpi) return fail(c, PMCB200_ERR_ARG, "posterior_log_pdf: bad arguments");
+  return launch_posterior(c, N, dX, nullptr, dlogpi, derr);
+}
+
+extern "C" int pmcb200_importance_weights(pmcb200_ctx *c, int64_t N, const double *dX, double beta,
+                                          int16_t *dflg, double *dlogw) {
+  int rc = need(c, true, true);
+  if (rc) return rc;
+  if (N < 0 || !dX || !dflg || !dlogw) return fail(c, PMCB200_ERR_ARG, "importance_weights: bad arguments");
+  if ((rc = ensure(c, c->sLogpi, (size_t)std::max<int64_t>(N, 1) * sizeof(double)))) return rc;
+  if ((rc = ensure(c, c->sErr, (size_t)std::max<int64_t>(N, 1) * sizeof(int32_t)))) return rc;
+  // keep nok_box of a preceding simulate; reset max / nok
+  CUDA_OK(c, cudaMemsetAsync(c->d_scal, 0, 2 * sizeof(unsigned long long), c->stream));
+  if ((rc = launch_posterior(c, N, dX, dflg, (double *)c->sLogpi.p, (int32_t *)c->sErr.p))) return rc;
+  return launch_weights(c, N, dX, (double *)c->sLogpi.p, (int32_t *)c->sErr.p, beta, dflg, dlogw);
+}
+
+extern "C" int pmcb200_normalize_weights(pmcb200_ctx *c, int64_t N, const int16_t *dflg, double *dw) {
+  int rc = need(c, false, false);
+  if (rc) return rc;
+  if (N < 0 || !dflg || !dw) return fail(c, PMCB200_ERR_ARG, "normalize_weights: bad arguments");
+  // M and S come from the last em_finish (they are global over all ranks)
+  double M = c->h_result[0], S = c->h_result[1];
+  if (!(S > 0.0)) return fail(c, PMCB200_ERR_STATE, "normalize_weights: call pmcb200_em_finish first");
+  if (N == 0) return 0;
+  k_normalize<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(N, dflg, dw, M, 1.0 / S);
+  LAUNCH_OK(c);
+  return 0;
+}
+
+extern "C" int64_t pmcb200_stat_block_len(const pmcb200_ctx *c) {
+  if (!c || !c->have_prop) return 0;
+  return stat_len(c->h.K, c->h.d);
+}
+
+extern "C" int pmcb200_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const int32_t *didx,
+                                const int16_t *dflg, const double *dlogw, double *dblock) {
+  int rc = need(c, true, false);
+  if (rc) return rc;
+  if (N < 0 || !dblock || (N > 0 && (!dX || !didx || !dflg || !dlogw)))
+    return fail(c, PMCB200_ERR_ARG, "em_local: bad arguments");
+  return launch_em_local(c, N, dX, didx, dflg, dlogw, dblock);
+}
+
+extern "C" int pmcb200_em_finish(pmcb200_ctx *c, int nranks, const double *dall, int64_t N_global,
+                                 pmcb200_stats_t *stats) {
+  int rc = need(c, true, false);
+  if (rc) return rc;
+  if (nranks < 1 || nranks > 64 || !dall || N_global < 1) return fail(c, PMCB200_ERR_ARG, "em_finish: bad arguments");
+  const int K = c->h.K, d = c->h.d;
+  k_em_finish<<<1, 64, 0, c->stream>>>(c->d_mix, c->h, nranks, dall, N_global, c->d_work, c->d_result);
+  LAUNCH_OK(c);
+  size_t rlen = RES_HDR + (size_t)K * (1 + d + (size_t)d * d);
+  CUDA_OK(c, cudaMemcpyAsync(c->h_result, c->d_result, rlen * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  const double *r = c->h_result;
+  pmcb200_stats_t st;
+  memset(&st, 0, sizeof(st));
+  st.nsamples = N_global;
+  st.maxW = r[0]; st.sum_shift = r[1]; st.logSum = r[2]; st.perplexity = r[3]; st.ess = r[4];
+  st.ln_evidence = r[5]; st.enc = r[6]; st.ndead = (int32_t)r[7];
+  st.nok = (int64_t)r[8]; st.nok_box = (int64_t)r[9];
+  if (stats) *stats = st;
+  if (st.nok == 0 || !(st.sum_shift > 0.0)) {
+    c->h_result[1] = 0.0;
+    return fail(c, PMCB200_ERR_NOSAMPLE, "no sample with finite importance weight (nok_box=%lld)", (long long)st.nok_box);
+  }
+  const double *w = r + RES_HDR, *mean = w + K, *chol = mean + (size_t)K * d;
+  double wsum = 0.0;
+  for (int k = 0; k < K; k++) wsum += w[k];
+  if (!(wsum > 0.0)) return fail(c, PMCB200_ERR_NOSAMPLE, "all proposal components died in the update");
+  std::vector<double> w2(w, w + K), m2(mean, mean + (size_t)K * d), c2(chol, chol + (size_t)K * d * d);
+  double M = r[0], S = r[1];
+  rc = install_proposal(c, K, d, c->h.df, w2.data(), m2.data(), c2.data());
+  c->h_result[0] = M; c->h_result[1] = S;
+  return rc;
+}
+
+// ---- whole iteration -----------------------------------------------------------------------
+extern "C" int pmcb200_iteration_local(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter,
+                                       int64_t offset, double beta, double *dX, int32_t *didx,
+                                       int16_t *dflg, double *dlogw, double *dblock) {
+  int rc = need(c, true, true);
+  if (rc) return rc;
+  if (N < 0 || !dblock) return fail(c, PMCB200_ERR_ARG, "iteration_local: bad arguments");
+  const int d = c->h.d;
+  const size_t n1 = (size_t)std::max<int64_t>(N, 1);
+  if (!dX) { if ((rc = ensure(c, c->sX, n1 * d * sizeof(double)))) return rc; dX = (double *)c->sX.p; }
+  if (!didx) { if ((rc = ensure(c, c->sIdx, n1 * sizeof(int32_t)))) return rc; didx = (int32_t *)c->sIdx.p; }
+  if (!dflg) { if ((rc = ensure(c, c->sFlg, n1 * sizeof(int16_t)))) return rc; dflg = (int16_t *)c->sFlg.p; }
+  if (!dlogw) { if ((rc = ensure(c, c->sLogw, n1 * sizeof(double)))) return rc; dlogw = (double *)c->sLogw.p; }
+  if ((rc = ensure(c, c->sLogpi, n1 * sizeof(double)))) return rc;
+  if ((rc = ensure(c, c->sErr, n1 * sizeof(int32_t)))) return rc;
+  if ((rc = reset_scal(c))) return rc;
+  if ((rc = launch_simulate(c, N, seed, iter, offset, dX, didx, dflg))) return rc;
+  if ((rc = launch_posterior(c, N, dX, dflg, (double *)c->sLogpi.p, (int32_t *)c->sErr.p))) return rc;
+  if ((rc = launch_weights(c, N, dX, (double *)c->sLogpi.p, (int32_t *)c->sErr.p, beta, dflg, dlogw))) return rc;
+  return launch_em_local(c, N, dX, didx, dflg, dlogw, dblock);
+}
+
+extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, double beta,
+                                      double *hX, int32_t *hidx, int16_t *hflg, double *hw,
+                                      pmcb200_stats_t *stats) {
+  int rc = need(c, true, true);
+  if (rc) return rc;
+  if (N < 1) return fail(c, PMCB200_ERR_ARG, "iteration_host: N = %lld", (long long)N);
+  const int d = c->h.d;
+  if ((rc = ensure(c, c->sBlock, (size_t)stat_len(c->h.K, d) * sizeof(double)))) return rc;
+  double *dblock = (double *)c->sBlock.p;
+  if ((rc = pmcb200_iteration_local(c, N, seed, iter, 0, beta, nullptr, nullptr, nullptr, nullptr, dblock))) return rc;
+  double *dX = (double *)c->sX.p, *dlogw = (double *)c->sLogw.p;
+  int32_t *didx = (int32_t *)c->sIdx.p;
+  int16_t *dflg = (int16_t *)c->sFlg.p;
+  // sample / index / flag copies overlap nothing they depend on: issue them before the M-step sync
+  if (hX) CUDA_OK(c, cudaMemcpyAsync(hX, dX, (size_t)N * d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (hidx) CUDA_OK(c, cudaMemcpyAsync(hidx, didx, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (hflg) CUDA_OK(c, cudaMemcpyAsync(hflg, dflg, (size_t)N * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = pmcb200_em_finish(c, 1, dblock, N, stats))) return rc;
+  if (hw) {
+    if ((rc = pmcb200_normalize_weights(c, N, dflg, dlogw))) return rc;
+    CUDA_OK(c, cudaMemcpyAsync(hw, dlogw, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- measurement helpers -------------------------------------------------------------------
+extern "C" int pmcb200_counters(pmcb200_ctx *c, int64_t out[4]) {
+  if (!c || !out) return PMCB200_ERR_ARG;
+  DevCount h;
+  CUDA_OK(c, cudaMemcpyAsync(&h, c->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCount), c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  out[0] = (int64_t)h.sn_evals; out[1] = (int64_t)h.sn_zsteps; out[2] = 0; out[3] = 0;
+  return 0;
+}
+
+// DFMA-only kernel: 8 independent chains per thread, 8 warps/SMSP resident
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;
+}
+
+extern "C" int pmcb200_fp64_peak(pmcb200_ctx *c, double *tflops) {
+  if (!c || !tflops) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  double *d = nullptr;
+  CUDA_OK(c, cudaMalloc((void **)&d, 8));
+  cudaEvent_t e0, e1;
+  CUDA_OK(c, cudaEventCreate(&e0));
+  CUDA_OK(c, cudaEventCreate(&e1));
+  const int blocks = c->sm_count * 8, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    CUDA_OK(c, cudaEventRecord(e0, c->stream));
+    k_fp64_peak<<<blocks, 256, 0, c->stream>>>(d, iters, 0.999999, 1e-9);
+    CUDA_OK(c, cudaEventRecord(e1, c->stream));
+    CUDA_OK(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(c, cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8 * 16 * (double)iters * 256.0 * blocks;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
+  return 0;
+}

@@ -1,0 +1,282 @@
+/* ============================================================================
+ * pmcb200.h -- C-ABI of the B200-native Population Monte Carlo iteration.
+ *
+ * This is the drop-in boundary for CosmoPMC's hot path (one PMC iteration:
+ * sample -> log-posterior -> importance weights -> Rao-Blackwellised EM
+ * update), `run_pmc_iteration_MPI`, reference exec/cosmo_pmc.c:293-402.
+ *
+ * Plain C: pointers, sizes and POD structs only.  No torch / C++ types.
+ * Every entry point returns 0 on success or a negative pmclib-style error
+ * code (see PMCB200_ERR_*); pmcb200_last_error() returns the message.
+ *
+ * There is no CPU fallback: every compute entry point launches sm_100a CUDA
+ * kernels and fails with PMCB200_ERR_CUDA when no device is usable.
+ *
+ * Each declaration cites the reference interface (file:line under the
+ * reference tree) that it replaces.  pmclib / nicaea are external to the
+ * reference tree (install_CosmoPMC.sh:247,261), so for those the citation is
+ * the reference's *call site*.
+ * ========================================================================== */
+#ifndef PMCB200_H
+#define PMCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMCB200_VERSION      100
+#define PMCB200_MAX_DIM      32   /* max. parameter dimension d            */
+#define PMCB200_MAX_COMP     64   /* max. mixture components K             */
+#define PMCB200_MAX_DATA     4    /* max. data sets in one posterior       */
+#define PMCB200_MINCOUNT     20   /* dead-component rule, manual.tex:482-490 */
+
+/* ---- error codes (negative, pmclib convention: errorlist.h) -------------- */
+#define PMCB200_OK            0
+#define PMCB200_ERR_CUDA     (-9001)  /* CUDA runtime / no device           */
+#define PMCB200_ERR_ARG      (-9002)  /* bad argument                        */
+#define PMCB200_ERR_DIM      (-9003)  /* dimension mismatch (mv_dimension)   */
+#define PMCB200_ERR_CHOLESKY (-9004)  /* not positive definite (mv_cholesky) */
+#define PMCB200_ERR_NOSAMPLE (-9005)  /* no point simulated (pmc_nosamplep)  */
+#define PMCB200_ERR_UNSUP    (-9006)  /* unsupported mode (e.g. chi2_dust)   */
+#define PMCB200_ERR_STATE    (-9007)  /* call order (proposal/target unset)  */
+
+/* ---- parameter roles ------------------------------------------------------
+ * The integer values are *identical* to the reference's `par_t` enum
+ * (tools/include/par.h:11-34) so a binding passes `like->par[]` straight in.
+ * Only the roles consumed by the SNIa / BAO / CMBDistPrior wrappers
+ * (wrappers/src/sn.c:167-224, bao.c:100-147, wmap.c:966-1019) are named. */
+enum {
+  PMCB200_P_Omegam = 0, PMCB200_P_Omegab = 1, PMCB200_P_Omegade = 2,
+  PMCB200_P_h100 = 3, PMCB200_P_Omeganumass = 4, PMCB200_P_Omegac = 5,
+  PMCB200_P_OmegaK = 6, PMCB200_P_omegam = 7, PMCB200_P_omegab = 8,
+  PMCB200_P_100_omegab = 9, PMCB200_P_omegade = 10, PMCB200_P_omeganumass = 11,
+  PMCB200_P_omegac = 12, PMCB200_P_omegaK = 13, PMCB200_P_w0de = 14,
+  PMCB200_P_w1de = 15, PMCB200_P_Neffnumass = 20,
+  PMCB200_P_M = 37, PMCB200_P_alpha = 38, PMCB200_P_beta = 39,
+  PMCB200_P_beta_z = 40, PMCB200_P_logbeta = 41,
+  PMCB200_P_stretch = 42, PMCB200_P_color = 43
+};
+
+/* ---- likelihood kinds: values match `data_t` (wrappers/include/types.h:5-24)
+ * for the in-tree kinds; PMCB200_LIKE_BANANA is this repo's C3 stress target
+ * (Wraith et al. 2009), plugged in as a posterior_log_pdf_func. */
+enum {
+  PMCB200_LIKE_Mvdens = 0, PMCB200_LIKE_MixMvdens = 1, PMCB200_LIKE_SNIa = 3,
+  PMCB200_LIKE_CMBDistPrior = 6, PMCB200_LIKE_BAO = 7,
+  PMCB200_LIKE_BANANA = 100
+};
+
+/* special_t, wrappers/include/init_wrappers.h (none, unity, de_conservative) */
+enum { PMCB200_SPECIAL_none = 0, PMCB200_SPECIAL_unity = 1,
+       PMCB200_SPECIAL_de_conservative = 2 };
+
+/* chi2mode_t of nicaea sn1a.h as used at wrappers/src/sn.c:33-44,238-257 */
+enum { PMCB200_CHI2_simple = 0, PMCB200_CHI2_Theta2_denom_fixed = 1,
+       PMCB200_CHI2_no_sc = 2, PMCB200_CHI2_betaz = 3 };
+
+/* method_t, wrappers/include/bao.h:31 */
+enum { PMCB200_BAO_distance_A = 0, PMCB200_BAO_distance_d_z = 1,
+       PMCB200_BAO_distance_D_V_ratio = 2 };
+
+/* de_param_t of nicaea cosmo.h (par_files/cosmo.par:39-44) */
+enum { PMCB200_DE_jassal = 0, PMCB200_DE_linder = 1 };
+
+/* Default cosmological model: the fields of nicaea's `cosmo` that the three
+ * distance likelihoods read (par_files/cosmo.par:3-13,44). */
+typedef struct {
+  double Omega_m, Omega_de, w0_de, w1_de, h_100, Omega_b, Omega_nu_mass,
+         Neff_nu_mass;
+  int    de_param;
+  int    _pad;
+} pmcb200_cosmo_t;
+
+/* One data set of the posterior: replaces `common_like` + the plug-in state
+ * (wrappers/include/init_wrappers.h:15-22; Sn_state sn.h:31-47; bao_state
+ * bao.h:41-48; cmbDP_state wmap.h:55-60).  All pointers are HOST pointers;
+ * pmcb200_set_target deep-copies the arrays to the device. */
+typedef struct {
+  int kind;                        /* PMCB200_LIKE_*                          */
+  int npar;                        /* = like->npar                            */
+  int par[PMCB200_MAX_DIM];        /* = like->par[] (par_t values)            */
+  int special;                     /* state->special                          */
+  pmcb200_cosmo_t model;           /* state->model (default cosmology)        */
+
+  /* SNIa (sn.c:138-281; formula Manual/manual.tex:1290-1325) */
+  int    sn_chi2mode, sn_add_logdetCov;
+  double sn_Theta2[4];             /* (-M, alpha, -beta, beta_z) cosmo_SN.par:9 */
+  double sn_Theta2_denom[3];
+  double sn_sig_int, sn_v_pec;     /* @INTRINSIC_DISPERSION, @PECULIAR_VELOCITY */
+  int    sn_n;                     /* number of supernovae                    */
+  const double *sn_z, *sn_m, *sn_s, *sn_c;  /* each [sn_n]                   */
+  const double *sn_cov;            /* [sn_n*6]: Vmm Vss Vcc Cms Cmc Csc       */
+
+  /* BAO (bao.c:80-184) and CMBDistPrior (wmap.c:945-1049): Gaussian data */
+  int    bao_method;
+  int    g_ndim;                   /* dimension of the data mvdens            */
+  const double *g_z;               /* BAO redshifts [g_ndim or 2*g_ndim]      */
+  const double *g_mean;            /* data vector [g_ndim]                    */
+  const double *g_chol;            /* lower Cholesky of data covariance
+                                      [g_ndim*g_ndim] row-major               */
+
+  /* Mvdens / MixMvdens analytic targets (param.c:1485-1537), BANANA */
+  int    mix_ncomp, mix_ndim, mix_df;
+  const double *mix_wght, *mix_mean, *mix_chol; /* [K], [K*d], [K*d*d]        */
+  double banana_b, banana_sigma1sq;
+} pmcb200_like_t;
+
+/* The posterior: replaces `config_base` as consumed by
+ * posterior_log_pdf_common (wrappers/src/param.c:958-1041). */
+typedef struct {
+  int    npar;                     /* config->npar                            */
+  int    ndata;                    /* config->ndata                           */
+  double min[PMCB200_MAX_DIM];     /* config->min (flat box prior, parabox)   */
+  double max[PMCB200_MAX_DIM];     /* config->max                             */
+  pmcb200_like_t like[PMCB200_MAX_DATA];
+  /* optional Gaussian prior (param.c:1009-1026): nprior==0 && prior_mean!=NULL
+   * means "all parameters"; indprior[i]==1 selects parameter i otherwise */
+  int    nprior;
+  int    indprior[PMCB200_MAX_DIM];
+  int    prior_ndim;
+  const double *prior_mean, *prior_chol;
+} pmcb200_target_t;
+
+/* Per-iteration summary (host struct).  perplexity/ess: perplexity_and_ess
+ * (cosmo_pmc.c:46); ln_evidence: evidence() (cosmo_pmc.c:62); enc:
+ * effective_number_of_components (cosmo_pmc.c:84); logSum/maxW: fields of
+ * pmc_simu read at exec_helper.c:408-420. */
+typedef struct {
+  int64_t nsamples;      /* N (global over all ranks)                        */
+  int64_t nok_box;       /* samples inside the box (simulate_mix_mvdens nok) */
+  int64_t nok;           /* samples with finite weight (importance nok)      */
+  double  maxW;          /* max log w                                        */
+  double  logSum;        /* log sum_n w_n (unnormalised)                     */
+  double  sum_shift;     /* sum exp(log w - maxW) (normalize_... return)     */
+  double  perplexity;    /* exp(-sum wbar log wbar)/N                        */
+  double  ess;           /* 1/sum wbar^2                                     */
+  double  ln_evidence;   /* logSum - log N                                   */
+  double  enc;           /* 1/sum alpha_d^2 of the UPDATED proposal          */
+  int32_t ndead;         /* components killed by the update                  */
+  int32_t _pad;
+} pmcb200_stats_t;
+
+typedef struct pmcb200_ctx pmcb200_ctx;
+
+/* ---- life cycle ----------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: a cudaStream_t (as void*); NULL = the legacy
+ * default stream; (void*)-1 = a private non-blocking stream owned by the
+ * library.  Replaces pmc_simu_init_mpi (cosmo_pmc.c:633). */
+int  pmcb200_create(int device, void *stream, pmcb200_ctx **out);
+void pmcb200_destroy(pmcb200_ctx *ctx);
+const char *pmcb200_last_error(const pmcb200_ctx *ctx);
+int  pmcb200_version(void);
+int  pmcb200_device_count(void);
+int  pmcb200_sync(pmcb200_ctx *ctx);
+void *pmcb200_stream(pmcb200_ctx *ctx);
+
+/* ---- proposal: replaces the `mix_mvdens` handed to every pmclib call
+ * (cosmo_pmc.c:320,343,247).  HOST arrays: wght[K], mean[K*d],
+ * chol[K*d*d] = lower Cholesky factors, row-major (std with chol==1).
+ * df = -1 Gaussian, >0 Student-t (manual.tex:444-450). */
+int pmcb200_set_proposal(pmcb200_ctx *ctx, int ncomp, int ndim, int df,
+                         const double *wght, const double *mean,
+                         const double *chol);
+/* same from covariances (does the Cholesky, mix_mvdens_cholesky_decomp
+ * param.c:700); returns PMCB200_ERR_CHOLESKY if a component fails */
+int pmcb200_set_proposal_cov(pmcb200_ctx *ctx, int ncomp, int ndim, int df,
+                             const double *wght, const double *mean,
+                             const double *cov);
+/* read back the (updated) proposal; cov may be NULL */
+int pmcb200_get_proposal(pmcb200_ctx *ctx, double *wght, double *mean,
+                         double *chol, double *cov);
+
+/* ---- target: replaces (posterior_log_pdf_common_void, &config->base)
+ * passed at cosmo_pmc.c:343-345 */
+int pmcb200_set_target(pmcb200_ctx *ctx, const pmcb200_target_t *t);
+
+/* ---- stage entry points on DEVICE arrays --------------------------------- *
+ * X[N*d] row-major (pmc_simu->X), idx[N] int32 (pmc_simu->indices),
+ * flg[N] int16 (pmc_simu->flg), logw[N] (pmc_simu->weights while isLog).    */
+
+/* simulate_mix_mvdens, cosmo_pmc.c:320.  Sample index g = offset+n is the
+ * Philox counter, so a shard's draws do not depend on the rank count. */
+int pmcb200_simulate(pmcb200_ctx *ctx, int64_t N, uint64_t seed, uint32_t iter,
+                     int64_t offset, double *dX, int32_t *didx, int16_t *dflg);
+/* same transform from caller-supplied draws (parity: component selection
+ * bit-exact for identical uniforms): u[N] uniforms, z[N*d] normals */
+int pmcb200_simulate_from_draws(pmcb200_ctx *ctx, int64_t N, const double *du,
+                                const double *dz, double *dX, int32_t *didx,
+                                int16_t *dflg);
+/* mix_mvdens_log_pdf_void, cosmo_pmc.c:343 */
+int pmcb200_proposal_log_pdf(pmcb200_ctx *ctx, int64_t N, const double *dX,
+                             double *dlogq);
+/* posterior_log_pdf_common_void, param.c:948-1041.  derr[n] != 0 marks a
+ * sample whose likelihood raised an error (manual.tex:507-512). derr may be
+ * NULL. */
+int pmcb200_posterior_log_pdf(pmcb200_ctx *ctx, int64_t N, const double *dX,
+                              double *dlogpi, int32_t *derr);
+/* generic_get_importance_weight_and_deduced_verb, cosmo_pmc.c:343-345:
+ * log w = beta*log pi - log q for flagged samples; clears flg on error or
+ * non-finite weight; tracks max log w and nok on the device. */
+int pmcb200_importance_weights(pmcb200_ctx *ctx, int64_t N, const double *dX,
+                               double beta, int16_t *dflg, double *dlogw);
+/* normalize_importance_weight, cosmo_pmc.c:378 (in place: logw -> wbar) */
+int pmcb200_normalize_weights(pmcb200_ctx *ctx, int64_t N, const int16_t *dflg,
+                              double *dw);
+
+/* ---- EM sufficient statistics (update_prop_rb, cosmo_pmc.c:247) -----------
+ * Local step: accumulates this rank's block of pmcb200_stat_block_len()
+ * doubles into dblock (device).  The caller all-gathers the blocks of all
+ * ranks (NCCL over NVLink; one collective per iteration) into dall
+ * [nranks * len] and calls pmcb200_em_finish on every rank, which combines
+ * them in rank order (bit-identical on all ranks), performs the M-step, the
+ * dead-component rule and the Cholesky on the device, installs the new
+ * proposal in ctx and fills *stats.  nranks==1: dall == dblock. */
+int64_t pmcb200_stat_block_len(const pmcb200_ctx *ctx);
+int pmcb200_em_local(pmcb200_ctx *ctx, int64_t N, const double *dX,
+                     const int32_t *didx, const int16_t *dflg,
+                     const double *dlogw, double *dblock);
+int pmcb200_em_finish(pmcb200_ctx *ctx, int nranks, const double *dall,
+                      int64_t N_global, pmcb200_stats_t *stats);
+
+/* ---- whole iteration ------------------------------------------------------ */
+/* Device-resident shard: simulate + weights + em_local on N samples starting
+ * at global index `offset`; leaves the stat block in dblock.  Any of
+ * dX/didx/dflg/dlogw may be NULL (library scratch is used). */
+int pmcb200_iteration_local(pmcb200_ctx *ctx, int64_t N, uint64_t seed,
+                            uint32_t iter, int64_t offset, double beta,
+                            double *dX, int32_t *didx, int16_t *dflg,
+                            double *dlogw, double *dblock);
+/* Single-GPU, HOST buffers, what the pmclib-named shims call: proposal is
+ * taken from ctx; fills the pmc_simu arrays on the host (any may be NULL to
+ * skip the copy) and updates the proposal.  hw receives NORMALISED weights
+ * (isLog = 0) as after normalize_importance_weight. */
+int pmcb200_iteration_host(pmcb200_ctx *ctx, int64_t N, uint64_t seed,
+                           uint32_t iter, double beta, double *hX,
+                           int32_t *hidx, int16_t *hflg, double *hw,
+                           pmcb200_stats_t *stats);
+
+/* number of kernels launched by this context since creation (bench's
+ * gpu_launches claim) */
+int64_t pmcb200_launch_count(const pmcb200_ctx *ctx);
+/* measurement helpers (not part of the reference's API):
+ * counters[0] = SN integrand evaluations summed over all posterior launches
+ * since the last call (resets on read), counters[1] = samples x redshifts
+ * walked by the SN kernel; fp64_peak runs a DFMA-only kernel and returns the
+ * measured vector-FP64 peak in TFLOP/s (the roofline denominator that
+ * MEASURED_PEAKS.json does not carry). */
+int pmcb200_counters(pmcb200_ctx *ctx, int64_t out[4]);
+int pmcb200_fp64_peak(pmcb200_ctx *ctx, double *tflops);
+
+/* raw device helpers so C hosts need not link the CUDA runtime */
+int pmcb200_dev_alloc(pmcb200_ctx *ctx, size_t bytes, void **dptr);
+int pmcb200_dev_free(pmcb200_ctx *ctx, void *dptr);
+int pmcb200_h2d(pmcb200_ctx *ctx, void *dptr, const void *hptr, size_t bytes);
+int pmcb200_d2h(pmcb200_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMCB200_H */

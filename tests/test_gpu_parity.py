@@ -1,0 +1,368 @@
+"""GPU parity tests: every stage of the PMC iteration through the C-ABI
+(libpmc_b200.so) against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): log-likelihoods and log-weights 1e-10
+relative; updated proposal (alpha, mu, Sigma), perplexity, ENC 1e-8 relative;
+component selection bit-exact for identical uniforms.
+"""
+import numpy as np
+import pytest
+import torch
+
+from cosmopmc_b200 import targets as T
+
+pytestmark = pytest.mark.gpu
+
+RTOL_LOG = 1e-10
+RTOL_EM = 1e-8
+
+
+def rel(a, b, floor=1e-300):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)) if a.size else 0.0
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def sn_setup(oracle, pmc, K=10, spec=None, df=-1):
+    spec = spec or T.target_sn_demo()
+    w, m, cov = T.proposal_sn(K)
+    ch = oracle.cholesky_stack(cov)
+    pmc.set_target(spec)
+    pmc.set_proposal(w, m, chol=ch, df=df)
+    return spec, w, m, ch
+
+
+# ---------------------------------------------------------------- sampler ----
+def test_component_selection_bit_exact(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec, w, m, ch = sn_setup(oracle, pmc)
+    w = np.array([0.05, 0.0, 0.2, 0.15, 0.0, 0.1, 0.1, 0.25, 0.05, 0.1])
+    w /= w.sum()
+    pmc.set_proposal(w, m, chol=ch)
+    rng = np.random.default_rng(5)
+    N = 200000
+    u = rng.random(N)
+    cw = np.cumsum(w)
+    # adversarial uniforms: exactly on, just below and just above the cumulative sums
+    edge = np.concatenate([cw, np.nextafter(cw, 0), np.nextafter(cw, 2), [0.0, np.nextafter(1.0, 0)]])
+    u[:edge.size] = np.clip(edge, 0.0, np.nextafter(1.0, 0))
+    z = rng.standard_normal((N, 5))
+    X0, idx0, flg0, _ = oracle.simulate_from_draws(u, z, w, m, ch, *spec.box)
+    b = pmc.alloc(N)
+    pmc.simulate_from_draws(dev(u), dev(z), b["X"], b["idx"], b["flg"])
+    assert np.array_equal(b["idx"].cpu().numpy(), idx0)          # bit-exact
+    assert not np.isin(idx0, [1, 4]).any()                        # dead components never drawn
+    assert rel(b["X"].cpu().numpy(), X0, 1e-3) < 1e-13
+    assert np.array_equal(b["flg"].cpu().numpy(), flg0)
+
+
+@pytest.mark.parametrize("df", [-1, 3])
+def test_philox_sampler_matches_oracle(oracle, pmc_factory, df):
+    pmc = pmc_factory()
+    spec, w, m, ch = sn_setup(oracle, pmc, df=df)
+    N, seed, it, off = 50000, 20090903, 3, 123456789012
+    X0, idx0, flg0, nok0 = oracle.simulate(N, seed, it, off, w, m, ch, *spec.box, df=df)
+    b = pmc.alloc(N)
+    pmc.simulate_mix_mvdens(N, seed, it, off, b["X"], b["idx"], b["flg"])
+    X1 = b["X"].cpu().numpy()
+    assert np.array_equal(b["idx"].cpu().numpy(), idx0)
+    assert rel(X1, X0, 1e-2) < 1e-11
+    assert (b["flg"].cpu().numpy() != flg0).sum() == 0
+    # shard independence: the draws of a sub-range do not depend on the shard layout
+    b2 = pmc.alloc(1000)
+    pmc.simulate_mix_mvdens(1000, seed, it, off + 777, b2["X"], b2["idx"], b2["flg"])
+    assert torch.equal(b2["X"], b["X"][777:1777])
+
+
+def test_sampler_moments(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.target_gauss2d()
+    pmc.set_target(spec)
+    mean = np.array([[0.3, 0.6]])
+    cov = np.array([[[0.01, 0.004], [0.004, 0.02]]])
+    pmc.set_proposal([1.0], mean, cov=cov)
+    N = 2000000
+    b = pmc.alloc(N)
+    pmc.simulate_mix_mvdens(N, 7, 0, 0, b["X"], b["idx"], b["flg"])
+    X = b["X"].cpu().numpy()
+    assert np.allclose(X.mean(0), mean[0], atol=5e-4)
+    assert np.allclose(np.cov(X.T), cov[0], atol=2e-4)
+
+
+# ------------------------------------------------------------- log-pdf -------
+@pytest.mark.parametrize("K,d,df", [(10, 5, -1), (9, 5, 3), (30, 8, -1), (20, 20, -1), (3, 2, -1), (4, 32, -1)])
+def test_mix_mvdens_log_pdf(oracle, pmc_factory, K, d, df):
+    pmc = pmc_factory()
+    rng = np.random.default_rng(K * 100 + d)
+    A = rng.standard_normal((K, d, d)) * 0.3
+    cov = A @ A.transpose(0, 2, 1) + np.eye(d)[None] * 0.5
+    mean = rng.standard_normal((K, d))
+    w = rng.random(K); w[K // 2] = 0.0; w /= w.sum()
+    ch = oracle.cholesky_stack(cov)
+    pmc.set_proposal(w, mean, chol=ch, df=df)
+    N = 20000
+    X = mean[rng.integers(0, K, N)] + rng.standard_normal((N, d)) * 1.5
+    X[:10] += 1e3                      # far tail -> log 0 = -inf on both sides
+    ref = oracle.mix_log_pdf(X, w, mean, ch, df)
+    got = pmc.mix_mvdens_log_pdf(dev(X)).cpu().numpy()
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert (~fin).sum() >= (10 if df < 0 else 0)
+    assert rel(got[fin], ref[fin]) < RTOL_LOG
+
+
+def test_empty_batches(oracle, pmc_factory):
+    pmc = pmc_factory()
+    sn_setup(oracle, pmc)
+    X = torch.empty((0, 5), dtype=torch.float64, device="cuda")
+    assert pmc.mix_mvdens_log_pdf(X).numel() == 0
+    lp, err = pmc.posterior_log_pdf(X)
+    assert lp.numel() == 0 and err.numel() == 0
+
+
+# --------------------------------------------------------- likelihoods -------
+def box_samples(spec, N, seed, shrink=0.0):
+    lo, hi = spec.box
+    rng = np.random.default_rng(seed)
+    return lo + (shrink + (1 - 2 * shrink) * rng.random((N, len(lo)))) * (hi - lo)
+
+
+def check_posterior(oracle, pmc, spec, X):
+    ref, eref = oracle.posterior_log_pdf(spec, X)
+    got, egot = pmc.posterior_log_pdf(dev(X))
+    got, egot = got.cpu().numpy(), egot.cpu().numpy()
+    assert np.array_equal(egot != 0, eref != 0)
+    ok = eref == 0
+    assert ok.sum() > 0.5 * len(X)
+    r = rel(got[ok], ref[ok])
+    assert r < RTOL_LOG, r
+    return r
+
+
+def test_posterior_sn_golden_fiducial(oracle, pmc_factory):
+    """log-posterior at the reference test-suite's fiducial point
+    (bin/test_suite_cosmo_pmc.pl:51) and at the manual's posterior mean,
+    against the committed golden values generated from the oracle."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sn_logpost.json")))
+    pmc = pmc_factory()
+    spec = T.target_sn_demo()
+    pmc.set_target(spec)
+    X = np.array(g["x"])
+    got, err = pmc.posterior_log_pdf(dev(X))
+    assert int(err.sum()) == 0
+    assert rel(got.cpu().numpy(), np.array(g["logpost"])) < RTOL_LOG
+
+
+def test_posterior_sn_box(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.target_sn_demo()
+    pmc.set_target(spec)
+    check_posterior(oracle, pmc, spec, box_samples(spec, 3000, 11))
+
+
+def test_posterior_sn_curved(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.target_sn_curved()
+    pmc.set_target(spec)
+    X = box_samples(spec, 3000, 12)
+    X[:50, 1] = 1.0 - X[:50, 0]          # exactly flat rows exercise the |Omega_K| < eps branch
+    check_posterior(oracle, pmc, spec, X)
+
+
+@pytest.mark.parametrize("mode,logdet", [("chi2_no_sc", 0), ("chi2_betaz", 1), ("chi2_Theta2_denom_fixed", 1)])
+def test_posterior_sn_modes(oracle, pmc_factory, mode, logdet):
+    pmc = pmc_factory()
+    spec = T.TargetSpec(["Omega_m", "w_0_de", "M", "alpha", "beta", "beta_z"],
+                        [0.1, -2.0, 19.1, 0.5, -3.5, -1.0], [0.9, -0.3, 19.8, 2.6, -0.8, 1.0])
+    spec.add_snia(chi2mode=mode, add_logdetCov=logdet, Theta2_denom=(0.0, 1.5, -2.0))
+    pmc.set_target(spec)
+    check_posterior(oracle, pmc, spec, box_samples(spec, 1000, 13))
+
+
+def test_posterior_sn_bao_w0wa(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.target_sn_bao_w0wa()
+    pmc.set_target(spec)
+    check_posterior(oracle, pmc, spec, box_samples(spec, 1500, 14))
+
+
+def test_posterior_cmb_bao_sn(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.target_cmb_bao_sn()
+    pmc.set_target(spec)
+    check_posterior(oracle, pmc, spec, box_samples(spec, 1000, 15))
+
+
+def test_posterior_bao_A_and_prior(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.TargetSpec(["Omega_m", "Omega_de", "h_100"], [0.05, 0.2, 0.5], [0.8, 1.2, 0.9])
+    spec.add_bao(T.BAO_REID10_A)
+    spec.set_prior([0.3, 0.72], [[0.01, 0.0002], [0.0002, 0.0064]], indprior=[1, 0, 1])   # (Omega_m, h_100)
+    pmc.set_target(spec)
+    check_posterior(oracle, pmc, spec, box_samples(spec, 1500, 16))
+
+
+def test_posterior_banana_and_mixture(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.target_banana(20)
+    pmc.set_target(spec)
+    check_posterior(oracle, pmc, spec, box_samples(spec, 5000, 17))
+    spec = T.TargetSpec(["dummy0", "dummy1"], [0, 0], [1, 1]).add_mix(
+        [0.5, 0.5], [[0.3, 0.3], [0.7, 0.7]], [np.eye(2) * 0.01, [[0.02, 0.005], [0.005, 0.01]]],
+        special="unity")
+    pmc.set_target(spec)
+    check_posterior(oracle, pmc, spec, box_samples(spec, 5000, 18))
+
+
+def test_likelihood_error_policy(oracle, pmc_factory):
+    """Errors inside a likelihood give the sample zero weight (manual.tex:507-512):
+    unphysical cosmologies (negative a^4 E^2) must be flagged on both sides."""
+    pmc = pmc_factory()
+    spec = T.TargetSpec(["Omega_m", "Omega_de", "M", "alpha", "beta"],
+                        [0.0, 0.0, 19.1, 0.5, -3.5], [1.2, 4.0, 19.8, 2.6, -0.8]).add_snia()
+    pmc.set_target(spec)
+    X = box_samples(spec, 2000, 19)
+    X[:, 1] = 1.5 + 2.5 * np.random.default_rng(3).random(2000)    # bouncing / no-big-bang region
+    ref, eref = oracle.posterior_log_pdf(spec, X)
+    got, egot = pmc.posterior_log_pdf(dev(X))
+    egot = egot.cpu().numpy()
+    assert (eref != 0).sum() > 100 and (eref == 0).sum() > 100
+    assert np.array_equal(egot != 0, eref != 0)
+    ok = eref == 0
+    assert rel(got.cpu().numpy()[ok], ref[ok]) < RTOL_LOG
+
+
+# ------------------------------------------------- weights + EM update -------
+def run_both(oracle, pmc, spec, w, m, ch, N, seed=1, it=0, beta=1.0, df=-1):
+    o = oracle.iteration(spec, N, seed, it, beta, w, m, ch, df=df, nthreads=8)
+    hX = np.empty((N, len(m[0]))); hidx = np.empty(N, np.int32)
+    hflg = np.empty(N, np.int16); hw = np.empty(N)
+    st = pmc.iteration_host(N, seed, it, beta, hX, hidx, hflg, hw)
+    return o, st, hX, hidx, hflg, hw
+
+
+def check_iteration(o, st, pmc, hX, hidx, hflg, hw, rtol_w=1e-9):
+    so = o["stats"]
+    assert st["nok_box"] == so["nok_box"] and st["nok"] == so["nok"]
+    assert np.array_equal(hidx, o["idx"]) and np.array_equal(hflg, o["flg"])
+    assert rel(hX, o["X"], 1e-2) < 1e-11
+    assert abs(st["maxW"] - so["maxW"]) < RTOL_LOG * abs(so["maxW"])
+    assert abs(st["logSum"] - so["logSum"]) < RTOL_LOG * abs(so["logSum"])
+    for k in ("perplexity", "ess", "ln_evidence", "enc", "sum_shift"):
+        assert abs(st[k] - so[k]) <= RTOL_EM * abs(so[k]), (k, st[k], so[k])
+    assert st["ndead"] == so["ndead"]
+    ok = o["flg"] != 0
+    big = ok & (o["w"] > 1e-12 * o["w"].max())
+    assert rel(hw[big], o["w"][big]) < rtol_w
+    assert np.all(hw[~ok] == 0.0)
+    wg, mg, chg, covg = pmc.get_proposal()
+    assert rel(wg, o["wght"], 1e-300) < RTOL_EM
+    live = o["wght"] > 0
+    assert np.array_equal(wg > 0, live)
+    assert rel(mg[live], o["mean"][live], 1e-3) < RTOL_EM
+    covo = o["chol"] @ o["chol"].transpose(0, 2, 1)
+    scale = np.sqrt(np.einsum("kii,kjj->kij", covo, covo))
+    assert np.max(np.abs(covg[live] - covo[live]) / scale[live]) < RTOL_EM
+
+
+def test_iteration_sn_demo(oracle, pmc_factory):
+    """C1: the SN demo shape (d=5, K=10, N=10^4), full iteration vs oracle."""
+    pmc = pmc_factory()
+    spec, w, m, ch = sn_setup(oracle, pmc)
+    o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 10000, seed=20090903)
+    check_iteration(o, st, pmc, *h)
+    assert 0.0 < st["perplexity"] <= 1.0 and 1.0 <= st["ess"] <= 10000
+
+
+def test_iteration_dead_components_and_tempering(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec, w, m, ch = sn_setup(oracle, pmc)
+    m = m.copy(); m[3] += [0.5, 2.0, 0.4, 1.0, 1.0]     # a component far off: dies (alpha < 1/N)
+    w = w.copy(); w[7] = 1e-4; w /= w.sum()               # a component with < MINCOUNT draws
+    pmc.set_proposal(w, m, chol=ch)
+    o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 20000, seed=5, it=2, beta=0.7)
+    assert o["stats"]["ndead"] >= 2
+    check_iteration(o, st, pmc, *h)
+
+
+def test_iteration_student_t(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec, w, m, ch = sn_setup(oracle, pmc, K=6, df=3)
+    o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 8000, seed=9, df=3)
+    check_iteration(o, st, pmc, *h)
+
+
+def test_iteration_banana(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.target_banana(20)
+    w, m, cov = T.proposal_banana(10, 20)
+    ch = oracle.cholesky_stack(cov)
+    pmc.set_target(spec)
+    pmc.set_proposal(w, m, chol=ch)
+    o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 30000, seed=3)
+    check_iteration(o, st, pmc, *h)
+
+
+def test_iteration_cmb_bao_sn(oracle, pmc_factory):
+    pmc = pmc_factory()
+    spec = T.target_cmb_bao_sn()
+    center = [0.045, 0.27, 0.73, 0.71, -1.0, 19.31, 1.4, -2.4]
+    sigma = [0.003, 0.02, 0.02, 0.02, 0.1, 0.03, 0.1, 0.1]
+    w, m, cov = T.proposal_generic(spec, 30, 4, center, sigma)
+    ch = oracle.cholesky_stack(cov)
+    pmc.set_target(spec)
+    pmc.set_proposal(w, m, chol=ch)
+    o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 6000, seed=4)
+    check_iteration(o, st, pmc, *h)
+
+
+def test_multi_iteration_convergence_gauss2d(pmc_factory):
+    """Statistical known answer of the reference: Demo/tempering/README.md:11-36,
+    2-D Gaussian on the unit square => evidence consistent with 1 and the
+    perplexity climbs towards 1."""
+    pmc = pmc_factory()
+    spec = T.target_gauss2d()
+    pmc.set_target(spec)
+    rng = np.random.default_rng(1)
+    K = 5
+    mean = 0.5 + 0.2 * (rng.random((K, 2)) - 0.5)
+    cov = np.repeat((np.eye(2) * 0.05)[None], K, 0)
+    pmc.set_proposal(np.full(K, 1 / K), mean, cov=cov)
+    st = None
+    for it in range(6):
+        st = pmc.iteration_host(100000, 42, it)
+    assert abs(np.exp(st["ln_evidence"]) - 1.0) < 0.01
+    assert st["perplexity"] > 0.9
+
+
+def test_sharded_blocks_combine_like_one_rank(oracle, pmc_factory):
+    """(e) multi-GPU logic on one device: 4 shards' stat blocks combined by
+    em_finish must give the same update as one rank over all samples."""
+    spec = T.target_sn_demo()
+    w, m, cov = T.proposal_sn(10)
+    ch = oracle.cholesky_stack(cov)
+    N, world = 40000, 4
+    one = pmc_factory(); one.set_target(spec); one.set_proposal(w, m, chol=ch)
+    blk = torch.empty(one.stat_block_len(), dtype=torch.float64, device="cuda")
+    one.iteration_local(N, 11, 0, 0, 1.0, blk)
+    s1 = one.update_prop_rb(1, blk, N)
+    many = pmc_factory(); many.set_target(spec); many.set_proposal(w, m, chol=ch)
+    allb = torch.empty((world, many.stat_block_len()), dtype=torch.float64, device="cuda")
+    per = N // world
+    for r in range(world):
+        many.iteration_local(per, 11, 0, r * per, 1.0, allb[r])
+    s2 = many.update_prop_rb(world, allb, N)
+    for k in ("nok", "nok_box", "ndead"):
+        assert s1[k] == s2[k]
+    for k in ("maxW", "logSum", "perplexity", "ess", "enc"):
+        assert abs(s1[k] - s2[k]) <= 1e-12 * abs(s1[k])
+    p1, p2 = one.get_proposal(), many.get_proposal()
+    for a, b in zip(p1, p2):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-14)
