@@ -20,7 +20,8 @@ struct DevLike {
   const double2 *nodes;   // [sn_nz][SN_NODES] {a, ln a}; entry 0 = a(z), entry i in
                           // [2^(j-2), 2^(j-1)) = nodes of trapezoid stage j >= 2
   const int *first;       // [sn_nz+1] ranges of supernovae sharing a redshift
-  const double *sn;       // [sn_n][SN_ROW]: m s c z Vmm Vss Vcc Cms Cmc Csc pv2 -
+  const double *sn;       // [sn_n][SN_ROW]: m s | c z | Vmm+pv2+int2 Vss | Vcc Cms | Cmc Csc | - -
+  int sn_hasq, sn_flat;   // launch-uniform specialisation flags (set by the host)
   // Gaussian data (BAO, CMB distance priors): packed like a mixture component
   int bao_method, g_ndim;
   const double *g_z;
@@ -203,13 +204,73 @@ __device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t
   else { logpi[n] += res; if (err && e) err[n] = 1; }
 }
 
-// ---- SN Ia: one sample per thread; the whole warp walks the same redshift
-// so node loads are warp-uniform and the adaptive stage count is resolved by
-// a warp vote ---------------------------------------------------------------
-__device__ __forceinline__ double sn_f(const ECoef &e, double2 nd) {
-  return rsqrt(a4E2(e, nd.x, nd.y));
+// ---- fast FP64 primitives for the SN hot loop ---------------------------------
+// exp(t) for |t| < 700: Cody-Waite reduction t = k ln2 + r, |r| <= ln2/2, degree-11
+// near-minimax polynomial (Chebyshev interpolant, max rel. error 1.6e-17 before
+// rounding), scaling by exponent-field addition.  Branch-free: 16 FP64 ops.
+__device__ __forceinline__ double fast_exp(double t) {
+  const double MAGIC = 6755399441055744.0;       // 1.5 * 2^52
+  double kf = fma(t, 1.4426950408889634074, MAGIC);
+  int k = __double2loint(kf);
+  kf -= MAGIC;
+  double r = fma(kf, -6.93147180369123816490e-01, t);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 0x1.af632a0f7e2cep-26;
+  p = fma(p, r, 0x1.28b4101c77212p-22);
+  p = fma(p, r, 0x1.71ddf56d8deb5p-19);
+  p = fma(p, r, 0x1.a01991a10d9aep-16);
+  p = fma(p, r, 0x1.a01a01b1461c5p-13);
+  p = fma(p, r, 0x1.6c16c1880029fp-10);
+  p = fma(p, r, 0x1.111111110f21ep-7);
+  p = fma(p, r, 0x1.555555554f0bap-5);
+  p = fma(p, r, 0x1.555555555555ap-3);
+  p = fma(p, r, 0x1.0000000000011p-1);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+// 1/sqrt(v): MUFU.RSQ64H seed (rel. error 2^-22) + one third-order step -> 2^-66.
+// v < 0 -> NaN, v = 0 -> NaN (both are the reference's error condition).
+__device__ __forceinline__ double fast_rsqrt(double v) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+  double t = v * y;
+  double e = fma(-t, y, 1.0);
+  double c = fma(0.375, e, 0.5);
+  return fma(y * e, c, y);
+}
+// 1/s for s > 0: MUFU.RCP64H seed + two Newton steps
+__device__ __forceinline__ double fast_rcp(double s) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  double e = fma(-s, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-s, y, 1.0);
+  return fma(y, e, y);
 }
 
+// ---- SN Ia: one sample per thread; the whole warp walks the same redshift
+// so node loads are warp-uniform and the adaptive stage count is resolved by
+// a warp vote.  HASQ: w1 != 0 or jassal (second exponent term); FLAT: the
+// curvature term is identically zero for every sample of the launch. -----------
+struct SNCoef {
+  double Om, OK, Ode, p, q;
+  int jassal, slow;
+};
+template <bool HASQ, bool FLAT>
+__device__ __forceinline__ double sn_f(const SNCoef &e, double2 nd) {
+  const double a = nd.x;
+  double t = e.p * nd.y;
+  if (HASQ) {
+    double oma = 1.0 - a;
+    t = e.jassal ? fma(e.q * oma, oma, t) : fma(e.q, oma, t);
+  }
+  double ex = e.slow ? exp(t) : fast_exp(t);
+  double v = FLAT ? fma(e.Om, a, e.Ode * ex) : fma(a, fma(e.OK, a, e.Om), e.Ode * ex);
+  return fast_rsqrt(v);
+}
+
+template <bool HASQ, bool FLAT>
 __global__ void __launch_bounds__(PMC_BLOCK)
 k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
           const int16_t *__restrict__ flg, double *__restrict__ logpi,
@@ -220,46 +281,70 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   Model m;
   int e = 0;
   if (active) e = apply_params(L, X + n * d, m);
-  if (!active || e) { DevLike const &LL = L; m.c = LL.model; for (int i = 0; i < 4; i++) m.Theta2[i] = LL.Theta2[i]; m.stretch = 1.0; m.color = 0.0; }
-  const ECoef ec = make_ecoef(m.c, 0);
+  if (!active || e) {   // keep the warp's control flow uniform on a benign model
+    m.c = L.model;
+#pragma unroll
+    for (int i = 0; i < 4; i++) m.Theta2[i] = L.Theta2[i];
+    m.stretch = 1.0; m.color = 0.0;
+  }
+  SNCoef ec;
+  {
+    const ECoef g = make_ecoef(m.c, 0);
+    ec.Om = g.Om; ec.OK = g.OK; ec.Ode = g.Ode; ec.p = g.p; ec.q = g.q; ec.jassal = g.jassal;
+    // |t| bound over a in [a_min, 1]; beyond the fast_exp range use libdevice exp
+    const double lna_min = -__ldg(&L.nodes[(size_t)(L.sn_nz - 1) * SN_NODES]).y;
+    ec.slow = !(fabs(g.p) * lna_min + fabs(g.q) < 690.0);
+  }
   const double f1 = rsqrt(ec.Om + ec.OK + ec.Ode);      // integrand at a = 1
   const bool flat = fabs(ec.OK) < FLAT_EPS;
   const double sk = sqrt(fabs(ec.OK)) / R_HUBBLE;
-  double t1 = m.Theta2[1], t2base = m.Theta2[2];
   const int mode = L.sn_chi2mode;
+  const double t1 = m.Theta2[1], t2base = m.Theta2[2];
+  double d1 = t1, d2 = t2base;
+  if (mode == PMCB200_CHI2_no_sc) { d1 = 0.0; d2 = 0.0; }
+  if (mode == PMCB200_CHI2_Theta2_denom_fixed) { d1 = L.Theta2_denom[1]; d2 = L.Theta2_denom[2]; }
   double chi2 = 0.0, logdet = 0.0;
 
   for (int iz = 0; iz < L.sn_nz; iz++) {
     const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
     const double2 n0 = __ldg(&nd[0]);
     const double az = n0.x, h = 1.0 - az;
-    double y[5];
-    // trapezoid stages 1..5 (17 integrand evaluations)
-    double st = 0.5 * h * (sn_f(ec, n0) + f1);
-    y[0] = st;
-    st = 0.5 * (st + h * sn_f(ec, __ldg(&nd[1])));
-    y[1] = st;
+    // trapezoid stages 1..5 (17 integrand evaluations), Romberg tableau by rows:
+    // R[m] <- T_{j,m} = T_{j,m-1} + (T_{j,m-1} - T_{j-1,m-1}) / (4^m - 1)
+    double R0, R1, R2, R3, R4, st;
+    st = 0.5 * h * (sn_f<HASQ, FLAT>(ec, n0) + f1);
+    R0 = st;
+    st = 0.5 * fma(h, sn_f<HASQ, FLAT>(ec, __ldg(&nd[1])), st);
+    { double n1 = fma(st - R0, 1.0 / 3.0, st); R0 = st; R1 = n1; }
     {
-      double s = sn_f(ec, __ldg(&nd[2]));
-      s += sn_f(ec, __ldg(&nd[3]));
-      st = 0.5 * (st + h * s * 0.5);
-      y[2] = st;
+      double s = sn_f<HASQ, FLAT>(ec, __ldg(&nd[2]));
+      s += sn_f<HASQ, FLAT>(ec, __ldg(&nd[3]));
+      st = 0.5 * fma(h * 0.5, s, st);
+      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1);
+      R0 = st; R1 = n1; R2 = n2;
     }
     {
       double s = 0.0;
 #pragma unroll
-      for (int i = 4; i < 8; i++) s += sn_f(ec, __ldg(&nd[i]));
-      st = 0.5 * (st + h * s * 0.25);
-      y[3] = st;
+      for (int i = 4; i < 8; i++) s += sn_f<HASQ, FLAT>(ec, __ldg(&nd[i]));
+      st = 0.5 * fma(h * 0.25, s, st);
+      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
+             n3 = fma(n2 - R2, 1.0 / 63.0, n2);
+      R0 = st; R1 = n1; R2 = n2; R3 = n3;
     }
+    double ss, dss;
     {
       double s = 0.0;
 #pragma unroll
-      for (int i = 8; i < 16; i++) s += sn_f(ec, __ldg(&nd[i]));
-      st = 0.5 * (st + h * s * 0.125);
-      y[4] = st;
+      for (int i = 8; i < 16; i++) s += sn_f<HASQ, FLAT>(ec, __ldg(&nd[i]));
+      st = 0.5 * fma(h * 0.125, s, st);
+      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
+             n3 = fma(n2 - R2, 1.0 / 63.0, n2);
+      dss = (n3 - R3) * (1.0 / 255.0);
+      ss = n3 + dss;
+      R0 = st; R1 = n1; R2 = n2; R3 = n3; R4 = ss;
     }
-    double dss, ss = romb_extrap(y, dss);
+    (void)R4;
     bool done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
     nev += 17;
     int j = 5;                      // stages completed
@@ -270,45 +355,45 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
         double s = 0.0;
         if (2 * it <= SN_NODES) {
 #pragma unroll 4
-          for (int i = it; i < 2 * it; i++) s += sn_f(ec, __ldg(&nd[i]));
+          for (int i = it; i < 2 * it; i++) s += sn_f<HASQ, FLAT>(ec, __ldg(&nd[i]));
         } else {
           const double del = h / (double)it;
           for (int i = 0; i < it; i++) {
             double a = fma((double)i + 0.5, del, az);
-            s += rsqrt(a4E2(ec, a, log(a)));
+            s += sn_f<HASQ, FLAT>(ec, make_double2(a, log(a)));
           }
         }
         nev += it;
         st = 0.5 * (st + h * s / (double)it);
-        y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4]; y[4] = st;
-        ss = romb_extrap(y, dss);
+        double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
+               n3 = fma(n2 - R2, 1.0 / 63.0, n2);
+        dss = (n3 - R3) * (1.0 / 255.0);
+        ss = n3 + dss;
+        R0 = st; R1 = n1; R2 = n2; R3 = n3;
         done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
       }
       j++;
     }
     // luminosity distance [Mpc/h] and distance modulus
     double ww = R_HUBBLE * ss;
-    double fk = flat ? ww : (ec.OK > 0.0 ? sinh(sk * ww) : sin(sk * ww)) / sk;
-    double dl = fk / az;
-    if (!(dl > 0.0)) e = 1;         // also catches NaN
-    double mu_th = fma(5.0, log10(dl / SN_H_FID), 25.0);
+    double fk = (FLAT || flat) ? ww : (ec.OK > 0.0 ? sinh(sk * ww) : sin(sk * ww)) / sk;
+    if (!(fk > 0.0)) e = 1;         // also catches NaN
+    // mu_th = 5 log10(fk / (az H_fid)) + 25; the az part is tabulated (nodes[.][0].y = ln az)
+    const double mu_th = fma(5.0 / M_LN10, log(fk) - n0.y, 25.0 - 5.0 * log10(SN_H_FID));
     const int i0 = __ldg(&L.first[iz]), i1 = __ldg(&L.first[iz + 1]);
     for (int i = i0; i < i1; i++) {
-      const double *__restrict__ r = L.sn + (size_t)i * SN_ROW;
-      double t2 = t2base;
-      if (mode == PMCB200_CHI2_betaz) t2 = fma(m.Theta2[3], r[3], t2base);
-      double mu_obs, d1, d2;
-      if (mode == PMCB200_CHI2_no_sc) {
-        mu_obs = r[0] + m.Theta2[0]; d1 = 0.0; d2 = 0.0;
-      } else {
-        mu_obs = r[0] + m.Theta2[0] + t1 * (r[1] - m.stretch) + t2 * (r[2] - m.color);
-        d1 = t1; d2 = t2;
-        if (mode == PMCB200_CHI2_Theta2_denom_fixed) { d1 = L.Theta2_denom[1]; d2 = L.Theta2_denom[2]; }
-      }
-      double sig2 = r[4] + d1 * d1 * r[5] + d2 * d2 * r[6]
-                    + 2.0 * (d1 * r[7] + d2 * r[8] + d1 * d2 * r[9]) + r[10];
+      const double2 *__restrict__ r = reinterpret_cast<const double2 *>(L.sn + (size_t)i * SN_ROW);
+      const double2 ms = __ldg(&r[0]), cz = __ldg(&r[1]), w01 = __ldg(&r[2]), w23 = __ldg(&r[3]),
+                    w45 = __ldg(&r[4]);
+      double t2 = t2base, e2 = d2;
+      if (mode == PMCB200_CHI2_betaz) { t2 = fma(m.Theta2[3], cz.y, t2base); e2 = t2; }
+      double mu_obs = ms.x + m.Theta2[0];
+      if (mode != PMCB200_CHI2_no_sc) mu_obs += t1 * (ms.y - m.stretch) + t2 * (cz.x - m.color);
+      // sigma^2 = theta^T W theta + sigma_pv^2 + sigma_int^2 (w01.x carries Vmm + pv^2 + int^2)
+      double sig2 = w01.x + d1 * d1 * w01.y + e2 * e2 * w23.x
+                    + 2.0 * (d1 * w23.y + e2 * w45.x + d1 * e2 * w45.y);
       double res = mu_obs - mu_th;
-      chi2 += res * res / sig2;
+      chi2 = fma(res * res, fast_rcp(sig2), chi2);
       if (L.sn_add_logdetCov) logdet += log(sig2);
     }
   }

@@ -401,7 +401,7 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
     row[0] = L.sn_m[i]; row[1] = L.sn_s[i]; row[2] = L.sn_c[i]; row[3] = z;
     for (int q = 0; q < 6; q++) row[4 + q] = L.sn_cov[(size_t)i * 6 + q];
     double spv = pv_fac / z;
-    row[10] = spv * spv + L.sn_sig_int * L.sn_sig_int;
+    row[4] += spv * spv + L.sn_sig_int * L.sn_sig_int;   // Vmm + sigma_pv^2 + sigma_int^2
   }
   first.push_back(n);
   D.sn_n = n;
@@ -412,6 +412,21 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
   for (int i = 0; i < 3; i++) D.Theta2_denom[i] = L.sn_Theta2_denom[i];
   D.sig_int2 = L.sn_sig_int * L.sn_sig_int;
   D.pv_fac = pv_fac;
+  // launch-uniform specialisation: second exponent term only if w1 can be non-zero;
+  // curvature term dropped only if flatness is structural (Omega_de = 1 - Omega_m - 0 - Omega_nu)
+  bool has_w1 = L.model.w1_de != 0.0 || L.model.de_param == PMCB200_DE_jassal;
+  bool s_Om = false, s_other = false;
+  for (int j = 0; j < L.npar; j++) {
+    int pj = L.par[j];
+    if (pj == PMCB200_P_w1de) has_w1 = true;
+    if (pj == PMCB200_P_Omegam) s_Om = true;
+    if (pj == PMCB200_P_Omegade || pj == PMCB200_P_OmegaK || pj == PMCB200_P_Omegab || pj == PMCB200_P_Omegac ||
+        (pj >= PMCB200_P_omegam && pj <= PMCB200_P_omegaK))
+      s_other = true;
+  }
+  double OK0 = 1.0 - L.model.Omega_m - L.model.Omega_de - L.model.Omega_nu_mass;
+  D.sn_hasq = has_w1 ? 1 : 0;
+  D.sn_flat = (!s_other && (s_Om || std::fabs(OK0) < 1e-15)) ? 1 : 0;
   int rc;
   if ((rc = dev_copy<double2>(c, nodes.data(), nodes.size(), &D.nodes))) return rc;
   if ((rc = dev_copy<int>(c, first.data(), first.size(), &D.first))) return rc;
@@ -551,7 +566,10 @@ static int launch_posterior(pmcb200_ctx *c, int64_t N, const double *dX, const i
     const double add = set ? c->logpr_const : 0.0;
     switch (L.kind) {
       case PMCB200_LIKE_SNIa:
-        k_like_sn<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
+        if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
+        else if (L.sn_hasq) k_like_sn<true, false><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
+        else if (L.sn_flat) k_like_sn<false, true><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
+        else k_like_sn<false, false><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
         break;
       case PMCB200_LIKE_BAO:
         k_like_bao<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add);
@@ -623,7 +641,7 @@ extern "C" int pmcb200_simulate(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32
                                 double *dX, int32_t *didx, int16_t *dflg) {
   int rc = need(c, true, false);
   if (rc) return rc;
-  if (N < 0 || !dX || !didx || !dflg) return fail(c, PMCB200_ERR_ARG, "simulate: bad arguments");
+  if (N < 0 || (N > 0 && (!dX || !didx || !dflg))) return fail(c, PMCB200_ERR_ARG, "simulate: bad arguments");
   if ((rc = reset_scal(c))) return rc;
   return launch_simulate(c, N, seed, iter, offset, dX, didx, dflg);
 }
@@ -632,7 +650,7 @@ extern "C" int pmcb200_simulate_from_draws(pmcb200_ctx *c, int64_t N, const doub
                                            double *dX, int32_t *didx, int16_t *dflg) {
   int rc = need(c, true, false);
   if (rc) return rc;
-  if (N < 0 || !du || !dz || !dX || !didx || !dflg) return fail(c, PMCB200_ERR_ARG, "simulate_from_draws: bad arguments");
+  if (N < 0 || (N > 0 && (!du || !dz || !dX || !didx || !dflg))) return fail(c, PMCB200_ERR_ARG, "simulate_from_draws: bad arguments");
   if (!c->d_box) return fail(c, PMCB200_ERR_STATE, "simulate needs the target's box (pmcb200_set_target)");
   if (c->h.df > 0) return fail(c, PMCB200_ERR_UNSUP, "simulate_from_draws: Gaussian proposals only");
   if (N == 0) return 0;
@@ -645,7 +663,7 @@ extern "C" int pmcb200_simulate_from_draws(pmcb200_ctx *c, int64_t N, const doub
 extern "C" int pmcb200_proposal_log_pdf(pmcb200_ctx *c, int64_t N, const double *dX, double *dlogq) {
   int rc = need(c, true, false);
   if (rc) return rc;
-  if (N < 0 || !dX || !dlogq) return fail(c, PMCB200_ERR_ARG, "proposal_log_pdf: bad arguments");
+  if (N < 0 || (N > 0 && (!dX || !dlogq))) return fail(c, PMCB200_ERR_ARG, "proposal_log_pdf: bad arguments");
   if (N == 0) return 0;
   DISPATCH_D(c->h.d, (k_logq<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(c->d_mix, c->h, N, dX, dlogq)));
   LAUNCH_OK(c);
@@ -656,7 +674,7 @@ extern "C" int pmcb200_posterior_log_pdf(pmcb200_ctx *c, int64_t N, const double
                                          int32_t *derr) {
   int rc = need(c, false, true);
   if (rc) return rc;
-  if (N < 0 || !dX || !dlogpi) return fail(c, PMCB200_ERR_ARG, "posterior_log_pdf: bad arguments");
+  if (N < 0 || (N > 0 && (!dX || !dlogpi))) return fail(c, PMCB200_ERR_ARG, "posterior_log_pdf: bad arguments");
   return launch_posterior(c, N, dX, nullptr, dlogpi, derr);
 }
 
@@ -664,7 +682,7 @@ extern "C" int pmcb200_importance_weights(pmcb200_ctx *c, int64_t N, const doubl
                                           int16_t *dflg, double *dlogw) {
   int rc = need(c, true, true);
   if (rc) return rc;
-  if (N < 0 || !dX || !dflg || !dlogw) return fail(c, PMCB200_ERR_ARG, "importance_weights: bad arguments");
+  if (N < 0 || (N > 0 && (!dX || !dflg || !dlogw))) return fail(c, PMCB200_ERR_ARG, "importance_weights: bad arguments");
   if ((rc = ensure(c, c->sLogpi, (size_t)std::max<int64_t>(N, 1) * sizeof(double)))) return rc;
   if ((rc = ensure(c, c->sErr, (size_t)std::max<int64_t>(N, 1) * sizeof(int32_t)))) return rc;
   // keep nok_box of a preceding simulate; reset max / nok
@@ -676,7 +694,7 @@ extern "C" int pmcb200_importance_weights(pmcb200_ctx *c, int64_t N, const doubl
 extern "C" int pmcb200_normalize_weights(pmcb200_ctx *c, int64_t N, const int16_t *dflg, double *dw) {
   int rc = need(c, false, false);
   if (rc) return rc;
-  if (N < 0 || !dflg || !dw) return fail(c, PMCB200_ERR_ARG, "normalize_weights: bad arguments");
+  if (N < 0 || (N > 0 && (!dflg || !dw))) return fail(c, PMCB200_ERR_ARG, "normalize_weights: bad arguments");
   // M and S come from the last em_finish (they are global over all ranks)
   double M = c->h_result[0], S = c->h_result[1];
   if (!(S > 0.0)) return fail(c, PMCB200_ERR_STATE, "normalize_weights: call pmcb200_em_finish first");
