@@ -208,23 +208,27 @@ __device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t
 // exp(t) for |t| < 700: Cody-Waite reduction t = k ln2 + r, |r| <= ln2/2, degree-11
 // near-minimax polynomial (Chebyshev interpolant, max rel. error 1.6e-17 before
 // rounding), scaling by exponent-field addition.  Branch-free: 16 FP64 ops.
+// The coefficients live in constant memory so every DFMA takes its literal as a
+// c[bank][offset] operand (no per-use UMOV/IMAD materialisation).
+__constant__ double EXPC[16] = {
+    1.4426950408889634074,          // [0] log2(e)
+    -6.93147180369123816490e-01,    // [1] -ln2_hi
+    -1.90821492927058770002e-10,    // [2] -ln2_lo
+    0x1.af632a0f7e2cep-26,          // [3] c11
+    0x1.28b4101c77212p-22, 0x1.71ddf56d8deb5p-19, 0x1.a01991a10d9aep-16, 0x1.a01a01b1461c5p-13,
+    0x1.6c16c1880029fp-10, 0x1.111111110f21ep-7, 0x1.555555554f0bap-5, 0x1.555555555555ap-3,
+    0x1.0000000000011p-1,           // [12] c2
+    6755399441055744.0,             // [13] 1.5 * 2^52
+    0.0, 0.0};
 __device__ __forceinline__ double fast_exp(double t) {
-  const double MAGIC = 6755399441055744.0;       // 1.5 * 2^52
-  double kf = fma(t, 1.4426950408889634074, MAGIC);
+  double kf = fma(t, EXPC[0], EXPC[13]);
   int k = __double2loint(kf);
-  kf -= MAGIC;
-  double r = fma(kf, -6.93147180369123816490e-01, t);
-  r = fma(kf, -1.90821492927058770002e-10, r);
-  double p = 0x1.af632a0f7e2cep-26;
-  p = fma(p, r, 0x1.28b4101c77212p-22);
-  p = fma(p, r, 0x1.71ddf56d8deb5p-19);
-  p = fma(p, r, 0x1.a01991a10d9aep-16);
-  p = fma(p, r, 0x1.a01a01b1461c5p-13);
-  p = fma(p, r, 0x1.6c16c1880029fp-10);
-  p = fma(p, r, 0x1.111111110f21ep-7);
-  p = fma(p, r, 0x1.555555554f0bap-5);
-  p = fma(p, r, 0x1.555555555555ap-3);
-  p = fma(p, r, 0x1.0000000000011p-1);
+  kf -= EXPC[13];
+  double r = fma(kf, EXPC[1], t);
+  r = fma(kf, EXPC[2], r);
+  double p = EXPC[3];
+#pragma unroll
+  for (int i = 4; i <= 12; i++) p = fma(p, r, EXPC[i]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
@@ -257,7 +261,7 @@ struct SNCoef {
   double Om, OK, Ode, p, q;
   int jassal, slow;
 };
-template <bool HASQ, bool FLAT>
+template <bool HASQ, bool FLAT, bool SLOW>
 __device__ __forceinline__ double sn_f(const SNCoef &e, double2 nd) {
   const double a = nd.x;
   double t = e.p * nd.y;
@@ -265,9 +269,115 @@ __device__ __forceinline__ double sn_f(const SNCoef &e, double2 nd) {
     double oma = 1.0 - a;
     t = e.jassal ? fma(e.q * oma, oma, t) : fma(e.q, oma, t);
   }
-  double ex = e.slow ? exp(t) : fast_exp(t);
+  double ex = SLOW ? exp(t) : fast_exp(t);
   double v = FLAT ? fma(e.Om, a, e.Ode * ex) : fma(a, fma(e.OK, a, e.Om), e.Ode * ex);
   return fast_rsqrt(v);
+}
+
+// The redshift loop: per unique z one adaptive Romberg integral (tabulated
+// nodes), then the chi^2 terms of the supernovae at that z.
+struct SNPer {           // per-sample constants of the chi^2 part
+  double Theta0, Theta3, t1, t2base, d1, d2, stretch, color;
+};
+template <bool HASQ, bool FLAT, bool SLOW>
+__device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, const SNPer &m_, double f1,
+                                         double &chi2, double &logdet, int &e, unsigned &nev) {
+  const bool flat = fabs(ec.OK) < FLAT_EPS;
+  const double sk = sqrt(fabs(ec.OK)) / R_HUBBLE;
+  const int mode = L.sn_chi2mode;
+  const double t1 = m_.t1, t2base = m_.t2base, d1 = m_.d1, d2 = m_.d2;
+  for (int iz = 0; iz < L.sn_nz; iz++) {
+    const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
+    const double2 n0 = __ldg(&nd[0]);
+    const double az = n0.x, h = 1.0 - az;
+    // trapezoid stages 1..5 (17 integrand evaluations), Romberg tableau by rows:
+    // R[m] <- T_{j,m} = T_{j,m-1} + (T_{j,m-1} - T_{j-1,m-1}) / (4^m - 1)
+    double R0, R1, R2, R3, R4, st;
+    st = 0.5 * h * (sn_f<HASQ, FLAT, SLOW>(ec, n0) + f1);
+    R0 = st;
+    st = 0.5 * fma(h, sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[1])), st);
+    { double n1 = fma(st - R0, 1.0 / 3.0, st); R0 = st; R1 = n1; }
+    {
+      double s = sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[2]));
+      s += sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[3]));
+      st = 0.5 * fma(h * 0.5, s, st);
+      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1);
+      R0 = st; R1 = n1; R2 = n2;
+    }
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 4; i < 8; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[i]));
+      st = 0.5 * fma(h * 0.25, s, st);
+      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
+             n3 = fma(n2 - R2, 1.0 / 63.0, n2);
+      R0 = st; R1 = n1; R2 = n2; R3 = n3;
+    }
+    double ss, dss;
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 8; i < 16; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[i]));
+      st = 0.5 * fma(h * 0.125, s, st);
+      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
+             n3 = fma(n2 - R2, 1.0 / 63.0, n2);
+      dss = (n3 - R3) * (1.0 / 255.0);
+      ss = n3 + dss;
+      R0 = st; R1 = n1; R2 = n2; R3 = n3; R4 = ss;
+    }
+    (void)R4;
+    bool done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
+    nev += 17;
+    int j = 5;                      // stages completed
+    while (!__all_sync(0xffffffffu, done)) {
+      if (j >= ROMB_JMAX) { if (!done) { ss = NAN; done = true; } break; }
+      if (!done) {
+        const int it = 1 << (j - 1);
+        double s = 0.0;
+        if (2 * it <= SN_NODES) {
+#pragma unroll 4
+          for (int i = it; i < 2 * it; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[i]));
+        } else {
+          const double del = h / (double)it;
+          for (int i = 0; i < it; i++) {
+            double a = fma((double)i + 0.5, del, az);
+            s += sn_f<HASQ, FLAT, SLOW>(ec, make_double2(a, log(a)));
+          }
+        }
+        nev += it;
+        st = 0.5 * (st + h * s / (double)it);
+        double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
+               n3 = fma(n2 - R2, 1.0 / 63.0, n2);
+        dss = (n3 - R3) * (1.0 / 255.0);
+        ss = n3 + dss;
+        R0 = st; R1 = n1; R2 = n2; R3 = n3;
+        done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
+      }
+      j++;
+    }
+    // luminosity distance [Mpc/h] and distance modulus
+    double ww = R_HUBBLE * ss;
+    double fk = (FLAT || flat) ? ww : (ec.OK > 0.0 ? sinh(sk * ww) : sin(sk * ww)) / sk;
+    if (!(fk > 0.0)) e = 1;         // also catches NaN
+    // mu_th = 5 log10(fk / (az H_fid)) + 25; the az part is tabulated (nodes[.][0].y = ln az)
+    const double mu_th = fma(5.0 / M_LN10, log(fk) - n0.y, 25.0 - 5.0 * log10(SN_H_FID));
+    const int i0 = __ldg(&L.first[iz]), i1 = __ldg(&L.first[iz + 1]);
+    for (int i = i0; i < i1; i++) {
+      const double2 *__restrict__ r = reinterpret_cast<const double2 *>(L.sn + (size_t)i * SN_ROW);
+      const double2 ms = __ldg(&r[0]), cz = __ldg(&r[1]), w01 = __ldg(&r[2]), w23 = __ldg(&r[3]),
+                    w45 = __ldg(&r[4]);
+      double t2 = t2base, e2 = d2;
+      if (mode == PMCB200_CHI2_betaz) { t2 = fma(m_.Theta3, cz.y, t2base); e2 = t2; }
+      double mu_obs = ms.x + m_.Theta0;
+      if (mode != PMCB200_CHI2_no_sc) mu_obs += t1 * (ms.y - m_.stretch) + t2 * (cz.x - m_.color);
+      // sigma^2 = theta^T W theta + sigma_pv^2 + sigma_int^2 (w01.x carries Vmm + pv^2 + int^2)
+      double sig2 = w01.x + d1 * d1 * w01.y + e2 * e2 * w23.x
+                    + 2.0 * (d1 * w23.y + e2 * w45.x + d1 * e2 * w45.y);
+      double res = mu_obs - mu_th;
+      chi2 = fma(res * res, fast_rcp(sig2), chi2);
+      if (L.sn_add_logdetCov) logdet += log(sig2);
+    }
+  }
 }
 
 template <bool HASQ, bool FLAT>
@@ -296,107 +406,15 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
     ec.slow = !(fabs(g.p) * lna_min + fabs(g.q) < 690.0);
   }
   const double f1 = rsqrt(ec.Om + ec.OK + ec.Ode);      // integrand at a = 1
-  const bool flat = fabs(ec.OK) < FLAT_EPS;
-  const double sk = sqrt(fabs(ec.OK)) / R_HUBBLE;
-  const int mode = L.sn_chi2mode;
-  const double t1 = m.Theta2[1], t2base = m.Theta2[2];
-  double d1 = t1, d2 = t2base;
-  if (mode == PMCB200_CHI2_no_sc) { d1 = 0.0; d2 = 0.0; }
-  if (mode == PMCB200_CHI2_Theta2_denom_fixed) { d1 = L.Theta2_denom[1]; d2 = L.Theta2_denom[2]; }
+  SNPer pm;
+  pm.Theta0 = m.Theta2[0]; pm.Theta3 = m.Theta2[3]; pm.t1 = m.Theta2[1]; pm.t2base = m.Theta2[2];
+  pm.d1 = pm.t1; pm.d2 = pm.t2base; pm.stretch = m.stretch; pm.color = m.color;
+  if (L.sn_chi2mode == PMCB200_CHI2_no_sc) { pm.d1 = 0.0; pm.d2 = 0.0; }
+  if (L.sn_chi2mode == PMCB200_CHI2_Theta2_denom_fixed) { pm.d1 = L.Theta2_denom[1]; pm.d2 = L.Theta2_denom[2]; }
   double chi2 = 0.0, logdet = 0.0;
-
-  for (int iz = 0; iz < L.sn_nz; iz++) {
-    const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
-    const double2 n0 = __ldg(&nd[0]);
-    const double az = n0.x, h = 1.0 - az;
-    // trapezoid stages 1..5 (17 integrand evaluations), Romberg tableau by rows:
-    // R[m] <- T_{j,m} = T_{j,m-1} + (T_{j,m-1} - T_{j-1,m-1}) / (4^m - 1)
-    double R0, R1, R2, R3, R4, st;
-    st = 0.5 * h * (sn_f<HASQ, FLAT>(ec, n0) + f1);
-    R0 = st;
-    st = 0.5 * fma(h, sn_f<HASQ, FLAT>(ec, __ldg(&nd[1])), st);
-    { double n1 = fma(st - R0, 1.0 / 3.0, st); R0 = st; R1 = n1; }
-    {
-      double s = sn_f<HASQ, FLAT>(ec, __ldg(&nd[2]));
-      s += sn_f<HASQ, FLAT>(ec, __ldg(&nd[3]));
-      st = 0.5 * fma(h * 0.5, s, st);
-      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1);
-      R0 = st; R1 = n1; R2 = n2;
-    }
-    {
-      double s = 0.0;
-#pragma unroll
-      for (int i = 4; i < 8; i++) s += sn_f<HASQ, FLAT>(ec, __ldg(&nd[i]));
-      st = 0.5 * fma(h * 0.25, s, st);
-      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
-             n3 = fma(n2 - R2, 1.0 / 63.0, n2);
-      R0 = st; R1 = n1; R2 = n2; R3 = n3;
-    }
-    double ss, dss;
-    {
-      double s = 0.0;
-#pragma unroll
-      for (int i = 8; i < 16; i++) s += sn_f<HASQ, FLAT>(ec, __ldg(&nd[i]));
-      st = 0.5 * fma(h * 0.125, s, st);
-      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
-             n3 = fma(n2 - R2, 1.0 / 63.0, n2);
-      dss = (n3 - R3) * (1.0 / 255.0);
-      ss = n3 + dss;
-      R0 = st; R1 = n1; R2 = n2; R3 = n3; R4 = ss;
-    }
-    (void)R4;
-    bool done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
-    nev += 17;
-    int j = 5;                      // stages completed
-    while (!__all_sync(0xffffffffu, done)) {
-      if (j >= ROMB_JMAX) { if (!done) { ss = NAN; done = true; } break; }
-      if (!done) {
-        const int it = 1 << (j - 1);
-        double s = 0.0;
-        if (2 * it <= SN_NODES) {
-#pragma unroll 4
-          for (int i = it; i < 2 * it; i++) s += sn_f<HASQ, FLAT>(ec, __ldg(&nd[i]));
-        } else {
-          const double del = h / (double)it;
-          for (int i = 0; i < it; i++) {
-            double a = fma((double)i + 0.5, del, az);
-            s += sn_f<HASQ, FLAT>(ec, make_double2(a, log(a)));
-          }
-        }
-        nev += it;
-        st = 0.5 * (st + h * s / (double)it);
-        double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
-               n3 = fma(n2 - R2, 1.0 / 63.0, n2);
-        dss = (n3 - R3) * (1.0 / 255.0);
-        ss = n3 + dss;
-        R0 = st; R1 = n1; R2 = n2; R3 = n3;
-        done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
-      }
-      j++;
-    }
-    // luminosity distance [Mpc/h] and distance modulus
-    double ww = R_HUBBLE * ss;
-    double fk = (FLAT || flat) ? ww : (ec.OK > 0.0 ? sinh(sk * ww) : sin(sk * ww)) / sk;
-    if (!(fk > 0.0)) e = 1;         // also catches NaN
-    // mu_th = 5 log10(fk / (az H_fid)) + 25; the az part is tabulated (nodes[.][0].y = ln az)
-    const double mu_th = fma(5.0 / M_LN10, log(fk) - n0.y, 25.0 - 5.0 * log10(SN_H_FID));
-    const int i0 = __ldg(&L.first[iz]), i1 = __ldg(&L.first[iz + 1]);
-    for (int i = i0; i < i1; i++) {
-      const double2 *__restrict__ r = reinterpret_cast<const double2 *>(L.sn + (size_t)i * SN_ROW);
-      const double2 ms = __ldg(&r[0]), cz = __ldg(&r[1]), w01 = __ldg(&r[2]), w23 = __ldg(&r[3]),
-                    w45 = __ldg(&r[4]);
-      double t2 = t2base, e2 = d2;
-      if (mode == PMCB200_CHI2_betaz) { t2 = fma(m.Theta2[3], cz.y, t2base); e2 = t2; }
-      double mu_obs = ms.x + m.Theta2[0];
-      if (mode != PMCB200_CHI2_no_sc) mu_obs += t1 * (ms.y - m.stretch) + t2 * (cz.x - m.color);
-      // sigma^2 = theta^T W theta + sigma_pv^2 + sigma_int^2 (w01.x carries Vmm + pv^2 + int^2)
-      double sig2 = w01.x + d1 * d1 * w01.y + e2 * e2 * w23.x
-                    + 2.0 * (d1 * w23.y + e2 * w45.x + d1 * e2 * w45.y);
-      double res = mu_obs - mu_th;
-      chi2 = fma(res * res, fast_rcp(sig2), chi2);
-      if (L.sn_add_logdetCov) logdet += log(sig2);
-    }
-  }
+  // libdevice exp only for warps holding a sample outside fast_exp's range
+  if (__any_sync(0xffffffffu, ec.slow)) sn_zloop<HASQ, FLAT, true>(L, ec, pm, f1, chi2, logdet, e, nev);
+  else sn_zloop<HASQ, FLAT, false>(L, ec, pm, f1, chi2, logdet, e, nev);
   double res = -0.5 * chi2;
   if (L.sn_add_logdetCov) res -= 0.5 * logdet;
   if (!isfinite(res)) e = 1;
