@@ -79,7 +79,8 @@ class Stats(C.Structure):
 
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "cosmopmc_b200", "libpmc_b200.so")
+# PMCB200_LIB selects another build of the same library (A/B kernel experiments)
+LIB_PATH = os.environ.get("PMCB200_LIB") or os.path.join(ROOT, "cosmopmc_b200", "libpmc_b200.so")
 
 # every symbol include/pmcb200.h declares: name -> (restype, argtypes)
 _vp, _i, _i64, _u64, _u32, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_double

@@ -1,29 +1,59 @@
-"""Build recipe for libpmc_b200.so (sm_100a only, in-tree)."""
+"""Build recipe for libpmc_b200.so (sm_100a only, in-tree, parallel nvcc)."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpmc_b200.so")
+OBJ = os.environ.get("PMCB200_OBJ_DIR") or os.path.join(HERE, "build")
+LIB = os.environ.get("PMCB200_LIB_OUT") or os.path.join(HERE, "libpmc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "--extended-lambda", "-Xcompiler", "-fPIC,-O2", "-shared"]
+         "--extended-lambda", "-Xcompiler", "-fPIC,-O2"] + os.environ.get("PMCB200_NVCC_FLAGS", "").split()
+
+# (object name, source, extra flags)
+UNITS = [("pmcb200.o", "pmcb200.cu", []),
+         ("k_cosmo.o", "k_cosmo.cu", []),
+         ("k_mix0.o", "k_mix.cu", ["-DMIX_GROUP=0"]),
+         ("k_mix1.o", "k_mix.cu", ["-DMIX_GROUP=1"]),
+         ("k_mix2.o", "k_mix.cu", ["-DMIX_GROUP=2"]),
+         ("k_mix3.o", "k_mix.cu", ["-DMIX_GROUP=3"])]
 
 
-def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
            [os.path.join(os.path.dirname(HERE), "include", "pmcb200.h")]
 
 
+def _stale(target, srcs):
+    return not os.path.exists(target) or any(os.path.getmtime(target) < os.path.getmtime(s) for s in srcs)
+
+
+def _compile(unit, verbose):
+    obj, src, extra = unit
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return obj, r.returncode, r.stdout + r.stderr
+
+
 def build(force=False, verbose=False):
-    srcs = sources()
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
-        return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB, os.path.join(CSRC, "pmcb200.cu")]
-    print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    deps = _deps()
+    todo = [u for u in UNITS
+            if force or _stale(os.path.join(OBJ, u[0]), deps + [os.path.join(CSRC, u[1])])]
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
+            for obj, rc, out in ex.map(lambda u: _compile(u, verbose), todo):
+                if verbose or rc:
+                    sys.stderr.write("== %s\n%s" % (obj, out))
+                if rc:
+                    raise RuntimeError("nvcc failed for %s" % obj)
+    objs = [os.path.join(OBJ, u[0]) for u in UNITS]
+    if todo or _stale(LIB, objs):
+        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-o", LIB] + objs)
     return LIB
 
 

@@ -6,31 +6,7 @@
 #pragma once
 #include "common.cuh"
 
-#define SN_NODES 64      // tabulated Romberg nodes per redshift: stages 1..7
-#define SN_ROW 12        // doubles per supernova row in the device table
-
-// Device-side likelihood descriptor (pointers are device pointers).
-struct DevLike {
-  int kind, npar, special, pad0;
-  int par[PMCB200_MAX_DIM];
-  pmcb200_cosmo_t model;
-  // SN Ia
-  int sn_chi2mode, sn_add_logdetCov, sn_n, sn_nz;
-  double Theta2[4], Theta2_denom[3], sig_int2, pv_fac;
-  const double2 *nodes;   // [sn_nz][SN_NODES] {a, ln a}; entry 0 = a(z), entry i in
-                          // [2^(j-2), 2^(j-1)) = nodes of trapezoid stage j >= 2
-  const int *first;       // [sn_nz+1] ranges of supernovae sharing a redshift
-  const double *sn;       // [sn_n][SN_ROW]: m s | c z | Vmm+pv2+int2 Vss | Vcc Cms | Cmc Csc | - -
-  int sn_hasq, sn_flat;   // launch-uniform specialisation flags (set by the host)
-  // Gaussian data (BAO, CMB distance priors): packed like a mixture component
-  int bao_method, g_ndim;
-  const double *g_z;
-  const double *g_comp;   // [2 + 2n + tri(n)] = wght, lognorm, mean, L packed, 1/diag
-  // analytic targets
-  MixHdr mixh;
-  const double *mix;
-  double banana_b, banana_sigma1sq;
-};
+#include "cosmo_types.cuh"
 
 struct Model {
   pmcb200_cosmo_t c;
@@ -205,33 +181,38 @@ __device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t
 }
 
 // ---- fast FP64 primitives for the SN hot loop ---------------------------------
-// exp(t) for |t| < 700: Cody-Waite reduction t = k ln2 + r, |r| <= ln2/2, degree-11
-// near-minimax polynomial (Chebyshev interpolant, max rel. error 1.6e-17 before
-// rounding), scaling by exponent-field addition.  Branch-free: 16 FP64 ops.
-// The coefficients live in constant memory so every DFMA takes its literal as a
-// c[bank][offset] operand (no per-use UMOV/IMAD materialisation).
-__constant__ double EXPC[16] = {
-    1.4426950408889634074,          // [0] log2(e)
-    -6.93147180369123816490e-01,    // [1] -ln2_hi
-    -1.90821492927058770002e-10,    // [2] -ln2_lo
-    0x1.af632a0f7e2cep-26,          // [3] c11
-    0x1.28b4101c77212p-22, 0x1.71ddf56d8deb5p-19, 0x1.a01991a10d9aep-16, 0x1.a01a01b1461c5p-13,
-    0x1.6c16c1880029fp-10, 0x1.111111110f21ep-7, 0x1.555555554f0bap-5, 0x1.555555555555ap-3,
-    0x1.0000000000011p-1,           // [12] c2
-    6755399441055744.0,             // [13] 1.5 * 2^52
-    0.0, 0.0};
-__device__ __forceinline__ double fast_exp(double t) {
-  double kf = fma(t, EXPC[0], EXPC[13]);
-  int k = __double2loint(kf);
-  kf -= EXPC[13];
-  double r = fma(kf, EXPC[1], t);
-  r = fma(kf, EXPC[2], r);
-  double p = EXPC[3];
-#pragma unroll
-  for (int i = 4; i <= 12; i++) p = fma(p, r, EXPC[i]);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+// 2^s for |s| < 1000: s = k/16 + f with |f| <= 1/32 (one magic-number add, the
+// remainder is exact), 2^f by a degree-6 near-minimax polynomial (Chebyshev
+// interpolant, max rel. error 7.8e-18 before rounding), 2^(j/16) from a
+// 16-entry shared-memory table (16 doubles = 32 banks: conflict-free), power of
+// two by exponent-field addition.  Branch-free: 10 FP64 ops + 1 LDS.
+// Constants live in constant memory so DFMA takes them as c[bank][offset]
+// operands (no per-use UMOV/IMAD materialisation).
+__constant__ double EXP2C[8] = {
+    0x1.62e42fefa39fdp-1, 0x1.ebfbdff82c594p-3, 0x1.c6b08d6e8a0a6p-5, 0x1.3b2ab6fb09a33p-7,
+    0x1.5d89be630066dp-10, 0x1.430a4970f3ce1p-13,
+    422212465065984.0,              // [6] 1.5 * 2^48: ulp = 2^-4
+    0.0};
+__constant__ double EXP2T[16] = {
+    0x1.0000000000000p+0, 0x1.0b5586cf9890fp+0, 0x1.172b83c7d517bp+0, 0x1.2387a6e756238p+0,
+    0x1.306fe0a31b715p+0, 0x1.3dea64c123422p+0, 0x1.4bfdad5362a27p+0, 0x1.5ab07dd485429p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.7a11473eb0187p+0, 0x1.8ace5422aa0dbp+0, 0x1.9c49182a3f090p+0,
+    0x1.ae89f995ad3adp+0, 0x1.c199bdd85529cp+0, 0x1.d5818dcfba487p+0, 0x1.ea4afa2a490dap+0};
+// returns sign * 2^s, sign given as an XOR mask for the high word
+__device__ __forceinline__ double fast_exp2_signed(double s, const double *__restrict__ T, unsigned sgn) {
+  double kf = s + EXP2C[6];
+  const int k16 = __double2loint(kf);
+  kf -= EXP2C[6];
+  const double f = s - kf;
+  double p = EXP2C[5];
+  p = fma(p, f, EXP2C[4]);
+  p = fma(p, f, EXP2C[3]);
+  p = fma(p, f, EXP2C[2]);
+  p = fma(p, f, EXP2C[1]);
+  p = fma(p, f, EXP2C[0]);
+  p = fma(p, f, 1.0);
+  p *= T[k16 & 15];
+  return __hiloint2double((__double2hiint(p) + ((k16 >> 4) << 20)) ^ sgn, __double2loint(p));
 }
 // 1/sqrt(v): MUFU.RSQ64H seed (rel. error 2^-22) + one third-order step -> 2^-66.
 // v < 0 -> NaN, v = 0 -> NaN (both are the reference's error condition).
@@ -256,21 +237,28 @@ __device__ __forceinline__ double fast_rcp(double s) {
 // ---- SN Ia: one sample per thread; the whole warp walks the same redshift
 // so node loads are warp-uniform and the adaptive stage count is resolved by
 // a warp vote.  HASQ: w1 != 0 or jassal (second exponent term); FLAT: the
-// curvature term is identically zero for every sample of the launch. -----------
+// curvature term is identically zero for every sample of the launch; SLOW:
+// libdevice exp for warps holding a sample outside the fast path's range. -------
 struct SNCoef {
-  double Om, OK, Ode, p, q;
+  double Om, OK, Ode, p, q;        // a^4 E^2 = a (Om + OK a) + Ode exp(p ln a + q g(a))
+  double p2, q2, lg;               // base-2 form: Ode exp(.) = sgn 2^(p2 ln a + q2 g(a) + lg)
+  unsigned sgn;
   int jassal, slow;
 };
 template <bool HASQ, bool FLAT, bool SLOW>
-__device__ __forceinline__ double sn_f(const SNCoef &e, double2 nd) {
+__device__ __forceinline__ double sn_f(const SNCoef &e, const double *__restrict__ T, double2 nd) {
   const double a = nd.x;
-  double t = e.p * nd.y;
-  if (HASQ) {
-    double oma = 1.0 - a;
-    t = e.jassal ? fma(e.q * oma, oma, t) : fma(e.q, oma, t);
+  double de;
+  if (SLOW) {
+    double t = e.p * nd.y;
+    if (HASQ) { double oma = 1.0 - a; t = e.jassal ? fma(e.q * oma, oma, t) : fma(e.q, oma, t); }
+    de = e.Ode * exp(t);
+  } else {
+    double s = fma(e.p2, nd.y, e.lg);
+    if (HASQ) { double oma = 1.0 - a; s = e.jassal ? fma(e.q2 * oma, oma, s) : fma(e.q2, oma, s); }
+    de = fast_exp2_signed(s, T, e.sgn);
   }
-  double ex = SLOW ? exp(t) : fast_exp(t);
-  double v = FLAT ? fma(e.Om, a, e.Ode * ex) : fma(a, fma(e.OK, a, e.Om), e.Ode * ex);
+  double v = FLAT ? fma(e.Om, a, de) : fma(a, fma(e.OK, a, e.Om), de);
   return fast_rsqrt(v);
 }
 
@@ -278,28 +266,29 @@ __device__ __forceinline__ double sn_f(const SNCoef &e, double2 nd) {
 // nodes), then the chi^2 terms of the supernovae at that z.
 struct SNPer {           // per-sample constants of the chi^2 part
   double Theta0, Theta3, t1, t2base, d1, d2, stretch, color;
+  double base0, k1, k2, k3, k4, k5;   // folded forms for the non-betaz modes
 };
 template <bool HASQ, bool FLAT, bool SLOW>
-__device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, const SNPer &m_, double f1,
-                                         double &chi2, double &logdet, int &e, unsigned &nev) {
+__device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, const double *__restrict__ T,
+                                         const SNPer &m_, double f1, double &chi2, double &logdet, int &e,
+                                         unsigned &nev) {
   const bool flat = fabs(ec.OK) < FLAT_EPS;
   const double sk = sqrt(fabs(ec.OK)) / R_HUBBLE;
   const int mode = L.sn_chi2mode;
-  const double t1 = m_.t1, t2base = m_.t2base, d1 = m_.d1, d2 = m_.d2;
   for (int iz = 0; iz < L.sn_nz; iz++) {
     const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
     const double2 n0 = __ldg(&nd[0]);
     const double az = n0.x, h = 1.0 - az;
     // trapezoid stages 1..5 (17 integrand evaluations), Romberg tableau by rows:
     // R[m] <- T_{j,m} = T_{j,m-1} + (T_{j,m-1} - T_{j-1,m-1}) / (4^m - 1)
-    double R0, R1, R2, R3, R4, st;
-    st = 0.5 * h * (sn_f<HASQ, FLAT, SLOW>(ec, n0) + f1);
+    double R0, R1, R2, R3, st;
+    st = 0.5 * h * (sn_f<HASQ, FLAT, SLOW>(ec, T, n0) + f1);
     R0 = st;
-    st = 0.5 * fma(h, sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[1])), st);
+    st = 0.5 * fma(h, sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[1])), st);
     { double n1 = fma(st - R0, 1.0 / 3.0, st); R0 = st; R1 = n1; }
     {
-      double s = sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[2]));
-      s += sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[3]));
+      double s = sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[2]));
+      s += sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[3]));
       st = 0.5 * fma(h * 0.5, s, st);
       double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1);
       R0 = st; R1 = n1; R2 = n2;
@@ -307,7 +296,7 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
     {
       double s = 0.0;
 #pragma unroll
-      for (int i = 4; i < 8; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[i]));
+      for (int i = 4; i < 8; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
       st = 0.5 * fma(h * 0.25, s, st);
       double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
              n3 = fma(n2 - R2, 1.0 / 63.0, n2);
@@ -317,15 +306,14 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
     {
       double s = 0.0;
 #pragma unroll
-      for (int i = 8; i < 16; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[i]));
+      for (int i = 8; i < 16; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
       st = 0.5 * fma(h * 0.125, s, st);
       double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
              n3 = fma(n2 - R2, 1.0 / 63.0, n2);
       dss = (n3 - R3) * (1.0 / 255.0);
       ss = n3 + dss;
-      R0 = st; R1 = n1; R2 = n2; R3 = n3; R4 = ss;
+      R0 = st; R1 = n1; R2 = n2; R3 = n3;
     }
-    (void)R4;
     bool done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
     nev += 17;
     int j = 5;                      // stages completed
@@ -336,12 +324,12 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
         double s = 0.0;
         if (2 * it <= SN_NODES) {
 #pragma unroll 4
-          for (int i = it; i < 2 * it; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, __ldg(&nd[i]));
+          for (int i = it; i < 2 * it; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
         } else {
           const double del = h / (double)it;
           for (int i = 0; i < it; i++) {
             double a = fma((double)i + 0.5, del, az);
-            s += sn_f<HASQ, FLAT, SLOW>(ec, make_double2(a, log(a)));
+            s += sn_f<HASQ, FLAT, SLOW>(ec, T, make_double2(a, log(a)));
           }
         }
         nev += it;
@@ -366,25 +354,35 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
       const double2 *__restrict__ r = reinterpret_cast<const double2 *>(L.sn + (size_t)i * SN_ROW);
       const double2 ms = __ldg(&r[0]), cz = __ldg(&r[1]), w01 = __ldg(&r[2]), w23 = __ldg(&r[3]),
                     w45 = __ldg(&r[4]);
-      double t2 = t2base, e2 = d2;
-      if (mode == PMCB200_CHI2_betaz) { t2 = fma(m_.Theta3, cz.y, t2base); e2 = t2; }
-      double mu_obs = ms.x + m_.Theta0;
-      if (mode != PMCB200_CHI2_no_sc) mu_obs += t1 * (ms.y - m_.stretch) + t2 * (cz.x - m_.color);
-      // sigma^2 = theta^T W theta + sigma_pv^2 + sigma_int^2 (w01.x carries Vmm + pv^2 + int^2)
-      double sig2 = w01.x + d1 * d1 * w01.y + e2 * e2 * w23.x
-                    + 2.0 * (d1 * w23.y + e2 * w45.x + d1 * e2 * w45.y);
-      double res = mu_obs - mu_th;
+      double mu_obs, sig2;
+      if (mode == PMCB200_CHI2_betaz) {
+        const double t2 = fma(m_.Theta3, cz.y, m_.t2base);
+        mu_obs = ms.x + m_.Theta0 + m_.t1 * (ms.y - m_.stretch) + t2 * (cz.x - m_.color);
+        sig2 = w01.x + m_.d1 * m_.d1 * w01.y + t2 * t2 * w23.x
+               + 2.0 * (m_.d1 * w23.y + t2 * w45.x + m_.d1 * t2 * w45.y);
+      } else {
+        // mu_obs = m + Theta0 + t1 (s - stretch) + t2 (c - color); sigma^2 = theta^T W theta + const
+        mu_obs = fma(m_.t1, ms.y, fma(m_.t2base, cz.x, ms.x + m_.base0));
+        sig2 = fma(m_.k1, w01.y, fma(m_.k2, w23.x, fma(m_.k3, w23.y, fma(m_.k4, w45.x, fma(m_.k5, w45.y, w01.x)))));
+      }
+      const double res = mu_obs - mu_th;
       chi2 = fma(res * res, fast_rcp(sig2), chi2);
       if (L.sn_add_logdetCov) logdet += log(sig2);
     }
   }
 }
 
+#ifndef SN_MIN_BLOCKS
+#define SN_MIN_BLOCKS 2
+#endif
 template <bool HASQ, bool FLAT>
-__global__ void __launch_bounds__(PMC_BLOCK)
+__global__ void __launch_bounds__(PMC_BLOCK, SN_MIN_BLOCKS)
 k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
           const int16_t *__restrict__ flg, double *__restrict__ logpi,
-          int32_t *__restrict__ err, int set, double add_const, DevCount *cnt) {
+          int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow) {
+  __shared__ double T[16];
+  if (threadIdx.x < 16) T[threadIdx.x] = EXP2T[threadIdx.x];
+  __syncthreads();
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = (n < N) && (!flg || flg[n]);
   unsigned nev = 0;
@@ -401,20 +399,27 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   {
     const ECoef g = make_ecoef(m.c, 0);
     ec.Om = g.Om; ec.OK = g.OK; ec.Ode = g.Ode; ec.p = g.p; ec.q = g.q; ec.jassal = g.jassal;
-    // |t| bound over a in [a_min, 1]; beyond the fast_exp range use libdevice exp
+    ec.p2 = g.p * M_LOG2E; ec.q2 = g.q * M_LOG2E;
+    const double aO = fabs(g.Ode);
+    ec.lg = log2(aO);
+    ec.sgn = (g.Ode < 0.0) ? 0x80000000u : 0u;
+    // bound on |s| over a in [a_min, 1]; outside the fast path's range (or Ode = 0,
+    // non-finite input) the warp takes the libdevice path
     const double lna_min = -__ldg(&L.nodes[(size_t)(L.sn_nz - 1) * SN_NODES]).y;
-    ec.slow = !(fabs(g.p) * lna_min + fabs(g.q) < 690.0);
+    ec.slow = force_slow || !(fabs(ec.p2) * lna_min + fabs(ec.q2) + fabs(ec.lg) < 990.0);
   }
   const double f1 = rsqrt(ec.Om + ec.OK + ec.Ode);      // integrand at a = 1
   SNPer pm;
   pm.Theta0 = m.Theta2[0]; pm.Theta3 = m.Theta2[3]; pm.t1 = m.Theta2[1]; pm.t2base = m.Theta2[2];
   pm.d1 = pm.t1; pm.d2 = pm.t2base; pm.stretch = m.stretch; pm.color = m.color;
-  if (L.sn_chi2mode == PMCB200_CHI2_no_sc) { pm.d1 = 0.0; pm.d2 = 0.0; }
+  if (L.sn_chi2mode == PMCB200_CHI2_no_sc) { pm.d1 = 0.0; pm.d2 = 0.0; pm.t1 = 0.0; pm.t2base = 0.0; }
   if (L.sn_chi2mode == PMCB200_CHI2_Theta2_denom_fixed) { pm.d1 = L.Theta2_denom[1]; pm.d2 = L.Theta2_denom[2]; }
+  pm.base0 = pm.Theta0 - pm.t1 * pm.stretch - pm.t2base * pm.color;
+  pm.k1 = pm.d1 * pm.d1; pm.k2 = pm.d2 * pm.d2; pm.k3 = 2.0 * pm.d1; pm.k4 = 2.0 * pm.d2;
+  pm.k5 = 2.0 * pm.d1 * pm.d2;
   double chi2 = 0.0, logdet = 0.0;
-  // libdevice exp only for warps holding a sample outside fast_exp's range
-  if (__any_sync(0xffffffffu, ec.slow)) sn_zloop<HASQ, FLAT, true>(L, ec, pm, f1, chi2, logdet, e, nev);
-  else sn_zloop<HASQ, FLAT, false>(L, ec, pm, f1, chi2, logdet, e, nev);
+  if (__any_sync(0xffffffffu, ec.slow)) sn_zloop<HASQ, FLAT, true>(L, ec, T, pm, f1, chi2, logdet, e, nev);
+  else sn_zloop<HASQ, FLAT, false>(L, ec, T, pm, f1, chi2, logdet, e, nev);
   double res = -0.5 * chi2;
   if (L.sn_add_logdetCov) res -= 0.5 * logdet;
   if (!isfinite(res)) e = 1;

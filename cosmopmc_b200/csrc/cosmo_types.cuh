@@ -1,0 +1,31 @@
+// cosmo_types.cuh -- device-side likelihood descriptor shared by the host API
+// (which fills it) and the likelihood kernels.
+#pragma once
+#include "common.cuh"
+
+#define SN_NODES 64      // tabulated Romberg nodes per redshift: stages 1..7
+#define SN_ROW 12        // doubles per supernova row in the device table
+
+// Device-side likelihood descriptor (pointers are device pointers).
+struct DevLike {
+  int kind, npar, special, pad0;
+  int par[PMCB200_MAX_DIM];
+  pmcb200_cosmo_t model;
+  // SN Ia
+  int sn_chi2mode, sn_add_logdetCov, sn_n, sn_nz;
+  double Theta2[4], Theta2_denom[3], sig_int2, pv_fac;
+  const double2 *nodes;   // [sn_nz][SN_NODES] {a, ln a}; entry 0 = a(z), entry i in
+                          // [2^(j-2), 2^(j-1)) = nodes of trapezoid stage j >= 2
+  const int *first;       // [sn_nz+1] ranges of supernovae sharing a redshift
+  const double *sn;       // [sn_n][SN_ROW]: m s | c z | Vmm+pv2+int2 Vss | Vcc Cms | Cmc Csc | - -
+  int sn_hasq, sn_flat;   // launch-uniform specialisation flags (set by the host)
+  // Gaussian data (BAO, CMB distance priors): packed like a mixture component
+  int bao_method, g_ndim;
+  const double *g_z;
+  const double *g_comp;   // [2 + 2n + tri(n)] = wght, lognorm, mean, L packed, 1/diag
+  // analytic targets
+  MixHdr mixh;
+  const double *mix;
+  double banana_b, banana_sigma1sq;
+};
+

@@ -1,0 +1,50 @@
+// k_cosmo.cu -- the cosmology / analytic likelihood kernels and the small
+// non-templated kernels, with their host launch wrappers.
+#include "cosmo.cuh"
+#include "small_kernels.cuh"
+#include "launch.h"
+#include <cstdlib>
+
+static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
+
+void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const int16_t *flg, double *logpi,
+                     int32_t *err, int set, double add, DevCount *cnt, cudaStream_t s) {
+  const int g = nblk(N);
+  // PMCB200_SN_FORCE_SLOW=1 routes every warp through libdevice exp (used by the
+  // tests to validate the fast path against it)
+  static const int force_slow = getenv("PMCB200_SN_FORCE_SLOW") ? atoi(getenv("PMCB200_SN_FORCE_SLOW")) : 0;
+  switch (L.kind) {
+    case PMCB200_LIKE_SNIa:
+      if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+      else if (L.sn_hasq) k_like_sn<true, false><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+      else if (L.sn_flat) k_like_sn<false, true><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+      else k_like_sn<false, false><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+      break;
+    case PMCB200_LIKE_BAO:
+      k_like_bao<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
+      break;
+    case PMCB200_LIKE_CMBDistPrior:
+      k_like_cmbdp<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
+      break;
+    case PMCB200_LIKE_BANANA:
+      k_like_banana<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
+      break;
+    default:
+      break;
+  }
+}
+
+void pmc_launch_normalize(int64_t N, const int16_t *flg, double *w, double M, double invS, cudaStream_t s) {
+  k_normalize<<<nblk(N), PMC_BLOCK, 0, s>>>(N, flg, w, M, invS);
+}
+void pmc_launch_em_reduce(const double *partials, int nblocks, int64_t len, const DevScal *scal, int64_t N_local,
+                          double *block, cudaStream_t s) {
+  k_em_reduce<<<1, PMC_BLOCK, 0, s>>>(partials, nblocks, len, scal, N_local, block);
+}
+void pmc_launch_em_finish(const double *mix, MixHdr h, int nranks, const double *all, int64_t N_global,
+                          double *work, double *result, cudaStream_t s) {
+  k_em_finish<<<1, 64, 0, s>>>(mix, h, nranks, all, N_global, work, result);
+}
+void pmc_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t s) {
+  k_fp64_peak<<<blocks, 256, 0, s>>>(out, iters, 0.999999, 1e-9);
+}

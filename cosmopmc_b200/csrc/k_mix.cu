@@ -1,0 +1,63 @@
+// k_mix.cu -- instantiates the dimension-templated kernels (sampler, mixture
+// log-pdf, weights, EM statistics) for one group of padded dimensions.
+// Compiled four times with -DMIX_GROUP=0..3 (parallel build).
+#include "pmc_kernels.cuh"
+#include "launch.h"
+
+#if MIX_GROUP == 0
+#define DLIST(X) X(2) X(3) X(4) X(5)
+#define FN pmc_mix_launch_g0
+#elif MIX_GROUP == 1
+#define DLIST(X) X(6) X(7) X(8) X(10)
+#define FN pmc_mix_launch_g1
+#elif MIX_GROUP == 2
+#define DLIST(X) X(12) X(16) X(20)
+#define FN pmc_mix_launch_g2
+#else
+#define DLIST(X) X(24) X(32)
+#define FN pmc_mix_launch_g3
+#endif
+
+static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
+
+template <int DD>
+static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
+  switch (op) {
+    case OP_SIMULATE:
+      k_simulate<DD><<<nblk(a.N), PMC_BLOCK, 0, s>>>(a.mix, a.h, a.box, a.N, a.seed, a.iter, a.offset, a.X, a.idx,
+                                                     a.flg, a.scal);
+      break;
+    case OP_SIMULATE_DRAWS:
+      k_simulate_from_draws<DD><<<nblk(a.N), PMC_BLOCK, 0, s>>>(a.mix, a.h, a.box, a.N, a.U, a.Z, a.X, a.idx, a.flg);
+      break;
+    case OP_LOGQ:
+      k_logq<DD><<<nblk(a.N), PMC_BLOCK, 0, s>>>(a.mix, a.h, a.N, a.Xc, a.out);
+      break;
+    case OP_LIKE_MIX:
+      k_like_mix<DD><<<nblk(a.N), PMC_BLOCK, 0, s>>>(a.mix, a.h, a.is_mixture, a.N, a.Xc, a.dX, a.sel, a.flgc,
+                                                     a.logpi, a.err, a.set, a.add_const);
+      break;
+    case OP_WEIGHTS:
+      k_weights<DD><<<nblk(a.N), PMC_BLOCK, 0, s>>>(a.mix, a.h, a.N, a.Xc, a.logpic, a.errc, a.beta, a.flg, a.logw,
+                                                    a.scal);
+      break;
+    case OP_EM: {
+      cudaError_t e = cudaFuncSetAttribute(k_em_stats<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
+      if (e != cudaSuccess) return e;
+      k_em_stats<DD><<<a.blocks, PMC_BLOCK, a.smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal,
+                                                         a.partials);
+      break;
+    }
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+bool FN(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e) {
+  const int dd = pmc_pad_dim(a.h.d);
+#define X(D) if (dd == D) { *e = run<D>(op, a, s); return true; }
+  DLIST(X)
+#undef X
+  return false;
+}

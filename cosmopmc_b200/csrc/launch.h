@@ -1,0 +1,56 @@
+// launch.h -- host-side launch interface between the C-ABI translation unit
+// (pmcb200.cu) and the kernel translation units (k_mix.cu x4 dimension groups,
+// k_cosmo.cu).  Split so the kernels compile in parallel.
+#pragma once
+#include "common.cuh"
+
+struct DevLike;
+
+enum MixOp { OP_SIMULATE, OP_SIMULATE_DRAWS, OP_LOGQ, OP_LIKE_MIX, OP_WEIGHTS, OP_EM };
+
+struct MixArgs {
+  const double *mix = nullptr; MixHdr h{};
+  int64_t N = 0;
+  // sampler
+  const double *box = nullptr; uint64_t seed = 0; uint32_t iter = 0; int64_t offset = 0;
+  double *X = nullptr; int32_t *idx = nullptr; int16_t *flg = nullptr; DevScal *scal = nullptr;
+  const double *U = nullptr, *Z = nullptr;
+  // log-pdf / weights / EM inputs
+  const double *Xc = nullptr; const int32_t *idxc = nullptr; const int16_t *flgc = nullptr;
+  double *out = nullptr;
+  int is_mixture = 0, dX = 0; const int *sel = nullptr;
+  double *logpi = nullptr; const double *logpic = nullptr; int32_t *err = nullptr; const int32_t *errc = nullptr;
+  int set = 0; double add_const = 0.0, beta = 1.0;
+  double *logw = nullptr; const double *logwc = nullptr;
+  double *partials = nullptr; int blocks = 0; size_t smem = 0;
+};
+
+// padded template dimension for a runtime dimension d
+static inline int pmc_pad_dim(int d) {
+  const int list[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32};
+  for (int v : list) if (d <= v) return v;
+  return 32;
+}
+
+bool pmc_mix_launch_g0(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e);
+bool pmc_mix_launch_g1(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e);
+bool pmc_mix_launch_g2(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e);
+bool pmc_mix_launch_g3(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e);
+static inline cudaError_t pmc_mix_launch(int op, const MixArgs &a, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  if (pmc_mix_launch_g0(op, a, s, &e) || pmc_mix_launch_g1(op, a, s, &e) ||
+      pmc_mix_launch_g2(op, a, s, &e) || pmc_mix_launch_g3(op, a, s, &e))
+    return e;
+  return cudaErrorInvalidValue;
+}
+
+// cosmology / analytic likelihood kernels (k_cosmo.cu)
+void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const int16_t *flg, double *logpi,
+                     int32_t *err, int set, double add_const, DevCount *cnt, cudaStream_t s);
+// small kernels (k_cosmo.cu)
+void pmc_launch_normalize(int64_t N, const int16_t *flg, double *w, double M, double invS, cudaStream_t s);
+void pmc_launch_em_reduce(const double *partials, int nblocks, int64_t len, const DevScal *scal, int64_t N_local,
+                          double *block, cudaStream_t s);
+void pmc_launch_em_finish(const double *mix, MixHdr h, int nranks, const double *all, int64_t N_global,
+                          double *work, double *result, cudaStream_t s);
+void pmc_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t s);

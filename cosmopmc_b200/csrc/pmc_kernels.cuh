@@ -3,6 +3,7 @@
 // dimension) is a template parameter so x/y live in registers.
 #pragma once
 #include "common.cuh"
+#include "stat_layout.cuh"
 
 // ---- K1: mixture sampler (replaces simulate_mix_mvdens, cosmo_pmc.c:320) ------
 // Philox counter = (g_lo, g_hi, call, iter), key = seed; g = global sample
@@ -186,14 +187,6 @@ k_weights(const double *__restrict__ mix, const MixHdr h, int64_t N,
   }
 }
 
-// normalize_importance_weight (cosmo_pmc.c:378): wbar = exp(lw - M)/S
-__global__ void __launch_bounds__(PMC_BLOCK)
-k_normalize(int64_t N, const int16_t *__restrict__ flg, double *__restrict__ w, double M, double invS) {
-  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  w[n] = flg[n] ? exp(w[n] - M) * invS : 0.0;
-}
-
 // ---- K5: Rao-Blackwellised EM sufficient statistics (update_prop_rb,
 // cosmo_pmc.c:247).  Stat block layout (doubles):
 //   [0] M = local max log w  [1] S = sum e^(lw-M)  [2] S2 = sum e^2(lw-M)
@@ -202,15 +195,10 @@ k_normalize(int64_t N, const int16_t *__restrict__ flg, double *__restrict__ w, 
 //   A = sum w rho, G = sum w rho gamma, count (points drawn from k),
 //   B[d] = sum w rho gamma (x - p), C[tri] = sum w rho gamma (x-p)(x-p)^T (lower)
 // with w = e^(lw-M) and p the common pivot (weighted mean of the old means).
-#define STAT_HDR 8
-__host__ __device__ inline int stat_cs(int d) { return 3 + d + mix_tri(d); }
-__host__ __device__ inline int64_t stat_len(int K, int d) { return STAT_HDR + (int64_t)K * stat_cs(d); }
-
 // Phase 1 (per tile of PMC_BLOCK samples): each thread computes its sample's
 // w and responsibilities into shared memory.  Phase 2: the K x M outputs are
 // distributed over the threads, each accumulating over the tile (a K x tile x M
 // contraction) in registers across all tiles of a persistent block.
-#define EM_MAXOUT 20     // max outputs per thread: K*cs <= PMC_BLOCK*EM_MAXOUT
 template <int D>
 __global__ void __launch_bounds__(PMC_BLOCK)
 k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
@@ -316,141 +304,3 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
   (void)tri;
 }
 
-// fixed-order sum of the block partials -> this rank's stat block
-__global__ void __launch_bounds__(PMC_BLOCK)
-k_em_reduce(const double *__restrict__ partials, int nblocks, int64_t len,
-            const DevScal *__restrict__ scal, int64_t N_local, double *__restrict__ block) {
-  for (int64_t o = threadIdx.x; o < len; o += blockDim.x) {
-    double s = 0.0;
-    if (o >= 1 && o != 4 && o != 5 && o != 6 && o != 7)
-      for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * len + o];
-    if (o == 0) s = dunkey(scal->max_key);
-    if (o == 4) s = (double)scal->nok;
-    if (o == 5) s = (double)scal->nok_box;
-    if (o == 6) s = (double)N_local;
-    block[o] = s;
-  }
-}
-
-// ---- M-step: combine the rank blocks in rank order, update alpha/mu/Sigma,
-// dead-component rule (manual.tex:482-490), Cholesky, diagnostics ---------------
-// result layout (doubles): [0..16) stats, then wght[K], mean[K*d], chol[K*d*d]
-#define RES_HDR 16
-__global__ void __launch_bounds__(64)
-k_em_finish(const double *__restrict__ mix, const MixHdr h, int nranks,
-            const double *__restrict__ all, int64_t N_global, double *__restrict__ work,
-            double *__restrict__ result) {
-  const int K = h.K, d = h.d, tri = mix_tri(d), cs = stat_cs(d);
-  const int64_t len = stat_len(K, d);
-  const double *pivot = mix + (size_t)K * h.stride;
-  __shared__ double sh[8];
-  __shared__ double s_scale[64];
-  __shared__ int s_dead[PMCB200_MAX_COMP];
-  __shared__ double s_alpha[PMCB200_MAX_COMP];
-  const int tid = threadIdx.x;
-  // global max and per-rank rescale
-  if (tid == 0) {
-    double M = -INFINITY;
-    for (int g = 0; g < nranks; g++) M = fmax(M, all[g * len]);
-    sh[0] = M;
-  }
-  __syncthreads();
-  const double M = sh[0];
-  for (int g = tid; g < nranks; g += blockDim.x) {
-    double Mg = all[g * len];
-    s_scale[g] = (Mg == -INFINITY) ? 0.0 : exp(Mg - M);
-  }
-  __syncthreads();
-  // combined block into work[len] (fixed rank order)
-  for (int64_t o = tid; o < len; o += blockDim.x) {
-    double s = 0.0;
-    if (o == 0) s = M;
-    else if (o == 1 || o >= STAT_HDR) {
-      bool is_count = (o >= STAT_HDR) && (((o - STAT_HDR) % cs) == 2);
-      for (int g = 0; g < nranks; g++) s += all[g * len + o] * (is_count ? 1.0 : s_scale[g]);
-    } else if (o == 2) {
-      for (int g = 0; g < nranks; g++) s += all[g * len + o] * s_scale[g] * s_scale[g];
-    } else if (o == 3) {   // T_g shifts: sum w_g (lw - M) = e^(Mg-M) [T_g + (Mg-M) S_g]
-      for (int g = 0; g < nranks; g++) {
-        double Mg = all[g * len];
-        if (s_scale[g] > 0.0) s += s_scale[g] * (all[g * len + 3] + (Mg - M) * all[g * len + 1]);
-      }
-    } else {
-      for (int g = 0; g < nranks; g++) s += all[g * len + o];
-    }
-    work[o] = s;
-  }
-  __syncthreads();
-  const double S = work[1], S2 = work[2], T = work[3];
-  // per-component M-step, one thread per component
-  for (int k = tid; k < K; k += blockDim.x) {
-    const double *st = work + STAT_HDR + (size_t)k * cs;
-    const double *comp = mix + (size_t)k * h.stride;
-    double *o_mean = result + RES_HDR + K + (size_t)k * d;
-    double *o_chol = result + RES_HDR + K + (size_t)K * d + (size_t)k * d * d;
-    const double A = st[0], G = st[1], count = st[2];
-    const double alpha = A / S;
-    int was_alive = comp[0] != 0.0;
-    int dead = !was_alive || !(alpha >= 1.0 / (double)N_global) || count < (double)PMCB200_MINCOUNT;
-    if (!dead) {
-      // delta = B/G, mu' = p + delta, Sigma' = (C - G delta delta^T)/A; Cholesky in place
-      const double *B = st + 3, *Cc = st + 3 + d;
-      for (int i = 0; i < d; i++)
-        for (int j = 0; j <= i; j++) {
-          double di = B[i] / G, dj = B[j] / G;
-          o_chol[i * d + j] = (Cc[i * (i + 1) / 2 + j] - G * di * dj) / A;
-        }
-      for (int j = 0; j < d && !dead; j++) {
-        double s = o_chol[j * d + j];
-        for (int q = 0; q < j; q++) s -= o_chol[j * d + q] * o_chol[j * d + q];
-        if (!(s > 0.0) || !isfinite(s)) { dead = 1; break; }
-        double ljj = sqrt(s);
-        o_chol[j * d + j] = ljj;
-        for (int i = j + 1; i < d; i++) {
-          double t = o_chol[i * d + j];
-          for (int q = 0; q < j; q++) t -= o_chol[i * d + q] * o_chol[j * d + q];
-          o_chol[i * d + j] = t / ljj;
-        }
-      }
-      if (!dead) {
-        for (int i = 0; i < d; i++) {
-          o_mean[i] = pivot[i] + B[i] / G;
-          for (int j = i + 1; j < d; j++) o_chol[i * d + j] = 0.0;
-        }
-      }
-    }
-    if (dead) {   // keep the old mean / factor, weight 0
-      const double *mean = comp + 2, *L = comp + 2 + d;
-      for (int i = 0; i < d; i++) {
-        o_mean[i] = mean[i];
-        for (int j = 0; j < d; j++) o_chol[i * d + j] = (j <= i) ? L[i * (i + 1) / 2 + j] : 0.0;
-      }
-    }
-    s_dead[k] = dead && was_alive;
-    s_alpha[k] = dead ? 0.0 : alpha;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double wsum = 0.0, enc = 0.0;
-    int ndead = 0;
-    for (int k = 0; k < K; k++) { wsum += s_alpha[k]; ndead += s_dead[k]; }
-    for (int k = 0; k < K; k++) {
-      double a = (wsum > 0.0) ? s_alpha[k] / wsum : 0.0;
-      result[RES_HDR + k] = a;
-      enc = fma(a, a, enc);
-    }
-    const double Ng = (double)N_global;
-    result[0] = M;                                   // maxW
-    result[1] = S;                                   // sum_shift
-    result[2] = log(S) + M;                          // logSum
-    result[3] = exp(log(S) - T / S) / Ng;            // perplexity = exp(-sum wbar log wbar)/N
-    result[4] = S * S / S2;                          // ESS
-    result[5] = log(S) + M - log(Ng);                // ln evidence
-    result[6] = 1.0 / enc;                           // ENC (updated proposal)
-    result[7] = (double)ndead;
-    result[8] = work[4];                             // nok
-    result[9] = work[5];                             // nok_box
-    result[10] = work[6];                            // N summed over ranks
-  }
-  (void)tri;
-}

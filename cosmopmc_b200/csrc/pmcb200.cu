@@ -10,8 +10,9 @@
 #include <algorithm>
 
 #include "common.cuh"
-#include "cosmo.cuh"
-#include "pmc_kernels.cuh"
+#include "cosmo_types.cuh"
+#include "stat_layout.cuh"
+#include "launch.h"
 
 // ---- context ----------------------------------------------------------------
 struct DevBuf {
@@ -77,6 +78,15 @@ static int fail(pmcb200_ctx *c, int code, const char *fmt, ...) {
                   cudaGetErrorString(e__), __FILE__, __LINE__);                     \
   } while (0)
 
+#define MIX_OK(c, op, a)                                                            \
+  do {                                                                              \
+    (c)->launches++;                                                                \
+    cudaError_t e__ = pmc_mix_launch(op, a, (c)->stream);                           \
+    if (e__ != cudaSuccess)                                                         \
+      return fail(c, PMCB200_ERR_CUDA, "kernel launch (op %d): %s (%s:%d)", (int)(op), \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                     \
+  } while (0)
+
 static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
 
 static int ensure(pmcb200_ctx *c, DevBuf &b, size_t bytes) {
@@ -87,24 +97,6 @@ static int ensure(pmcb200_ctx *c, DevBuf &b, size_t bytes) {
   b.cap = bytes;
   return 0;
 }
-
-// dispatch on the padded dimension
-#define DISPATCH_D(d, CALL)                                  \
-  do {                                                       \
-    if ((d) <= 2) { constexpr int DD = 2; CALL; }            \
-    else if ((d) <= 3) { constexpr int DD = 3; CALL; }       \
-    else if ((d) <= 4) { constexpr int DD = 4; CALL; }       \
-    else if ((d) <= 5) { constexpr int DD = 5; CALL; }       \
-    else if ((d) <= 6) { constexpr int DD = 6; CALL; }       \
-    else if ((d) <= 7) { constexpr int DD = 7; CALL; }       \
-    else if ((d) <= 8) { constexpr int DD = 8; CALL; }       \
-    else if ((d) <= 10) { constexpr int DD = 10; CALL; }     \
-    else if ((d) <= 12) { constexpr int DD = 12; CALL; }     \
-    else if ((d) <= 16) { constexpr int DD = 16; CALL; }     \
-    else if ((d) <= 20) { constexpr int DD = 20; CALL; }     \
-    else if ((d) <= 24) { constexpr int DD = 24; CALL; }     \
-    else { constexpr int DD = 32; CALL; }                    \
-  } while (0)
 
 // ---- host-side packing ---------------------------------------------------------
 static int host_cholesky(int d, double *A) {
@@ -550,9 +542,9 @@ static int launch_simulate(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t it
                            double *dX, int32_t *didx, int16_t *dflg) {
   if (N <= 0) return 0;
   if (!c->d_box) return fail(c, PMCB200_ERR_STATE, "simulate needs the target's box (pmcb200_set_target)");
-  DISPATCH_D(c->h.d, (k_simulate<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
-                         c->d_mix, c->h, c->d_box, N, seed, iter, offset, dX, didx, dflg, c->d_scal)));
-  LAUNCH_OK(c);
+  MixArgs a; a.mix = c->d_mix; a.h = c->h; a.box = c->d_box; a.N = N; a.seed = seed; a.iter = iter;
+  a.offset = offset; a.X = dX; a.idx = didx; a.flg = dflg; a.scal = c->d_scal;
+  MIX_OK(c, OP_SIMULATE, a);
   return 0;
 }
 
@@ -564,37 +556,20 @@ static int launch_posterior(pmcb200_ctx *c, int64_t N, const double *dX, const i
     const DevLike &L = c->like[i];
     const int set = (i == 0);
     const double add = set ? c->logpr_const : 0.0;
-    switch (L.kind) {
-      case PMCB200_LIKE_SNIa:
-        if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
-        else if (L.sn_hasq) k_like_sn<true, false><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
-        else if (L.sn_flat) k_like_sn<false, true><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
-        else k_like_sn<false, false><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt);
-        break;
-      case PMCB200_LIKE_BAO:
-        k_like_bao<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add);
-        break;
-      case PMCB200_LIKE_CMBDistPrior:
-        k_like_cmbdp<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add);
-        break;
-      case PMCB200_LIKE_BANANA:
-        k_like_banana<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(L, N, dX, d, dflg, dlogpi, derr, set, add);
-        break;
-      case PMCB200_LIKE_Mvdens:
-      case PMCB200_LIKE_MixMvdens:
-        DISPATCH_D(d, (k_like_mix<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
-                          L.mix, L.mixh, L.kind == PMCB200_LIKE_MixMvdens, N, dX, d, nullptr, dflg, dlogpi,
-                          derr, set, add)));
-        break;
-      default:
-        return fail(c, PMCB200_ERR_UNSUP, "likelihood kind %d", L.kind);
+    if (L.kind == PMCB200_LIKE_Mvdens || L.kind == PMCB200_LIKE_MixMvdens) {
+      MixArgs a; a.mix = L.mix; a.h = L.mixh; a.is_mixture = (L.kind == PMCB200_LIKE_MixMvdens); a.N = N;
+      a.Xc = dX; a.dX = d; a.sel = nullptr; a.flgc = dflg; a.logpi = dlogpi; a.err = derr; a.set = set;
+      a.add_const = add;
+      MIX_OK(c, OP_LIKE_MIX, a);
+      continue;
     }
+    pmc_launch_like(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt, c->stream);
     LAUNCH_OK(c);
   }
   if (c->d_prior) {
-    DISPATCH_D(c->prior_h.d, (k_like_mix<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
-                                 c->d_prior, c->prior_h, 0, N, dX, d, c->d_prior_sel, dflg, dlogpi, derr, 0, 0.0)));
-    LAUNCH_OK(c);
+    MixArgs a; a.mix = c->d_prior; a.h = c->prior_h; a.is_mixture = 0; a.N = N; a.Xc = dX; a.dX = d;
+    a.sel = c->d_prior_sel; a.flgc = dflg; a.logpi = dlogpi; a.err = derr; a.set = 0; a.add_const = 0.0;
+    MIX_OK(c, OP_LIKE_MIX, a);
   }
   return 0;
 }
@@ -602,20 +577,10 @@ static int launch_posterior(pmcb200_ctx *c, int64_t N, const double *dX, const i
 static int launch_weights(pmcb200_ctx *c, int64_t N, const double *dX, const double *dlogpi,
                           const int32_t *derr, double beta, int16_t *dflg, double *dlogw) {
   if (N <= 0) return 0;
-  DISPATCH_D(c->h.d, (k_weights<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
-                         c->d_mix, c->h, N, dX, dlogpi, derr, beta, dflg, dlogw, c->d_scal)));
-  LAUNCH_OK(c);
+  MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.logpic = dlogpi; a.errc = derr; a.beta = beta;
+  a.flg = dflg; a.logw = dlogw; a.scal = c->d_scal;
+  MIX_OK(c, OP_WEIGHTS, a);
   return 0;
-}
-
-template <int DD>
-static cudaError_t em_launch(pmcb200_ctx *c, int blocks, size_t smem, int64_t N, const double *dX,
-                             const int32_t *didx, const int16_t *dflg, const double *dlogw) {
-  cudaError_t e = cudaFuncSetAttribute(k_em_stats<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k_em_stats<DD><<<blocks, PMC_BLOCK, smem, c->stream>>>(c->d_mix, c->h, N, dX, didx, dflg, dlogw, c->d_scal,
-                                                         c->d_partials);
-  return cudaSuccess;
 }
 
 static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const int32_t *didx,
@@ -627,11 +592,10 @@ static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const in
   size_t smem = ((size_t)K * PMC_BLOCK * (c->h.df > 0 ? 2 : 1) + (size_t)PMC_BLOCK * (d | 1)) * sizeof(double) +
                 PMC_BLOCK * sizeof(int);
   if (smem > 227 * 1024) return fail(c, PMCB200_ERR_UNSUP, "EM kernel needs %zu B shared memory", smem);
-  cudaError_t e = cudaSuccess;
-  DISPATCH_D(d, (e = em_launch<DD>(c, blocks, smem, N, dX, didx, dflg, dlogw)));
-  if (e != cudaSuccess) return fail(c, PMCB200_ERR_CUDA, "k_em_stats attribute: %s", cudaGetErrorString(e));
-  LAUNCH_OK(c);
-  k_em_reduce<<<1, PMC_BLOCK, 0, c->stream>>>(c->d_partials, blocks, len, c->d_scal, N, dblock);
+  MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.idxc = didx; a.flgc = dflg; a.logwc = dlogw;
+  a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.smem = smem;
+  MIX_OK(c, OP_EM, a);
+  pmc_launch_em_reduce(c->d_partials, blocks, len, c->d_scal, N, dblock, c->stream);
   LAUNCH_OK(c);
   return 0;
 }
@@ -654,9 +618,9 @@ extern "C" int pmcb200_simulate_from_draws(pmcb200_ctx *c, int64_t N, const doub
   if (!c->d_box) return fail(c, PMCB200_ERR_STATE, "simulate needs the target's box (pmcb200_set_target)");
   if (c->h.df > 0) return fail(c, PMCB200_ERR_UNSUP, "simulate_from_draws: Gaussian proposals only");
   if (N == 0) return 0;
-  DISPATCH_D(c->h.d, (k_simulate_from_draws<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(
-                         c->d_mix, c->h, c->d_box, N, du, dz, dX, didx, dflg)));
-  LAUNCH_OK(c);
+  MixArgs a; a.mix = c->d_mix; a.h = c->h; a.box = c->d_box; a.N = N; a.U = du; a.Z = dz; a.X = dX; a.idx = didx;
+  a.flg = dflg;
+  MIX_OK(c, OP_SIMULATE_DRAWS, a);
   return 0;
 }
 
@@ -665,8 +629,8 @@ extern "C" int pmcb200_proposal_log_pdf(pmcb200_ctx *c, int64_t N, const double 
   if (rc) return rc;
   if (N < 0 || (N > 0 && (!dX || !dlogq))) return fail(c, PMCB200_ERR_ARG, "proposal_log_pdf: bad arguments");
   if (N == 0) return 0;
-  DISPATCH_D(c->h.d, (k_logq<DD><<<nblk(N), PMC_BLOCK, 0, c->stream>>>(c->d_mix, c->h, N, dX, dlogq)));
-  LAUNCH_OK(c);
+  MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.out = dlogq;
+  MIX_OK(c, OP_LOGQ, a);
   return 0;
 }
 
@@ -699,7 +663,7 @@ extern "C" int pmcb200_normalize_weights(pmcb200_ctx *c, int64_t N, const int16_
   double M = c->h_result[0], S = c->h_result[1];
   if (!(S > 0.0)) return fail(c, PMCB200_ERR_STATE, "normalize_weights: call pmcb200_em_finish first");
   if (N == 0) return 0;
-  k_normalize<<<nblk(N), PMC_BLOCK, 0, c->stream>>>(N, dflg, dw, M, 1.0 / S);
+  pmc_launch_normalize(N, dflg, dw, M, 1.0 / S, c->stream);
   LAUNCH_OK(c);
   return 0;
 }
@@ -724,7 +688,7 @@ extern "C" int pmcb200_em_finish(pmcb200_ctx *c, int nranks, const double *dall,
   if (rc) return rc;
   if (nranks < 1 || nranks > 64 || !dall || N_global < 1) return fail(c, PMCB200_ERR_ARG, "em_finish: bad arguments");
   const int K = c->h.K, d = c->h.d;
-  k_em_finish<<<1, 64, 0, c->stream>>>(c->d_mix, c->h, nranks, dall, N_global, c->d_work, c->d_result);
+  pmc_launch_em_finish(c->d_mix, c->h, nranks, dall, N_global, c->d_work, c->d_result, c->stream);
   LAUNCH_OK(c);
   size_t rlen = RES_HDR + (size_t)K * (1 + d + (size_t)d * d);
   CUDA_OK(c, cudaMemcpyAsync(c->h_result, c->d_result, rlen * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -811,20 +775,6 @@ extern "C" int pmcb200_counters(pmcb200_ctx *c, int64_t out[4]) {
   return 0;
 }
 
-// DFMA-only kernel: 8 independent chains per thread, 8 warps/SMSP resident
-__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
-  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-  for (int i = 0; i < iters; i++) {
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-    }
-  }
-  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
-  if (s == 123.456) out[0] = s;
-}
-
 extern "C" int pmcb200_fp64_peak(pmcb200_ctx *c, double *tflops) {
   if (!c || !tflops) return PMCB200_ERR_ARG;
   CUDA_OK(c, cudaSetDevice(c->device));
@@ -837,7 +787,7 @@ extern "C" int pmcb200_fp64_peak(pmcb200_ctx *c, double *tflops) {
   double best = 0.0;
   for (int rep = 0; rep < 6; rep++) {
     CUDA_OK(c, cudaEventRecord(e0, c->stream));
-    k_fp64_peak<<<blocks, 256, 0, c->stream>>>(d, iters, 0.999999, 1e-9);
+    pmc_launch_fp64_peak(d, blocks, iters, c->stream);
     CUDA_OK(c, cudaEventRecord(e1, c->stream));
     CUDA_OK(c, cudaEventSynchronize(e1));
     float ms = 0.f;

@@ -366,3 +366,35 @@ def test_sharded_blocks_combine_like_one_rank(oracle, pmc_factory):
     p1, p2 = one.get_proposal(), many.get_proposal()
     for a, b in zip(p1, p2):
         assert np.allclose(a, b, rtol=1e-10, atol=1e-14)
+
+
+def test_sn_fast_path_matches_libdevice_path(oracle, pmc_factory, tmp_path):
+    """The SN kernel's table-based exp2 / MUFU-seeded rsqrt path against the same
+    kernel forced through libdevice exp (PMCB200_SN_FORCE_SLOW=1, separate
+    process): agreement far inside the parity tolerance."""
+    import os, subprocess, sys
+    spec = T.target_sn_bao_w0wa()       # w0-wa + curvature: exercises HASQ and !FLAT
+    X = box_samples(spec, 4000, 21)
+    np.save(tmp_path / "X.npy", X)
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from cosmopmc_b200 import targets as T\n"
+        "from cosmopmc_b200.pmc import PMC\n"
+        "spec = T.target_sn_bao_w0wa(); pmc = PMC(0); pmc.set_target(spec)\n"
+        "X = torch.from_numpy(np.load(%r)).cuda()\n"
+        "lp, err = pmc.posterior_log_pdf(X)\n"
+        "np.save(%r, np.stack([lp.cpu().numpy(), err.cpu().numpy().astype(float)]))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "X.npy"),
+         str(tmp_path / "slow.npy"))
+    env = dict(os.environ, PMCB200_SN_FORCE_SLOW="1")
+    subprocess.check_call([sys.executable, "-c", code], env=env)
+    slow = np.load(tmp_path / "slow.npy")
+    pmc = pmc_factory()
+    pmc.set_target(spec)
+    lp, err = pmc.posterior_log_pdf(dev(X))
+    lp, err = lp.cpu().numpy(), err.cpu().numpy()
+    assert np.array_equal(err != 0, slow[1] != 0)
+    ok = err == 0
+    assert ok.sum() > 2000
+    assert rel(lp[ok], slow[0][ok]) < 1e-12
