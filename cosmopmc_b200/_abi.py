@@ -13,7 +13,7 @@ MAX_DIM, MAX_COMP, MAX_DATA = 32, 64, 4
 P = dict(Omegam=0, Omegab=1, Omegade=2, h100=3, Omeganumass=4, Omegac=5, OmegaK=6,
          omegam=7, omegab=8, omegab100=9, omegade=10, omeganumass=11, omegac=12,
          omegaK=13, w0de=14, w1de=15, Neffnumass=20, M=37, alpha=38, beta=39,
-         beta_z=40, logbeta=41, stretch=42, color=43, dummy=112)
+         beta_z=40, logbeta=41, stretch=42, color=43, dummy=111)
 # spar_t strings of the reference config files -> par_t (tools/include/par.h:36-149)
 SPAR = {"Omega_m": P["Omegam"], "Omega_b": P["Omegab"], "Omega_de": P["Omegade"],
         "h_100": P["h100"], "Omega_nu_mass": P["Omeganumass"], "Omega_c": P["Omegac"],
