@@ -108,6 +108,11 @@ SYMBOLS = {
     "pmcb200_iteration_local": (_i, [_vp, _i64, _u64, _u32, _i64, _d, _vp, _vp, _vp, _vp, _vp]),
     "pmcb200_iteration_host": (_i, [_vp, _i64, _u64, _u32, _d, _vp, _vp, _vp, _vp, C.POINTER(Stats)]),
     "pmcb200_launch_count": (_i64, [_vp]),
+    "pmcb200_set_box": (_i, [_vp, _i, _vp, _vp]),
+    "pmcb200_read_counts": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "pmcb200_weight_stats": (_i, [_vp, _i64, _vp, _vp, _i, C.POINTER(C.c_double * 8)]),
+    "pmcb200_normalize_log_weights": (_i, [_vp, _i64, _vp, _vp, C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),
+    "pmcb200_em_local_linear": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "pmcb200_counters": (_i, [_vp, C.POINTER(C.c_int64 * 4)]),
     "pmcb200_fp64_peak": (_i, [_vp, C.POINTER(C.c_double)]),
     "pmcb200_dev_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),

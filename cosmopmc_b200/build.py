@@ -21,6 +21,27 @@ UNITS = [("pmcb200.o", "pmcb200.cu", []),
          ("k_mix3.o", "k_mix.cu", ["-DMIX_GROUP=3"])]
 
 
+HOST = os.path.join(HERE, "host")
+INC = os.path.join(os.path.dirname(HERE), "include")
+GCC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+HOST_UNITS = ["errorlist.c", "gsl_shim.c", "mvdens.c", "pmc.c"]
+
+
+def _compile_host(src):
+    obj = os.path.join(OBJ, "host_" + src.replace(".c", ".o"))
+    cmd = [GCC, "-std=gnu99", "-O2", "-g", "-fPIC", "-Wall", "-Wno-format-truncation", "-I", INC,
+           "-c", os.path.join(HOST, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return obj, r.returncode, r.stdout + r.stderr
+
+
+def _host_deps():
+    out = []
+    for root, _, files in os.walk(INC):
+        out += [os.path.join(root, f) for f in files if f.endswith(".h")]
+    return out
+
+
 def _deps():
     return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
            [os.path.join(os.path.dirname(HERE), "include", "pmcb200.h")]
@@ -50,8 +71,18 @@ def build(force=False, verbose=False):
                     sys.stderr.write("== %s\n%s" % (obj, out))
                 if rc:
                     raise RuntimeError("nvcc failed for %s" % obj)
-    objs = [os.path.join(OBJ, u[0]) for u in UNITS]
-    if todo or _stale(LIB, objs):
+    hdeps = _host_deps()
+    htodo = [h for h in HOST_UNITS
+             if force or _stale(os.path.join(OBJ, "host_" + h.replace(".c", ".o")), hdeps + [os.path.join(HOST, h)])]
+    for h in htodo:
+        obj, rc, out = _compile_host(h)
+        if verbose or rc:
+            sys.stderr.write("== %s\n%s" % (obj, out))
+        if rc:
+            raise RuntimeError("gcc failed for %s" % h)
+    objs = [os.path.join(OBJ, u[0]) for u in UNITS] + \
+           [os.path.join(OBJ, "host_" + h.replace(".c", ".o")) for h in HOST_UNITS]
+    if todo or htodo or _stale(LIB, objs):
         subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
                                "-o", LIB] + objs)
     return LIB

@@ -375,8 +375,11 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
 #ifndef SN_MIN_BLOCKS
 #define SN_MIN_BLOCKS 2
 #endif
+#ifndef SN_BLOCK
+#define SN_BLOCK 256
+#endif
 template <bool HASQ, bool FLAT>
-__global__ void __launch_bounds__(PMC_BLOCK, SN_MIN_BLOCKS)
+__global__ void __launch_bounds__(SN_BLOCK, SN_MIN_BLOCKS)
 k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
           const int16_t *__restrict__ flg, double *__restrict__ logpi,
           int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow) {

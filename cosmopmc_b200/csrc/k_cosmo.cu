@@ -10,15 +10,16 @@ static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK
 void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const int16_t *flg, double *logpi,
                      int32_t *err, int set, double add, DevCount *cnt, cudaStream_t s) {
   const int g = nblk(N);
+  const int gs = (int)((N + SN_BLOCK - 1) / SN_BLOCK);
   // PMCB200_SN_FORCE_SLOW=1 routes every warp through libdevice exp (used by the
   // tests to validate the fast path against it)
   static const int force_slow = getenv("PMCB200_SN_FORCE_SLOW") ? atoi(getenv("PMCB200_SN_FORCE_SLOW")) : 0;
   switch (L.kind) {
     case PMCB200_LIKE_SNIa:
-      if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
-      else if (L.sn_hasq) k_like_sn<true, false><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
-      else if (L.sn_flat) k_like_sn<false, true><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
-      else k_like_sn<false, false><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+      if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+      else if (L.sn_hasq) k_like_sn<true, false><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+      else if (L.sn_flat) k_like_sn<false, true><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+      else k_like_sn<false, false><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
       break;
     case PMCB200_LIKE_BAO:
       k_like_bao<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
@@ -45,6 +46,12 @@ void pmc_launch_em_finish(const double *mix, MixHdr h, int nranks, const double 
                           double *work, double *result, cudaStream_t s) {
   k_em_finish<<<1, 64, 0, s>>>(mix, h, nranks, all, N_global, work, result);
 }
-void pmc_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t s) {
-  k_fp64_peak<<<blocks, 256, 0, s>>>(out, iters, 0.999999, 1e-9);
+void pmc_launch_fp64_peak(double *out, const double *in, int blocks, int iters, cudaStream_t s) {
+  k_fp64_peak<<<blocks, 256, 0, s>>>(out, in, iters);
+}
+void pmc_launch_wstat(int64_t N, const int16_t *flg, const double *w, int is_log, int blocks, double *maxpart,
+                      double *part, double *out8, cudaStream_t s) {
+  if (is_log) k_wstat_max<<<blocks, PMC_BLOCK, 0, s>>>(N, flg, w, maxpart);
+  k_wstat_sums<<<blocks, PMC_BLOCK, 0, s>>>(N, flg, w, is_log, maxpart, blocks, part);
+  k_wstat_final<<<1, 32, 0, s>>>(part, blocks, out8);
 }

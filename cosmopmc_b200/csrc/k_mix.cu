@@ -45,7 +45,7 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
       cudaError_t e = cudaFuncSetAttribute(k_em_stats<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
       if (e != cudaSuccess) return e;
       k_em_stats<DD><<<a.blocks, PMC_BLOCK, a.smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal,
-                                                         a.partials);
+                                                         a.partials, a.linear);
       break;
     }
     default:

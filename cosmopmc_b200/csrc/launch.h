@@ -22,7 +22,7 @@ struct MixArgs {
   double *logpi = nullptr; const double *logpic = nullptr; int32_t *err = nullptr; const int32_t *errc = nullptr;
   int set = 0; double add_const = 0.0, beta = 1.0;
   double *logw = nullptr; const double *logwc = nullptr;
-  double *partials = nullptr; int blocks = 0; size_t smem = 0;
+  double *partials = nullptr; int blocks = 0; size_t smem = 0; int linear = 0;
 };
 
 // padded template dimension for a runtime dimension d
@@ -53,4 +53,6 @@ void pmc_launch_em_reduce(const double *partials, int nblocks, int64_t len, cons
                           double *block, cudaStream_t s);
 void pmc_launch_em_finish(const double *mix, MixHdr h, int nranks, const double *all, int64_t N_global,
                           double *work, double *result, cudaStream_t s);
-void pmc_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t s);
+void pmc_launch_fp64_peak(double *out, const double *in, int blocks, int iters, cudaStream_t s);
+void pmc_launch_wstat(int64_t N, const int16_t *flg, const double *w, int is_log, int blocks, double *maxpart,
+                      double *part, double *out8, cudaStream_t s);

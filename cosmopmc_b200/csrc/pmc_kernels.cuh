@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(PMC_BLOCK)
 k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
            const double *__restrict__ X, const int32_t *__restrict__ idx,
            const int16_t *__restrict__ flg, const double *__restrict__ logw,
-           const DevScal *__restrict__ scal, double *__restrict__ partials) {
+           const DevScal *__restrict__ scal, double *__restrict__ partials, int linear) {
   extern __shared__ double sm[];
   const int K = h.K, d = h.d, tri = mix_tri(d), cs = stat_cs(d);
   const int XS = d | 1;                       // padded row stride (bank spread)
@@ -215,12 +215,14 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
   int *s_idx = (int *)(s_x + (size_t)PMC_BLOCK * XS);   // [PMC_BLOCK] drawn comp or -1
   __shared__ double red[32];
   const double *pivot = mix + (size_t)K * h.stride;
-  const double M = dunkey(scal->max_key);
+  // linear != 0: logw holds normalised (linear) weights, as after
+  // normalize_importance_weight; the shift is then 0
+  const double M = linear ? 0.0 : dunkey(scal->max_key);
   const int nout = K * cs;
   double acc[EM_MAXOUT];
 #pragma unroll
   for (int o = 0; o < EM_MAXOUT; o++) acc[o] = 0.0;
-  double tS = 0.0, tS2 = 0.0, tT = 0.0;
+  double tS = 0.0, tS2 = 0.0, tT = 0.0, tN = 0.0;
   const int tid = threadIdx.x;
   const int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
 
@@ -228,14 +230,15 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
     const int64_t n = tile * PMC_BLOCK + tid;
     __syncthreads();
     // ---- phase 1
-    const bool ok = (n < N) && flg[n];
+    const bool ok = (n < N) && flg[n] && (!linear || logw[n] > 0.0);
     double w = 0.0;
     if (ok) {
       double x[D], y[D];
       load_x<D>(X, n, d, x);
-      const double lw = logw[n] - M;
-      w = exp(lw);
-      tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT);
+      double lw;
+      if (linear) { w = logw[n]; lw = log(w); }
+      else { lw = logw[n] - M; w = exp(lw); }
+      tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT); tN += 1.0;
       double rt = 0.0;
       for (int k = 0; k < K; k++) {
         const double *comp = mix + (size_t)k * h.stride;
@@ -294,8 +297,8 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
   }
   // ---- write this block's partial
   double *P = partials + (size_t)blockIdx.x * stat_len(K, d);
-  double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red);
-  if (tid == 0) { P[0] = M; P[1] = bS; P[2] = bS2; P[3] = bT; P[4] = 0; P[5] = 0; P[6] = 0; P[7] = 0; }
+  double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red), bN = block_sum(tN, red);
+  if (tid == 0) { P[0] = M; P[1] = bS; P[2] = bS2; P[3] = bT; P[4] = bN; P[5] = 0; P[6] = 0; P[7] = 0; }
 #pragma unroll
   for (int o = 0; o < EM_MAXOUT; o++) {
     const int out = tid + o * PMC_BLOCK;

@@ -38,6 +38,7 @@ struct pmcb200_ctx {
   DevLike like[PMCB200_MAX_DATA];
   std::vector<void *> tgt_allocs;
   double *d_box = nullptr;                // [2*d]: min, max
+  int box_d = 0;
   double logpr_const = 0.0;
   MixHdr prior_h{};
   double *d_prior = nullptr;
@@ -175,7 +176,7 @@ static void free_target(pmcb200_ctx *c) {
   for (void *p : c->tgt_allocs) cudaFree(p);
   c->tgt_allocs.clear();
   c->have_target = false;
-  c->d_box = nullptr; c->d_prior = nullptr; c->d_prior_sel = nullptr;
+  c->d_box = nullptr; c->box_d = 0; c->d_prior = nullptr; c->d_prior_sel = nullptr;
 }
 
 // ---- life cycle ------------------------------------------------------------------
@@ -453,6 +454,7 @@ extern "C" int pmcb200_set_target(pmcb200_ctx *c, const pmcb200_target_t *t) {
   const double *dbox;
   if ((rc = dev_copy<double>(c, box.data(), box.size(), &dbox))) return rc;
   c->d_box = (double *)dbox;
+  c->box_d = d;
 
   for (int i = 0; i < t->ndata; i++) {
     const pmcb200_like_t &L = t->like[i];
@@ -584,7 +586,7 @@ static int launch_weights(pmcb200_ctx *c, int64_t N, const double *dX, const dou
 }
 
 static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const int32_t *didx,
-                           const int16_t *dflg, const double *dlogw, double *dblock) {
+                           const int16_t *dflg, const double *dlogw, double *dblock, int linear = 0) {
   const int K = c->h.K, d = c->h.d;
   const int64_t len = stat_len(K, d);
   int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
@@ -593,7 +595,7 @@ static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const in
                 PMC_BLOCK * sizeof(int);
   if (smem > 227 * 1024) return fail(c, PMCB200_ERR_UNSUP, "EM kernel needs %zu B shared memory", smem);
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.idxc = didx; a.flgc = dflg; a.logwc = dlogw;
-  a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.smem = smem;
+  a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.smem = smem; a.linear = linear;
   MIX_OK(c, OP_EM, a);
   pmc_launch_em_reduce(c->d_partials, blocks, len, c->d_scal, N, dblock, c->stream);
   LAUNCH_OK(c);
@@ -764,6 +766,84 @@ extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, 
   return 0;
 }
 
+
+// ---- entry points used by the pmclib-named host shims -------------------------------------
+extern "C" int pmcb200_set_box(pmcb200_ctx *c, int d, const double *bmin, const double *bmax) {
+  if (!c || !bmin || !bmax || d < 1 || d > PMCB200_MAX_DIM) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  std::vector<double> box(2 * d);
+  for (int j = 0; j < d; j++) { box[j] = bmin[j]; box[d + j] = bmax[j]; }
+  if (c->d_box && c->box_d == d) {      // reuse the buffer (called once per iteration by the host shims)
+    CUDA_OK(c, cudaMemcpyAsync(c->d_box, box.data(), box.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  const double *dbox;
+  int rc = dev_copy<double>(c, box.data(), box.size(), &dbox);
+  if (rc) return rc;
+  c->d_box = (double *)dbox;
+  c->box_d = d;
+  return 0;
+}
+
+extern "C" int pmcb200_read_counts(pmcb200_ctx *c, int64_t *nok_box, int64_t *nok, double *maxW) {
+  if (!c) return PMCB200_ERR_ARG;
+  DevScal h;
+  CUDA_OK(c, cudaMemcpyAsync(&h, c->d_scal, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (nok_box) *nok_box = (int64_t)h.nok_box;
+  if (nok) *nok = (int64_t)h.nok;
+  if (maxW) {
+    unsigned long long k = h.max_key;
+    if (k == 0ull) *maxW = -INFINITY;
+    else {
+      unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+      memcpy(maxW, &b, 8);
+    }
+  }
+  return 0;
+}
+
+extern "C" int pmcb200_weight_stats(pmcb200_ctx *c, int64_t N, const int16_t *dflg, const double *dw,
+                                    int is_log, double out[8]) {
+  int rc = need(c, false, false);
+  if (rc) return rc;
+  if (N < 1 || !dflg || !dw || !out) return fail(c, PMCB200_ERR_ARG, "weight_stats: bad arguments");
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(2 * c->sm_count, (N + PMC_BLOCK - 1) / PMC_BLOCK));
+  if ((rc = ensure(c, c->sBlock, (size_t)std::max<int64_t>(stat_len(PMCB200_MAX_COMP, 1), 16 + 9 * blocks) * sizeof(double)))) return rc;
+  double *buf = (double *)c->sBlock.p;      // [0..8) result, then max partials, then sum partials
+  pmc_launch_wstat(N, dflg, dw, is_log, blocks, buf + 8, buf + 8 + blocks, buf, c->stream);
+  c->launches += is_log ? 3 : 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, PMCB200_ERR_CUDA, "weight_stats launch: %s", cudaGetErrorString(e));
+  CUDA_OK(c, cudaMemcpyAsync(out, buf, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int pmcb200_normalize_log_weights(pmcb200_ctx *c, int64_t N, const int16_t *dflg, double *dw,
+                                             double *sum_shift, double *logSum, double *maxW) {
+  double o[8];
+  int rc = pmcb200_weight_stats(c, N, dflg, dw, 1, o);
+  if (rc) return rc;
+  if (!(o[1] > 0.0)) return fail(c, PMCB200_ERR_NOSAMPLE, "normalize: no sample with finite weight");
+  pmc_launch_normalize(N, dflg, dw, o[0], 1.0 / o[1], c->stream);
+  LAUNCH_OK(c);
+  if (sum_shift) *sum_shift = o[1];
+  if (logSum) *logSum = std::log(o[1]) + o[0];
+  if (maxW) *maxW = o[0];
+  return 0;
+}
+
+extern "C" int pmcb200_em_local_linear(pmcb200_ctx *c, int64_t N, const double *dX, const int32_t *didx,
+                                       const int16_t *dflg, const double *dwbar, double *dblock) {
+  int rc = need(c, true, false);
+  if (rc) return rc;
+  if (N < 0 || !dblock || (N > 0 && (!dX || !didx || !dflg || !dwbar)))
+    return fail(c, PMCB200_ERR_ARG, "em_local_linear: bad arguments");
+  return launch_em_local(c, N, dX, didx, dflg, dwbar, dblock, 1);
+}
+
 // ---- measurement helpers -------------------------------------------------------------------
 extern "C" int pmcb200_counters(pmcb200_ctx *c, int64_t out[4]) {
   if (!c || !out) return PMCB200_ERR_ARG;
@@ -779,15 +859,20 @@ extern "C" int pmcb200_fp64_peak(pmcb200_ctx *c, double *tflops) {
   if (!c || !tflops) return PMCB200_ERR_ARG;
   CUDA_OK(c, cudaSetDevice(c->device));
   double *d = nullptr;
-  CUDA_OK(c, cudaMalloc((void **)&d, 8));
+  CUDA_OK(c, cudaMalloc((void **)&d, 8 + 64));
+  {
+    double h[8];
+    for (int i = 0; i < 8; i++) h[i] = 0.999999 + 1e-9 * i;
+    CUDA_OK(c, cudaMemcpy(d + 1, h, 64, cudaMemcpyHostToDevice));
+  }
   cudaEvent_t e0, e1;
   CUDA_OK(c, cudaEventCreate(&e0));
   CUDA_OK(c, cudaEventCreate(&e1));
-  const int blocks = c->sm_count * 8, iters = 4096;
+  const int blocks = c->sm_count * 8, iters = 2048;
   double best = 0.0;
   for (int rep = 0; rep < 6; rep++) {
     CUDA_OK(c, cudaEventRecord(e0, c->stream));
-    pmc_launch_fp64_peak(d, blocks, iters, c->stream);
+    pmc_launch_fp64_peak(d, d + 1, blocks, iters, c->stream);
     CUDA_OK(c, cudaEventRecord(e1, c->stream));
     CUDA_OK(c, cudaEventSynchronize(e1));
     float ms = 0.f;

@@ -17,10 +17,9 @@ k_em_reduce(const double *__restrict__ partials, int nblocks, int64_t len,
             const DevScal *__restrict__ scal, int64_t N_local, double *__restrict__ block) {
   for (int64_t o = threadIdx.x; o < len; o += blockDim.x) {
     double s = 0.0;
-    if (o >= 1 && o != 4 && o != 5 && o != 6 && o != 7)
+    if (o >= 1 && o != 5 && o != 6 && o != 7)
       for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * len + o];
-    if (o == 0) s = dunkey(scal->max_key);
-    if (o == 4) s = (double)scal->nok;
+    if (o == 0) s = partials[0];          // the shift every block used
     if (o == 5) s = (double)scal->nok_box;
     if (o == 6) s = (double)N_local;
     block[o] = s;
@@ -149,16 +148,64 @@ k_em_finish(const double *__restrict__ mix, const MixHdr h, int nranks,
   (void)tri;
 }
 
-// DFMA-only kernel: 8 independent chains per thread (roofline denominator probe)
-__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+// DFMA-only kernel: 8 independent chains per thread, 2 register operands + 1
+// constant per DFMA (roofline denominator probe; see tools/micro/fp64_operands.cu)
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, const double *in, int iters) {
+  const double y = in[threadIdx.x & 7];
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
   for (int i = 0; i < iters; i++) {
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+      x0 = fma(x0, y, 1e-9); x1 = fma(x1, y, 1e-9); x2 = fma(x2, y, 1e-9); x3 = fma(x3, y, 1e-9);
+      x4 = fma(x4, y, 1e-9); x5 = fma(x5, y, 1e-9); x6 = fma(x6, y, 1e-9); x7 = fma(x7, y, 1e-9);
     }
   }
   double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
   if (s == 123.456) out[0] = s;
+}
+
+// ---- stand-alone weight statistics (normalize_importance_weight, perplexity_and_ess,
+// evidence on a pmc_simu's weight column): pass 1 max, pass 2 sums relative to it.
+// Persistent blocks, fixed-order final reduction.  out8: M, S, S2, T, nok.
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_wstat_max(int64_t N, const int16_t *__restrict__ flg, const double *__restrict__ w, double *__restrict__ part) {
+  __shared__ double red[32];
+  double m = -INFINITY;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x)
+    if (flg[n]) m = fmax(m, w[n]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+    v = warp_max(v);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_wstat_sums(int64_t N, const int16_t *__restrict__ flg, const double *__restrict__ w, int is_log,
+             const double *__restrict__ maxpart, int nmax, double *__restrict__ part) {
+  __shared__ double red[32];
+  double M = 0.0;
+  if (is_log) { M = -INFINITY; for (int b = 0; b < nmax; b++) M = fmax(M, maxpart[b]); }
+  double tS = 0.0, tS2 = 0.0, tT = 0.0, tN = 0.0;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    if (!flg[n]) continue;
+    double v, lw;
+    if (is_log) { lw = w[n] - M; v = exp(lw); }
+    else { v = w[n]; if (!(v > 0.0)) { tN += 1.0; continue; } lw = log(v); }
+    tS += v; tS2 = fma(v, v, tS2); tT = fma(v, lw, tT); tN += 1.0;
+  }
+  double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red), bN = block_sum(tN, red);
+  if (threadIdx.x == 0) {
+    double *P = part + (size_t)blockIdx.x * 8;
+    P[0] = M; P[1] = bS; P[2] = bS2; P[3] = bT; P[4] = bN;
+  }
+}
+__global__ void k_wstat_final(const double *__restrict__ part, int nblocks, double *__restrict__ out8) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double S = 0, S2 = 0, T = 0, Nn = 0;
+    for (int b = 0; b < nblocks; b++) { S += part[b * 8 + 1]; S2 += part[b * 8 + 2]; T += part[b * 8 + 3]; Nn += part[b * 8 + 4]; }
+    out8[0] = part[0]; out8[1] = S; out8[2] = S2; out8[3] = T; out8[4] = Nn; out8[5] = 0; out8[6] = 0; out8[7] = 0;
+  }
 }

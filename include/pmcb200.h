@@ -241,6 +241,25 @@ int pmcb200_em_local(pmcb200_ctx *ctx, int64_t N, const double *dX,
 int pmcb200_em_finish(pmcb200_ctx *ctx, int nranks, const double *dall,
                       int64_t N_global, pmcb200_stats_t *stats);
 
+/* ---- pieces for callers that drive the stages on a host pmc_simu ------------ */
+/* flat box prior without a target (parabox, cosmo_pmc.c:624) */
+int pmcb200_set_box(pmcb200_ctx *ctx, int ndim, const double *min, const double *max);
+/* device counters of the last simulate / importance_weights call */
+int pmcb200_read_counts(pmcb200_ctx *ctx, int64_t *nok_box, int64_t *nok, double *maxW);
+/* out = {M, S, S2, T, n_flagged}: is_log: M = max log w, S = sum e^(lw-M),
+ * S2 = sum e^2(lw-M), T = sum e^(lw-M)(lw-M); linear (normalised) weights: M = 0,
+ * S = sum w, S2 = sum w^2, T = sum w log w.  perplexity_and_ess (cosmo_pmc.c:46)
+ * and evidence (cosmo_pmc.c:62) follow from these. */
+int pmcb200_weight_stats(pmcb200_ctx *ctx, int64_t N, const int16_t *dflg, const double *dw,
+                         int is_log, double out[8]);
+/* normalize_importance_weight (cosmo_pmc.c:378) without a preceding em_finish */
+int pmcb200_normalize_log_weights(pmcb200_ctx *ctx, int64_t N, const int16_t *dflg, double *dw,
+                                  double *sum_shift, double *logSum, double *maxW);
+/* update_prop_rb (cosmo_pmc.c:247) on NORMALISED weights (isLog = 0), as the
+ * reference calls it after normalize_importance_weight */
+int pmcb200_em_local_linear(pmcb200_ctx *ctx, int64_t N, const double *dX, const int32_t *didx,
+                            const int16_t *dflg, const double *dwbar, double *dblock);
+
 /* ---- whole iteration ------------------------------------------------------ */
 /* Device-resident shard: simulate + weights + em_local on N samples starting
  * at global index `offset`; leaves the stat block in dblock.  Any of

@@ -1,0 +1,100 @@
+"""GPU test of the pmclib-named C host API (include/pmclib/pmc.h): a C driver
+runs one iteration in the order of run_pmc_iteration_MPI (cosmo_pmc.c:305-401)
+and its results are compared with the oracle and with the C-ABI fused call."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cosmopmc_b200 import _abi as A
+from cosmopmc_b200 import targets as T
+
+pytestmark = pytest.mark.gpu
+ROOT = A.ROOT
+
+
+def write_mix(path, w, mean, cov, df=-1):
+    K, d = mean.shape
+    with open(path, "w") as f:
+        f.write("%d %d\n" % (K, d))
+        for k in range(K):
+            f.write("%.17g\n%d %d %d 0\n" % (w[k], d, df, d))
+            f.write(" ".join("%.17g" % v for v in mean[k]) + "\n")
+            for r in cov[k]:
+                f.write(" ".join("%.17g" % v for v in r) + "\n")
+
+
+def parse(out):
+    res = {}
+    for line in out.strip().split("\n"):
+        t = line.split()
+        res[t[0]] = [float(v) for v in t[1:]]
+    return res
+
+
+def read_mix(path):
+    tok = open(path).read().split()
+    K, d = int(tok[0]), int(tok[1])
+    p = 2
+    w, mean, cov = [], [], []
+    for _ in range(K):
+        w.append(float(tok[p])); p += 1
+        assert int(tok[p]) == d and int(tok[p + 3]) == 0
+        p += 4
+        mean.append([float(v) for v in tok[p:p + d]]); p += d
+        cov.append(np.array([float(v) for v in tok[p:p + d * d]]).reshape(d, d)); p += d * d
+    return np.array(w), np.array(mean), np.array(cov)
+
+
+def test_pmclib_named_iteration(oracle, tmp_path):
+    exe = tmp_path / "test_pmclib_api"
+    libdir = os.path.join(ROOT, "cosmopmc_b200")
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([gcc, "-std=gnu99", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "test_pmclib_api.c"), "-o", str(exe),
+                           "-L", libdir, "-lpmc_b200", "-Wl,-rpath," + libdir, "-lm"])
+    w, m, cov = T.proposal_sn(6)
+    write_mix(tmp_path / "proposal_in", w, m, cov)
+    N, seed, beta = 20000, 1234, 0.9
+    out = subprocess.run([str(exe), T.SN_FIXTURE, str(tmp_path / "proposal_in"), str(N), str(seed), str(beta),
+                          str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = parse(out.stdout)
+    assert r["done"] == [1.0] and "MISMATCH" not in out.stdout
+    # oracle on the same seeded iteration (seed = gsl seed, iter = stream 0)
+    spec = T.target_sn_demo()
+    ch = oracle.cholesky_stack(cov)
+    o = oracle.iteration(spec, N, seed, 0, beta, w, m, ch, nthreads=8)
+    so = o["stats"]
+    K, d = m.shape
+    assert r["nok_box"][0] == so["nok_box"] and r["nok"][0] == so["nok"]
+    assert r["isLog"] == [1.0] and r["isLog_after"] == [0.0]
+    for key, ref in (("maxW", so["maxW"]), ("logSum", so["logSum"]), ("norm", so["sum_shift"]),
+                     ("perplexity", so["perplexity"]), ("ess", so["ess"]), ("ln_evidence", so["ln_evidence"]),
+                     ("ln_evidence_from_log", so["ln_evidence"]), ("enc", so["enc"])):
+        assert abs(r[key][0] - ref) <= 1e-8 * abs(ref), (key, r[key][0], ref)
+    assert abs(r["enc0"][0] - K) < 1e-12
+    assert abs(r["wsum"][0] - 1.0) < 1e-12 and abs(r["mean0"][0] - r["mean0_lib"][0]) < 1e-14
+    assert [int(v) for v in r["idx_first"]] == list(o["idx"][:4])
+    assert np.allclose(r["x_first"], o["X"][0], rtol=1e-12)
+    for tag in ("staged", "fused"):
+        assert np.allclose(r[tag + "_wght"], o["wght"], rtol=1e-8, atol=0)
+        assert np.allclose(np.array(r[tag + "_mean"]).reshape(K, d), o["mean"], rtol=1e-8)
+        chol = np.array(r[tag + "_chol"]).reshape(K, d, d)
+        covo = o["chol"] @ o["chol"].transpose(0, 2, 1)
+        assert np.allclose(chol @ chol.transpose(0, 2, 1), covo, rtol=1e-7, atol=1e-12)
+    assert abs(r["fused_perplexity"][0] - so["perplexity"]) <= 1e-8 * so["perplexity"]
+    assert r["fused_nok"][0] == so["nok"] and r["max_abs_dw"][0] < 1e-15
+    # an unregistered posterior callback is an error (no silent host fallback)
+    assert r["unregistered_is_error"][0] == 1.0 and r["unregistered_is_error"][1] == -6008     # pmc_undef
+    # file formats: proposal written before sampling (cosmo_pmc.c:316) round-trips at %g precision
+    w0, m0, c0 = read_mix(tmp_path / "proposal")
+    assert np.allclose(w0, w, rtol=1e-5) and np.allclose(m0, m, rtol=1e-5) and np.allclose(c0, cov, rtol=1e-5, atol=1e-12)
+    w1, m1, c1 = read_mix(tmp_path / "proposal_updated")
+    assert np.allclose(w1, o["wght"], rtol=1e-5) and np.allclose(m1, o["mean"], rtol=1e-5)
+    # the reference's own parser of the format (bin/neff_proposal.pl) where the tree exists
+    if os.path.isdir("/root/reference"):
+        p = subprocess.run(["perl", "/root/reference/bin/neff_proposal.pl", str(tmp_path / "proposal_updated")],
+                           capture_output=True, text=True).stdout.split("\n")[1].split()
+        assert abs(float(p[1]) - so["enc"]) < 2e-3

@@ -135,3 +135,18 @@ def test_par_t_values_match_reference():
             assert par[val] == "p_100_omegab"
         else:
             assert par[val] == "p_" + name
+
+
+def test_pmclib_named_host_api_cpu(tmp_path):
+    """tests/c/test_host_cpu.c: error stack, mvdens/mix_mvdens formats and helpers, parabox,
+    gsl shim, pmc_simu container, loud failure of the batched calls without a GPU."""
+    exe = tmp_path / "test_host_cpu"
+    libdir = os.path.join(ROOT, "cosmopmc_b200")
+    A.load_library()
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([gcc, "-std=gnu99", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "test_host_cpu.c"), "-o", str(exe),
+                           "-L", libdir, "-lpmc_b200", "-Wl,-rpath," + libdir, "-lm"])
+    out = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("ok ") and int(out.stdout.split()[1]) > 100
