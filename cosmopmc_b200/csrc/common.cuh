@@ -31,6 +31,13 @@ struct MixHdr {
 __host__ __device__ inline int mix_tri(int d) { return d * (d + 1) / 2; }
 __host__ __device__ inline int mix_stride(int d) { return 2 + 2 * d + mix_tri(d); }
 
+// padded template dimension for a runtime dimension d
+__host__ __device__ inline int pmc_pad_dim(int d) {
+  const int list[13] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32};
+  for (int i = 0; i < 13; i++) if (d <= list[i]) return list[i];
+  return 32;
+}
+
 // ---- per-iteration device scalars --------------------------------------------
 struct DevScal {
   unsigned long long max_key;   // order-preserving key of max log w (0 = none)

@@ -3,6 +3,7 @@
 // Compiled four times with -DMIX_GROUP=0..3 (parallel build).
 #include "pmc_kernels.cuh"
 #include "launch.h"
+#include <algorithm>
 
 #if MIX_GROUP == 0
 #define DLIST(X) X(2) X(3) X(4) X(5)
@@ -44,7 +45,14 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
     case OP_EM: {
       cudaError_t e = cudaFuncSetAttribute(k_em_stats<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
       if (e != cudaSuccess) return e;
-      k_em_stats<DD><<<a.blocks, PMC_BLOCK, a.smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal,
+      // persistent grid: as many blocks as are resident (a.blocks = buffer capacity)
+      int per_sm = 1, dev = 0, sms = 148;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_em_stats<DD>, PMC_BLOCK, a.smem);
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      int blocks = std::max(1, std::min(a.blocks, std::max(1, per_sm) * sms));
+      if (a.nblocks_out) *a.nblocks_out = blocks;
+      k_em_stats<DD><<<blocks, PMC_BLOCK, a.smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal,
                                                          a.partials, a.linear);
       break;
     }

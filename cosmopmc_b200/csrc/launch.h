@@ -22,15 +22,8 @@ struct MixArgs {
   double *logpi = nullptr; const double *logpic = nullptr; int32_t *err = nullptr; const int32_t *errc = nullptr;
   int set = 0; double add_const = 0.0, beta = 1.0;
   double *logw = nullptr; const double *logwc = nullptr;
-  double *partials = nullptr; int blocks = 0; size_t smem = 0; int linear = 0;
+  double *partials = nullptr; int blocks = 0; size_t smem = 0; int linear = 0; int *nblocks_out = nullptr;
 };
-
-// padded template dimension for a runtime dimension d
-static inline int pmc_pad_dim(int d) {
-  const int list[] = {2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32};
-  for (int v : list) if (d <= v) return v;
-  return 32;
-}
 
 bool pmc_mix_launch_g0(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e);
 bool pmc_mix_launch_g1(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e);

@@ -195,35 +195,108 @@ k_weights(const double *__restrict__ mix, const MixHdr h, int64_t N,
 //   A = sum w rho, G = sum w rho gamma, count (points drawn from k),
 //   B[d] = sum w rho gamma (x - p), C[tri] = sum w rho gamma (x-p)(x-p)^T (lower)
 // with w = e^(lw-M) and p the common pivot (weighted mean of the old means).
-// Phase 1 (per tile of PMC_BLOCK samples): each thread computes its sample's
-// w and responsibilities into shared memory.  Phase 2: the K x M outputs are
-// distributed over the threads, each accumulating over the tile (a K x tile x M
-// contraction) in registers across all tiles of a persistent block.
+// Phase 1 (per tile of PMC_BLOCK samples): each thread computes its sample's w and
+// responsibilities into shared memory (and bumps the per-component draw counter).
+// Phase 2: the K x M' statistics (M' = 2 + d + d(d+1)/2 weighted features per
+// component) are a K x tile x M' contraction.  Thread (g, f) owns feature f for
+// a contiguous sample chunk g of the tile (G = 256 / M' chunks when M' < 256,
+// else several features per thread); it forms the feature once per sample and
+// 8-component chunk and accumulates 8 components in registers, so each FMA
+// costs one broadcast LDS.  The per-thread partials live in shared memory across
+// the tiles of a persistent block and are combined in a fixed order.
+#define EM_KCHUNK 8
+__host__ __device__ inline int em_nfeat(int d) { return 2 + d + mix_tri(d); }             // A, G, B[d], C[tri]
+__host__ __device__ inline int em_nf(int Mp) { return (Mp + PMC_BLOCK - 1) / PMC_BLOCK; }  // features per thread
+__host__ __device__ inline int em_xs(int d) { return pmc_pad_dim(d) | 1; }                // smem row stride of x
+__host__ __device__ inline size_t em_smem_bytes(int K, int d, int student) {
+  const int KP = (K + EM_KCHUNK - 1) / EM_KCHUNK * EM_KCHUNK;   // zero-padded rows
+  return ((size_t)KP * PMC_BLOCK * (student ? 2 : 1)           // s_wr (, s_wg)
+          + (size_t)PMC_BLOCK * em_xs(d)                        // s_x
+          + (size_t)em_nf(em_nfeat(d)) * K * PMC_BLOCK) * sizeof(double)  // s_acc
+         + (size_t)K * sizeof(unsigned long long);              // s_cnt
+}
+
+// weighted feature f: 0 -> 1 with weight w rho (A), 1 -> 1 with weight w rho gamma (G),
+// 2..2+d -> x_i, then x_i x_j (lower triangle), all with weight w rho gamma
+__device__ __forceinline__ void em_decode(int f, int d, int &type, int &i, int &j) {
+  i = 0; j = 0;
+  if (f < 2) { type = f; return; }
+  if (f < 2 + d) { type = 3; i = f - 2; return; }
+  type = 4;
+  int q = f - 2 - d;
+  while ((i + 1) * (i + 2) / 2 <= q) i++;
+  j = q - i * (i + 1) / 2;
+}
+
+template <int KC, int XS>
+__device__ __forceinline__ void em_chunk(const double *__restrict__ wp, const double *__restrict__ xi,
+                                         const double *__restrict__ xj, int type, int t0, int t1,
+                                         double *__restrict__ accp, int kleft) {
+  double acc[KC];
+#pragma unroll
+  for (int q = 0; q < KC; q++) acc[q] = 0.0;
+  const double *w = wp + t0;
+  const double *pi = xi + (size_t)t0 * XS, *pj = xj + (size_t)t0 * XS;
+  if (type == 4) {
+#pragma unroll 4
+    for (int t = t0; t < t1; t++, w++, pi += XS, pj += XS) {
+      const double feat = pi[0] * pj[0];
+#pragma unroll
+      for (int q = 0; q < KC; q++) acc[q] = fma(w[q * PMC_BLOCK], feat, acc[q]);
+    }
+  } else if (type == 3) {
+#pragma unroll 4
+    for (int t = t0; t < t1; t++, w++, pi += XS) {
+      const double feat = pi[0];
+#pragma unroll
+      for (int q = 0; q < KC; q++) acc[q] = fma(w[q * PMC_BLOCK], feat, acc[q]);
+    }
+  } else {
+#pragma unroll 4
+    for (int t = t0; t < t1; t++, w++) {
+#pragma unroll
+      for (int q = 0; q < KC; q++) acc[q] += w[q * PMC_BLOCK];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < KC; q++) if (q < kleft) accp[(size_t)q * PMC_BLOCK] += acc[q];
+}
+
 template <int D>
-__global__ void __launch_bounds__(PMC_BLOCK)
+__global__ void __launch_bounds__(PMC_BLOCK, 2)
 k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
            const double *__restrict__ X, const int32_t *__restrict__ idx,
            const int16_t *__restrict__ flg, const double *__restrict__ logw,
            const DevScal *__restrict__ scal, double *__restrict__ partials, int linear) {
   extern __shared__ double sm[];
-  const int K = h.K, d = h.d, tri = mix_tri(d), cs = stat_cs(d);
-  const int XS = d | 1;                       // padded row stride (bank spread)
+  constexpr int XS = D | 1;                   // padded row stride (bank spread), compile-time
+  const int K = h.K, d = h.d, M = stat_cs(d), Mp = em_nfeat(d);
   const bool student = h.df > 0;
-  double *s_wr = sm;                          // [K][PMC_BLOCK]  w*rho
-  double *s_wg = student ? s_wr + (size_t)K * PMC_BLOCK : s_wr;   // w*rho*gamma (Gaussian: gamma = 1)
-  double *s_x = s_wg + (size_t)K * PMC_BLOCK;   // [PMC_BLOCK][XS] x - pivot
-  int *s_idx = (int *)(s_x + (size_t)PMC_BLOCK * XS);   // [PMC_BLOCK] drawn comp or -1
+  const int NF = em_nf(Mp);
+  const int KP = (K + EM_KCHUNK - 1) / EM_KCHUNK * EM_KCHUNK;
+  double *s_wr = sm;                          // [KP][PMC_BLOCK]  w*rho (rows >= K stay zero)
+  double *s_wg = student ? s_wr + (size_t)KP * PMC_BLOCK : s_wr;   // w*rho*gamma (Gaussian: gamma = 1)
+  double *s_x = s_wg + (size_t)KP * PMC_BLOCK;  // [PMC_BLOCK][XS] x - pivot
+  double *s_acc = s_x + (size_t)PMC_BLOCK * XS; // [NF][K][PMC_BLOCK] per-thread partial statistics
+  unsigned long long *s_cnt = (unsigned long long *)(s_acc + (size_t)NF * K * PMC_BLOCK);   // [K] draws per component
   __shared__ double red[32];
   const double *pivot = mix + (size_t)K * h.stride;
   // linear != 0: logw holds normalised (linear) weights, as after
   // normalize_importance_weight; the shift is then 0
-  const double M = linear ? 0.0 : dunkey(scal->max_key);
-  const int nout = K * cs;
-  double acc[EM_MAXOUT];
-#pragma unroll
-  for (int o = 0; o < EM_MAXOUT; o++) acc[o] = 0.0;
+  const double M0 = linear ? 0.0 : dunkey(scal->max_key);
   double tS = 0.0, tS2 = 0.0, tT = 0.0, tN = 0.0;
   const int tid = threadIdx.x;
+  // thread -> (sample chunk g, feature f)
+  const int G = (Mp < PMC_BLOCK) ? PMC_BLOCK / Mp : 1;
+  const int g = (Mp < PMC_BLOCK) ? tid / Mp : 0;
+  const int f0 = (Mp < PMC_BLOCK) ? tid - g * Mp : tid;
+  const bool worker = (Mp < PMC_BLOCK) ? (g < G) : true;
+  const int TS = (PMC_BLOCK + G - 1) / G;
+  const int t0 = g * TS, t1 = min(PMC_BLOCK, t0 + TS);
+  for (int p = 0; p < NF; p++)
+    for (int k = 0; k < K; k++) s_acc[((size_t)p * K + k) * PMC_BLOCK + tid] = 0.0;
+  for (int k = K; k < KP; k++) { s_wr[k * PMC_BLOCK + tid] = 0.0; if (student) s_wg[k * PMC_BLOCK + tid] = 0.0; }
+  if (tid < K) s_cnt[tid] = 0ull;
   const int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -237,7 +310,7 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
       load_x<D>(X, n, d, x);
       double lw;
       if (linear) { w = logw[n]; lw = log(w); }
-      else { lw = logw[n] - M; w = exp(lw); }
+      else { lw = logw[n] - M0; w = exp(lw); }
       tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT); tN += 1.0;
       double rt = 0.0;
       for (int k = 0; k < K; k++) {
@@ -247,7 +320,7 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
         if (a != 0.0) {
           double m = comp_maha<D>(comp, d, x, y);
           r = a * exp(comp_logpdf_from_maha(comp, d, h.df, m));
-          if (h.df > 0) gam = (double)(h.df + d) / ((double)h.df + m);
+          if (student) gam = (double)(h.df + d) / ((double)h.df + m);
         }
         rt += r;
         s_wr[k * PMC_BLOCK + tid] = r;
@@ -260,50 +333,48 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
         if (student) s_wg[k * PMC_BLOCK + tid] *= r;
       }
 #pragma unroll
-      for (int i = 0; i < D; i++) if (i < d) s_x[tid * XS + i] = x[i] - pivot[i];
-      s_idx[tid] = idx[n];
+      for (int i = 0; i < D; i++) s_x[tid * XS + i] = (i < d) ? x[i] - pivot[i] : 0.0;
+      atomicAdd(&s_cnt[idx[n]], 1ull);
     } else {
       for (int k = 0; k < K; k++) { s_wr[k * PMC_BLOCK + tid] = 0.0; if (student) s_wg[k * PMC_BLOCK + tid] = 0.0; }
-      for (int i = 0; i < d; i++) s_x[tid * XS + i] = 0.0;
-      s_idx[tid] = -1;
+#pragma unroll
+      for (int i = 0; i < D; i++) s_x[tid * XS + i] = 0.0;
     }
     __syncthreads();
-    // ---- phase 2: out(k, f) += sum_t weight(k,t) * feature(f,t)
-#pragma unroll
-    for (int o = 0; o < EM_MAXOUT; o++) {
-      const int out = tid + o * PMC_BLOCK;
-      if (out < nout) {
-        const int k = out / cs, f = out - k * cs;
-        double a = acc[o];
-        if (f == 0) {
-          for (int t = 0; t < PMC_BLOCK; t++) a += s_wr[k * PMC_BLOCK + t];
-        } else if (f == 1) {
-          for (int t = 0; t < PMC_BLOCK; t++) a += s_wg[k * PMC_BLOCK + t];
-        } else if (f == 2) {
-          for (int t = 0; t < PMC_BLOCK; t++) a += (s_idx[t] == k) ? 1.0 : 0.0;
-        } else if (f < 3 + d) {
-          const int i = f - 3;
-          for (int t = 0; t < PMC_BLOCK; t++) a = fma(s_wg[k * PMC_BLOCK + t], s_x[t * XS + i], a);
-        } else {
-          int q = f - 3 - d, i = 0;
-          while ((i + 1) * (i + 2) / 2 <= q) i++;
-          const int j = q - i * (i + 1) / 2;
-          for (int t = 0; t < PMC_BLOCK; t++)
-            a = fma(s_wg[k * PMC_BLOCK + t] * s_x[t * XS + i], s_x[t * XS + j], a);
+    // ---- phase 2 (rows k >= K of s_wr/s_wg are zero padding up to KP, so the
+    // chunk loops need no predicates and every LDS has an immediate offset)
+    if (worker) {
+      for (int p = 0; p < NF; p++) {
+        const int f = f0 + p * PMC_BLOCK;
+        if (f >= Mp) break;
+        int type, fi, fj;
+        em_decode(f, d, type, fi, fj);
+        const double *wsrc = (type == 0) ? s_wr : s_wg;
+        double *accp = s_acc + (size_t)p * K * PMC_BLOCK + tid;
+        for (int kc = 0; kc < K; kc += EM_KCHUNK) {
+          const double *wp = wsrc + (size_t)kc * PMC_BLOCK;
+          if (K - kc > EM_KCHUNK / 2)
+            em_chunk<EM_KCHUNK, XS>(wp, s_x + fi, s_x + fj, type, t0, t1, accp + (size_t)kc * PMC_BLOCK, K - kc);
+          else
+            em_chunk<EM_KCHUNK / 2, XS>(wp, s_x + fi, s_x + fj, type, t0, t1, accp + (size_t)kc * PMC_BLOCK, K - kc);
         }
-        acc[o] = a;
       }
     }
   }
-  // ---- write this block's partial
+  __syncthreads();
+  // ---- this block's partial: combine the G sample chunks in fixed order
   double *P = partials + (size_t)blockIdx.x * stat_len(K, d);
   double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red), bN = block_sum(tN, red);
-  if (tid == 0) { P[0] = M; P[1] = bS; P[2] = bS2; P[3] = bT; P[4] = bN; P[5] = 0; P[6] = 0; P[7] = 0; }
-#pragma unroll
-  for (int o = 0; o < EM_MAXOUT; o++) {
-    const int out = tid + o * PMC_BLOCK;
-    if (out < nout) P[STAT_HDR + out] = acc[o];
+  if (tid == 0) { P[0] = M0; P[1] = bS; P[2] = bS2; P[3] = bT; P[4] = bN; P[5] = 0; P[6] = 0; P[7] = 0; }
+  for (int out = tid; out < K * M; out += PMC_BLOCK) {
+    const int k = out / M, fo = out - k * M;       // fo: position in the stat block (count at 2)
+    double s = 0.0;
+    if (fo == 2) s = (double)s_cnt[k];
+    else {
+      const int f = fo < 2 ? fo : fo - 1;
+      if (Mp < PMC_BLOCK) { for (int gg = 0; gg < G; gg++) s += s_acc[(size_t)k * PMC_BLOCK + gg * Mp + f]; }
+      else s = s_acc[((size_t)(f / PMC_BLOCK) * K + k) * PMC_BLOCK + (f % PMC_BLOCK)];
+    }
+    P[STAT_HDR + out] = s;
   }
-  (void)tri;
 }
-

@@ -11,7 +11,7 @@
 
 #include "common.cuh"
 #include "cosmo_types.cuh"
-#include "stat_layout.cuh"
+#include "pmc_kernels.cuh"
 #include "launch.h"
 
 // ---- context ----------------------------------------------------------------
@@ -275,9 +275,9 @@ static int install_proposal(pmcb200_ctx *c, int K, int d, int df, const double *
   if (K < 1 || K > PMCB200_MAX_COMP || d < 1 || d > PMCB200_MAX_DIM)
     return fail(c, PMCB200_ERR_DIM, "proposal: ncomp=%d (max %d), ndim=%d (max %d)", K, PMCB200_MAX_COMP, d,
                 PMCB200_MAX_DIM);
-  if ((int64_t)K * stat_cs(d) > (int64_t)PMC_BLOCK * EM_MAXOUT)
-    return fail(c, PMCB200_ERR_UNSUP, "proposal: K*(3+d+d(d+1)/2)=%lld exceeds the EM kernel limit %d",
-                (long long)K * stat_cs(d), PMC_BLOCK * EM_MAXOUT);
+  if (em_smem_bytes(K, d, df > 0) > 227 * 1024)
+    return fail(c, PMCB200_ERR_UNSUP, "proposal: K=%d, d=%d needs %zu B of shared memory in the EM kernel (max 227 KB)",
+                K, d, em_smem_bytes(K, d, df > 0));
   for (int k = 0; k < K; k++) {
     if (!(w[k] >= 0.0) || !std::isfinite(w[k])) return fail(c, PMCB200_ERR_ARG, "proposal weight %d = %g", k, w[k]);
     for (int i = 0; i < d; i++)
@@ -294,7 +294,7 @@ static int install_proposal(pmcb200_ctx *c, int K, int d, int df, const double *
   if (rc) return rc;
   // EM work buffers
   int64_t len = stat_len(K, d);
-  c->em_blocks = 2 * c->sm_count;
+  c->em_blocks = 4 * c->sm_count;     // capacity of the partials buffer; the launch uses the resident count
   size_t need = (size_t)c->em_blocks * len;
   if (c->partials_cap < need) {
     if (c->d_partials) CUDA_OK(c, cudaFree(c->d_partials));
@@ -591,13 +591,14 @@ static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const in
   const int64_t len = stat_len(K, d);
   int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->em_blocks, ntiles));
-  size_t smem = ((size_t)K * PMC_BLOCK * (c->h.df > 0 ? 2 : 1) + (size_t)PMC_BLOCK * (d | 1)) * sizeof(double) +
-                PMC_BLOCK * sizeof(int);
+  size_t smem = em_smem_bytes(K, d, c->h.df > 0);
   if (smem > 227 * 1024) return fail(c, PMCB200_ERR_UNSUP, "EM kernel needs %zu B shared memory", smem);
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.idxc = didx; a.flgc = dflg; a.logwc = dlogw;
   a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.smem = smem; a.linear = linear;
+  int used = blocks;
+  a.nblocks_out = &used;
   MIX_OK(c, OP_EM, a);
-  pmc_launch_em_reduce(c->d_partials, blocks, len, c->d_scal, N, dblock, c->stream);
+  pmc_launch_em_reduce(c->d_partials, used, len, c->d_scal, N, dblock, c->stream);
   LAUNCH_OK(c);
   return 0;
 }
