@@ -26,11 +26,15 @@ METRIC = "pmc_samples_per_sec_full_iteration"
 UNIT = "samples/s"
 SEED = 20090903
 
-# algorithmic FLOPs of the SN likelihood (convention SURVEY.md 8d: + - * = 1,
-# FMA = 2, / sqrt exp log pow = 1 each); derivation in DESIGN.md
-FLOP_PER_EVAL = 14.0       # one integrand evaluation 1/sqrt(a^4 E^2(a))
-FLOP_PER_ZSTEP = 58.0      # per (sample, redshift): trapezoid combine 5x3, Neville 34, test 3, D_L + modulus 6
-FLOP_PER_SN = 24.0         # per (sample, supernova): mu_obs 6, sigma^2 14, chi^2 term 4
+# algorithmic FLOPs of the SN likelihood = operation count of the REFERENCE algorithm as
+# restated in oracle/pmc_oracle.c (convention SURVEY.md 8d: + - * = 1, FMA = 2,
+# / sqrt exp log pow = 1 each); derivation in DESIGN.md section 6
+FLOP_PER_EVAL = 18.0       # int_for_w: a^4 E^2(a) incl. 1 pow + 1 exp (14), sqrt, 1/x, sum += (4)
+FLOP_PER_ZSTEP = 86.0      # per (sample, redshift): 5 trapzd combines (22), NR polint K=5 (54), test (4), D_L + modulus (6)
+FLOP_PER_SN = 29.0         # per (sample, supernova): mu_obs 7, sigma^2 18, chi^2 term 4
+# ncu evidence for the dominant kernel (profiles/sn_r01_v3_summary.txt), N = 2e6 capture
+NCU_SN = {"fp64_pipe_active_pct": 70.5, "dram_bytes_per_sample": 44.2,
+          "source": "profiles/sn_r01_v3_summary.txt"}
 
 
 def parse():
@@ -275,7 +279,10 @@ def main():
         peak = pmc.fp64_peak_tflops()
         ach = flops / (k_ms * 1e-3) * 1e-12
         roof = {"kernel": "k_like_sn", "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak if peak else None, "traffic": None,
+                "frac": ach / peak if peak else None,
+                "traffic": NCU_SN["dram_bytes_per_sample"] * n_loc,
+                "traffic_source": "ncu dram__bytes_read+write per sample (%s) x samples per launch; algorithmic = %d B/sample" % (NCU_SN["source"], 8 * d + 12),
+                "fp64_pipe_active_pct_ncu": NCU_SN["fp64_pipe_active_pct"],
                 "kernel_ms": k_ms, "flop_per_launch": flops,
                 "evals_per_sample": c["sn_evals"] / reps / n_loc,
                 "peak_source": "measured live: DFMA-only kernel (pmcb200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",

@@ -334,12 +334,13 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
       }
 #pragma unroll
       for (int i = 0; i < D; i++) s_x[tid * XS + i] = (i < d) ? x[i] - pivot[i] : 0.0;
-      atomicAdd(&s_cnt[idx[n]], 1ull);
     } else {
       for (int k = 0; k < K; k++) { s_wr[k * PMC_BLOCK + tid] = 0.0; if (student) s_wg[k * PMC_BLOCK + tid] = 0.0; }
 #pragma unroll
       for (int i = 0; i < D; i++) s_x[tid * XS + i] = 0.0;
     }
+    // draws per component count every flagged sample (also zero-weight ones)
+    if ((n < N) && flg[n]) atomicAdd(&s_cnt[idx[n]], 1ull);
     __syncthreads();
     // ---- phase 2 (rows k >= K of s_wr/s_wg are zero padding up to KP, so the
     // chunk loops need no predicates and every LDS has an immediate offset)

@@ -24,6 +24,8 @@ struct pmcb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;     // D2H of finished arrays overlaps the likelihood kernel
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   char errmsg[512] = {0};
   int64_t launches = 0;
   // proposal
@@ -205,6 +207,9 @@ extern "C" int pmcb200_create(int device, void *stream, pmcb200_ctx **out) {
   // with plain cudaMemcpy in C hosts); (void*)-1 = a private non-blocking stream
   if (stream == (void *)-1) { CUDA_OK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   else c->stream = (cudaStream_t)stream;
+  CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
   cudaDeviceProp prop;
   CUDA_OK(c, cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -231,6 +236,9 @@ extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
   if (c->d_work) cudaFree(c->d_work);
   if (c->d_result) cudaFree(c->d_result);
   if (c->h_result) cudaFreeHost(c->h_result);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -748,23 +756,45 @@ extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, 
   if (rc) return rc;
   if (N < 1) return fail(c, PMCB200_ERR_ARG, "iteration_host: N = %lld", (long long)N);
   const int d = c->h.d;
+  const size_t n1 = (size_t)N;
   if ((rc = ensure(c, c->sBlock, (size_t)stat_len(c->h.K, d) * sizeof(double)))) return rc;
-  double *dblock = (double *)c->sBlock.p;
-  if ((rc = pmcb200_iteration_local(c, N, seed, iter, 0, beta, nullptr, nullptr, nullptr, nullptr, dblock))) return rc;
-  double *dX = (double *)c->sX.p, *dlogw = (double *)c->sLogw.p;
+  if ((rc = ensure(c, c->sX, n1 * d * sizeof(double)))) return rc;
+  if ((rc = ensure(c, c->sIdx, n1 * sizeof(int32_t)))) return rc;
+  if ((rc = ensure(c, c->sFlg, n1 * sizeof(int16_t)))) return rc;
+  if ((rc = ensure(c, c->sLogw, n1 * sizeof(double)))) return rc;
+  if ((rc = ensure(c, c->sLogpi, n1 * sizeof(double)))) return rc;
+  if ((rc = ensure(c, c->sErr, n1 * sizeof(int32_t)))) return rc;
+  double *dblock = (double *)c->sBlock.p, *dX = (double *)c->sX.p, *dlogw = (double *)c->sLogw.p;
   int32_t *didx = (int32_t *)c->sIdx.p;
   int16_t *dflg = (int16_t *)c->sFlg.p;
-  // sample / index / flag copies overlap nothing they depend on: issue them before the M-step sync
-  if (hX) CUDA_OK(c, cudaMemcpyAsync(hX, dX, (size_t)N * d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (hidx) CUDA_OK(c, cudaMemcpyAsync(hidx, didx, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (hflg) CUDA_OK(c, cudaMemcpyAsync(hflg, dflg, (size_t)N * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
-  if ((rc = pmcb200_em_finish(c, 1, dblock, N, stats))) return rc;
-  if (hw) {
-    if ((rc = pmcb200_normalize_weights(c, N, dflg, dlogw))) return rc;
-    CUDA_OK(c, cudaMemcpyAsync(hw, dlogw, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = reset_scal(c))) return rc;
+  if ((rc = launch_simulate(c, N, seed, iter, 0, dX, didx, dflg))) return rc;
+  // X and idx are final after the sampler: copy them out on the copy stream
+  // while the likelihood kernel runs
+  if (hX || hidx) {
+    CUDA_OK(c, cudaEventRecord(c->ev_a, c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_a, 0));
+    if (hX) CUDA_OK(c, cudaMemcpyAsync(hX, dX, n1 * d * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (hidx) CUDA_OK(c, cudaMemcpyAsync(hidx, didx, n1 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
   }
+  if ((rc = launch_posterior(c, N, dX, dflg, (double *)c->sLogpi.p, (int32_t *)c->sErr.p))) return rc;
+  if ((rc = launch_weights(c, N, dX, (double *)c->sLogpi.p, (int32_t *)c->sErr.p, beta, dflg, dlogw))) return rc;
+  if (hflg) {     // flags are final after the weight stage
+    CUDA_OK(c, cudaEventRecord(c->ev_b, c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_b, 0));
+    CUDA_OK(c, cudaMemcpyAsync(hflg, dflg, n1 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  if ((rc = launch_em_local(c, N, dX, didx, dflg, dlogw, dblock))) return rc;
+  rc = pmcb200_em_finish(c, 1, dblock, N, stats);
+  if (rc == 0 && hw) {
+    if ((rc = pmcb200_normalize_weights(c, N, dflg, dlogw)) == 0) {
+      cudaError_t e = cudaMemcpyAsync(hw, dlogw, n1 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+      if (e != cudaSuccess) rc = fail(c, PMCB200_ERR_CUDA, "D2H weights: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaStreamSynchronize(c->copy_stream);
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  return 0;
+  return rc;
 }
 
 
