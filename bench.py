@@ -216,15 +216,10 @@ def main():
         pmc.set_proposal(w_pin.numpy(), m_pin.numpy(), chol=ch_pin.numpy())
         if world == 1:
             return pmc.iteration_host(n_loc, SEED, it, 1.0, hX, hidx, hflg, hw)
-        pmc.iteration_local(n_loc, SEED, it, off, 1.0, block, bufs)
+        pmc.iteration_shard_host(n_loc, SEED, it, off, 1.0, block, hX, hidx, hflg)
         dist.all_gather_into_tensor(allb, block)
-        hX.copy_(bufs["X"], non_blocking=True)
-        hidx.copy_(bufs["idx"], non_blocking=True)
         st = pmc.update_prop_rb(world, allb, n_glob)
-        pmc.normalize_importance_weight(bufs["flg"], bufs["logw"], n_loc)
-        hflg.copy_(bufs["flg"], non_blocking=True)
-        hw.copy_(bufs["logw"], non_blocking=True)
-        torch.cuda.synchronize()
+        pmc.shard_weights_host(n_loc, hw)
         return st
 
     def timed(fn, steps, warmup, sampler=None):

@@ -106,6 +106,8 @@ SYMBOLS = {
     "pmcb200_em_local": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "pmcb200_em_finish": (_i, [_vp, _i, _vp, _i64, C.POINTER(Stats)]),
     "pmcb200_iteration_local": (_i, [_vp, _i64, _u64, _u32, _i64, _d, _vp, _vp, _vp, _vp, _vp]),
+    "pmcb200_iteration_shard_host": (_i, [_vp, _i64, _u64, _u32, _i64, _d, _vp, _vp, _vp, _vp]),
+    "pmcb200_shard_weights_host": (_i, [_vp, _i64, _vp]),
     "pmcb200_iteration_host": (_i, [_vp, _i64, _u64, _u32, _d, _vp, _vp, _vp, _vp, C.POINTER(Stats)]),
     "pmcb200_launch_count": (_i64, [_vp]),
     "pmcb200_set_box": (_i, [_vp, _i, _vp, _vp]),

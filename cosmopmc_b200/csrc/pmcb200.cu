@@ -728,14 +728,14 @@ extern "C" int pmcb200_em_finish(pmcb200_ctx *c, int nranks, const double *dall,
 }
 
 // ---- whole iteration -----------------------------------------------------------------------
-extern "C" int pmcb200_iteration_local(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter,
-                                       int64_t offset, double beta, double *dX, int32_t *didx,
-                                       int16_t *dflg, double *dlogw, double *dblock) {
-  int rc = need(c, true, true);
-  if (rc) return rc;
-  if (N < 0 || !dblock) return fail(c, PMCB200_ERR_ARG, "iteration_local: bad arguments");
+// shard iteration with the D2H of the finished arrays overlapped with the
+// likelihood kernel (copy stream); leaves the statistics block in dblock
+static int iteration_core(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, int64_t offset, double beta,
+                          double *dX, int32_t *didx, int16_t *dflg, double *dlogw, double *dblock,
+                          double *hX, int32_t *hidx, int16_t *hflg) {
+  int rc;
   const int d = c->h.d;
-  const size_t n1 = (size_t)std::max<int64_t>(N, 1);
+  const size_t n1 = (size_t)std::max<int64_t>(N, 1), n = (size_t)N;
   if (!dX) { if ((rc = ensure(c, c->sX, n1 * d * sizeof(double)))) return rc; dX = (double *)c->sX.p; }
   if (!didx) { if ((rc = ensure(c, c->sIdx, n1 * sizeof(int32_t)))) return rc; didx = (int32_t *)c->sIdx.p; }
   if (!dflg) { if ((rc = ensure(c, c->sFlg, n1 * sizeof(int16_t)))) return rc; dflg = (int16_t *)c->sFlg.p; }
@@ -744,9 +744,51 @@ extern "C" int pmcb200_iteration_local(pmcb200_ctx *c, int64_t N, uint64_t seed,
   if ((rc = ensure(c, c->sErr, n1 * sizeof(int32_t)))) return rc;
   if ((rc = reset_scal(c))) return rc;
   if ((rc = launch_simulate(c, N, seed, iter, offset, dX, didx, dflg))) return rc;
+  if (N > 0 && (hX || hidx)) {   // X and idx are final after the sampler
+    CUDA_OK(c, cudaEventRecord(c->ev_a, c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_a, 0));
+    if (hX) CUDA_OK(c, cudaMemcpyAsync(hX, dX, n * d * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (hidx) CUDA_OK(c, cudaMemcpyAsync(hidx, didx, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
   if ((rc = launch_posterior(c, N, dX, dflg, (double *)c->sLogpi.p, (int32_t *)c->sErr.p))) return rc;
   if ((rc = launch_weights(c, N, dX, (double *)c->sLogpi.p, (int32_t *)c->sErr.p, beta, dflg, dlogw))) return rc;
+  if (N > 0 && hflg) {           // flags are final after the weight stage
+    CUDA_OK(c, cudaEventRecord(c->ev_b, c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_b, 0));
+    CUDA_OK(c, cudaMemcpyAsync(hflg, dflg, n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
   return launch_em_local(c, N, dX, didx, dflg, dlogw, dblock);
+}
+
+extern "C" int pmcb200_iteration_local(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter,
+                                       int64_t offset, double beta, double *dX, int32_t *didx,
+                                       int16_t *dflg, double *dlogw, double *dblock) {
+  int rc = need(c, true, true);
+  if (rc) return rc;
+  if (N < 0 || !dblock) return fail(c, PMCB200_ERR_ARG, "iteration_local: bad arguments");
+  return iteration_core(c, N, seed, iter, offset, beta, dX, didx, dflg, dlogw, dblock, nullptr, nullptr, nullptr);
+}
+
+extern "C" int pmcb200_iteration_shard_host(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter,
+                                            int64_t offset, double beta, double *hX, int32_t *hidx,
+                                            int16_t *hflg, double *dblock) {
+  int rc = need(c, true, true);
+  if (rc) return rc;
+  if (N < 0 || !dblock) return fail(c, PMCB200_ERR_ARG, "iteration_shard_host: bad arguments");
+  return iteration_core(c, N, seed, iter, offset, beta, nullptr, nullptr, nullptr, nullptr, dblock, hX, hidx, hflg);
+}
+
+extern "C" int pmcb200_shard_weights_host(pmcb200_ctx *c, int64_t N, double *hw) {
+  int rc = need(c, true, false);
+  if (rc) return rc;
+  if (N < 0 || !hw || (size_t)N * sizeof(double) > c->sLogw.cap) return fail(c, PMCB200_ERR_ARG, "shard_weights_host: bad arguments");
+  if (N > 0) {
+    if ((rc = pmcb200_normalize_weights(c, N, (int16_t *)c->sFlg.p, (double *)c->sLogw.p))) return rc;
+    CUDA_OK(c, cudaMemcpyAsync(hw, c->sLogw.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  cudaStreamSynchronize(c->copy_stream);
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return 0;
 }
 
 extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, double beta,
@@ -755,43 +797,11 @@ extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, 
   int rc = need(c, true, true);
   if (rc) return rc;
   if (N < 1) return fail(c, PMCB200_ERR_ARG, "iteration_host: N = %lld", (long long)N);
-  const int d = c->h.d;
-  const size_t n1 = (size_t)N;
-  if ((rc = ensure(c, c->sBlock, (size_t)stat_len(c->h.K, d) * sizeof(double)))) return rc;
-  if ((rc = ensure(c, c->sX, n1 * d * sizeof(double)))) return rc;
-  if ((rc = ensure(c, c->sIdx, n1 * sizeof(int32_t)))) return rc;
-  if ((rc = ensure(c, c->sFlg, n1 * sizeof(int16_t)))) return rc;
-  if ((rc = ensure(c, c->sLogw, n1 * sizeof(double)))) return rc;
-  if ((rc = ensure(c, c->sLogpi, n1 * sizeof(double)))) return rc;
-  if ((rc = ensure(c, c->sErr, n1 * sizeof(int32_t)))) return rc;
-  double *dblock = (double *)c->sBlock.p, *dX = (double *)c->sX.p, *dlogw = (double *)c->sLogw.p;
-  int32_t *didx = (int32_t *)c->sIdx.p;
-  int16_t *dflg = (int16_t *)c->sFlg.p;
-  if ((rc = reset_scal(c))) return rc;
-  if ((rc = launch_simulate(c, N, seed, iter, 0, dX, didx, dflg))) return rc;
-  // X and idx are final after the sampler: copy them out on the copy stream
-  // while the likelihood kernel runs
-  if (hX || hidx) {
-    CUDA_OK(c, cudaEventRecord(c->ev_a, c->stream));
-    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_a, 0));
-    if (hX) CUDA_OK(c, cudaMemcpyAsync(hX, dX, n1 * d * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
-    if (hidx) CUDA_OK(c, cudaMemcpyAsync(hidx, didx, n1 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
-  }
-  if ((rc = launch_posterior(c, N, dX, dflg, (double *)c->sLogpi.p, (int32_t *)c->sErr.p))) return rc;
-  if ((rc = launch_weights(c, N, dX, (double *)c->sLogpi.p, (int32_t *)c->sErr.p, beta, dflg, dlogw))) return rc;
-  if (hflg) {     // flags are final after the weight stage
-    CUDA_OK(c, cudaEventRecord(c->ev_b, c->stream));
-    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_b, 0));
-    CUDA_OK(c, cudaMemcpyAsync(hflg, dflg, n1 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->copy_stream));
-  }
-  if ((rc = launch_em_local(c, N, dX, didx, dflg, dlogw, dblock))) return rc;
+  if ((rc = ensure(c, c->sBlock, (size_t)stat_len(c->h.K, c->h.d) * sizeof(double)))) return rc;
+  double *dblock = (double *)c->sBlock.p;
+  if ((rc = iteration_core(c, N, seed, iter, 0, beta, nullptr, nullptr, nullptr, nullptr, dblock, hX, hidx, hflg))) return rc;
   rc = pmcb200_em_finish(c, 1, dblock, N, stats);
-  if (rc == 0 && hw) {
-    if ((rc = pmcb200_normalize_weights(c, N, dflg, dlogw)) == 0) {
-      cudaError_t e = cudaMemcpyAsync(hw, dlogw, n1 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-      if (e != cudaSuccess) rc = fail(c, PMCB200_ERR_CUDA, "D2H weights: %s", cudaGetErrorString(e));
-    }
-  }
+  if (rc == 0 && hw) rc = pmcb200_shard_weights_host(c, N, hw);
   cudaStreamSynchronize(c->copy_stream);
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return rc;

@@ -157,6 +157,16 @@ class PMC:
         self._ck(rc)
         return self.last_stats
 
+    def iteration_shard_host(self, N, seed, it, offset, beta, block, hX=None, hidx=None, hflg=None):
+        def hp(a):
+            return None if a is None else C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+        self._ck(self.lib.pmcb200_iteration_shard_host(self.h, N, seed, it, offset, beta, hp(hX), hp(hidx),
+                                                        hp(hflg), _dp(block)))
+
+    def shard_weights_host(self, N, hw):
+        p = C.c_void_p(hw.data_ptr() if isinstance(hw, torch.Tensor) else hw.ctypes.data)
+        self._ck(self.lib.pmcb200_shard_weights_host(self.h, N, p))
+
     def launch_count(self):
         return int(self.lib.pmcb200_launch_count(self.h))
 

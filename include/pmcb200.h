@@ -268,6 +268,15 @@ int pmcb200_iteration_local(pmcb200_ctx *ctx, int64_t N, uint64_t seed,
                             uint32_t iter, int64_t offset, double beta,
                             double *dX, int32_t *didx, int16_t *dflg,
                             double *dlogw, double *dblock);
+/* Multi-GPU with HOST buffers: one rank's shard; X / idx / flg are copied to the
+ * host on a copy stream while the likelihood kernel runs.  The caller then
+ * all-gathers dblock, calls pmcb200_em_finish, and fetches the shard's
+ * NORMALISED weights with pmcb200_shard_weights_host (which also waits for the
+ * outstanding copies). */
+int pmcb200_iteration_shard_host(pmcb200_ctx *ctx, int64_t N, uint64_t seed, uint32_t iter,
+                                 int64_t offset, double beta, double *hX, int32_t *hidx,
+                                 int16_t *hflg, double *dblock);
+int pmcb200_shard_weights_host(pmcb200_ctx *ctx, int64_t N, double *hw);
 /* Single-GPU, HOST buffers, what the pmclib-named shims call: proposal is
  * taken from ctx; fills the pmc_simu arrays on the host (any may be NULL to
  * skip the copy) and updates the proposal.  hw receives NORMALISED weights
