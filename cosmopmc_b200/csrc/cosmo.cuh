@@ -279,34 +279,35 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
     const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
     const double2 n0 = __ldg(&nd[0]);
     const double az = n0.x, h = 1.0 - az;
-    // trapezoid stages 1..5 (17 integrand evaluations), Romberg tableau by rows:
+    // trapezoid stages 1..5: the 16 tabulated nodes are independent evaluations
+    // (issued together for ILP), then the Romberg tableau by rows:
     // R[m] <- T_{j,m} = T_{j,m-1} + (T_{j,m-1} - T_{j-1,m-1}) / (4^m - 1)
-    double R0, R1, R2, R3, st;
-    st = 0.5 * h * (sn_f<HASQ, FLAT, SLOW>(ec, T, n0) + f1);
+    double fv[16];
+    fv[0] = sn_f<HASQ, FLAT, SLOW>(ec, T, n0);
+#pragma unroll
+    for (int i = 1; i < 16; i++) fv[i] = sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
+    double R0, R1, R2, R3, st, ss, dss;
+    st = 0.5 * h * (fv[0] + f1);
     R0 = st;
-    st = 0.5 * fma(h, sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[1])), st);
+    st = 0.5 * fma(h, fv[1], st);
     { double n1 = fma(st - R0, 1.0 / 3.0, st); R0 = st; R1 = n1; }
     {
-      double s = sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[2]));
-      s += sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[3]));
+      double s = fv[2] + fv[3];
       st = 0.5 * fma(h * 0.5, s, st);
       double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1);
       R0 = st; R1 = n1; R2 = n2;
     }
     {
-      double s = 0.0;
-#pragma unroll
-      for (int i = 4; i < 8; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
+      double s = ((fv[4] + fv[5]) + fv[6]) + fv[7];
       st = 0.5 * fma(h * 0.25, s, st);
       double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
              n3 = fma(n2 - R2, 1.0 / 63.0, n2);
       R0 = st; R1 = n1; R2 = n2; R3 = n3;
     }
-    double ss, dss;
     {
-      double s = 0.0;
+      double s = fv[8];
 #pragma unroll
-      for (int i = 8; i < 16; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
+      for (int i = 9; i < 16; i++) s += fv[i];
       st = 0.5 * fma(h * 0.125, s, st);
       double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
              n3 = fma(n2 - R2, 1.0 / 63.0, n2);
