@@ -24,7 +24,7 @@ UNITS = [("pmcb200.o", "pmcb200.cu", []),
 HOST = os.path.join(HERE, "host")
 INC = os.path.join(os.path.dirname(HERE), "include")
 GCC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-HOST_UNITS = ["errorlist.c", "gsl_shim.c", "mvdens.c", "pmc.c"]
+HOST_UNITS = ["errorlist.c", "gsl_shim.c", "mvdens.c", "pmc.c", "io.c", "maths.c", "pmc_mpi.c", "nicaea.c"]
 
 
 def _compile_host(src):

@@ -157,6 +157,19 @@ static void activate_target(pmcb200_ctx *ctx, posterior_log_pdf_func *f, void *d
          }
          return;
       }
+   {  /* not registered: give the caller-side glue a chance to flatten its own config */
+      static pmcb200_target_t t;
+      memset(&t, 0, sizeof(t));
+      int bound = pmc_b200_autobind(f, data, &t, err);
+      forwardError(*err, __LINE__, );
+      if (bound) {
+         pmc_b200_register_target(f, data, &t, err);
+         forwardError(*err, __LINE__, );
+         activate_target(ctx, f, data, err);
+         forwardError(*err, __LINE__, );
+         return;
+      }
+   }
    *err = addError(pmc_undef, "No device target registered for this posterior callback "
                    "(pmc_b200_register_target); the scalar host callback cannot be batched and there is no CPU path",
                    *err, __LINE__);
@@ -235,6 +248,43 @@ static void push_samples(pmcb200_ctx *ctx, pmc_simu *p, int with_idx, int with_w
       free(t);
       B200_OK(ctx, rc, pmc_badComm, );
    }
+}
+
+__attribute__((weak)) int pmc_b200_autobind(posterior_log_pdf_func *f, void *data, pmcb200_target_t *t, error **err)
+{
+   (void)f; (void)data; (void)t; (void)err;
+   return 0;
+}
+
+/* one log-likelihood on the device with N = 1 (own context, so the PMC run's
+ * target stays resident).  Box = [x-1/2, x+1/2] so the flat-prior term is 0. */
+double pmc_b200_single_loglike(const pmcb200_like_t *like, const double *x, error **err)
+{
+   static pmcb200_ctx *ctx1 = NULL;
+   static void *dx = NULL, *dlp = NULL, *derr = NULL;
+   if (!ctx1) {
+      const char *e = getenv("PMCB200_DEVICE");
+      int rc = pmcb200_create(e ? atoi(e) : 0, NULL, &ctx1);
+      if (rc != 0) { ctx1 = NULL;
+         *err = addErrorVA(pmc_undef, "No usable CUDA device (pmcb200 code %d); no CPU path", *err, __LINE__, rc);
+         return 0.0; }
+      pmcb200_dev_alloc(ctx1, sizeof(double) * PMCB200_MAX_DIM, &dx);
+      pmcb200_dev_alloc(ctx1, sizeof(double), &dlp);
+      pmcb200_dev_alloc(ctx1, sizeof(int32_t), &derr);
+   }
+   static pmcb200_target_t t;
+   memset(&t, 0, sizeof(t));
+   t.npar = like->npar; t.ndata = 1; t.like[0] = *like;
+   for (int j = 0; j < like->npar; j++) { t.min[j] = x[j] - 0.5; t.max[j] = x[j] + 0.5; }
+   B200_OK(ctx1, pmcb200_set_target(ctx1, &t), pmc_incompat, 0.0);
+   B200_OK(ctx1, pmcb200_h2d(ctx1, dx, x, sizeof(double) * like->npar), pmc_badComm, 0.0);
+   B200_OK(ctx1, pmcb200_posterior_log_pdf(ctx1, 1, (double *)dx, (double *)dlp, (int32_t *)derr), pmc_undef, 0.0);
+   double lp = 0.0; int32_t e1 = 0;
+   B200_OK(ctx1, pmcb200_d2h(ctx1, &lp, dlp, sizeof(double)), pmc_badComm, 0.0);
+   B200_OK(ctx1, pmcb200_d2h(ctx1, &e1, derr, sizeof(int32_t)), pmc_badComm, 0.0);
+   testErrorRet(e1 != 0, pmc_infnan, "Likelihood could not be evaluated for this model (unphysical distance integral)",
+                *err, __LINE__, 0.0);
+   return lp;
 }
 
 /* ---- simulate_mix_mvdens (cosmo_pmc.c:320) -------------------------------------------- */

@@ -21,7 +21,6 @@ extern "C" {
 #define MC_AF_REJECT  0
 #define MC_NORM       0     /* perplexity_and_ess: normalise the weights first   */
 #define MC_UNORM      1     /* weights are already normalised (cosmo_pmc.c:46)   */
-#define MC_LOGBIG     1.0e30
 #define MINCOUNT      PMCB200_MINCOUNT
 
 /* The sample container.  Field names and meanings are ABI: the reference reads
@@ -94,6 +93,16 @@ pmcb200_ctx *pmc_b200_context(error **err);          /* lazily created; device =
 void pmc_b200_shutdown(void);
 void pmc_b200_register_target(posterior_log_pdf_func *posterior_log_pdf, void *target_data,
                               const pmcb200_target_t *t, error **err);
+/* Auto-binding hook: called for a (callback, data) pair that has no registered
+ * target.  The library's weak default returns 0 (=> pmc_undef).  A glue unit
+ * compiled against the caller's headers (cosmopmc_b200/glue/pmcb200_glue.c for
+ * CosmoPMC's config_base) overrides it, fills *t and returns 1, which lets the
+ * UNCHANGED exec/cosmo_pmc.c run on the device path. */
+int pmc_b200_autobind(posterior_log_pdf_func *posterior_log_pdf, void *target_data, pmcb200_target_t *t,
+                      error **err);
+/* one log-likelihood on the device (N = 1), used by the scalar nicaea-named
+ * functions (chi2_SN, chi2_bao_*, chi2_cmbDP); x has like->npar entries */
+double pmc_b200_single_loglike(const pmcb200_like_t *like, const double *x, error **err);
 /* whole iteration on a host psim + proposal in one call (the fast path used by
  * a binding that replaces the body of run_pmc_iteration_MPI) */
 size_t pmc_b200_iteration(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, double beta,

@@ -50,26 +50,28 @@ error *unmanagedError(void);
 #define addErrorVA(errV, fmt, prev, li, ...) newErrorVA((errV), _PMC_WHERE(li), (fmt), (prev), __VA_ARGS__)
 #define topError(errV, txt, li) newError((errV), _PMC_WHERE(li), (txt), NULL)
 
+/* The macros are plain brace blocks (not do-while): the reference uses them both
+ * with and without a trailing semicolon (wrappers/src/param.c:1345). */
 #define forwardError(err, li, ret) \
-  do { if (_isError(err)) { (err) = newError(forwardErr, _PMC_WHERE(li), "", (err)); return ret; } } while (0)
+  { if (_isError(err)) { (err) = newError(forwardErr, _PMC_WHERE(li), "", (err)); return ret; } }
 #define forwardErrorNoReturn(err, li) \
-  do { if (_isError(err)) { (err) = newError(forwardErr, _PMC_WHERE(li), "", (err)); } } while (0)
+  { if (_isError(err)) { (err) = newError(forwardErr, _PMC_WHERE(li), "", (err)); } }
 #define testErrorRet(test, errV, txt, err, li, ret) \
-  do { if (test) { (err) = newError((errV), _PMC_WHERE(li), (txt), (err)); return ret; } } while (0)
+  { if (test) { (err) = newError((errV), _PMC_WHERE(li), (txt), (err)); return ret; } }
 #define testErrorRetVA(test, errV, fmt, err, li, ret, ...) \
-  do { if (test) { (err) = newErrorVA((errV), _PMC_WHERE(li), (fmt), (err), __VA_ARGS__); return ret; } } while (0)
+  { if (test) { (err) = newErrorVA((errV), _PMC_WHERE(li), (fmt), (err), __VA_ARGS__); return ret; } }
 #define testError(test, errV, txt, err, li) testErrorRet(test, errV, txt, err, li, )
 #define exitOnError(err, F) \
-  do { if (_isError(err)) { printError((F), (err)); exit(getErrorValue(err)); } } while (0)
+  { if (_isError(err)) { printError((F), (err)); exit(getErrorValue(err)); } }
 #define quitOnError(err, li, F) \
-  do { if (_isError(err)) { (err) = newError(forwardErr, _PMC_WHERE(li), "", (err)); printError((F), (err)); exit(getErrorValue(err)); } } while (0)
+  { if (_isError(err)) { (err) = newError(forwardErr, _PMC_WHERE(li), "", (err)); printError((F), (err)); exit(getErrorValue(err)); } }
 #define quitOnErrorStr(err, li, F, str) \
-  do { if (_isError(err)) { fprintf((F), "%s\n", (str)); quitOnError(err, li, F); } } while (0)
+  { if (_isError(err)) { fprintf((F), "%s\n", (str)); quitOnError(err, li, F); } }
 /* print and drop the error, continue (manual.tex:507-520) */
 #define ParameterErrorVerb(err, param, quiet, ndim) \
-  do { if (_isError(err)) { if (!(quiet)) { int i_; fprintf(stderr, "Error at parameter ("); \
+  { if (_isError(err)) { if (!(quiet)) { int i_; fprintf(stderr, "Error at parameter ("); \
          for (i_ = 0; i_ < (int)(ndim); i_++) fprintf(stderr, "%g ", (param)[i_]); fprintf(stderr, "): "); \
-         printError(stderr, (err)); } purgeError(&(err)); } } while (0)
+         printError(stderr, (err)); } purgeError(&(err)); } }
 
 /* allocation / file helpers (pmctools/io.h in upstream) */
 void *malloc_err(size_t sz, error **err);
@@ -111,6 +113,22 @@ FILE *fopen_err(const char *name, const char *mode, error **err);
 #define pmc_infinite (-17 + pmc_base)
 #define pmc_isLog    (-18 + pmc_base)
 #define pmc_tooManySteps (-19 + pmc_base)
+#define math_base         (-500)
+#define math_negative     (-1 + math_base)
+#define math_singularValue (-2 + math_base)
+#define math_tooManySteps (-3 + math_base)
+#define math_underflow    (-4 + math_base)
+#define math_infnan       (-5 + math_base)
+#define math_wrongValue   (-6 + math_base)
+#define math_alloc        (-7 + math_base)
+#define math_interpoloutofrange (-8 + math_base)
+#define math_interpol2small (-9 + math_base)
+#define math_interpol2big (-10 + math_base)
+#define math_stackTooSmall (-11 + math_base)
+#define math_overflow     (-12 + math_base)
+#define math_unknown      (-13 + math_base)
+
+#define tls_base     (-700)
 #define pb_base      (-6100)
 #define pb_allocate  (-1 + pb_base)
 #define pb_outOfBound (-2 + pb_base)

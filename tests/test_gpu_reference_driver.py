@@ -1,0 +1,63 @@
+"""End-to-end: the reference's OWN, UNCHANGED PMC driver (exec/cosmo_pmc.c +
+wrappers/ + tools/, compiled where they lie by tools/build_ref_cosmo_pmc.py and
+linked against libpmc_b200.so) runs the SN Ia demo (Demo/MC_Demo/SN) on the GPU.
+
+The binary and the demo inputs are built in the container (they derive from the
+reference tree, so they are git-ignored) and travel to the GPU box; the test is
+skipped where they are absent.  Checks are the reference's own documented
+diagnostics: perplexity >= 0.8 and ENC >= 1.5 mean "explored sufficiently"
+(README.md:166-169), and the posterior mean must agree with the SN posterior
+printed in the manual (Manual/manual.tex:3226-3234)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from cosmopmc_b200 import _abi as A
+from cosmopmc_b200 import targets as T
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(A.ROOT, "build_ref", "cosmo_pmc")
+DEMO = os.path.join(A.ROOT, "build_ref", "demo_SN")
+
+
+def write_fisher(path):
+    """stands for max_post + go_fishing (exec/go_fishing.c): inverse of the manual's SN covariance"""
+    F = np.linalg.inv(T.SN_POST_COV)
+    with open(path, "w") as f:
+        f.write("5 -1 5 0\n" + " ".join("%.10g" % v for v in T.SN_POST_MEAN) + "\n")
+        for r in F:
+            f.write(" ".join("%.10g" % v for v in r) + "\n")
+
+
+@pytest.mark.skipif(not (os.path.exists(EXE) and os.path.isdir(DEMO)),
+                    reason="build_ref/cosmo_pmc not built (tools/build_ref_cosmo_pmc.py, container only)")
+def test_unchanged_reference_driver_runs_sn_demo(tmp_path):
+    run = tmp_path / "run"
+    shutil.copytree(DEMO, run, ignore=shutil.ignore_patterns("iter_*", "perplexity", "enc", "evidence*", "log_pmc",
+                                                             "temperature", "proposal_fin", "run.log"))
+    write_fisher(run / "fisher")
+    out = subprocess.run([EXE, "-c", "config_pmc", "-s", "1", "-q"], cwd=run, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    perp = np.loadtxt(run / "perplexity")
+    enc = np.loadtxt(run / "enc")
+    assert perp.shape == (18, 5) and enc.shape == (19, 2)          # niter 18 (config_pmc:29)
+    assert perp[-1, 1] == 190000                                     # 17 x 10000 + 2 x 10000 (fsfinal 2)
+    assert perp[-1, 2] >= 0.8 and perp[0, 2] < perp[-1, 2]           # README.md:166-169
+    assert enc[-1, 1] >= 1.5
+    assert np.all(np.isfinite(np.loadtxt(run / "evidence")))
+    # weighted mean of the final sample (exec/exec_helper.c:63-119) vs the manual's posterior
+    rows = [l.split() for l in open(run / "iter_17" / "mean") if not l.startswith("#")]
+    mean = np.array([float(r[2]) for r in rows])
+    sig = np.sqrt(np.diag(T.SN_POST_COV))
+    assert np.all(np.abs(mean - T.SN_POST_MEAN) < 1.0 * sig), (mean, T.SN_POST_MEAN, sig)
+    # pmcsim format: 2 header lines, then log w, -component, 5 parameters (exec_helper.c:351-424)
+    lines = open(run / "iter_17" / "pmcsim").read().split("\n")
+    assert lines[0].startswith("# npar = 5, n_ded = 0") and len(lines[2].split()) == 7
+    # resume path (cosmo_pmc.c:680-704): a second run re-reads iter_*/pmcsim + proposal instead of re-running
+    out2 = subprocess.run([EXE, "-c", "config_pmc", "-s", "1", "-q"], cwd=run, capture_output=True, text=True, timeout=600)
+    assert out2.returncode == 0, out2.stdout[-2000:] + out2.stderr[-2000:]
+    perp2 = np.loadtxt(run / "perplexity")
+    assert np.allclose(perp2[:, 2], perp[:, 2], rtol=2e-4)           # recomputed from the 9-digit text files
