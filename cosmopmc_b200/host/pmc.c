@@ -515,7 +515,10 @@ pmc_simu *pmc_simu_from_file(FILE *F, int nsamples, int npar, int n_ded, mix_mvd
       n++;
    }
    testErrorRet(n == 0, pmc_nosamplep, "No sample point in pmcsim file", *err, __LINE__, NULL);
-   p->nsamples = n; p->isLog = 1; p->maxW = maxW;
+   /* nsamples stays the number of DRAWS (the file holds the flagged points only; the tail has flg = 0),
+      so perplexity / evidence keep their denominators across a restart */
+   for (long i = n; i < nsamples; i++) { p->flg[i] = 0; p->weights[i] = 0.0; p->indices[i] = 0; }
+   p->isLog = 1; p->maxW = maxW;
    normalize_importance_weight(p, err);
    forwardError(*err, __LINE__, NULL);
    if (nclipw > 0) { clip_weights(p, nclipw, NULL, err); forwardError(*err, __LINE__, NULL); }

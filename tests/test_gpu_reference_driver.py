@@ -53,9 +53,9 @@ def test_unchanged_reference_driver_runs_sn_demo(tmp_path):
     mean = np.array([float(r[2]) for r in rows])
     sig = np.sqrt(np.diag(T.SN_POST_COV))
     assert np.all(np.abs(mean - T.SN_POST_MEAN) < 1.0 * sig), (mean, T.SN_POST_MEAN, sig)
-    # pmcsim format: 2 header lines, then log w, -component, 5 parameters (exec_helper.c:351-424)
+    # pmcsim format: 3 header lines, then log w, -component, 5 parameters (exec_helper.c:351-424)
     lines = open(run / "iter_17" / "pmcsim").read().split("\n")
-    assert lines[0].startswith("# npar = 5, n_ded = 0") and len(lines[2].split()) == 7
+    assert lines[0].startswith("# npar = 5, n_ded = 0") and len(lines[3].split()) == 7
     # resume path (cosmo_pmc.c:680-704): a second run re-reads iter_*/pmcsim + proposal instead of re-running
     out2 = subprocess.run([EXE, "-c", "config_pmc", "-s", "1", "-q"], cwd=run, capture_output=True, text=True, timeout=600)
     assert out2.returncode == 0, out2.stdout[-2000:] + out2.stderr[-2000:]
