@@ -61,3 +61,38 @@ def test_unchanged_reference_driver_runs_sn_demo(tmp_path):
     assert out2.returncode == 0, out2.stdout[-2000:] + out2.stderr[-2000:]
     perp2 = np.loadtxt(run / "perplexity")
     assert np.allclose(perp2[:, 2], perp[:, 2], rtol=2e-4)           # recomputed from the 9-digit text files
+
+
+def _run_tempering_demo(name, fisher_mean, fisher_invcov, tmp_path, seed):
+    demo = os.path.join(A.ROOT, "build_ref", "demo_" + name)
+    if not (os.path.exists(EXE) and os.path.isdir(demo)):
+        pytest.skip("build_ref not built (container only)")
+    run = tmp_path / name
+    shutil.copytree(demo, run, ignore=shutil.ignore_patterns("iter_*", "perplexity", "enc", "evidence*", "log_pmc",
+                                                             "temperature", "proposal_fin"))
+    with open(run / "fisher", "w") as f:        # stands for max_post + go_fishing at the peak
+        d = len(fisher_mean)
+        f.write("%d -1 %d 0\n" % (d, d) + " ".join("%g" % v for v in fisher_mean) + "\n")
+        for r in fisher_invcov:
+            f.write(" ".join("%g" % v for v in r) + "\n")
+    out = subprocess.run([EXE, "-c", "config_pmc", "-s", str(seed), "-q"], cwd=run, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    return np.loadtxt(run / "evidence"), np.loadtxt(run / "perplexity")
+
+
+def test_reference_driver_tempering_demo_gaussian_evidence(tmp_path):
+    """Demo/tempering/README.md:11-36: normalised 2-D Gaussian on the unit square =>
+    the file `evidence` 'should be consistent with 1'."""
+    evi, perp = _run_tempering_demo("1_mvnorm_2D_temp_none", [0.5, 0.5], [[100.0, 0.0], [0.0, 50.0]], tmp_path, 3)
+    assert evi.shape[0] == 5
+    assert abs(evi[-1, 3] - 1.0) < 0.05                # 5000 samples in the final iteration
+    assert perp[-1, 2] > 0.8
+
+
+def test_reference_driver_tempering_demo_mixture_evidence(tmp_path):
+    """Demo/tempering/README.md:64-106: two separated modes => evidence approaches 1 (both
+    modes found) or 0.5 (one mode); quoted runs 0.998802, 0.50055, 0.499927."""
+    evi, perp = _run_tempering_demo("2_mixmvnorm_2D_temp_none", [0.2, 0.2], [[500.0, 0.0], [0.0, 500.0]], tmp_path, 5)
+    e = evi[-1, 3]
+    assert abs(e - 1.0) < 0.05 or abs(e - 0.5) < 0.03, e

@@ -52,6 +52,11 @@ def build():
     for f in ["Demo/MC_Demo/SN/config_pmc", "data/Sn/Union/sne_union_marek.list", "par_files/cosmo_SN.par",
               "par_files/cosmo.par"]:
         shutil.copy(os.path.join(REF, f), demo)
+    # the tempering demos (Demo/tempering/README.md: evidence known answers)
+    for sub in ["1_mvnorm_2D_temp_none", "2_mixmvnorm_2D_temp_none"]:
+        dst = os.path.join(OUT, "demo_" + sub)
+        os.makedirs(dst, exist_ok=True)
+        shutil.copy(os.path.join(REF, "Demo/tempering", sub, "config_pmc"), dst)
     return exe
 
 
