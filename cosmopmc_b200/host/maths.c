@@ -152,3 +152,46 @@ void indexx(unsigned long n, double arr[], unsigned long indx[], error **err)
       indx[j] = t;
    }
 }
+
+/* Ridders' method (NR dfridr) on the symmetric 4-point estimate of d^2 f/dx_a dx_b */
+static double mixed_stencil(double (*func)(void *, const double *, error **), int a, int b, double *x, double ha,
+                            double hb, void *extra, error **err)
+{
+   double xa = x[a], xb = x[b], f[4];
+   const int sg[4][2] = {{+1, +1}, {+1, -1}, {-1, +1}, {-1, -1}};
+   for (int j = 0; j < 4; j++) {
+      x[a] = xa; x[b] = xb;
+      x[a] += sg[j][0] * ha;
+      x[b] += sg[j][1] * hb;      /* a == b: x_a +- 2h or x_a, the second-difference stencil */
+      f[j] = func(extra, x, err);
+      if (isError(*err)) { x[a] = xa; x[b] = xb; return 0.0; }
+   }
+   x[a] = xa; x[b] = xb;
+   return (f[0] - f[1] - f[2] + f[3]) / (4.0 * ha * hb);
+}
+
+double nd_dfridr2(double (*func)(void *, const double *, error **), int a, int b, double *x, double ha, double hb,
+                  void *extra, double *errn, error **err)
+{
+   enum { NTAB = 8 };
+   const double CON = 1.4, CON2 = CON * CON, SAFE = 2.0;
+   double A[NTAB][NTAB], ans = 0.0;
+   testErrorRet(ha == 0.0 || hb == 0.0, math_wrongValue, "Step size must be non-zero", *err, __LINE__, 0.0);
+   A[0][0] = mixed_stencil(func, a, b, x, ha, hb, extra, err);
+   forwardError(*err, __LINE__, 0.0);
+   *errn = 1.0e30;
+   for (int i = 1; i < NTAB; i++) {
+      ha /= CON; hb /= CON;
+      A[0][i] = mixed_stencil(func, a, b, x, ha, hb, extra, err);
+      forwardError(*err, __LINE__, 0.0);
+      double fac = CON2;
+      for (int j = 1; j <= i; j++) {
+         A[j][i] = (A[j - 1][i] * fac - A[j - 1][i - 1]) / (fac - 1.0);
+         fac = CON2 * fac;
+         double errt = fmax(fabs(A[j][i] - A[j - 1][i]), fabs(A[j][i] - A[j - 1][i - 1]));
+         if (errt <= *errn) { *errn = errt; ans = A[j][i]; }
+      }
+      if (fabs(A[i][i] - A[i - 1][i - 1]) >= SAFE * (*errn)) break;
+   }
+   return ans;
+}

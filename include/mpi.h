@@ -11,4 +11,15 @@ static inline int MPI_Init(int *argc, char ***argv) { (void)argc; (void)argv; re
 static inline int MPI_Comm_rank(MPI_Comm c, int *rank) { (void)c; *rank = 0; return MPI_SUCCESS; }
 static inline int MPI_Comm_size(MPI_Comm c, int *size) { (void)c; *size = 1; return MPI_SUCCESS; }
 static inline int MPI_Finalize(void) { return MPI_SUCCESS; }
+/* point-to-point calls of exec/go_fishing.c:179-185,397-408: unreachable with size == 1 */
+typedef int MPI_Datatype;
+typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR; } MPI_Status;
+#define MPI_INT 1
+#define MPI_DOUBLE 2
+#define MPI_STATUS_IGNORE ((MPI_Status *)0)
+static inline int MPI_Send(const void *b, int n, MPI_Datatype t, int dest, int tag, MPI_Comm c)
+{ (void)b; (void)n; (void)t; (void)dest; (void)tag; (void)c; return 1; }
+static inline int MPI_Recv(void *b, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Status *s)
+{ (void)b; (void)n; (void)t; (void)src; (void)tag; (void)c; (void)s; return 1; }
+static inline int MPI_Barrier(MPI_Comm c) { (void)c; return MPI_SUCCESS; }
 #endif

@@ -14,5 +14,7 @@
 #define mcmc_file      (-6 + mcmc_base)
 #define mcmc_unknown   (-7 + mcmc_base)
 #define mcmc_outOfBound (-8 + mcmc_base)
+#define mcmc_tooManySteps (-9 + mcmc_base)
+#define mcmc_undef     (-10 + mcmc_base)
 #define MC_AF_ACCEPT 1
 #endif

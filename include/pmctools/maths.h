@@ -34,6 +34,10 @@ double  sm2_inverse(double *C, int N, error **err);
 void    jacobi_transform(double *a, int n, double *d, double **v, int *nrot, error **err);
 /* NR indexx: 1-based arrays arr[1..n], indx[1..n]; ascending */
 void    indexx(unsigned long n, double arr[], unsigned long indx[], error **err);
+/* mixed second derivative d^2 f / dx_a dx_b by Ridders' extrapolation of the 4-point
+ * central stencil (exec/go_fishing.c:26); errn = error estimate */
+double  nd_dfridr2(double (*func)(void *, const double *, error **), int a, int b, double *x, double ha, double hb,
+                   void *extra, double *errn, error **err);
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@
 #define ABS(a) ((a) < 0 ? -(a) : (a))
 #define MIN(a, b) ((a) < (b) ? (a) : (b))
 #define MAX(a, b) ((a) > (b) ? (a) : (b))
+#define SIGN(a, b) ((b) >= 0.0 ? fabs(a) : -fabs(a))
 #define DSQR(a) ((a) * (a))
 #define dsqr(a) ((a) * (a))
 #define DCUB(a) ((a) * (a) * (a))

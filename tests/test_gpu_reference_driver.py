@@ -96,3 +96,39 @@ def test_reference_driver_tempering_demo_mixture_evidence(tmp_path):
     evi, perp = _run_tempering_demo("2_mixmvnorm_2D_temp_none", [0.2, 0.2], [[500.0, 0.0], [0.0, 500.0]], tmp_path, 5)
     e = evi[-1, 3]
     assert abs(e - 1.0) < 0.05 or abs(e - 0.5) < 0.03, e
+
+
+def test_full_reference_pipeline_max_fisher_pmc(tmp_path):
+    """bin/cosmo_pmc.pl:103-137 end to end with the reference's unchanged executables:
+    max_post (amoeba) -> config_pmc_to_max_and_fish.pl -> go_fishing -> cosmo_pmc.  Every scalar
+    likelihood call of max_post / go_fishing runs the batched CUDA kernels with N = 1."""
+    ref = os.path.join(A.ROOT, "build_ref")
+    pipe = os.path.join(ref, "demo_SN_pipeline")
+    need = [os.path.join(ref, f) for f in ("cosmo_pmc", "max_post", "go_fishing", "config_pmc_to_max_and_fish.pl")]
+    if not (all(os.path.exists(f) for f in need) and os.path.isdir(pipe) and shutil.which("perl")):
+        pytest.skip("build_ref pipeline not built (container only)")
+    run = tmp_path / "pipe"
+    shutil.copytree(pipe, run, ignore=shutil.ignore_patterns("iter_*", "perplexity", "enc", "evidence*", "log_*",
+                                                             "temperature", "proposal_fin", "maxlogP", "fisher",
+                                                             "config_fish"))
+    r = subprocess.run([need[1], "-t", "-m", "a", "-s", "1"], cwd=run, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and (run / "maxlogP").exists(), r.stdout[-2000:] + r.stderr[-2000:]
+    tok = open(run / "maxlogP").read().split()
+    maxlogp = float(tok[tok.index("=") + 1])
+    best = np.array([float(v) for v in tok[-5:]])
+    assert -182.0 < maxlogp < -176.0
+    assert np.all(np.abs(best - T.SN_POST_MEAN) < 2.0 * np.sqrt(np.diag(T.SN_POST_COV)))
+    with open(run / "config_fish", "w") as fo:
+        subprocess.check_call(["perl", need[3], "-F", "-p", "maxlogP", "-c", "config_pmc"], cwd=run, stdout=fo)
+    r = subprocess.run([need[2], "-q"], cwd=run, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and (run / "fisher").exists(), r.stdout[-2000:] + r.stderr[-2000:]
+    tok = open(run / "fisher").read().split()
+    F = np.array([float(v) for v in tok[9:34]]).reshape(5, 5)
+    assert np.allclose(F, F.T, rtol=1e-3) and np.all(np.linalg.eigvalsh(F) > 0)
+    # the Fisher matrix is the inverse posterior covariance to within the posterior's non-Gaussianity
+    sig_f = np.sqrt(np.diag(np.linalg.inv(F)))
+    assert np.all(sig_f < 1.5 * np.sqrt(np.diag(T.SN_POST_COV))) and np.all(sig_f > 0.3 * np.sqrt(np.diag(T.SN_POST_COV)))
+    r = subprocess.run([need[0], "-c", "config_pmc", "-s", "1", "-q"], cwd=run, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    perp = np.loadtxt(run / "perplexity")
+    assert perp[-1, 2] >= 0.8 and np.loadtxt(run / "enc")[-1, 1] >= 1.5

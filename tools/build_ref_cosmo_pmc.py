@@ -44,14 +44,35 @@ def build():
         objs.append(o)
     libdir = os.path.join(ROOT, "cosmopmc_b200")
     exe = os.path.join(OUT, "cosmo_pmc")
-    subprocess.check_call([GCC, "-o", exe] + objs + ["-L", libdir, "-lpmc_b200", "-Wl,-rpath,$ORIGIN/../cosmopmc_b200",
-                                                      "-lm"])
+    link = ["-L", libdir, "-lpmc_b200", "-Wl,-rpath,$ORIGIN/../cosmopmc_b200", "-lm"]
+    subprocess.check_call([GCC, "-o", exe] + objs + link)
+    # the two executables that precede cosmo_pmc in bin/cosmo_pmc.pl:103-116 (maximum + Fisher matrix);
+    # their scalar likelihood calls run the same CUDA kernels with N = 1
+    common = [o for o in objs if not o.endswith("cosmo_pmc.o")]
+    for main_src, extra in (("exec/max_post.c", ["exec/mkmax.c"]), ("exec/go_fishing.c", ["exec/mkmax.c"])):
+        eo = []
+        for s_ in [main_src] + extra:
+            o = os.path.join(OUT, "obj", os.path.basename(s_).replace(".c", ".o"))
+            subprocess.check_call([GCC] + CFLAGS + INC + ["-c", os.path.join(REF, s_), "-o", o])
+            eo.append(o)
+        subprocess.check_call([GCC, "-o", os.path.join(OUT, os.path.basename(main_src)[:-2])] + eo + common + link)
     # the SN demo's inputs (Demo/MC_Demo/SN): config + data + parameter files, as bin/cosmo_pmc.pl stages them
     demo = os.path.join(OUT, "demo_SN")
     os.makedirs(demo, exist_ok=True)
     for f in ["Demo/MC_Demo/SN/config_pmc", "data/Sn/Union/sne_union_marek.list", "par_files/cosmo_SN.par",
               "par_files/cosmo.par"]:
         shutil.copy(os.path.join(REF, f), demo)
+    # the full pipeline of bin/cosmo_pmc.pl:103-137 (max_post -> go_fishing -> cosmo_pmc) needs the
+    # reference's config converter at run time; stage it next to the binaries
+    pipe = os.path.join(OUT, "demo_SN_pipeline")
+    os.makedirs(pipe, exist_ok=True)
+    for f in os.listdir(demo):
+        if os.path.isfile(os.path.join(demo, f)) and f not in ("fisher",):
+            shutil.copy(os.path.join(demo, f), pipe)
+    shutil.copy(os.path.join(REF, "bin/config_pmc_to_max_and_fish.pl"), OUT)
+    with open(os.path.join(pipe, "config_max"), "w") as fo:
+        subprocess.check_call(["perl", os.path.join(REF, "bin/config_pmc_to_max_and_fish.pl"), "-M", "-f",
+                               "0.3 -1.0 19.3 1.5 -2.0", "-c", os.path.join(pipe, "config_pmc")], stdout=fo)
     # the tempering demos (Demo/tempering/README.md: evidence known answers)
     for sub in ["1_mvnorm_2D_temp_none", "2_mixmvnorm_2D_temp_none"]:
         dst = os.path.join(OUT, "demo_" + sub)
