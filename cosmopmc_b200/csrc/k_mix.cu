@@ -53,7 +53,7 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
       int blocks = std::max(1, std::min(a.blocks, std::max(1, per_sm) * sms));
       if (a.nblocks_out) *a.nblocks_out = blocks;
       k_em_stats<DD><<<blocks, PMC_BLOCK, a.smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal,
-                                                         a.partials, a.linear);
+                                                         a.partials, a.linear, a.k0, a.Kg);
       break;
     }
     default:

@@ -267,10 +267,12 @@ __global__ void __launch_bounds__(PMC_BLOCK, 2)
 k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
            const double *__restrict__ X, const int32_t *__restrict__ idx,
            const int16_t *__restrict__ flg, const double *__restrict__ logw,
-           const DevScal *__restrict__ scal, double *__restrict__ partials, int linear) {
+           const DevScal *__restrict__ scal, double *__restrict__ partials, int linear, int k0, int Kg) {
+  // Kall components in the mixture; this launch accumulates the group [k0, k0 + K)
+  // (one launch unless K x 256 doubles of shared memory per array is too much)
   extern __shared__ double sm[];
   constexpr int XS = D | 1;                   // padded row stride (bank spread), compile-time
-  const int K = h.K, d = h.d, M = stat_cs(d), Mp = em_nfeat(d);
+  const int Kall = h.K, K = Kg, d = h.d, M = stat_cs(d), Mp = em_nfeat(d);
   const bool student = h.df > 0;
   const int NF = em_nf(Mp);
   const int KP = (K + EM_KCHUNK - 1) / EM_KCHUNK * EM_KCHUNK;
@@ -280,7 +282,7 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
   double *s_acc = s_x + (size_t)PMC_BLOCK * XS; // [NF][K][PMC_BLOCK] per-thread partial statistics
   unsigned long long *s_cnt = (unsigned long long *)(s_acc + (size_t)NF * K * PMC_BLOCK);   // [K] draws per component
   __shared__ double red[32];
-  const double *pivot = mix + (size_t)K * h.stride;
+  const double *pivot = mix + (size_t)Kall * h.stride;
   // linear != 0: logw holds normalised (linear) weights, as after
   // normalize_importance_weight; the shift is then 0
   const double M0 = linear ? 0.0 : dunkey(scal->max_key);
@@ -313,8 +315,8 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
       else { lw = logw[n] - M0; w = exp(lw); }
       tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT); tN += 1.0;
       double rt = 0.0;
-      for (int k = 0; k < K; k++) {
-        const double *comp = mix + (size_t)k * h.stride;
+      for (int ka = 0; ka < Kall; ka++) {
+        const double *comp = mix + (size_t)ka * h.stride;
         const double a = comp[0];
         double r = 0.0, gam = 1.0;
         if (a != 0.0) {
@@ -323,8 +325,11 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
           if (student) gam = (double)(h.df + d) / ((double)h.df + m);
         }
         rt += r;
-        s_wr[k * PMC_BLOCK + tid] = r;
-        if (student) s_wg[k * PMC_BLOCK + tid] = gam;
+        const int k = ka - k0;
+        if (k >= 0 && k < K) {
+          s_wr[k * PMC_BLOCK + tid] = r;
+          if (student) s_wg[k * PMC_BLOCK + tid] = gam;
+        }
       }
       const double sc = w / rt;
       for (int k = 0; k < K; k++) {
@@ -340,7 +345,7 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
       for (int i = 0; i < D; i++) s_x[tid * XS + i] = 0.0;
     }
     // draws per component count every flagged sample (also zero-weight ones)
-    if ((n < N) && flg[n]) atomicAdd(&s_cnt[idx[n]], 1ull);
+    if ((n < N) && flg[n]) { const int c = idx[n] - k0; if (c >= 0 && c < K) atomicAdd(&s_cnt[c], 1ull); }
     __syncthreads();
     // ---- phase 2 (rows k >= K of s_wr/s_wg are zero padding up to KP, so the
     // chunk loops need no predicates and every LDS has an immediate offset)
@@ -364,9 +369,12 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
   }
   __syncthreads();
   // ---- this block's partial: combine the G sample chunks in fixed order
-  double *P = partials + (size_t)blockIdx.x * stat_len(K, d);
+  double *P = partials + (size_t)blockIdx.x * stat_len(Kall, d) + (size_t)k0 * M;
   double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red), bN = block_sum(tN, red);
-  if (tid == 0) { P[0] = M0; P[1] = bS; P[2] = bS2; P[3] = bT; P[4] = bN; P[5] = 0; P[6] = 0; P[7] = 0; }
+  if (tid == 0) {
+    double *P0 = partials + (size_t)blockIdx.x * stat_len(Kall, d);
+    P0[0] = M0; P0[1] = bS; P0[2] = bS2; P0[3] = bT; P0[4] = bN; P0[5] = 0; P0[6] = 0; P0[7] = 0;
+  }
   for (int out = tid; out < K * M; out += PMC_BLOCK) {
     const int k = out / M, fo = out - k * M;       // fo: position in the stat block (count at 2)
     double s = 0.0;

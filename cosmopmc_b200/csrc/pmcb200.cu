@@ -283,9 +283,9 @@ static int install_proposal(pmcb200_ctx *c, int K, int d, int df, const double *
   if (K < 1 || K > PMCB200_MAX_COMP || d < 1 || d > PMCB200_MAX_DIM)
     return fail(c, PMCB200_ERR_DIM, "proposal: ncomp=%d (max %d), ndim=%d (max %d)", K, PMCB200_MAX_COMP, d,
                 PMCB200_MAX_DIM);
-  if (em_smem_bytes(K, d, df > 0) > 227 * 1024)
-    return fail(c, PMCB200_ERR_UNSUP, "proposal: K=%d, d=%d needs %zu B of shared memory in the EM kernel (max 227 KB)",
-                K, d, em_smem_bytes(K, d, df > 0));
+  if (em_smem_bytes(1, d, df > 0) > 200 * 1024)
+    return fail(c, PMCB200_ERR_UNSUP, "proposal: d=%d needs %zu B of shared memory per component in the EM kernel",
+                d, em_smem_bytes(1, d, df > 0));
   for (int k = 0; k < K; k++) {
     if (!(w[k] >= 0.0) || !std::isfinite(w[k])) return fail(c, PMCB200_ERR_ARG, "proposal weight %d = %g", k, w[k]);
     for (int i = 0; i < d; i++)
@@ -599,13 +599,19 @@ static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const in
   const int64_t len = stat_len(K, d);
   int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->em_blocks, ntiles));
-  size_t smem = em_smem_bytes(K, d, c->h.df > 0);
-  if (smem > 227 * 1024) return fail(c, PMCB200_ERR_UNSUP, "EM kernel needs %zu B shared memory", smem);
+  // component groups: one launch unless the K x 256 shared-memory arrays exceed the budget
+  int Kg = K;
+  while (Kg > 1 && em_smem_bytes(Kg, d, c->h.df > 0) > 200 * 1024) Kg = (Kg + 1) / 2;
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.idxc = didx; a.flgc = dflg; a.logwc = dlogw;
-  a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.smem = smem; a.linear = linear;
+  a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.linear = linear;
   int used = blocks;
   a.nblocks_out = &used;
-  MIX_OK(c, OP_EM, a);
+  for (int k0 = 0; k0 < K; k0 += Kg) {
+    a.k0 = k0; a.Kg = std::min(Kg, K - k0);
+    a.smem = em_smem_bytes(a.Kg, d, c->h.df > 0);
+    a.blocks = (k0 == 0) ? blocks : used;     // every group must use the same grid (shared partials layout)
+    MIX_OK(c, OP_EM, a);
+  }
   pmc_launch_em_reduce(c->d_partials, used, len, c->d_scal, N, dblock, c->stream);
   LAUNCH_OK(c);
   return 0;
