@@ -783,7 +783,6 @@ int orc_update_prop_rb(int64_t N, const double *X, const int32_t *idx,
    double *B = calloc((size_t)K * d, sizeof(double));
    double *C = calloc((size_t)K * dd, sizeof(double));
    double *rho = malloc(((size_t)N * K) * sizeof(double));   /* rho*gamma cached */
-   double *rr = malloc(((size_t)N * K) * sizeof(double));    /* rho            */
    int64_t *count = calloc(K, sizeof(int64_t));
    int64_t Nall = N;
    int ndead = 0;
@@ -812,7 +811,6 @@ int orc_update_prop_rb(int64_t N, const double *X, const int32_t *idx,
       count[idx[n]]++;
       for (int k = 0; k < K; k++) {
          double rk = r[k] / rt;
-         rr[n * K + k] = rk;
          rho[n * K + k] = rk * gam[k];
          double wr = wbar[n] * rk;
          A[k] += wr;
@@ -875,7 +873,7 @@ int orc_update_prop_rb(int64_t N, const double *X, const int32_t *idx,
       wsum += wght[k];
    }
    if (wsum > 0.0) for (int k = 0; k < K; k++) wght[k] /= wsum;
-   free(A); free(G); free(B); free(C); free(rho); free(rr); free(count);
+   free(A); free(G); free(B); free(C); free(rho); free(count);
    return ndead;
 }
 
