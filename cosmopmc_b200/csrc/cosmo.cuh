@@ -181,38 +181,77 @@ __device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t
 }
 
 // ---- fast FP64 primitives for the SN hot loop ---------------------------------
-// 2^s for |s| < 1000: s = k/16 + f with |f| <= 1/32 (one magic-number add, the
-// remainder is exact), 2^f by a degree-6 near-minimax polynomial (Chebyshev
-// interpolant, max rel. error 7.8e-18 before rounding), 2^(j/16) from a
-// 16-entry shared-memory table (16 doubles = 32 banks: conflict-free), power of
-// two by exponent-field addition.  Branch-free: 10 FP64 ops + 1 LDS.
+// 2^s for |s| < 1000: s = k/32 + f with |f| <= 1/64 (one magic-number add, the
+// remainder is exact), 2^f by a degree-5 near-minimax polynomial (Chebyshev
+// interpolant, max rel. error 1.4e-16 before rounding), 2^(j/32) from a
+// 32-entry shared-memory table, power of two by exponent-field addition.
+// Branch-free: 9 FP64 ops + 1 LDS.
 // Constants live in constant memory so DFMA takes them as c[bank][offset]
 // operands (no per-use UMOV/IMAD materialisation).
 __constant__ double EXP2C[8] = {
-    0x1.62e42fefa39fdp-1, 0x1.ebfbdff82c594p-3, 0x1.c6b08d6e8a0a6p-5, 0x1.3b2ab6fb09a33p-7,
-    0x1.5d89be630066dp-10, 0x1.430a4970f3ce1p-13,
-    422212465065984.0,              // [6] 1.5 * 2^48: ulp = 2^-4
-    0.0};
-__constant__ double EXP2T[16] = {
-    0x1.0000000000000p+0, 0x1.0b5586cf9890fp+0, 0x1.172b83c7d517bp+0, 0x1.2387a6e756238p+0,
-    0x1.306fe0a31b715p+0, 0x1.3dea64c123422p+0, 0x1.4bfdad5362a27p+0, 0x1.5ab07dd485429p+0,
-    0x1.6a09e667f3bcdp+0, 0x1.7a11473eb0187p+0, 0x1.8ace5422aa0dbp+0, 0x1.9c49182a3f090p+0,
-    0x1.ae89f995ad3adp+0, 0x1.c199bdd85529cp+0, 0x1.d5818dcfba487p+0, 0x1.ea4afa2a490dap+0};
+    0x1.62e42fefa39efp-1, 0x1.ebfbdff7fee6fp-3, 0x1.c6b08d70380bfp-5, 0x1.3b2b30255298ap-7,
+    0x1.5d885e73db266p-10,
+    211106232532992.0,              // [5] 1.5 * 2^47: ulp = 2^-5
+    0.0, 0.0};
+__constant__ double EXP2T[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0,
+    0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0,
+    0x1.3dea64c123422p+0, 0x1.44e086061892dp+0, 0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0,
+    0x1.6247eb03a5585p+0, 0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0, 0x1.ae89f995ad3adp+0,
+    0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0,
+    0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+// ln(x) for positive normal x: x = 2^e m, m in [1,2); the top five mantissa bits
+// pick c_i = 1 + (i + 1/2)/32, r = m/c_i - 1 (|r| < 1/64, one FMA with the tabulated
+// rounded reciprocal), ln m = ln c_i + log1p(r) with a degree-8 Taylor polynomial
+// (abs. error 9e-18).  12 FP64 ops instead of libdevice's ~28.
+__constant__ double LOGRC[32] = {
+    0x1.f81f81f81f820p-1, 0x1.e9131abf0b767p-1, 0x1.dae6076b981dbp-1, 0x1.cd85689039b0bp-1, 0x1.c0e070381c0e0p-1,
+    0x1.b4e81b4e81b4fp-1, 0x1.a98ef606a63bep-1, 0x1.9ec8e951033d9p-1, 0x1.948b0fcd6e9e0p-1, 0x1.8acb90f6bf3aap-1,
+    0x1.8181818181818p-1, 0x1.78a4c8178a4c8p-1, 0x1.702e05c0b8170p-1, 0x1.6816816816817p-1, 0x1.6058160581606p-1,
+    0x1.58ed2308158edp-1, 0x1.51d07eae2f815p-1, 0x1.4afd6a052bf5bp-1, 0x1.446f86562d9fbp-1, 0x1.3e22cbce4a902p-1,
+    0x1.3813813813814p-1, 0x1.323e34a2b10bfp-1, 0x1.2c9fb4d812ca0p-1, 0x1.27350b8812735p-1, 0x1.21fb78121fb78p-1,
+    0x1.1cf06ada2811dp-1, 0x1.1811811811812p-1, 0x1.135c81135c811p-1, 0x1.0ecf56be69c90p-1, 0x1.0a6810a6810a7p-1,
+    0x1.0624dd2f1a9fcp-1, 0x1.0204081020408p-1};
+__constant__ double LOGLC[32] = {   // -ln(LOGRC[i]) of the ROUNDED reciprocals
+    0x1.fc0a8b0fc03c4p-7, 0x1.77458f632dcffp-5, 0x1.341d7961bd1d0p-4, 0x1.a926d3a4ad562p-4, 0x1.0d77e7cd08e5bp-3,
+    0x1.44d2b6ccb7d1cp-3, 0x1.7ab890210d907p-3, 0x1.af3c94e80bff3p-3, 0x1.e27076e2af2e8p-3, 0x1.0a324e27390e2p-2,
+    0x1.22941fbcf7966p-2, 0x1.3a64c556945eap-2, 0x1.51aad872df82ep-2, 0x1.686c81e9b14adp-2, 0x1.7eaf83b82afc2p-2,
+    0x1.947941c2116fbp-2, 0x1.a9cec9a9a084ap-2, 0x1.beb4d9da71b7ap-2, 0x1.d32fe7e00ebd5p-2, 0x1.e744261d68789p-2,
+    0x1.faf588f78f31dp-2, 0x1.0723e5c1cdf41p-1, 0x1.109f39e2d4c96p-1, 0x1.19ee6b467c96fp-1, 0x1.23130d7bebf43p-1,
+    0x1.2c0e9ed448e8cp-1, 0x1.34e289d9ce1d2p-1, 0x1.3d9026a7156fbp-1, 0x1.4618bc21c5ec2p-1, 0x1.4e7d811b75bb0p-1,
+    0x1.56bf9d5b3f399p-1, 0x1.5ee02a9241676p-1};
+// T: shared table [32 exp2 | 32 LOGRC | 32 LOGLC]
+__device__ __forceinline__ double fast_log(double x, const double *__restrict__ T) {
+  const int hi = __double2hiint(x);
+  const int i = (hi >> 15) & 31;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double r = fma(m, T[32 + i], -1.0);
+  double q = -1.0 / 8.0;
+  q = fma(q, r, 1.0 / 7.0);
+  q = fma(q, r, -1.0 / 6.0);
+  q = fma(q, r, 1.0 / 5.0);
+  q = fma(q, r, -1.0 / 4.0);
+  q = fma(q, r, 1.0 / 3.0);
+  q = fma(q, r, -0.5);
+  q = fma(q, r, 1.0);
+  const double e = (double)((hi >> 20) - 1023);
+  return fma(e, 0.693147180559945309417, fma(q, r, T[64 + i]));
+}
 // returns sign * 2^s, sign given as an XOR mask for the high word
 __device__ __forceinline__ double fast_exp2_signed(double s, const double *__restrict__ T, unsigned sgn) {
-  double kf = s + EXP2C[6];
-  const int k16 = __double2loint(kf);
-  kf -= EXP2C[6];
+  double kf = s + EXP2C[5];
+  const int k32 = __double2loint(kf);
+  kf -= EXP2C[5];
   const double f = s - kf;
-  double p = EXP2C[5];
-  p = fma(p, f, EXP2C[4]);
+  double p = EXP2C[4];
   p = fma(p, f, EXP2C[3]);
   p = fma(p, f, EXP2C[2]);
   p = fma(p, f, EXP2C[1]);
   p = fma(p, f, EXP2C[0]);
   p = fma(p, f, 1.0);
-  p *= T[k16 & 15];
-  return __hiloint2double((__double2hiint(p) + ((k16 >> 4) << 20)) ^ sgn, __double2loint(p));
+  p *= T[k32 & 31];
+  return __hiloint2double((__double2hiint(p) + ((k32 >> 5) << 20)) ^ sgn, __double2loint(p));
 }
 // 1/sqrt(v): MUFU.RSQ64H seed (rel. error 2^-22) + one third-order step -> 2^-66.
 // v < 0 -> NaN, v = 0 -> NaN (both are the reference's error condition).
@@ -286,38 +325,33 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
     fv[0] = sn_f<HASQ, FLAT, SLOW>(ec, T, n0);
 #pragma unroll
     for (int i = 1; i < 16; i++) fv[i] = sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
-    double R0, R1, R2, R3, st, ss, dss;
-    st = 0.5 * h * (fv[0] + f1);
-    R0 = st;
-    st = 0.5 * fma(h, fv[1], st);
-    { double n1 = fma(st - R0, 1.0 / 3.0, st); R0 = st; R1 = n1; }
-    {
-      double s = fv[2] + fv[3];
-      st = 0.5 * fma(h * 0.5, s, st);
-      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1);
-      R0 = st; R1 = n1; R2 = n2;
-    }
-    {
-      double s = ((fv[4] + fv[5]) + fv[6]) + fv[7];
-      st = 0.5 * fma(h * 0.25, s, st);
-      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
-             n3 = fma(n2 - R2, 1.0 / 63.0, n2);
-      R0 = st; R1 = n1; R2 = n2; R3 = n3;
-    }
-    {
-      double s = fv[8];
+    // Stage 5 of NR qromb in closed form.  With g0 = (f(a_z) + f(1))/2 and the sums S_j of the
+    // 2^(j-1) new nodes of stage j+1, T_j = h 2^(1-j) (g0 + S_1 + .. + S_(j-1)), so the K = 5
+    // extrapolant ss = R[5][4] and dss = R[5][4] - R[5][3] are fixed linear combinations (exact
+    // rational weights of the Neville tableau for step ratios 1/4).
+    const double g0 = 0.5 * (fv[0] + f1), S1 = fv[1], S2 = fv[2] + fv[3];
+    const double S3 = ((fv[4] + fv[5]) + fv[6]) + fv[7];
+    double S4 = fv[8];
 #pragma unroll
-      for (int i = 9; i < 16; i++) s += fv[i];
-      st = 0.5 * fma(h * 0.125, s, st);
-      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1),
-             n3 = fma(n2 - R2, 1.0 / 63.0, n2);
-      dss = (n3 - R3) * (1.0 / 255.0);
-      ss = n3 + dss;
-      R0 = st; R1 = n1; R2 = n2; R3 = n3;
-    }
+    for (int i = 9; i < 16; i++) S4 += fv[i];
+    double ss = h * fma(3937.0 / 103275.0, g0, fma(3062.0 / 80325.0, S1, fma(27728.0 / 722925.0, S2,
+                    fma(22016.0 / 722925.0, S3, (65536.0 / 722925.0) * S4))));
+    double dss = h * fma(-31.0 / 206550.0, g0, fma(-73.0 / 481950.0, S1, fma(-67.0 / 722925.0, S2,
+                     fma(-424.0 / 722925.0, S3, (256.0 / 722925.0) * S4))));
     bool done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
     nev += 17;
     int j = 5;                      // stages completed
+    double R0 = 0.0, R1 = 0.0, R2 = 0.0, R3 = 0.0, st = 0.0;
+    if (!__all_sync(0xffffffffu, done)) {   // rare: rebuild the tableau row of stage 5 to continue
+      const double T1 = h * g0, T2 = 0.5 * h * (g0 + S1), T3 = 0.25 * h * (g0 + S1 + S2),
+                   T4 = 0.125 * h * (g0 + S1 + S2 + S3), T5 = 0.0625 * h * (g0 + S1 + S2 + S3 + S4);
+      double a1 = fma(T2 - T1, 1.0 / 3.0, T2);
+      double b1 = fma(T3 - T2, 1.0 / 3.0, T3), b2 = fma(b1 - a1, 1.0 / 15.0, b1);
+      double c1 = fma(T4 - T3, 1.0 / 3.0, T4), c2 = fma(c1 - b1, 1.0 / 15.0, c1), c3 = fma(c2 - b2, 1.0 / 63.0, c2);
+      double d1 = fma(T5 - T4, 1.0 / 3.0, T5), d2 = fma(d1 - c1, 1.0 / 15.0, d1), d3 = fma(d2 - c2, 1.0 / 63.0, d2);
+      (void)c3;
+      st = T5; R0 = T5; R1 = d1; R2 = d2; R3 = d3;
+    }
     while (!__all_sync(0xffffffffu, done)) {
       if (j >= ROMB_JMAX) { if (!done) { ss = NAN; done = true; } break; }
       if (!done) {
@@ -349,7 +383,7 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
     double fk = (FLAT || flat) ? ww : (ec.OK > 0.0 ? sinh(sk * ww) : sin(sk * ww)) / sk;
     if (!(fk > 0.0)) e = 1;         // also catches NaN
     // mu_th = 5 log10(fk / (az H_fid)) + 25; the az part is tabulated (nodes[.][0].y = ln az)
-    const double mu_th = fma(5.0 / M_LN10, log(fk) - n0.y, 25.0 - 5.0 * log10(SN_H_FID));
+    const double mu_th = fma(5.0 / M_LN10, (SLOW ? log(fk) : fast_log(fk, T)) - n0.y, 25.0 - 5.0 * log10(SN_H_FID));
     const int i0 = __ldg(&L.first[iz]), i1 = __ldg(&L.first[iz + 1]);
     for (int i = i0; i < i1; i++) {
       const double2 *__restrict__ r = reinterpret_cast<const double2 *>(L.sn + (size_t)i * SN_ROW);
@@ -384,8 +418,10 @@ __global__ void __launch_bounds__(SN_BLOCK, SN_MIN_BLOCKS)
 k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
           const int16_t *__restrict__ flg, double *__restrict__ logpi,
           int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow) {
-  __shared__ double T[16];
-  if (threadIdx.x < 16) T[threadIdx.x] = EXP2T[threadIdx.x];
+  __shared__ double T[96];      // [32 exp2 | 32 log reciprocals | 32 log offsets]
+  if (threadIdx.x < 32) T[threadIdx.x] = EXP2T[threadIdx.x];
+  else if (threadIdx.x < 64) T[threadIdx.x] = LOGRC[threadIdx.x - 32];
+  else if (threadIdx.x < 96) T[threadIdx.x] = LOGLC[threadIdx.x - 64];
   __syncthreads();
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = (n < N) && (!flg || flg[n]);
