@@ -63,8 +63,10 @@ def make_config(name):
         label = "20-D banana (Wraith et al. 2009), K=10"
     elif name == "sn_bao":
         spec = T.target_sn_bao_w0wa()
+        # w0 + w1 stays well below 1/3: beyond it dark energy dominates the early universe and the
+        # sound-horizon integral stops converging (up to 2^19 evaluations per sample, as in the reference)
         w, m, cov = T.proposal_generic(spec, 10, 4, [0.28, 0.72, -1.0, 0.0, 19.31, 1.4, -2.4],
-                                       [0.04, 0.06, 0.2, 0.5, 0.03, 0.1, 0.1])
+                                       [0.04, 0.06, 0.15, 0.2, 0.03, 0.1, 0.1])
         label = "SN Ia + BAO d_z, w0-wa, 7 parameters, K=10"
     else:
         spec = T.target_cmb_bao_sn()

@@ -83,104 +83,7 @@ __device__ inline int apply_params(const DevLike &L, const double *__restrict__ 
   return bad;
 }
 
-// Coefficients of a^4 E^2(a) = a (Om + OK a) + Or + Ode exp(p ln a + q g(a)),
-// g = (1-a) [linder] or (1-a)^2 [jassal].
-struct ECoef {
-  double Om, OK, Ode, Or, p, q;
-  int jassal;
-};
-__device__ __forceinline__ ECoef make_ecoef(const pmcb200_cosmo_t &c, int wOmegar) {
-  ECoef e;
-  e.Om = c.Omega_m + c.Omega_nu_mass;
-  e.OK = 1.0 - c.Omega_m - c.Omega_de - c.Omega_nu_mass;
-  e.Ode = c.Omega_de;
-  e.Or = wOmegar ? OMEGA_GAMMA_H2 * (1.0 + 0.2271 * NEFF_NU) / (c.h_100 * c.h_100) : 0.0;
-  e.jassal = (c.de_param == PMCB200_DE_jassal);
-  if (e.jassal) { e.p = 4.0 - 3.0 * (1.0 + c.w0_de); e.q = 1.5 * c.w1_de; }
-  else { e.p = 4.0 - 3.0 * (1.0 + c.w0_de + c.w1_de); e.q = -3.0 * c.w1_de; }
-  return e;
-}
-__device__ __forceinline__ double a4E2(const ECoef &e, double a, double lna) {
-  double oma = 1.0 - a;
-  double t = e.jassal ? fma(e.q * oma, oma, e.p * lna) : fma(e.q, oma, e.p * lna);
-  double de = (a > 0.0) ? e.Ode * exp(t) : 0.0;
-  return fma(a, fma(e.OK, a, e.Om), e.Or) + de;
-}
-__device__ __forceinline__ double f_K(const pmcb200_cosmo_t &c, double w) {
-  double OK = 1.0 - c.Omega_m - c.Omega_de - c.Omega_nu_mass;
-  if (fabs(OK) < FLAT_EPS) return w;
-  double sk = sqrt(fabs(OK)) / R_HUBBLE;
-  return OK > 0.0 ? sinh(sk * w) / sk : sin(sk * w) / sk;
-}
-// comoving distance [Mpc/h] with on-the-fly nodes
-__device__ inline double w_generic(const pmcb200_cosmo_t &c, double a, int wOmegar, int &err) {
-  ECoef e = make_ecoef(c, wOmegar);
-  int bad = 0;
-  double r = romberg([&](double x) {
-    double dd = a4E2(e, x, log(x));
-    if (!(dd > 0.0)) bad = 1;
-    return rsqrt(dd);
-  }, a, 1.0, err);
-  if (bad) err = 1;
-  return R_HUBBLE * r;
-}
-__device__ inline double r_sound(const pmcb200_cosmo_t &c, double a, int &err) {
-  ECoef e = make_ecoef(c, 1);
-  double Rfac = 0.75 * c.Omega_b * c.h_100 * c.h_100 / OMEGA_GAMMA_H2;
-  int bad = 0;
-  double r = romberg([&](double x) {
-    double dd = a4E2(e, x, x > 0.0 ? log(x) : 0.0) * 3.0 * fma(Rfac, x, 1.0);
-    if (!(dd > 0.0)) bad = 1;
-    return rsqrt(dd);
-  }, 0.0, a, err);
-  if (bad) err = 1;
-  return R_HUBBLE * r;
-}
-__device__ inline double D_V(const pmcb200_cosmo_t &c, double z, int &err) {
-  double a = 1.0 / (1.0 + z);
-  double ww = w_generic(c, a, 0, err);
-  double fK = f_K(c, ww);
-  ECoef e = make_ecoef(c, 0);
-  double a2 = a * a;
-  double EE = a4E2(e, a, log(a)) / (a2 * a2);
-  if (!(EE > 0.0)) { err = 1; return NAN; }
-  return cbrt(fK * fK * R_HUBBLE * z / sqrt(EE));
-}
-__device__ inline double z_drag(const pmcb200_cosmo_t &c) {
-  double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
-  double b1 = 0.313 * pow(omm, -0.419) * (1.0 + 0.607 * pow(omm, 0.674));
-  double b2 = 0.238 * pow(omm, 0.223);
-  return 1291.0 * pow(omm, 0.251) / (1.0 + 0.659 * pow(omm, 0.828)) * (1.0 + b1 * pow(omb, b2));
-}
-__device__ inline double z_star(const pmcb200_cosmo_t &c) {
-  double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
-  double g1 = 0.0783 * pow(omb, -0.238) / (1.0 + 39.5 * pow(omb, 0.763));
-  double g2 = 0.560 / (1.0 + 21.1 * pow(omb, 1.81));
-  return 1048.0 * (1.0 + 0.00124 * pow(omb, -0.738)) * (1.0 + g1 * pow(omm, g2));
-}
-// Gaussian log-pdf of a model vector against data packed as a component
-__device__ inline double gauss_comp_logpdf(const double *__restrict__ comp, int n, const double *model) {
-  const double *mean = comp + 2, *L = comp + 2 + n, *rd = comp + 2 + n + mix_tri(n);
-  double y[4], m = 0.0;
-  int off = 0;
-  for (int i = 0; i < n; i++) {
-    double t = model[i] - mean[i];
-    for (int k = 0; k < i; k++) t = fma(-L[off + k], y[k], t);
-    y[i] = t * rd[i];
-    m = fma(y[i], y[i], m);
-    off += i + 1;
-  }
-  return fma(-0.5, m, comp[1]);
-}
-
-// write/accumulate one likelihood term
-__device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t n, int set,
-                                            double add_const, double res, int e) {
-  if (set) { logpi[n] = res + add_const; if (err) err[n] = e; }
-  else { logpi[n] += res; if (err && e) err[n] = 1; }
-}
-
-// ---- fast FP64 primitives for the SN hot loop ---------------------------------
+// ---- fast FP64 primitives (SN hot loop and the BAO / CMB integrals) ---------------------------------
 // 2^s for |s| < 1000: s = k/32 + f with |f| <= 1/64 (one magic-number add, the
 // remainder is exact), 2^f by a degree-5 near-minimax polynomial (Chebyshev
 // interpolant, max rel. error 1.4e-16 before rounding), 2^(j/32) from a
@@ -273,6 +176,162 @@ __device__ __forceinline__ double fast_rcp(double s) {
   return fma(y, e, y);
 }
 
+// load the shared table [32 exp2 | 32 log reciprocals | 32 log offsets]; blockDim.x >= 96
+__device__ __forceinline__ void load_fast_tables(double *T) {
+  if (threadIdx.x < 32) T[threadIdx.x] = EXP2T[threadIdx.x];
+  else if (threadIdx.x < 64) T[threadIdx.x] = LOGRC[threadIdx.x - 32];
+  else if (threadIdx.x < 96) T[threadIdx.x] = LOGLC[threadIdx.x - 64];
+  __syncthreads();
+}
+
+// Coefficients of a^4 E^2(a) = a (Om + OK a) + Or + Ode exp(p ln a + q g(a)),
+// g = (1-a) [linder] or (1-a)^2 [jassal].
+struct ECoef {
+  double Om, OK, Ode, Or, p, q;
+  int jassal;
+};
+__device__ __forceinline__ ECoef make_ecoef(const pmcb200_cosmo_t &c, int wOmegar) {
+  ECoef e;
+  e.Om = c.Omega_m + c.Omega_nu_mass;
+  e.OK = 1.0 - c.Omega_m - c.Omega_de - c.Omega_nu_mass;
+  e.Ode = c.Omega_de;
+  e.Or = wOmegar ? OMEGA_GAMMA_H2 * (1.0 + 0.2271 * NEFF_NU) / (c.h_100 * c.h_100) : 0.0;
+  e.jassal = (c.de_param == PMCB200_DE_jassal);
+  if (e.jassal) { e.p = 4.0 - 3.0 * (1.0 + c.w0_de); e.q = 1.5 * c.w1_de; }
+  else { e.p = 4.0 - 3.0 * (1.0 + c.w0_de + c.w1_de); e.q = -3.0 * c.w1_de; }
+  return e;
+}
+__device__ __forceinline__ double a4E2(const ECoef &e, double a, double lna) {
+  double oma = 1.0 - a;
+  double t = e.jassal ? fma(e.q * oma, oma, e.p * lna) : fma(e.q, oma, e.p * lna);
+  double de = (a > 0.0) ? e.Ode * exp(t) : 0.0;
+  return fma(a, fma(e.OK, a, e.Om), e.Or) + de;
+}
+// sinh(x)/x for u = x^2 > 0 and sin(x)/x for u = -x^2 < 0: one series in u, |u| < 1
+// (truncation 1/21! = 2e-20); replaces the branchy libdevice sinh / sin
+__device__ __forceinline__ double sinhc_series(double u) {
+  double p = 1.0 / 121645100408832000.0;      // 1/19!
+  p = fma(p, u, 1.0 / 355687428096000.0);     // 1/17!
+  p = fma(p, u, 1.0 / 1307674368000.0);       // 1/15!
+  p = fma(p, u, 1.0 / 6227020800.0);          // 1/13!
+  p = fma(p, u, 1.0 / 39916800.0);            // 1/11!
+  p = fma(p, u, 1.0 / 362880.0);              // 1/9!
+  p = fma(p, u, 1.0 / 5040.0);                // 1/7!
+  p = fma(p, u, 1.0 / 120.0);                 // 1/5!
+  p = fma(p, u, 1.0 / 6.0);                   // 1/3!
+  return fma(p, u, 1.0);
+}
+// transverse comoving distance from the comoving distance w [Mpc/h]
+__device__ __forceinline__ double f_K_from(double OK, double w) {
+  if (fabs(OK) < FLAT_EPS) return w;
+  const double x = w * (1.0 / R_HUBBLE), u = OK * x * x;
+  if (fabs(u) < 1.0) return w * sinhc_series(u);
+  const double sk = sqrt(fabs(OK)) / R_HUBBLE;
+  return OK > 0.0 ? sinh(sk * w) / sk : sin(sk * w) / sk;
+}
+__device__ __forceinline__ double f_K(const pmcb200_cosmo_t &c, double w) {
+  return f_K_from(1.0 - c.Omega_m - c.Omega_de - c.Omega_nu_mass, w);
+}
+// a^4 E^2(a) with the table-based primitives: base-2 exponent folded with log2|Ode|;
+// outside the fast range (|s| >= 990, Ode == 0, a == 0) the libdevice path is taken
+struct ECoefF {
+  ECoef e;
+  double p2, q2, lg;
+  unsigned sgn;
+  int ok;       // Ode != 0 and finite
+};
+__device__ __forceinline__ ECoefF make_ecoef_fast(const pmcb200_cosmo_t &c, int wOmegar) {
+  ECoefF f;
+  f.e = make_ecoef(c, wOmegar);
+  f.p2 = f.e.p * M_LOG2E; f.q2 = f.e.q * M_LOG2E;
+  f.lg = log2(fabs(f.e.Ode));
+  f.sgn = (f.e.Ode < 0.0) ? 0x80000000u : 0u;
+  f.ok = isfinite(f.lg) && isfinite(f.p2) && isfinite(f.q2);
+  return f;
+}
+__device__ __forceinline__ double a4E2_fast(const ECoefF &f, double a, const double *__restrict__ T) {
+  if (!(a > 0.0)) return f.e.Or;
+  const double oma = 1.0 - a;
+  double de;
+  if (f.ok) {
+    const double lna = fast_log(a, T);
+    const double s = f.e.jassal ? fma(f.q2 * oma, oma, fma(f.p2, lna, f.lg)) : fma(f.q2, oma, fma(f.p2, lna, f.lg));
+    de = (fabs(s) < 990.0) ? fast_exp2_signed(s, T, f.sgn) : f.e.Ode * exp2(s - f.lg);
+  } else {
+    const double lna = log(a);
+    const double t = f.e.jassal ? fma(f.e.q * oma, oma, f.e.p * lna) : fma(f.e.q, oma, f.e.p * lna);
+    de = f.e.Ode * exp(t);
+  }
+  return fma(a, fma(f.e.OK, a, f.e.Om), f.e.Or) + de;
+}
+// comoving distance [Mpc/h] with on-the-fly nodes
+__device__ inline double w_generic(const pmcb200_cosmo_t &c, double a, int wOmegar, int &err, const double *__restrict__ T) {
+  const ECoefF f = make_ecoef_fast(c, wOmegar);
+  int bad = 0;
+  double r = romberg([&](double x) {
+    double dd = a4E2_fast(f, x, T);
+    if (!(dd > 0.0)) bad = 1;
+    return fast_rsqrt(dd);
+  }, a, 1.0, err);
+  if (bad) err = 1;
+  return R_HUBBLE * r;
+}
+__device__ inline double r_sound(const pmcb200_cosmo_t &c, double a, int &err, const double *__restrict__ T) {
+  const ECoefF f = make_ecoef_fast(c, 1);
+  const double Rfac = 0.75 * c.Omega_b * c.h_100 * c.h_100 / OMEGA_GAMMA_H2;
+  int bad = 0;
+  double r = romberg([&](double x) {
+    double dd = a4E2_fast(f, x, T) * 3.0 * fma(Rfac, x, 1.0);
+    if (!(dd > 0.0)) bad = 1;
+    return fast_rsqrt(dd);
+  }, 0.0, a, err);
+  if (bad) err = 1;
+  return R_HUBBLE * r;
+}
+__device__ inline double D_V(const pmcb200_cosmo_t &c, double z, int &err, const double *__restrict__ T) {
+  double a = 1.0 / (1.0 + z);
+  double ww = w_generic(c, a, 0, err, T);
+  double fK = f_K(c, ww);
+  const ECoefF f = make_ecoef_fast(c, 0);
+  double a2 = a * a;
+  double EE = a4E2_fast(f, a, T) / (a2 * a2);
+  if (!(EE > 0.0)) { err = 1; return NAN; }
+  return cbrt(fK * fK * R_HUBBLE * z / sqrt(EE));
+}
+__device__ inline double z_drag(const pmcb200_cosmo_t &c) {
+  double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
+  double b1 = 0.313 * pow(omm, -0.419) * (1.0 + 0.607 * pow(omm, 0.674));
+  double b2 = 0.238 * pow(omm, 0.223);
+  return 1291.0 * pow(omm, 0.251) / (1.0 + 0.659 * pow(omm, 0.828)) * (1.0 + b1 * pow(omb, b2));
+}
+__device__ inline double z_star(const pmcb200_cosmo_t &c) {
+  double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
+  double g1 = 0.0783 * pow(omb, -0.238) / (1.0 + 39.5 * pow(omb, 0.763));
+  double g2 = 0.560 / (1.0 + 21.1 * pow(omb, 1.81));
+  return 1048.0 * (1.0 + 0.00124 * pow(omb, -0.738)) * (1.0 + g1 * pow(omm, g2));
+}
+// Gaussian log-pdf of a model vector against data packed as a component
+__device__ inline double gauss_comp_logpdf(const double *__restrict__ comp, int n, const double *model) {
+  const double *mean = comp + 2, *L = comp + 2 + n, *rd = comp + 2 + n + mix_tri(n);
+  double y[4], m = 0.0;
+  int off = 0;
+  for (int i = 0; i < n; i++) {
+    double t = model[i] - mean[i];
+    for (int k = 0; k < i; k++) t = fma(-L[off + k], y[k], t);
+    y[i] = t * rd[i];
+    m = fma(y[i], y[i], m);
+    off += i + 1;
+  }
+  return fma(-0.5, m, comp[1]);
+}
+
+// write/accumulate one likelihood term
+__device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t n, int set,
+                                            double add_const, double res, int e) {
+  if (set) { logpi[n] = res + add_const; if (err) err[n] = e; }
+  else { logpi[n] += res; if (err && e) err[n] = 1; }
+}
+
 // ---- SN Ia: one sample per thread; the whole warp walks the same redshift
 // so node loads are warp-uniform and the adaptive stage count is resolved by
 // a warp vote.  HASQ: w1 != 0 or jassal (second exponent term); FLAT: the
@@ -312,7 +371,6 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
                                          const SNPer &m_, double f1, double &chi2, double &logdet, int &e,
                                          unsigned &nev) {
   const bool flat = fabs(ec.OK) < FLAT_EPS;
-  const double sk = sqrt(fabs(ec.OK)) / R_HUBBLE;
   const int mode = L.sn_chi2mode;
   for (int iz = 0; iz < L.sn_nz; iz++) {
     const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
@@ -380,7 +438,7 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
     }
     // luminosity distance [Mpc/h] and distance modulus
     double ww = R_HUBBLE * ss;
-    double fk = (FLAT || flat) ? ww : (ec.OK > 0.0 ? sinh(sk * ww) : sin(sk * ww)) / sk;
+    double fk = (FLAT || flat) ? ww : f_K_from(ec.OK, ww);
     if (!(fk > 0.0)) e = 1;         // also catches NaN
     // mu_th = 5 log10(fk / (az H_fid)) + 25; the az part is tabulated (nodes[.][0].y = ln az)
     const double mu_th = fma(5.0 / M_LN10, (SLOW ? log(fk) : fast_log(fk, T)) - n0.y, 25.0 - 5.0 * log10(SN_H_FID));
@@ -419,10 +477,7 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
           const int16_t *__restrict__ flg, double *__restrict__ logpi,
           int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow) {
   __shared__ double T[96];      // [32 exp2 | 32 log reciprocals | 32 log offsets]
-  if (threadIdx.x < 32) T[threadIdx.x] = EXP2T[threadIdx.x];
-  else if (threadIdx.x < 64) T[threadIdx.x] = LOGRC[threadIdx.x - 32];
-  else if (threadIdx.x < 96) T[threadIdx.x] = LOGLC[threadIdx.x - 64];
-  __syncthreads();
+  load_fast_tables(T);
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = (n < N) && (!flg || flg[n]);
   unsigned nev = 0;
@@ -484,6 +539,8 @@ __global__ void __launch_bounds__(PMC_BLOCK)
 k_like_bao(const DevLike L, int64_t N, const double *__restrict__ X, int d,
            const int16_t *__restrict__ flg, double *__restrict__ logpi,
            int32_t *__restrict__ err, int set, double add_const) {
+  __shared__ double T[96];
+  load_fast_tables(T);
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   if (flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
@@ -497,15 +554,15 @@ k_like_bao(const DevLike L, int64_t N, const double *__restrict__ X, int d,
     if (L.bao_method == PMCB200_BAO_distance_A) {
       if (!(c.Omega_m > 0.0)) e = 1;
       else for (int i = 0; i < nd; i++)
-        model[i] = D_V(c, L.g_z[i], e) * sqrt(c.Omega_m) / (L.g_z[i] * R_HUBBLE);
+        model[i] = D_V(c, L.g_z[i], e, T) * sqrt(c.Omega_m) / (L.g_z[i] * R_HUBBLE);
     } else if (L.bao_method == PMCB200_BAO_distance_d_z) {
       if (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0)) e = 1;
       else {
-        double rs = r_sound(c, 1.0 / (1.0 + z_drag(c)), e);
-        for (int i = 0; i < nd; i++) model[i] = rs / D_V(c, L.g_z[i], e);
+        double rs = r_sound(c, 1.0 / (1.0 + z_drag(c)), e, T);
+        for (int i = 0; i < nd; i++) model[i] = rs / D_V(c, L.g_z[i], e, T);
       }
     } else {
-      for (int i = 0; i < nd; i++) model[i] = D_V(c, L.g_z[2 * i], e) / D_V(c, L.g_z[2 * i + 1], e);
+      for (int i = 0; i < nd; i++) model[i] = D_V(c, L.g_z[2 * i], e, T) / D_V(c, L.g_z[2 * i + 1], e, T);
     }
     if (!e) res = gauss_comp_logpdf(L.g_comp, nd, model);
     if (!isfinite(res)) e = 1;
@@ -517,6 +574,8 @@ __global__ void __launch_bounds__(PMC_BLOCK)
 k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
              const int16_t *__restrict__ flg, double *__restrict__ logpi,
              int32_t *__restrict__ err, int set, double add_const) {
+  __shared__ double T[96];
+  load_fast_tables(T);
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   if (flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
@@ -528,9 +587,9 @@ k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   if (!e) {
     double model[4];
     double zs = z_star(c), as = 1.0 / (1.0 + zs);
-    double ww = w_generic(c, as, 1, e);
+    double ww = w_generic(c, as, 1, e, T);
     double fK = f_K(c, ww);
-    double rs = r_sound(c, as, e);
+    double rs = r_sound(c, as, e, T);
     model[0] = M_PI * fK / rs;
     model[1] = sqrt(c.Omega_m) * fK / R_HUBBLE;
     model[2] = zs;
