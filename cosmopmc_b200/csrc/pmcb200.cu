@@ -190,18 +190,9 @@ extern "C" int pmcb200_device_count(void) {
   return n;
 }
 
-extern "C" int pmcb200_create(int device, void *stream, pmcb200_ctx **out) {
-  if (!out) return PMCB200_ERR_ARG;
-  *out = nullptr;
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
-    fprintf(stderr, "pmcb200_create: no usable CUDA device %d (%s); there is no CPU fallback\n",
-            device, e != cudaSuccess ? cudaGetErrorString(e) : "device count");
-    return PMCB200_ERR_CUDA;
-  }
-  pmcb200_ctx *c = new pmcb200_ctx();
-  c->device = device;
+extern "C" void pmcb200_destroy(pmcb200_ctx *c);
+
+static int create_impl(pmcb200_ctx *c, int device, void *stream) {
   CUDA_OK(c, cudaSetDevice(device));
   // NULL = the legacy default stream (orders with torch's default stream and
   // with plain cudaMemcpy in C hosts); (void*)-1 = a private non-blocking stream
@@ -218,6 +209,27 @@ extern "C" int pmcb200_create(int device, void *stream, pmcb200_ctx **out) {
   CUDA_OK(c, cudaMalloc((void **)&c->d_cnt, sizeof(DevCount)));
   CUDA_OK(c, cudaMemset(c->d_cnt, 0, sizeof(DevCount)));
   CUDA_OK(c, cudaMallocHost((void **)&c->h_result, sizeof(double) * (RES_HDR + PMCB200_MAX_COMP * (1 + PMCB200_MAX_DIM + PMCB200_MAX_DIM * PMCB200_MAX_DIM))));
+  return 0;
+}
+
+extern "C" int pmcb200_create(int device, void *stream, pmcb200_ctx **out) {
+  if (!out) return PMCB200_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    fprintf(stderr, "pmcb200_create: no usable CUDA device %d (%s); there is no CPU fallback\n",
+            device, e != cudaSuccess ? cudaGetErrorString(e) : "device count");
+    return PMCB200_ERR_CUDA;
+  }
+  pmcb200_ctx *c = new pmcb200_ctx();
+  c->device = device;
+  int rc = create_impl(c, device, stream);
+  if (rc) {
+    fprintf(stderr, "pmcb200_create: %s\n", c->errmsg);
+    pmcb200_destroy(c);
+    return rc;
+  }
   *out = c;
   return 0;
 }

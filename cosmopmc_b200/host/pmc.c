@@ -95,7 +95,9 @@ void pmc_simu_free(pmc_simu **p)
    free((*p)->buf); free(*p); *p = NULL;
 }
 
-/* ---- device context + target registry ------------------------------------------------ */
+/* ---- device context + target registry ------------------------------------------------
+ * One process drives one GPU and, like the reference (single-threaded, no locks anywhere,
+ * SURVEY.md 8b), this layer keeps process-wide state: it is not re-entrant. */
 #define MAX_TARGETS 8
 static pmcb200_ctx *g_ctx = NULL;
 static struct { posterior_log_pdf_func *f; void *data; pmcb200_target_t t; int used; } g_targets[MAX_TARGETS];
