@@ -216,20 +216,24 @@ static void push_proposal(pmcb200_ctx *ctx, mix_mvdens *m, error **err)
                                   pmcb200_last_error(ctx));
 }
 
-/* updated proposal <- device (components with weight 0 are dead: cleanup_after_update) */
+/* updated proposal <- device.  As in pmclib, update_prop_rb leaves the COVARIANCE in comp[k]->std
+ * (chol = 0; the Cholesky factor is recomputed on demand by the next use): the reference copies
+ * std between components as a covariance (revive_comp, exec/cosmo_pmc.c:225).  Components that died
+ * in the update (weight 0, cleanup_after_update) keep their previous mean and matrix. */
 static void pull_proposal(pmcb200_ctx *ctx, mix_mvdens *m, error **err)
 {
    size_t K = m->ncomp, d = m->ndim;
-   double *mean = (double *)malloc_err(sizeof(double) * K * d * (d + 1), err);
+   double *mean = (double *)malloc_err(sizeof(double) * K * d * (2 * d + 1), err);
    forwardError(*err, __LINE__, );
-   double *chol = mean + K * d;
-   int rc = pmcb200_get_proposal(ctx, m->wght, mean, chol, NULL);
+   double *chol = mean + K * d, *cov = chol + K * d * d;
+   int rc = pmcb200_get_proposal(ctx, m->wght, mean, chol, cov);
    if (rc == 0)
       for (size_t k = 0; k < K; k++) {
+         if (m->wght[k] == 0.0) continue;
          memcpy(m->comp[k]->mean, mean + k * d, d * sizeof(double));
-         memcpy(m->comp[k]->std, chol + k * d * d, d * d * sizeof(double));
-         m->comp[k]->chol = 1;
-         m->comp[k]->detL = determinant(m->comp[k]->std, d);
+         memcpy(m->comp[k]->std, cov + k * d * d, d * d * sizeof(double));
+         m->comp[k]->chol = 0;
+         m->comp[k]->detL = 0.0;
       }
    free(mean);
    m->init_cwght = 0;

@@ -113,6 +113,10 @@ int main(int argc, char **argv)
    double norm = normalize_importance_weight(psim, err);                      quitOnError(*err, __LINE__, stderr);
    printf("norm %.17g\nlogSum %.17g\nisLog_after %d\n", norm, psim->logSum, psim->isLog);
    update_prop_rb(proposal, psim, err);                                       quitOnError(*err, __LINE__, stderr);
+   /* pmclib semantics: the updated components hold covariances (chol = 0) */
+   for (size_t k = 0; k < proposal->ncomp; k++)
+      if (proposal->wght[k] > 0 && proposal->comp[k]->chol != 0) { printf("MISMATCH chol flag\n"); return 1; }
+   mix_mvdens_cholesky_decomp(proposal, err);                                 quitOnError(*err, __LINE__, stderr);
    /* ---- post_processing, cosmo_pmc.c:441-461 ---- */
    double ess, ln_evi;
    double perp = perplexity_and_ess(psim, MC_UNORM, &ess, err);               quitOnError(*err, __LINE__, stderr);
@@ -136,6 +140,7 @@ int main(int argc, char **argv)
    size_t nok2 = pmc_b200_iteration(psim2, proposal2, rng, beta, &st, err);   quitOnError(*err, __LINE__, stderr);
    printf("fused_nok %zu\nfused_perplexity %.17g\nfused_ess %.17g\nfused_logSum %.17g\nfused_enc %.17g\n", nok2,
           st.perplexity, st.ess, st.logSum, st.enc);
+   mix_mvdens_cholesky_decomp(proposal2, err);                                quitOnError(*err, __LINE__, stderr);
    print_prop("fused", proposal2);
    double dmax = 0.0;
    for (long i = 0; i < N; i++) {

