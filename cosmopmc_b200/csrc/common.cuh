@@ -20,16 +20,19 @@
 
 // ---- packed mixture ---------------------------------------------------------
 // One contiguous device buffer of doubles (mirrors pmclib keeping a mix_mvdens
-// in one lump): for component k at mix + k*stride
+// in one lump), laid out for the PADDED dimension D = pmc_pad_dim(d)
+// so that every offset is a compile-time constant in the D-templated kernels
+// (padded coordinates: mean 0, L = identity, so they contribute nothing):
+// for component k at mix + k*stride
 //   [0] wght   [1] lognorm = log-pdf constant (-d/2 ln2pi - log det L, or the
-//   Student-t lgamma form)   [2 .. 2+d) mean   [2+d .. 2+d+T) lower Cholesky
-//   factor packed by rows (row i holds L[i][0..i])   [2+d+T .. 2+2d+T) 1/L[i][i]
-// followed after K*stride by the common EM pivot p[d].
+//   Student-t lgamma form)   [2 .. 2+D) mean   [2+D .. 2+D+T) lower Cholesky
+//   factor packed by rows (row i holds L[i][0..i]), T = D(D+1)/2
+//   [2+D+T .. 2+2D+T) 1/L[i][i]
+// followed after K*stride by the common EM pivot p[D].
 struct MixHdr {
   int K, d, df, stride, tri;
 };
 __host__ __device__ inline int mix_tri(int d) { return d * (d + 1) / 2; }
-__host__ __device__ inline int mix_stride(int d) { return 2 + 2 * d + mix_tri(d); }
 
 // padded template dimension for a runtime dimension d
 __host__ __device__ inline int pmc_pad_dim(int d) {
@@ -37,6 +40,9 @@ __host__ __device__ inline int pmc_pad_dim(int d) {
   for (int i = 0; i < 13; i++) if (d <= list[i]) return list[i];
   return 32;
 }
+
+// stride of one packed component for runtime dimension d (layout uses D = pmc_pad_dim(d))
+__host__ __device__ inline int mix_stride(int d) { const int D = pmc_pad_dim(d); return 2 + 2 * D + mix_tri(D); }
 
 // ---- per-iteration device scalars --------------------------------------------
 struct DevScal {
@@ -127,19 +133,16 @@ __device__ __forceinline__ int select_component(const double *__restrict__ mix, 
 template <int D>
 __device__ __forceinline__ double comp_maha(const double *__restrict__ comp, int d,
                                             const double (&x)[D], double (&y)[D]) {
-  const double *mean = comp + 2, *L = comp + 2 + d, *rd = comp + 2 + d + mix_tri(d);
+  (void)d;       // the packed layout is padded to D: all offsets are compile-time constants
+  const double *mean = comp + 2, *L = comp + 2 + D, *rd = comp + 2 + D + D * (D + 1) / 2;
   double m = 0.0;
-  int off = 0;
 #pragma unroll
   for (int i = 0; i < D; i++) {
-    if (i < d) {
-      double t = x[i] - mean[i];
+    double t = x[i] - mean[i];
 #pragma unroll
-      for (int k = 0; k < i; k++) t = fma(-L[off + k], y[k], t);
-      y[i] = t * rd[i];
-      m = fma(y[i], y[i], m);
-      off += i + 1;
-    }
+    for (int k = 0; k < i; k++) t = fma(-L[i * (i + 1) / 2 + k], y[k], t);
+    y[i] = t * rd[i];
+    m = fma(y[i], y[i], m);
   }
   return m;
 }

@@ -44,18 +44,17 @@ __device__ __forceinline__ void transform_store(const double *__restrict__ comp,
                                                 const double *__restrict__ bmin,
                                                 const double *__restrict__ bmax,
                                                 double *__restrict__ xout, int &inbox) {
-  const double *mean = comp + 2, *L = comp + 2 + d;
-  int off = 0, ok = 1;
+  const double *mean = comp + 2, *L = comp + 2 + D;      // layout padded to D
+  int ok = 1;
 #pragma unroll
   for (int i = 0; i < D; i++) {
     if (i < d) {
       double t = 0.0;
 #pragma unroll
-      for (int k = 0; k <= i; k++) t = fma(L[off + k], z[k], t);
+      for (int k = 0; k <= i; k++) t = fma(L[i * (i + 1) / 2 + k], z[k], t);
       double x = fma(scale, t, mean[i]);
       xout[i] = x;
       if (!(x >= bmin[i] && x <= bmax[i])) ok = 0;
-      off += i + 1;
     }
   }
   inbox = ok;
@@ -338,7 +337,7 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
         if (student) s_wg[k * PMC_BLOCK + tid] *= r;
       }
 #pragma unroll
-      for (int i = 0; i < D; i++) s_x[tid * XS + i] = (i < d) ? x[i] - pivot[i] : 0.0;
+      for (int i = 0; i < D; i++) s_x[tid * XS + i] = x[i] - pivot[i];      // padded: 0 - 0
     } else {
       for (int k = 0; k < K; k++) { s_wr[k * PMC_BLOCK + tid] = 0.0; if (student) s_wg[k * PMC_BLOCK + tid] = 0.0; }
 #pragma unroll

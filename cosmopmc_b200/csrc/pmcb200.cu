@@ -120,16 +120,18 @@ static int host_cholesky(int d, double *A) {
   return 0;
 }
 
-// pack one component (wght, mean[d], chol[d*d] lower) at dst[stride]
-static void pack_comp(double *dst, int d, int df, double w, const double *mean, const double *chol) {
-  const int tri = mix_tri(d);
+// pack one component (wght, mean[d], chol[d*d] lower) at dst[2 + 2D + D(D+1)/2], layout padded
+// to D >= d (padded coordinates: mean 0, unit diagonal)
+static void pack_comp(double *dst, int d, int D, int df, double w, const double *mean, const double *chol) {
+  const int tri = mix_tri(D);
   double logdet = 0.0;
   dst[0] = w;
-  for (int i = 0; i < d; i++) {
-    dst[2 + i] = mean[i];
-    for (int j = 0; j <= i; j++) dst[2 + d + i * (i + 1) / 2 + j] = chol[i * d + j];
-    dst[2 + d + tri + i] = 1.0 / chol[i * d + i];
-    logdet += std::log(chol[i * d + i]);
+  for (int i = 0; i < D; i++) {
+    dst[2 + i] = i < d ? mean[i] : 0.0;
+    for (int j = 0; j <= i; j++)
+      dst[2 + D + i * (i + 1) / 2 + j] = (i < d) ? chol[i * d + j] : (i == j ? 1.0 : 0.0);
+    dst[2 + D + tri + i] = i < d ? 1.0 / chol[i * d + i] : 1.0;
+    if (i < d) logdet += std::log(chol[i * d + i]);
   }
   if (df <= 0) dst[1] = -0.5 * d * LN2PI - logdet;
   else {
@@ -140,12 +142,13 @@ static void pack_comp(double *dst, int d, int df, double w, const double *mean, 
 
 static int upload_mix(pmcb200_ctx *c, int K, int d, int df, const double *w, const double *mean,
                       const double *chol, MixHdr &h, double **dbuf, size_t *cap) {
-  h.K = K; h.d = d; h.df = df; h.stride = mix_stride(d); h.tri = mix_tri(d);
-  size_t n = (size_t)K * h.stride + d;
+  const int D = pmc_pad_dim(d);
+  h.K = K; h.d = d; h.df = df; h.stride = mix_stride(d); h.tri = mix_tri(D);
+  size_t n = (size_t)K * h.stride + D;
   std::vector<double> buf(n, 0.0);
   double wsum = 0.0;
   for (int k = 0; k < K; k++) {
-    pack_comp(buf.data() + (size_t)k * h.stride, d, df, w[k], mean + (size_t)k * d, chol + (size_t)k * d * d);
+    pack_comp(buf.data() + (size_t)k * h.stride, d, D, df, w[k], mean + (size_t)k * d, chol + (size_t)k * d * d);
     wsum += w[k];
   }
   for (int i = 0; i < d; i++) {   // common EM pivot: weighted mean of component means
@@ -375,8 +378,8 @@ extern "C" int pmcb200_get_proposal(pmcb200_ctx *c, double *w, double *mean, dou
 
 // ---- target ------------------------------------------------------------------------
 static int pack_gauss(pmcb200_ctx *c, int n, const double *mean, const double *chol, const double **out) {
-  std::vector<double> buf(mix_stride(n));
-  pack_comp(buf.data(), n, -1, 1.0, mean, chol);
+  std::vector<double> buf(2 + 2 * n + mix_tri(n));     // unpadded: read with runtime n (gauss_comp_logpdf)
+  pack_comp(buf.data(), n, n, -1, 1.0, mean, chol);
   return dev_copy<double>(c, buf.data(), buf.size(), out);
 }
 

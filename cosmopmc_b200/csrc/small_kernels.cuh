@@ -113,7 +113,8 @@ k_em_finish(const double *__restrict__ mix, const MixHdr h, int nranks,
       }
     }
     if (dead) {   // keep the old mean / factor, weight 0
-      const double *mean = comp + 2, *L = comp + 2 + d;
+      const int Dp = pmc_pad_dim(d);
+      const double *mean = comp + 2, *L = comp + 2 + Dp;
       for (int i = 0; i < d; i++) {
         o_mean[i] = mean[i];
         for (int j = 0; j < d; j++) o_chol[i * d + j] = (j <= i) ? L[i * (i + 1) / 2 + j] : 0.0;
