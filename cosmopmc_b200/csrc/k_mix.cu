@@ -43,17 +43,19 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
                                                     a.scal);
       break;
     case OP_EM: {
-      cudaError_t e = cudaFuncSetAttribute(k_em_stats<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
+      const bool reg = em_use_reg(a.Kg, a.h.d, a.h.df > 0);
+      auto kern = reg ? k_em_stats<DD, true> : k_em_stats<DD, false>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
       if (e != cudaSuccess) return e;
       // persistent grid: as many blocks as are resident (a.blocks = buffer capacity)
       int per_sm = 1, dev = 0, sms = 148;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_em_stats<DD>, PMC_BLOCK, a.smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PMC_BLOCK, a.smem);
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       int blocks = std::max(1, std::min(a.blocks, std::max(1, per_sm) * sms));
       if (a.nblocks_out) *a.nblocks_out = blocks;
-      k_em_stats<DD><<<blocks, PMC_BLOCK, a.smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal,
-                                                         a.partials, a.linear, a.k0, a.Kg);
+      kern<<<blocks, PMC_BLOCK, a.smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal,
+                                             a.partials, a.linear, a.k0, a.Kg);
       break;
     }
     default:

@@ -207,11 +207,22 @@ k_weights(const double *__restrict__ mix, const MixHdr h, int64_t N,
 __host__ __device__ inline int em_nfeat(int d) { return 2 + d + mix_tri(d); }             // A, G, B[d], C[tri]
 __host__ __device__ inline int em_nf(int Mp) { return (Mp + PMC_BLOCK - 1) / PMC_BLOCK; }  // features per thread
 __host__ __device__ inline int em_xs(int d) { return pmc_pad_dim(d) | 1; }                // smem row stride of x
+#define EM_RACC 32        // register accumulators per thread (one feature x up to 32 components)
+// register partials pay off only where the shared-memory partials would cost the second
+// resident block per SM (measured: C5 K=30,d=8 13.8 -> 10.7 ms; C2 and C3 are faster with s_acc)
+__host__ __device__ inline int em_use_reg(int K, int d, int student) {
+  if (em_nf(em_nfeat(d)) != 1 || K > EM_RACC) return 0;
+  const int KP = (K + EM_KCHUNK - 1) / EM_KCHUNK * EM_KCHUNK;
+  const size_t with_acc = ((size_t)KP * PMC_BLOCK * (student ? 2 : 1) + (size_t)PMC_BLOCK * em_xs(d) +
+                           (size_t)K * PMC_BLOCK) * sizeof(double);
+  return with_acc > 112 * 1024;
+}
 __host__ __device__ inline size_t em_smem_bytes(int K, int d, int student) {
   const int KP = (K + EM_KCHUNK - 1) / EM_KCHUNK * EM_KCHUNK;   // zero-padded rows
+  const size_t nacc = em_use_reg(K, d, student) ? 0 : (size_t)em_nf(em_nfeat(d)) * K * PMC_BLOCK;   // s_acc
   return ((size_t)KP * PMC_BLOCK * (student ? 2 : 1)           // s_wr (, s_wg)
           + (size_t)PMC_BLOCK * em_xs(d)                        // s_x
-          + (size_t)em_nf(em_nfeat(d)) * K * PMC_BLOCK) * sizeof(double)  // s_acc
+          + nacc) * sizeof(double)
          + (size_t)K * sizeof(unsigned long long);              // s_cnt
 }
 
@@ -228,12 +239,9 @@ __device__ __forceinline__ void em_decode(int f, int d, int &type, int &i, int &
 }
 
 template <int KC, int XS>
-__device__ __forceinline__ void em_chunk(const double *__restrict__ wp, const double *__restrict__ xi,
-                                         const double *__restrict__ xj, int type, int t0, int t1,
-                                         double *__restrict__ accp, int kleft) {
-  double acc[KC];
-#pragma unroll
-  for (int q = 0; q < KC; q++) acc[q] = 0.0;
+__device__ __forceinline__ void em_chunk_acc(const double *__restrict__ wp, const double *__restrict__ xi,
+                                             const double *__restrict__ xj, int type, int t0, int t1,
+                                             double (&acc)[KC]) {
   const double *w = wp + t0;
   const double *pi = xi + (size_t)t0 * XS, *pj = xj + (size_t)t0 * XS;
   if (type == 4) {
@@ -257,11 +265,21 @@ __device__ __forceinline__ void em_chunk(const double *__restrict__ wp, const do
       for (int q = 0; q < KC; q++) acc[q] += w[q * PMC_BLOCK];
     }
   }
+}
+// shared-memory accumulator variant (several features per thread)
+template <int KC, int XS>
+__device__ __forceinline__ void em_chunk(const double *__restrict__ wp, const double *__restrict__ xi,
+                                         const double *__restrict__ xj, int type, int t0, int t1,
+                                         double *__restrict__ accp, int kleft) {
+  double acc[KC];
+#pragma unroll
+  for (int q = 0; q < KC; q++) acc[q] = 0.0;
+  em_chunk_acc<KC, XS>(wp, xi, xj, type, t0, t1, acc);
 #pragma unroll
   for (int q = 0; q < KC; q++) if (q < kleft) accp[(size_t)q * PMC_BLOCK] += acc[q];
 }
 
-template <int D>
+template <int D, bool REG>
 __global__ void __launch_bounds__(PMC_BLOCK, 2)
 k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
            const double *__restrict__ X, const int32_t *__restrict__ idx,
@@ -278,8 +296,8 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
   double *s_wr = sm;                          // [KP][PMC_BLOCK]  w*rho (rows >= K stay zero)
   double *s_wg = student ? s_wr + (size_t)KP * PMC_BLOCK : s_wr;   // w*rho*gamma (Gaussian: gamma = 1)
   double *s_x = s_wg + (size_t)KP * PMC_BLOCK;  // [PMC_BLOCK][XS] x - pivot
-  double *s_acc = s_x + (size_t)PMC_BLOCK * XS; // [NF][K][PMC_BLOCK] per-thread partial statistics
-  unsigned long long *s_cnt = (unsigned long long *)(s_acc + (size_t)NF * K * PMC_BLOCK);   // [K] draws per component
+  unsigned long long *s_cnt = (unsigned long long *)(s_x + (size_t)PMC_BLOCK * XS);        // [K] draws per component
+  double *s_acc = (double *)(s_cnt + K);        // [NF][K][PMC_BLOCK] per-thread partials (absent on the register path)
   __shared__ double red[32];
   const double *pivot = mix + (size_t)Kall * h.stride;
   // linear != 0: logw holds normalised (linear) weights, as after
@@ -294,8 +312,13 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
   const bool worker = (Mp < PMC_BLOCK) ? (g < G) : true;
   const int TS = (PMC_BLOCK + G - 1) / G;
   const int t0 = g * TS, t1 = min(PMC_BLOCK, t0 + TS);
-  for (int p = 0; p < NF; p++)
-    for (int k = 0; k < K; k++) s_acc[((size_t)p * K + k) * PMC_BLOCK + tid] = 0.0;
+  constexpr bool use_reg = REG;     // one feature per thread: partials stay in registers (host: em_use_reg)
+  double racc[REG ? EM_RACC : 1];
+#pragma unroll
+  for (int q = 0; q < (REG ? EM_RACC : 1); q++) racc[q] = 0.0;
+  if (!use_reg)
+    for (int p = 0; p < NF; p++)
+      for (int k = 0; k < K; k++) s_acc[((size_t)p * K + k) * PMC_BLOCK + tid] = 0.0;
   for (int k = K; k < KP; k++) { s_wr[k * PMC_BLOCK + tid] = 0.0; if (student) s_wg[k * PMC_BLOCK + tid] = 0.0; }
   if (tid < K) s_cnt[tid] = 0ull;
   const int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
@@ -348,7 +371,20 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
     __syncthreads();
     // ---- phase 2 (rows k >= K of s_wr/s_wg are zero padding up to KP, so the
     // chunk loops need no predicates and every LDS has an immediate offset)
-    if (worker) {
+    if (worker && use_reg) {
+      if (f0 < Mp) {
+        int type, fi, fj;
+        em_decode(f0, d, type, fi, fj);
+        const double *wsrc = (type == 0) ? s_wr : s_wg;
+#pragma unroll
+        for (int c = 0; c < (REG ? EM_RACC / EM_KCHUNK : 0); c++) {
+          if (c * EM_KCHUNK < K) {
+            double (&acc8)[EM_KCHUNK] = *reinterpret_cast<double (*)[EM_KCHUNK]>(&racc[c * EM_KCHUNK]);
+            em_chunk_acc<EM_KCHUNK, XS>(wsrc + (size_t)c * EM_KCHUNK * PMC_BLOCK, s_x + fi, s_x + fj, type, t0, t1, acc8);
+          }
+        }
+      }
+    } else if (worker) {
       for (int p = 0; p < NF; p++) {
         const int f = f0 + p * PMC_BLOCK;
         if (f >= Mp) break;
@@ -367,6 +403,12 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
     }
   }
   __syncthreads();
+  if (use_reg) {        // park the register partials in the (now free) s_wr rows: [k][tid]
+    s_acc = s_wr;
+#pragma unroll
+    for (int q = 0; q < (REG ? EM_RACC : 0); q++) if (q < K) s_acc[(size_t)q * PMC_BLOCK + tid] = racc[q];
+    __syncthreads();
+  }
   // ---- this block's partial: combine the G sample chunks in fixed order
   double *P = partials + (size_t)blockIdx.x * stat_len(Kall, d) + (size_t)k0 * M;
   double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red), bN = block_sum(tN, red);
