@@ -4,6 +4,7 @@
  * statistics, include/pmcb200.h), so with nproc == 1 these are identities. */
 #ifndef PMCLIB_PMC_MPI_H
 #define PMCLIB_PMC_MPI_H
+#include <mpi.h>   /* pmclib's pmc_mpi.h pulls MPI in (exec/importance_sample.c:15,176-178) */
 #include "pmclib/pmc.h"
 #ifdef __cplusplus
 extern "C" {

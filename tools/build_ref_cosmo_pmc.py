@@ -56,6 +56,16 @@ def build():
             subprocess.check_call([GCC] + CFLAGS + INC + ["-c", os.path.join(REF, s_), "-o", o])
             eo.append(o)
         subprocess.check_call([GCC, "-o", os.path.join(OUT, os.path.basename(main_src)[:-2])] + eo + common + link)
+    # the post-processing executables bin/cosmo_pmc.pl:150-190 runs on the pmcsim / proposal files
+    # (host-side file tools; importance_sample re-weights through the scalar posterior = N=1 launches)
+    for name in ("importance_sample", "meanvar_sample", "histograms_sample", "add_pmc_proposal",
+                 "meanvar_mixmvdens", "cl_one_sided"):
+        src = os.path.join(REF, "exec", name + ".c")
+        if not os.path.exists(src):
+            continue
+        o = os.path.join(OUT, "obj", name + ".o")
+        subprocess.check_call([GCC] + CFLAGS + INC + ["-c", src, "-o", o])
+        subprocess.check_call([GCC, "-o", os.path.join(OUT, name), o] + common + link)
     # the SN demo's inputs (Demo/MC_Demo/SN): config + data + parameter files, as bin/cosmo_pmc.pl stages them
     demo = os.path.join(OUT, "demo_SN")
     os.makedirs(demo, exist_ok=True)
