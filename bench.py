@@ -32,9 +32,9 @@ SEED = 20090903
 FLOP_PER_EVAL = 18.0       # int_for_w: a^4 E^2(a) incl. 1 pow + 1 exp (14), sqrt, 1/x, sum += (4)
 FLOP_PER_ZSTEP = 86.0      # per (sample, redshift): 5 trapzd combines (22), NR polint K=5 (54), test (4), D_L + modulus (6)
 FLOP_PER_SN = 29.0         # per (sample, supernova): mu_obs 7, sigma^2 18, chi^2 term 4
-# ncu evidence for the dominant kernel (profiles/sn_r01_v5_summary.txt), N = 2e6 capture
-NCU_SN = {"fp64_pipe_active_pct": 68.8, "dram_bytes_per_sample": 44.8,
-          "source": "profiles/sn_r01_v5_summary.txt"}
+# ncu evidence for the dominant kernel (profiles/sn_r01_v8_summary.txt), N = 2e6 capture
+NCU_SN = {"fp64_pipe_active_pct": 64.6, "dram_bytes_per_sample": 44.1,
+          "source": "profiles/sn_r01_v8_summary.txt"}
 
 
 def parse():

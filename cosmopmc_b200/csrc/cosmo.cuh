@@ -104,6 +104,15 @@ __constant__ double EXP2T[32] = {
     0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0, 0x1.ae89f995ad3adp+0,
     0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0,
     0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+// SN integrand's 2^s: s = k/1024 + f, |f| <= 1/2048, 2^f by a degree-3 Chebyshev interpolant (max rel.
+// error 1.4e-16), 2^(j/1024) from a 1024-entry table staged in shared memory.  The table's high
+// words have j << 10 subtracted: adding k32 << 10 (k32 = 1024 n + j) to that high word in ONE
+// integer multiply-add lands n in the exponent field and cancels the j part.  Filled once per device
+// by pmc_init_sn_tables() (host long-double exp2l, rounded to double).
+#define SN_EXP2_N 1024
+__device__ double g_sn_exp2[SN_EXP2_N];
+__constant__ double EXP2D3[4] = {0x1.62e42fefa39efp-1, 0x1.ebfbe033445b4p-3, 0x1.c6b08d910ecbdp-5,
+                                 6597069766656.0};   // [3] 1.5 * 2^42: ulp = 2^-10
 // ln(x) for positive normal x: x = 2^e m, m in [1,2); the top five mantissa bits
 // pick c_i = 1 + (i + 1/2)/32, r = m/c_i - 1 (|r| < 1/64, one FMA with the tabulated
 // rounded reciprocal), ln m = ln c_i + log1p(r) with a degree-8 Taylor polynomial
@@ -124,22 +133,23 @@ __constant__ double LOGLC[32] = {   // -ln(LOGRC[i]) of the ROUNDED reciprocals
     0x1.faf588f78f31dp-2, 0x1.0723e5c1cdf41p-1, 0x1.109f39e2d4c96p-1, 0x1.19ee6b467c96fp-1, 0x1.23130d7bebf43p-1,
     0x1.2c0e9ed448e8cp-1, 0x1.34e289d9ce1d2p-1, 0x1.3d9026a7156fbp-1, 0x1.4618bc21c5ec2p-1, 0x1.4e7d811b75bb0p-1,
     0x1.56bf9d5b3f399p-1, 0x1.5ee02a9241676p-1};
+__constant__ double LOGP[8] = {-1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, 0.693147180559945309417, 0.0};
 // T: shared table [32 exp2 | 32 LOGRC | 32 LOGLC]
 __device__ __forceinline__ double fast_log(double x, const double *__restrict__ T) {
   const int hi = __double2hiint(x);
   const int i = (hi >> 15) & 31;
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
   const double r = fma(m, T[32 + i], -1.0);
-  double q = -1.0 / 8.0;
-  q = fma(q, r, 1.0 / 7.0);
-  q = fma(q, r, -1.0 / 6.0);
-  q = fma(q, r, 1.0 / 5.0);
-  q = fma(q, r, -1.0 / 4.0);
-  q = fma(q, r, 1.0 / 3.0);
+  double q = LOGP[0];
+  q = fma(q, r, LOGP[1]);
+  q = fma(q, r, LOGP[2]);
+  q = fma(q, r, LOGP[3]);
+  q = fma(q, r, LOGP[4]);
+  q = fma(q, r, LOGP[5]);
   q = fma(q, r, -0.5);
   q = fma(q, r, 1.0);
   const double e = (double)((hi >> 20) - 1023);
-  return fma(e, 0.693147180559945309417, fma(q, r, T[64 + i]));
+  return fma(e, LOGP[6], fma(q, r, T[64 + i]));
 }
 // returns sign * 2^s, sign given as an XOR mask for the high word
 __device__ __forceinline__ double fast_exp2_signed(double s, const double *__restrict__ T, unsigned sgn) {
@@ -182,6 +192,11 @@ __device__ __forceinline__ void load_fast_tables(double *T) {
   else if (threadIdx.x < 64) T[threadIdx.x] = LOGRC[threadIdx.x - 32];
   else if (threadIdx.x < 96) T[threadIdx.x] = LOGLC[threadIdx.x - 64];
   __syncthreads();
+}
+// the SN kernel's table: the three above + the pre-biased 1024-entry exp2 table
+__device__ __forceinline__ void load_fast_tables_sn(double *T) {
+  for (int i = threadIdx.x; i < SN_EXP2_N; i += blockDim.x) T[96 + i] = g_sn_exp2[i];
+  load_fast_tables(T);
 }
 
 // Coefficients of a^4 E^2(a) = a (Om + OK a) + Or + Ode exp(p ln a + q g(a)),
@@ -338,26 +353,102 @@ __device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t
 // curvature term is identically zero for every sample of the launch; SLOW:
 // libdevice exp for warps holding a sample outside the fast path's range. -------
 struct SNCoef {
-  double Om, OK, Ode, p, q;        // a^4 E^2 = a (Om + OK a) + Ode exp(p ln a + q g(a))
-  double p2, q2, lg;               // base-2 form: Ode exp(.) = sgn 2^(p2 ln a + q2 g(a) + lg)
-  unsigned sgn;
+  double Om, OK, Ode, p, q;        // a^3 E^2 = Om + OK a + Ode exp(p ln a + q g(a)),  p = -3 (w0 + w1) [linder]
+  double Oms, OKs, p2, q2;         // fast form, scaled by 1/|Ode|: Oms + OKs a + sgn 2^(p2 ln a + q2 g(a))
+  double scale;                    // |Ode|^-1/2 (fast): the integral of the scaled integrand times this
+  unsigned sgn;                    // sign of Ode as an XOR mask (NEG instantiation: some lane has Ode < 0)
   int jassal, slow;
 };
-template <bool HASQ, bool FLAT, bool SLOW>
-__device__ __forceinline__ double sn_f(const SNCoef &e, const double *__restrict__ T, double2 nd) {
-  const double a = nd.x;
-  double de;
+// Integrand of the comoving distance at a tabulated node, 1/sqrt(a^4 E^2) = a^-1/2 / sqrt(Q) with
+// Q = a^3 E^2: the a^-1/2 factor is tabulated with the node, so the sample-dependent part is one
+// 2^s (its last multiply fused into Q = T 2^f + Om) and one 1/sqrt.  The fast path works on
+// Q / |Ode| (the exponent needs no additive constant; |Ode|^-1/2 multiplies the finished integral).
+// 1/sqrt: MUFU.RSQ64H seed y (measured |1 - Q y^2| < 2^-19, tools/micro/rsqrt_err.cu) and a
+// third-order correction written so that no FP64 instruction reads three varying registers
+// except the final accumulate.  Returns acc + a^-1/2 / sqrt(Q).
+template <bool HASQ, bool FLAT, bool SLOW, bool NEG>
+__device__ __forceinline__ double sn_f(const SNCoef &e, const double *__restrict__ T, double lna, double rsa, double a,
+                                       double acc) {
+  double Q;
   if (SLOW) {
-    double t = e.p * nd.y;
+    double t = e.p * lna;
     if (HASQ) { double oma = 1.0 - a; t = e.jassal ? fma(e.q * oma, oma, t) : fma(e.q, oma, t); }
-    de = e.Ode * exp(t);
+    Q = fma(e.Ode, exp(t), FLAT ? e.Om : fma(e.OK, a, e.Om));
   } else {
-    double s = fma(e.p2, nd.y, e.lg);
-    if (HASQ) { double oma = 1.0 - a; s = e.jassal ? fma(e.q2 * oma, oma, s) : fma(e.q2, oma, s); }
-    de = fast_exp2_signed(s, T, e.sgn);
+    double kf, f;
+    if (HASQ) {
+      const double oma = 1.0 - a;
+      const double s = e.jassal ? fma(e.q2 * oma, oma, e.p2 * lna) : fma(e.q2, oma, e.p2 * lna);
+      kf = s + EXP2D3[3];
+      f = s - (kf - EXP2D3[3]);
+    } else {      // the product p2 ln a is never formed: both uses are fused
+      kf = fma(e.p2, lna, EXP2D3[3]);
+      f = fma(e.p2, lna, -(kf - EXP2D3[3]));
+    }
+    const int k32 = __double2loint(kf);
+    double p = EXP2D3[2];
+    p = fma(p, f, EXP2D3[1]);
+    p = fma(p, f, EXP2D3[0]);
+    p = fma(p, f, 1.0);
+    const double tj = T[96 + (k32 & (SN_EXP2_N - 1))];
+    int hi = __double2hiint(tj) + k32 * SN_EXP2_N;
+    if (NEG) hi ^= e.sgn;
+    Q = fma(__hiloint2double(hi, __double2loint(tj)), p, FLAT ? e.Oms : fma(e.OKs, a, e.Oms));
   }
-  double v = FLAT ? fma(e.Om, a, de) : fma(a, fma(e.OK, a, e.Om), de);
-  return fast_rsqrt(v);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(Q));
+  const double ry = rsa * y;
+  const double t = Q * y;
+  const double er = fma(-t, y, 1.0);
+  const double c = fma(0.375, er, 0.5);
+  const double w = fma(er, c, 1.0);
+  return fma(ry, w, acc);
+}
+// 32-byte global load (LDG.256): two {ln a, a^-1/2} nodes, or one {ln a, a^-1/2, a, -} node
+struct Ld4 { double x, y, z, w; };
+__device__ __forceinline__ Ld4 ld256(const void *p) {
+  Ld4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+// Stages 1..5 of NR qromb at redshift iz in closed form.  With g0 = (f(a_z) + f(1))/2 and the sums
+// S_j of the 2^(j-1) new nodes of stage j+1, T_j = h 2^(1-j) (g0 + S_1 + .. + S_(j-1)), so the K = 5
+// extrapolant ss = R[5][4] and dss = R[5][4] - R[5][3] are fixed linear combinations (exact
+// rational weights of the Neville tableau for step ratios 1/4).  The 16 tabulated nodes are
+// independent evaluations (issued together for ILP).
+__constant__ double ROMBW[10] = {3937.0 / 103275.0, 3062.0 / 80325.0, 27728.0 / 722925.0, 22016.0 / 722925.0,
+                                  65536.0 / 722925.0, -31.0 / 206550.0, -73.0 / 481950.0, -67.0 / 722925.0,
+                                  -424.0 / 722925.0, 256.0 / 722925.0};
+struct SNSums { double g0, S1, S2, S3, S4; };
+template <bool HASQ, bool FLAT, bool SLOW, bool NEG>
+__device__ __forceinline__ void sn_romb5(const SNCoef &ec, const double *__restrict__ T,
+                                         const double2 *__restrict__ nd, const double *__restrict__ na,
+                                         const double *__restrict__ n4, double f1, SNSums &S, double &ss,
+                                         double &dss, double &lnaz, double &h) {
+  double fv[16];
+  if (HASQ || !FLAT) {          // one 32-byte node {ln a, a^-1/2, a, -} per load
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const Ld4 n = ld256(n4 + 4 * i);
+      if (i == 0) { lnaz = n.x; h = 1.0 - n.z; }
+      fv[i] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.x, n.y, n.z, i == 0 ? f1 : 0.0);
+    }
+  } else {                      // two 16-byte nodes {ln a, a^-1/2} per load
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const Ld4 n = ld256(nd + i);
+      if (i == 0) { lnaz = n.x; h = 1.0 - __ldg(na); }
+      fv[i] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.x, n.y, 0.0, i == 0 ? f1 : 0.0);
+      fv[i + 1] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.z, n.w, 0.0, 0.0);
+    }
+  }
+  S.g0 = 0.5 * fv[0];
+  S.S1 = fv[1];
+  S.S2 = fv[2] + fv[3];
+  S.S3 = (fv[4] + fv[5]) + (fv[6] + fv[7]);
+  S.S4 = ((fv[8] + fv[9]) + (fv[10] + fv[11])) + ((fv[12] + fv[13]) + (fv[14] + fv[15]));
+  ss = h * fma(ROMBW[0], S.g0, fma(ROMBW[1], S.S1, fma(ROMBW[2], S.S2, fma(ROMBW[3], S.S3, ROMBW[4] * S.S4))));
+  dss = h * fma(ROMBW[5], S.g0, fma(ROMBW[6], S.S1, fma(ROMBW[7], S.S2, fma(ROMBW[8], S.S3, ROMBW[9] * S.S4))));
 }
 
 // The redshift loop: per unique z one adaptive Romberg integral (tabulated
@@ -366,36 +457,19 @@ struct SNPer {           // per-sample constants of the chi^2 part
   double Theta0, Theta3, t1, t2base, d1, d2, stretch, color;
   double base0, k1, k2, k3, k4, k5;   // folded forms for the non-betaz modes
 };
-template <bool HASQ, bool FLAT, bool SLOW>
+template <bool HASQ, bool FLAT, bool SLOW, bool NEG>
 __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, const double *__restrict__ T,
-                                         const SNPer &m_, double f1, double &chi2, double &logdet, int &e,
-                                         unsigned &nev) {
+                                         const SNPer &m_, double f1, double rh, double &chi2, double &logdet,
+                                         int &e, unsigned &nev) {
   const bool flat = fabs(ec.OK) < FLAT_EPS;
   const int mode = L.sn_chi2mode;
   for (int iz = 0; iz < L.sn_nz; iz++) {
     const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
-    const double2 n0 = __ldg(&nd[0]);
-    const double az = n0.x, h = 1.0 - az;
-    // trapezoid stages 1..5: the 16 tabulated nodes are independent evaluations
-    // (issued together for ILP), then the Romberg tableau by rows:
-    // R[m] <- T_{j,m} = T_{j,m-1} + (T_{j,m-1} - T_{j-1,m-1}) / (4^m - 1)
-    double fv[16];
-    fv[0] = sn_f<HASQ, FLAT, SLOW>(ec, T, n0);
-#pragma unroll
-    for (int i = 1; i < 16; i++) fv[i] = sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
-    // Stage 5 of NR qromb in closed form.  With g0 = (f(a_z) + f(1))/2 and the sums S_j of the
-    // 2^(j-1) new nodes of stage j+1, T_j = h 2^(1-j) (g0 + S_1 + .. + S_(j-1)), so the K = 5
-    // extrapolant ss = R[5][4] and dss = R[5][4] - R[5][3] are fixed linear combinations (exact
-    // rational weights of the Neville tableau for step ratios 1/4).
-    const double g0 = 0.5 * (fv[0] + f1), S1 = fv[1], S2 = fv[2] + fv[3];
-    const double S3 = ((fv[4] + fv[5]) + fv[6]) + fv[7];
-    double S4 = fv[8];
-#pragma unroll
-    for (int i = 9; i < 16; i++) S4 += fv[i];
-    double ss = h * fma(3937.0 / 103275.0, g0, fma(3062.0 / 80325.0, S1, fma(27728.0 / 722925.0, S2,
-                    fma(22016.0 / 722925.0, S3, (65536.0 / 722925.0) * S4))));
-    double dss = h * fma(-31.0 / 206550.0, g0, fma(-73.0 / 481950.0, S1, fma(-67.0 / 722925.0, S2,
-                     fma(-424.0 / 722925.0, S3, (256.0 / 722925.0) * S4))));
+    const double *__restrict__ na = L.nodes_a + (size_t)iz * SN_NODES;
+    SNSums S;
+    double ss, dss, lnaz, h;
+    sn_romb5<HASQ, FLAT, SLOW, NEG>(ec, T, nd, na, L.nodes4 + (size_t)iz * (4 * 16), f1, S, ss, dss, lnaz, h);
+    const double g0 = S.g0, S1 = S.S1, S2 = S.S2, S3 = S.S3, S4 = S.S4;
     bool done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
     nev += 17;
     int j = 5;                      // stages completed
@@ -417,12 +491,15 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
         double s = 0.0;
         if (2 * it <= SN_NODES) {
 #pragma unroll 4
-          for (int i = it; i < 2 * it; i++) s += sn_f<HASQ, FLAT, SLOW>(ec, T, __ldg(&nd[i]));
+          for (int i = it; i < 2 * it; i++) {
+            const double2 n = __ldg(&nd[i]);
+            s = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.x, n.y, (HASQ || !FLAT) ? __ldg(&na[i]) : 0.0, s);
+          }
         } else {
-          const double del = h / (double)it;
+          const double del = h / (double)it, az = __ldg(na);
           for (int i = 0; i < it; i++) {
             double a = fma((double)i + 0.5, del, az);
-            s += sn_f<HASQ, FLAT, SLOW>(ec, T, make_double2(a, log(a)));
+            s = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, log(a), rsqrt(a), a, s);
           }
         }
         nev += it;
@@ -437,11 +514,11 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
       j++;
     }
     // luminosity distance [Mpc/h] and distance modulus
-    double ww = R_HUBBLE * ss;
+    double ww = rh * ss;               // rh = c/H0 [Mpc/h] (times |Ode|^-1/2 on the fast path)
     double fk = (FLAT || flat) ? ww : f_K_from(ec.OK, ww);
     if (!(fk > 0.0)) e = 1;         // also catches NaN
-    // mu_th = 5 log10(fk / (az H_fid)) + 25; the az part is tabulated (nodes[.][0].y = ln az)
-    const double mu_th = fma(5.0 / M_LN10, (SLOW ? log(fk) : fast_log(fk, T)) - n0.y, 25.0 - 5.0 * log10(SN_H_FID));
+    // mu_th = 5 log10(fk / (az H_fid)) + 25; the az part is tabulated (ln az)
+    const double mu_th = fma(5.0 / M_LN10, (SLOW ? log(fk) : fast_log(fk, T)) - lnaz, SN_MU0);
     const int i0 = __ldg(&L.first[iz]), i1 = __ldg(&L.first[iz + 1]);
     for (int i = i0; i < i1; i++) {
       const double2 *__restrict__ r = reinterpret_cast<const double2 *>(L.sn + (size_t)i * SN_ROW);
@@ -476,8 +553,8 @@ __global__ void __launch_bounds__(SN_BLOCK, SN_MIN_BLOCKS)
 k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
           const int16_t *__restrict__ flg, double *__restrict__ logpi,
           int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow) {
-  __shared__ double T[96];      // [32 exp2 | 32 log reciprocals | 32 log offsets]
-  load_fast_tables(T);
+  __shared__ double T[96 + SN_EXP2_N];   // [32 exp2 | 32 log reciprocals | 32 log offsets | 2^(j/1024), pre-biased]
+  load_fast_tables_sn(T);
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = (n < N) && (!flg || flg[n]);
   unsigned nev = 0;
@@ -493,17 +570,20 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   SNCoef ec;
   {
     const ECoef g = make_ecoef(m.c, 0);
-    ec.Om = g.Om; ec.OK = g.OK; ec.Ode = g.Ode; ec.p = g.p; ec.q = g.q; ec.jassal = g.jassal;
-    ec.p2 = g.p * M_LOG2E; ec.q2 = g.q * M_LOG2E;
+    ec.Om = g.Om; ec.OK = g.OK; ec.Ode = g.Ode; ec.p = g.p - 1.0; ec.q = g.q; ec.jassal = g.jassal;
+    ec.p2 = ec.p * M_LOG2E; ec.q2 = g.q * M_LOG2E;
     const double aO = fabs(g.Ode);
-    ec.lg = log2(aO);
+    const double lg = log2(aO);
     ec.sgn = (g.Ode < 0.0) ? 0x80000000u : 0u;
+    ec.Oms = g.Om / aO; ec.OKs = g.OK / aO; ec.scale = rsqrt(aO);
     // bound on |s| over a in [a_min, 1]; outside the fast path's range (or Ode = 0,
     // non-finite input) the warp takes the libdevice path
-    const double lna_min = -__ldg(&L.nodes[(size_t)(L.sn_nz - 1) * SN_NODES]).y;
-    ec.slow = force_slow || !(fabs(ec.p2) * lna_min + fabs(ec.q2) + fabs(ec.lg) < 990.0);
+    const double lna_min = -__ldg(&L.nodes[(size_t)(L.sn_nz - 1) * SN_NODES]).x;
+    ec.slow = force_slow || !(fabs(ec.p2) * lna_min + fabs(ec.q2) + fabs(lg) < 990.0);
   }
-  const double f1 = rsqrt(ec.Om + ec.OK + ec.Ode);      // integrand at a = 1
+  // integrand at a = 1 (a^-1/2 = 1, 2^0 = 1), in both normalisations
+  const double f1 = rsqrt(ec.Om + ec.OK + ec.Ode);
+  const double f1s = rsqrt(ec.Oms + ec.OKs + (ec.sgn ? -1.0 : 1.0));
   SNPer pm;
   pm.Theta0 = m.Theta2[0]; pm.Theta3 = m.Theta2[3]; pm.t1 = m.Theta2[1]; pm.t2base = m.Theta2[2];
   pm.d1 = pm.t1; pm.d2 = pm.t2base; pm.stretch = m.stretch; pm.color = m.color;
@@ -513,8 +593,10 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   pm.k1 = pm.d1 * pm.d1; pm.k2 = pm.d2 * pm.d2; pm.k3 = 2.0 * pm.d1; pm.k4 = 2.0 * pm.d2;
   pm.k5 = 2.0 * pm.d1 * pm.d2;
   double chi2 = 0.0, logdet = 0.0;
-  if (__any_sync(0xffffffffu, ec.slow)) sn_zloop<HASQ, FLAT, true>(L, ec, T, pm, f1, chi2, logdet, e, nev);
-  else sn_zloop<HASQ, FLAT, false>(L, ec, T, pm, f1, chi2, logdet, e, nev);
+  if (__any_sync(0xffffffffu, ec.slow)) sn_zloop<HASQ, FLAT, true, false>(L, ec, T, pm, f1, R_HUBBLE, chi2, logdet, e, nev);
+  else if (__any_sync(0xffffffffu, ec.sgn != 0u))
+    sn_zloop<HASQ, FLAT, false, true>(L, ec, T, pm, f1s, R_HUBBLE * ec.scale, chi2, logdet, e, nev);
+  else sn_zloop<HASQ, FLAT, false, false>(L, ec, T, pm, f1s, R_HUBBLE * ec.scale, chi2, logdet, e, nev);
   double res = -0.5 * chi2;
   if (L.sn_add_logdetCov) res -= 0.5 * logdet;
   if (!isfinite(res)) e = 1;

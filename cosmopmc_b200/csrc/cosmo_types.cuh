@@ -14,8 +14,10 @@ struct DevLike {
   // SN Ia
   int sn_chi2mode, sn_add_logdetCov, sn_n, sn_nz;
   double Theta2[4], Theta2_denom[3], sig_int2, pv_fac;
-  const double2 *nodes;   // [sn_nz][SN_NODES] {a, ln a}; entry 0 = a(z), entry i in
+  const double2 *nodes;   // [sn_nz][SN_NODES] {ln a, a^-1/2}; entry 0 = a(z), entry i in
                           // [2^(j-2), 2^(j-1)) = nodes of trapezoid stage j >= 2
+  const double *nodes_a;  // [sn_nz][SN_NODES] a itself
+  const double *nodes4;   // [sn_nz][16][4] {ln a, a^-1/2, a, -}: stages 1..5, one 32-byte load per node (curved / w1)
   const int *first;       // [sn_nz+1] ranges of supernovae sharing a redshift
   const double *sn;       // [sn_n][SN_ROW]: m s | c z | Vmm+pv2+int2 Vss | Vcc Cms | Cmc Csc | - -
   int sn_hasq, sn_flat;   // launch-uniform specialisation flags (set by the host)

@@ -4,6 +4,25 @@
 #include "small_kernels.cuh"
 #include "launch.h"
 #include <cstdlib>
+#include <cstring>
+#include <cmath>
+
+// Fill the SN kernel's 2^(j/1024) table on the current device (pre-biased high words, cosmo.cuh).
+int pmc_init_sn_tables() {
+  static double tab[SN_EXP2_N];
+  static bool have = false;
+  if (!have) {
+    for (int j = 0; j < SN_EXP2_N; j++) {
+      const double v = (double)exp2l((long double)j / SN_EXP2_N);
+      unsigned long long b;
+      memcpy(&b, &v, 8);
+      b -= (unsigned long long)j << (32 + 10);     // high word -= j << 10
+      memcpy(&tab[j], &b, 8);
+    }
+    have = true;
+  }
+  return cudaMemcpyToSymbol(g_sn_exp2, tab, sizeof(tab)) == cudaSuccess ? 0 : 1;
+}
 
 static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
 

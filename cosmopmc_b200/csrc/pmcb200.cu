@@ -209,6 +209,7 @@ static int create_impl(pmcb200_ctx *c, int device, void *stream) {
   c->sm_count = prop.multiProcessorCount;
   CUDA_OK(c, cudaMalloc((void **)&c->d_scal, sizeof(DevScal)));
   CUDA_OK(c, cudaMemset(c->d_scal, 0, sizeof(DevScal)));
+  if (pmc_init_sn_tables()) return fail(c, PMCB200_ERR_CUDA, "SN table upload failed");
   CUDA_OK(c, cudaMalloc((void **)&c->d_cnt, sizeof(DevCount)));
   CUDA_OK(c, cudaMemset(c->d_cnt, 0, sizeof(DevCount)));
   CUDA_OK(c, cudaMallocHost((void **)&c->h_result, sizeof(double) * (RES_HDR + PMCB200_MAX_COMP * (1 + PMCB200_MAX_DIM + PMCB200_MAX_DIM * PMCB200_MAX_DIM))));
@@ -396,6 +397,8 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
   std::vector<double> rows((size_t)n * SN_ROW, 0.0);
   std::vector<int> first;
   std::vector<double2> nodes;
+  std::vector<double> nodes_a;
+  auto node = [](double x) { return make_double2(std::log(x), 1.0 / std::sqrt(x)); };
   const double pv_fac = 5.0 / M_LN10 * L.sn_v_pec / C_KMS;
   for (int r = 0; r < n; r++) {
     int i = ord[r];
@@ -406,11 +409,12 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
       double a = 1.0 / (1.0 + z), hh = 1.0 - a;
       size_t base = nodes.size();
       nodes.resize(base + SN_NODES);
-      nodes[base] = make_double2(a, std::log(a));
+      nodes_a.resize(base + SN_NODES, 1.0);
+      nodes[base] = node(a); nodes_a[base] = a;
       for (int j = 2; j <= 7; j++) {
         int it = 1 << (j - 2);
         double del = hh / (double)it, x = a + 0.5 * del;   // NR trapzd: x += del
-        for (int q = 0; q < it; q++, x += del) nodes[base + it + q] = make_double2(x, std::log(x));
+        for (int q = 0; q < it; q++, x += del) { nodes[base + it + q] = node(x); nodes_a[base + it + q] = x; }
       }
     }
     double *row = rows.data() + (size_t)r * SN_ROW;
@@ -445,6 +449,15 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
   D.sn_flat = (!s_other && (s_Om || std::fabs(OK0) < 1e-15)) ? 1 : 0;
   int rc;
   if ((rc = dev_copy<double2>(c, nodes.data(), nodes.size(), &D.nodes))) return rc;
+  if ((rc = dev_copy<double>(c, nodes_a.data(), nodes_a.size(), &D.nodes_a))) return rc;
+  std::vector<double> nodes4((size_t)D.sn_nz * 64, 0.0);
+  for (int z = 0; z < D.sn_nz; z++)
+    for (int i = 0; i < 16; i++) {
+      double *q = &nodes4[((size_t)z * 16 + i) * 4];
+      q[0] = nodes[(size_t)z * SN_NODES + i].x; q[1] = nodes[(size_t)z * SN_NODES + i].y;
+      q[2] = nodes_a[(size_t)z * SN_NODES + i];
+    }
+  if ((rc = dev_copy<double>(c, nodes4.data(), nodes4.size(), &D.nodes4))) return rc;
   if ((rc = dev_copy<int>(c, first.data(), first.size(), &D.first))) return rc;
   if ((rc = dev_copy<double>(c, rows.data(), rows.size(), &D.sn))) return rc;
   return 0;

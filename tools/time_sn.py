@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import make_config, SEED
 from cosmopmc_b200.pmc import PMC
-ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=4_000_000); ap.add_argument("--config", default="sn")
+ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=4_000_000); ap.add_argument("--config", default="sn"); ap.add_argument("--save", default="")
 a = ap.parse_args()
 spec, w, m, ch, label = make_config(a.config)
 pmc = PMC(0); pmc.set_target(spec); pmc.set_proposal(w, m, chol=ch)
@@ -19,3 +19,5 @@ for _ in range(5): lp, err = pmc.posterior_log_pdf(b["X"])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 print("%s: %.3f ms for %d samples -> %.3f ns/sample, checksum %.10f" % (os.environ.get("PMCB200_LIB", "default"), ms, a.n, ms * 1e6 / a.n, lp.sum().item()))
+if a.save:
+    torch.save({"lp": lp.cpu(), "err": err.cpu()}, a.save)
