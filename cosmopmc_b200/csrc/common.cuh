@@ -14,6 +14,7 @@
 #define ROMB_EPS 1.0e-6
 #define ROMB_JMAX 20
 #define SN_H_FID 0.7
+#define DE_A_ACC (2.0 / 3.0)   // a_acc of the de_conservative prior (param.c:1091)
 #define SN_MU0 25.774509799928715845   // 25 - 5 log10(SN_H_FID); a literal: nvcc does not fold log10() of a constant
 #define FLAT_EPS 1.0e-8
 #define OMEGA_GAMMA_H2 2.469e-5

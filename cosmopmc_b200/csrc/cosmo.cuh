@@ -83,6 +83,16 @@ __device__ inline int apply_params(const DevLike &L, const double *__restrict__ 
   return bad;
 }
 
+// nicaea test_range_de_conservative (sn.c:265, bao.c:156, wmap.c:1029): w(a) outside [-1, -1/3]
+// at a = 1 or a = a_acc.  A violating model gets log L = 0 from the probe (reference behaviour).
+__device__ __forceinline__ bool de_conservative_violated(const pmcb200_cosmo_t &c) {
+  const double w_now = c.w0_de;
+  double w_acc = w_now;
+  if (c.de_param == PMCB200_DE_linder) w_acc = c.w0_de + c.w1_de * (1.0 - DE_A_ACC);
+  else if (c.de_param == PMCB200_DE_jassal) w_acc = c.w0_de + c.w1_de * DE_A_ACC * (1.0 - DE_A_ACC);
+  return w_now < -1.0 || w_now > -1.0 / 3.0 || w_acc < -1.0 || w_acc > -1.0 / 3.0;
+}
+
 // ---- fast FP64 primitives (SN hot loop and the BAO / CMB integrals) ---------------------------------
 // 2^s for |s| < 1000: s = k/32 + f with |f| <= 1/64 (one magic-number add, the
 // remainder is exact), 2^f by a degree-5 near-minimax polynomial (Chebyshev
@@ -561,7 +571,8 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   Model m;
   int e = 0;
   if (active) e = apply_params(L, X + n * d, m);
-  if (!active || e) {   // keep the warp's control flow uniform on a benign model
+  const bool cut = active && !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c);
+  if (!active || e || cut) {   // keep the warp's control flow uniform on a benign model
     m.c = L.model;
 #pragma unroll
     for (int i = 0; i < 4; i++) m.Theta2[i] = L.Theta2[i];
@@ -600,6 +611,7 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   double res = -0.5 * chi2;
   if (L.sn_add_logdetCov) res -= 0.5 * logdet;
   if (!isfinite(res)) e = 1;
+  if (cut) { res = 0.0; e = 0; }     // de_conservative: log L = 0, sn.c:263-274
   if (active) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
   else if (n < N && set) { logpi[n] = 0.0; if (err) err[n] = 0; }
   if (cnt) {   // measurement only: one atomic pair per warp
@@ -629,7 +641,7 @@ k_like_bao(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   Model m;
   int e = apply_params(L, X + n * d, m);
   double res = 0.0;
-  if (!e) {
+  if (!e && !(L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c))) {
     double model[4];
     const int nd = L.g_ndim;
     const pmcb200_cosmo_t &c = m.c;
@@ -665,8 +677,9 @@ k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   int e = apply_params(L, X + n * d, m);
   double res = 0.0;
   const pmcb200_cosmo_t &c = m.c;
-  if (!e && (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0))) e = 1;
-  if (!e) {
+  const bool cut = !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(c);
+  if (!e && !cut && (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0))) e = 1;
+  if (!e && !cut) {
     double model[4];
     double zs = z_star(c), as = 1.0 / (1.0 + zs);
     double ww = w_generic(c, as, 1, e, T);

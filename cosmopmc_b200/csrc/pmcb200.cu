@@ -484,7 +484,21 @@ extern "C" int pmcb200_set_target(pmcb200_ctx *c, const pmcb200_target_t *t) {
   // special prior of data set 0 only, param.c:998-1001,1055-1101
   int special = t->like[0].special;
   if (special == PMCB200_SPECIAL_unity) for (int j = 0; j < d; j++) logpr += std::log(t->max[j] - t->min[j]);
-  else if (special != PMCB200_SPECIAL_none)
+  else if (special == PMCB200_SPECIAL_de_conservative) {   // volume term, param.c:1072-1094
+    int iw0 = -1, iw1 = -1;
+    for (int j = 0; j < d; j++) {
+      if (t->like[0].par[j] == PMCB200_P_w0de) iw0 = j;
+      if (t->like[0].par[j] == PMCB200_P_w1de) iw1 = j;
+    }
+    if (iw0 >= 0) {
+      if (t->min[iw0] > -1.0 || t->max[iw0] < -1.0 / 3.0)
+        return fail(c, PMCB200_ERR_ARG, "Range of w0_de [%g;%g] should not be smaller than de_conservative prior [-1;-1/3]",
+                    t->min[iw0], t->max[iw0]);
+      if (iw1 < 0) logpr += std::log(t->max[iw0] - t->min[iw0]) - std::log(2.0 / 3.0);
+      else logpr += std::log(t->max[iw0] - t->min[iw0]) + std::log(t->max[iw1] - t->min[iw1])
+                    - std::log(0.5 * 2.0 / 3.0 * 2.0 / 3.0 / (1.0 - DE_A_ACC)) - std::log(0.5 * 2.0 / 3.0 * 2.0 / 3.0);
+    }
+  } else if (special != PMCB200_SPECIAL_none)
     return fail(c, PMCB200_ERR_UNSUP, "target: special prior %d not supported", special);
   c->logpr_const = logpr;
   const double *dbox;

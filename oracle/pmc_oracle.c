@@ -614,9 +614,27 @@ static double loglike_banana(const pmcb200_like_t *L, const double *x)
    return -0.5 * q - 0.5 * (d * ORC_LN2PI + log(s1));
 }
 
+/* nicaea test_range_de_conservative (call sites sn.c:265, bao.c:156, wmap.c:1029) [UPSTREAM-RECALL]:
+ * 1 if w(a) leaves [-1, -1/3] at a = 1 or at a = ORC_A_ACC (the a_acc of param.c:1091). */
+#define ORC_A_ACC (2.0 / 3.0)
+static int de_conservative_violated(const pmcb200_cosmo_t *c)
+{
+   double w_now = c->w0_de, w_acc = w_now;
+   if (c->de_param == PMCB200_DE_linder) w_acc = c->w0_de + c->w1_de * (1.0 - ORC_A_ACC);
+   else if (c->de_param == PMCB200_DE_jassal) w_acc = c->w0_de + c->w1_de * ORC_A_ACC * (1.0 - ORC_A_ACC);
+   return (w_now < -1.0 || w_now > -1.0 / 3.0 || w_acc < -1.0 || w_acc > -1.0 / 3.0);
+}
+
 double orc_loglike(const pmcb200_like_t *L, const double *x, int *err)
 {
    model_t m;
+   /* hard cut of the de_conservative prior inside each probe: the reference returns log L = 0
+    * (not -inf) for a violating model, sn.c:263-274, bao.c:154-176, wmap.c:1027-1039 */
+   if (L->special == PMCB200_SPECIAL_de_conservative &&
+       (L->kind == PMCB200_LIKE_SNIa || L->kind == PMCB200_LIKE_BAO || L->kind == PMCB200_LIKE_CMBDistPrior)) {
+      if (apply_params(L, x, &m)) { *err = 1; return 0.0; }
+      if (de_conservative_violated(&m.c)) return 0.0;
+   }
    switch (L->kind) {
       case PMCB200_LIKE_Mvdens:
          return orc_mvdens_log_pdf(L->mix_ndim, L->mix_df, L->mix_mean, L->mix_chol, x);
@@ -662,6 +680,19 @@ double orc_posterior_log_pdf(const pmcb200_target_t *t, const double *x, int *er
    int special = t->like[0].special;
    if (special == PMCB200_SPECIAL_unity)
       for (int j = 0; j < t->npar; j++) logpr += log(t->max[j] - t->min[j]);
+   else if (special == PMCB200_SPECIAL_de_conservative) {   /* param.c:1072-1094 */
+      int iw0 = -1, iw1 = -1;
+      for (int j = 0; j < t->npar; j++) {
+         if (t->like[0].par[j] == PMCB200_P_w0de) iw0 = j;
+         if (t->like[0].par[j] == PMCB200_P_w1de) iw1 = j;
+      }
+      if (iw0 >= 0) {
+         if (t->min[iw0] > -1.0 || t->max[iw0] < -1.0 / 3.0) { *err = 1; return 0.0; }
+         if (iw1 < 0) logpr += log(t->max[iw0] - t->min[iw0]) - log(2.0 / 3.0);
+         else logpr += log(t->max[iw0] - t->min[iw0]) + log(t->max[iw1] - t->min[iw1])
+                       - log(0.5 * 2.0 / 3.0 * 2.0 / 3.0 / (1.0 - ORC_A_ACC)) - log(0.5 * 2.0 / 3.0 * 2.0 / 3.0);
+      }
+   }
    else if (special != PMCB200_SPECIAL_none) { *err = 1; return 0.0; }
    logpost += logpr;
    if (t->prior_mean) {

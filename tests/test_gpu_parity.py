@@ -193,6 +193,31 @@ def test_posterior_sn_bao_w0wa(oracle, pmc_factory):
     check_posterior(oracle, pmc, spec, box_samples(spec, 1500, 14))
 
 
+def test_posterior_de_conservative(oracle, pmc_factory):
+    """special prior de_conservative on every probe: volume term (param.c:1072-1094) and the
+    log L = 0 cut for violating models (sn.c:263-274, bao.c:154-176, wmap.c:1027-1039)."""
+    pmc = pmc_factory()
+    spec = (T.TargetSpec(["Omega_b", "Omega_m", "Omega_de", "h_100", "w_0_de", "w_1_de", "M", "alpha", "beta"],
+                         [0.02, 0.1, 0.3, 0.5, -1.5, -1.5, 19.1, 0.5, -3.5],
+                         [0.08, 0.6, 1.1, 0.9, 0.0, 1.5, 19.8, 2.6, -0.8])
+            .add_cmbdp(special="de_conservative").add_bao(T.BAO_BOSS12_DZ, special="de_conservative")
+            .add_snia(cosmo=T.COSMO_DP, special="de_conservative"))
+    pmc.set_target(spec)
+    X = box_samples(spec, 1500, 21)
+    w_now, w_acc = X[:, 4], X[:, 4] + X[:, 5] / 3.0
+    cutm = (w_now < -1) | (w_now > -1 / 3) | (w_acc < -1) | (w_acc > -1 / 3)
+    assert 0.2 < cutm.mean() < 0.95
+    check_posterior(oracle, pmc, spec, X)
+    got, err = pmc.posterior_log_pdf(dev(X))
+    got = got.cpu().numpy()
+    assert np.ptp(got[cutm]) < 1e-12            # every probe returned 0: only the constant prior is left
+    # narrower w0 range than the prior: refused like the reference does
+    bad = T.TargetSpec(["Omega_m", "w_0_de", "M", "alpha", "beta"], [0.0, -0.8, 19.1, 0.5, -3.5],
+                       [1.2, 0.5, 19.8, 2.6, -0.8]).add_snia(special="de_conservative")
+    with pytest.raises(Exception):
+        pmc.set_target(bad)
+
+
 def test_posterior_cmb_bao_sn(oracle, pmc_factory):
     pmc = pmc_factory()
     spec = T.target_cmb_bao_sn()

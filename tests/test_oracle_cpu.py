@@ -188,6 +188,41 @@ def test_parameter_mapping_rules(oracle):
     assert e4[0] != 0
 
 
+def test_de_conservative_prior(oracle):
+    """special prior de_conservative: volume term of wrappers/src/param.c:1072-1094 and the probes'
+    hard cut, which returns log L = 0 for a violating model (sn.c:263-274)."""
+    lo, hi = [0.0, -3.5, 19.1, 0.5, -3.5], [1.2, 0.5, 19.8, 2.6, -0.8]
+    names = ["Omega_m", "w_0_de", "M", "alpha", "beta"]
+    plain = T.TargetSpec(names, lo, hi).add_snia()
+    cons = T.TargetSpec(names, lo, hi).add_snia(special="de_conservative")
+    X = np.array([[0.3, -0.9, 19.3, 1.5, -2.0], [0.3, -1.2, 19.3, 1.5, -2.0], [0.3, -0.2, 19.3, 1.5, -2.0]])
+    p0, e0 = oracle.posterior_log_pdf(plain, X)
+    p1, e1 = oracle.posterior_log_pdf(cons, X)
+    assert not e0.any() and not e1.any()
+    vol = np.log(hi[1] - lo[1]) - np.log(2.0 / 3.0)
+    logpr = -np.sum(np.log(np.array(hi) - np.array(lo)))
+    assert abs((p1[0] - p0[0]) - vol) < 1e-12                  # inside [-1, -1/3]: only the volume changes
+    assert np.allclose(p1[1:], logpr + vol, rtol=0, atol=1e-12)   # outside: log L = 0
+    # w0-wa: both w(1) and w(a_acc = 2/3) must lie inside; two-triangle volume as written in the reference
+    names2 = ["Omega_m", "w_0_de", "w_1_de", "M", "alpha", "beta"]
+    lo2, hi2 = [0.0, -2.0, -3.0, 19.1, 0.5, -3.5], [1.2, 0.0, 2.0, 19.8, 2.6, -0.8]
+    cons2 = T.TargetSpec(names2, lo2, hi2).add_snia(special="de_conservative")
+    plain2 = T.TargetSpec(names2, lo2, hi2).add_snia()
+    X2 = np.array([[0.3, -0.9, 0.6, 19.3, 1.5, -2.0],      # w(2/3) = -0.7: inside
+                   [0.3, -0.9, 2.0, 19.3, 1.5, -2.0],      # w(2/3) = -0.233: outside
+                   [0.3, -0.5, -1.8, 19.3, 1.5, -2.0]])    # w(2/3) = -1.1: outside
+    q0, _ = oracle.posterior_log_pdf(plain2, X2)
+    q1, _ = oracle.posterior_log_pdf(cons2, X2)
+    vol2 = np.log(2.0) + np.log(5.0) - np.log(0.5 * 4.0 / 9.0 / (1.0 - 2.0 / 3.0)) - np.log(0.5 * 4.0 / 9.0)
+    logpr2 = -np.sum(np.log(np.array(hi2) - np.array(lo2)))
+    assert abs((q1[0] - q0[0]) - vol2) < 1e-12
+    assert np.allclose(q1[1:], logpr2 + vol2, rtol=0, atol=1e-12)
+    # a w0 range narrower than the prior is refused (param.c:1081-1083)
+    bad = T.TargetSpec(names, [0.0, -0.8, 19.1, 0.5, -3.5], hi).add_snia(special="de_conservative")
+    _, eb = oracle.posterior_log_pdf(bad, X[:1])
+    assert eb.all()
+
+
 def test_bao_cmb_sanity(oracle):
     """BAO / CMB distance-prior model values at the WMAP7 best fit are close to the data."""
     spec = T.TargetSpec(["Omega_m", "Omega_de", "h_100", "Omega_b"], [0.1, 0.3, 0.5, 0.02],
