@@ -121,6 +121,14 @@ SYMBOLS = {
     "pmcb200_dev_free": (_i, [_vp, _vp]),
     "pmcb200_h2d": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "pmcb200_d2h": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "pmcb200_h2d_async": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "pmcb200_d2h_async": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "pmcb200_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "pmcb200_host_free": (_i, [_vp]),
+    "pmcb200_allgather_blocks": (_i, [C.POINTER(_vp), _i, C.POINTER(_vp), C.POINTER(_vp), _i64]),
+    "pmcb200_iteration_host_multi": (_i, [C.POINTER(_vp), _i, _i64, _u64, _u32, _d, _vp, _vp, _vp, _vp,
+                                          C.POINTER(Stats)]),
+    "pmcb200_normalize_with": (_i, [_vp, _i64, _vp, _vp, _d, _d]),
 }
 
 _lib = None

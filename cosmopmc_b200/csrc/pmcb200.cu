@@ -26,6 +26,7 @@ struct pmcb200_ctx {
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;     // D2H of finished arrays overlaps the likelihood kernel
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_blk = nullptr;           // statistics block ready (all-gather between contexts)
   char errmsg[512] = {0};
   int64_t launches = 0;
   // proposal
@@ -54,7 +55,7 @@ struct pmcb200_ctx {
   int em_blocks = 0;
   int sm_count = 148;
   // scratch for the host-buffer API
-  DevBuf sX, sIdx, sFlg, sLogw, sLogpi, sErr, sBlock;
+  DevBuf sX, sIdx, sFlg, sLogw, sLogpi, sErr, sBlock, sAll;
 };
 
 static int fail(pmcb200_ctx *c, int code, const char *fmt, ...) {
@@ -204,6 +205,7 @@ static int create_impl(pmcb200_ctx *c, int device, void *stream) {
   CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
   CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+  CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_blk, cudaEventDisableTiming));
   cudaDeviceProp prop;
   CUDA_OK(c, cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -243,7 +245,7 @@ extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_target(c);
-  for (DevBuf *b : {&c->sX, &c->sIdx, &c->sFlg, &c->sLogw, &c->sLogpi, &c->sErr, &c->sBlock})
+  for (DevBuf *b : {&c->sX, &c->sIdx, &c->sFlg, &c->sLogw, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll})
     if (b->p) cudaFree(b->p);
   if (c->d_mix) cudaFree(c->d_mix);
   if (c->d_scal) cudaFree(c->d_scal);
@@ -255,6 +257,7 @@ extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->ev_blk) cudaEventDestroy(c->ev_blk);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -855,6 +858,143 @@ extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, 
   return rc;
 }
 
+
+// ---- several contexts in one process --------------------------------------------
+extern "C" int pmcb200_h2d_async(pmcb200_ctx *c, void *dptr, const void *hptr, size_t bytes) {
+  if (!c) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  if (bytes) CUDA_OK(c, cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+extern "C" int pmcb200_d2h_async(pmcb200_ctx *c, void *hptr, const void *dptr, size_t bytes) {
+  if (!c) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  if (bytes) CUDA_OK(c, cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+// Page-locked host lumps are remembered so that pmcb200_host_free can tell them from the
+// malloc fallback (no device: host-only callers such as the CPU tests still get memory).
+static std::vector<void *> g_pinned;
+extern "C" int pmcb200_host_alloc(size_t bytes, void **hptr) {
+  if (!hptr) return PMCB200_ERR_ARG;
+  *hptr = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0 &&
+      cudaHostAlloc(hptr, std::max<size_t>(bytes, 1), cudaHostAllocPortable) == cudaSuccess) {
+    g_pinned.push_back(*hptr);
+    return 0;
+  }
+  cudaGetLastError();
+  *hptr = malloc(std::max<size_t>(bytes, 1));
+  return *hptr ? 0 : PMCB200_ERR_ARG;
+}
+extern "C" int pmcb200_host_free(void *hptr) {
+  if (!hptr) return 0;
+  for (size_t i = 0; i < g_pinned.size(); i++)
+    if (g_pinned[i] == hptr) {
+      g_pinned.erase(g_pinned.begin() + i);
+      return cudaFreeHost(hptr) == cudaSuccess ? 0 : PMCB200_ERR_CUDA;
+    }
+  free(hptr);
+  return 0;
+}
+
+extern "C" int pmcb200_allgather_blocks(pmcb200_ctx *const *ctx, int n, double *const *dblock,
+                                        double *const *dall, int64_t len) {
+  if (!ctx || n < 1 || n > 64 || !dblock || !dall || len < 1) return PMCB200_ERR_ARG;
+  for (int r = 0; r < n; r++) {
+    if (!ctx[r] || !dblock[r] || !dall[r]) return PMCB200_ERR_ARG;
+    pmcb200_ctx *c = ctx[r];
+    CUDA_OK(c, cudaSetDevice(c->device));
+    CUDA_OK(c, cudaEventRecord(c->ev_blk, c->stream));
+  }
+  const size_t bytes = (size_t)len * sizeof(double);
+  for (int q = 0; q < n; q++) {
+    pmcb200_ctx *c = ctx[q];
+    CUDA_OK(c, cudaSetDevice(c->device));
+    for (int r = 0; r < n; r++) {
+      if (r != q) CUDA_OK(c, cudaStreamWaitEvent(c->stream, ctx[r]->ev_blk, 0));
+      if (ctx[r]->device == c->device)
+        CUDA_OK(c, cudaMemcpyAsync(dall[q] + (size_t)r * len, dblock[r], bytes, cudaMemcpyDeviceToDevice, c->stream));
+      else   // direct over NVLink when peer access is possible, staged by the driver otherwise
+        CUDA_OK(c, cudaMemcpyPeerAsync(dall[q] + (size_t)r * len, c->device, dblock[r], ctx[r]->device, bytes, c->stream));
+    }
+  }
+  return 0;
+}
+
+extern "C" int pmcb200_normalize_with(pmcb200_ctx *c, int64_t N, const int16_t *dflg, double *dw,
+                                      double maxW, double sum_shift) {
+  int rc = need(c, false, false);
+  if (rc) return rc;
+  if (N < 0 || (N > 0 && (!dflg || !dw)) || !(sum_shift > 0.0)) return fail(c, PMCB200_ERR_ARG, "normalize_with: bad arguments");
+  if (N == 0) return 0;
+  pmc_launch_normalize(N, dflg, dw, maxW, 1.0 / sum_shift, c->stream);
+  LAUNCH_OK(c);
+  return 0;
+}
+
+extern "C" int pmcb200_iteration_host_multi(pmcb200_ctx *const *ctx, int n, int64_t N, uint64_t seed,
+                                            uint32_t iter, double beta, double *hX, int32_t *hidx,
+                                            int16_t *hflg, double *hw, pmcb200_stats_t *stats) {
+  if (!ctx || n < 1 || n > 64 || !ctx[0]) return PMCB200_ERR_ARG;
+  if (n == 1) return pmcb200_iteration_host(ctx[0], N, seed, iter, beta, hX, hidx, hflg, hw, stats);
+  pmcb200_ctx *c0 = ctx[0];
+  if (N < 1) return fail(c0, PMCB200_ERR_ARG, "iteration_host_multi: N = %lld", (long long)N);
+  int rc;
+  for (int r = 0; r < n; r++) {
+    if (!ctx[r]) return fail(c0, PMCB200_ERR_ARG, "iteration_host_multi: null context %d", r);
+    if ((rc = need(ctx[r], true, true))) { if (r) fail(c0, rc, "shard %d: %s", r, ctx[r]->errmsg); return rc; }
+    if (ctx[r]->h.K != c0->h.K || ctx[r]->h.d != c0->h.d)
+      return fail(c0, PMCB200_ERR_DIM, "iteration_host_multi: shard %d holds another proposal shape", r);
+  }
+  const int d = c0->h.d;
+  const int64_t len = stat_len(c0->h.K, d), per = (N + n - 1) / n;
+  double *blk[64], *all[64];
+  // 1. queue every shard (sampler, likelihood, weights, local EM statistics, overlapped D2H)
+  for (int r = 0; r < n; r++) {
+    pmcb200_ctx *c = ctx[r];
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if ((rc = ensure(c, c->sBlock, (size_t)len * sizeof(double))) || (rc = ensure(c, c->sAll, (size_t)len * n * sizeof(double)))) {
+      if (r) fail(c0, rc, "shard %d: %s", r, c->errmsg);
+      return rc;
+    }
+    blk[r] = (double *)c->sBlock.p; all[r] = (double *)c->sAll.p;
+    const int64_t off = std::min<int64_t>(N, r * per), nr = std::max<int64_t>(0, std::min<int64_t>(per, N - off));
+    rc = iteration_core(c, nr, seed, iter, off, beta, nullptr, nullptr, nullptr, nullptr, blk[r],
+                        hX ? hX + (size_t)off * d : nullptr, hidx ? hidx + off : nullptr, hflg ? hflg + off : nullptr);
+    if (rc) { if (r) fail(c0, rc, "shard %d: %s", r, c->errmsg); return rc; }
+  }
+  // 2. the one exchange: statistics blocks to every context
+  if ((rc = pmcb200_allgather_blocks(ctx, n, blk, all, len))) return rc;
+  // 3. identical fixed-order combine + M-step on every context
+  pmcb200_stats_t st0;
+  int rc_fin = 0;
+  for (int r = 0; r < n; r++) {
+    pmcb200_stats_t st;
+    rc = pmcb200_em_finish(ctx[r], n, all[r], N, &st);
+    if (r == 0) { st0 = st; rc_fin = rc; }
+    else if (rc != rc_fin) return fail(c0, rc ? rc : PMCB200_ERR_STATE, "shard %d finished differently (%d vs %d): %s", r, rc, rc_fin, ctx[r]->errmsg);
+  }
+  if (stats) *stats = st0;
+  if (rc_fin) return rc_fin;
+  // 4. normalised weights of every shard to the host: queue all, then wait
+  for (int r = 0; r < n && hw; r++) {
+    pmcb200_ctx *c = ctx[r];
+    const int64_t off = std::min<int64_t>(N, r * per), nr = std::max<int64_t>(0, std::min<int64_t>(per, N - off));
+    if (nr == 0) continue;
+    if ((rc = pmcb200_normalize_weights(c, nr, (int16_t *)c->sFlg.p, (double *)c->sLogw.p))) { if (r) fail(c0, rc, "shard %d: %s", r, c->errmsg); return rc; }
+    CUDA_OK(c, cudaMemcpyAsync(hw + off, c->sLogw.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  for (int r = 0; r < n; r++) {
+    pmcb200_ctx *c = ctx[r];
+    CUDA_OK(c, cudaSetDevice(c->device));
+    CUDA_OK(c, cudaStreamSynchronize(c->copy_stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
 
 // ---- entry points used by the pmclib-named host shims -------------------------------------
 extern "C" int pmcb200_set_box(pmcb200_ctx *c, int d, const double *bmin, const double *bmax) {

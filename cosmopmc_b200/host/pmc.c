@@ -58,6 +58,17 @@ static size_t psim_bytes(long n, int ndim, int n_ded)
    return (size_t)n * (sizeof(double) * (ndim + n_ded + 1) + sizeof(size_t) + sizeof(short)) + 64;
 }
 
+/* The lump is page-locked (when a device exists) so that the slices of several shards move
+ * concurrently and the device-to-host copies overlap the likelihood kernel. */
+static void *psim_lump(size_t bytes, error **err)
+{
+   void *b = NULL;
+   testErrorRetVA(pmcb200_host_alloc(bytes, &b) != 0 || !b, pmc_allocate, "Cannot allocate %zu bytes for a pmc_simu", *err,
+                  __LINE__, NULL, bytes);
+   memset(b, 0, bytes);
+   return b;
+}
+
 pmc_simu *pmc_simu_init_plus_ded(long nsamples, int ndim, int n_ded, error **err)
 {
    testErrorRetVA(nsamples < 1 || ndim < 1 || n_ded < 0, pmc_dimension, "Invalid pmc_simu size (%ld,%d,%d)", *err,
@@ -65,7 +76,7 @@ pmc_simu *pmc_simu_init_plus_ded(long nsamples, int ndim, int n_ded, error **err
    pmc_simu *p = (pmc_simu *)calloc_err(1, sizeof(pmc_simu), err);
    forwardError(*err, __LINE__, NULL);
    p->nsamples = p->nsamples_alloc = nsamples; p->ndim = ndim; p->n_ded = n_ded;
-   p->buf = calloc_err(1, psim_bytes(nsamples, ndim, n_ded), err);
+   p->buf = psim_lump(psim_bytes(nsamples, ndim, n_ded), err);
    forwardError(*err, __LINE__, NULL);
    psim_carve(p, nsamples);
    p->isLog = 0; p->logSum = 0.0; p->maxW = 0.0; p->mpi_rank = 0; p->mpi_size = 1;
@@ -81,8 +92,8 @@ void pmc_simu_realloc(pmc_simu *p, long nsamples, error **err)
 {
    if (nsamples <= p->nsamples_alloc && nsamples == p->nsamples) return;
    testErrorRetVA(nsamples < 1, pmc_dimension, "Invalid number of samples %ld", *err, __LINE__, , nsamples);
-   free(p->buf);
-   p->buf = calloc_err(1, psim_bytes(nsamples, p->ndim, p->n_ded), err);
+   pmcb200_host_free(p->buf);
+   p->buf = psim_lump(psim_bytes(nsamples, p->ndim, p->n_ded), err);
    forwardError(*err, __LINE__, );
    p->nsamples = p->nsamples_alloc = nsamples;
    psim_carve(p, nsamples);
@@ -92,18 +103,30 @@ void pmc_simu_realloc(pmc_simu *p, long nsamples, error **err)
 void pmc_simu_free(pmc_simu **p)
 {
    if (!p || !*p) return;
-   free((*p)->buf); free(*p); *p = NULL;
+   pmcb200_host_free((*p)->buf); free(*p); *p = NULL;
 }
 
-/* ---- device context + target registry ------------------------------------------------
- * One process drives one GPU and, like the reference (single-threaded, no locks anywhere,
- * SURVEY.md 8b), this layer keeps process-wide state: it is not re-entrant. */
+/* ---- device contexts (shards) + target registry -------------------------------------
+ * One process drives G >= 1 GPUs: shard r of G owns the contiguous sample range
+ * [r*ceil(n/G), ...) of every psim (the reference's MPI ranks, cosmo_pmc.c:323-376, become
+ * contexts of one process).  G = $PMCB200_NGPU ("all" = every visible device; default 1);
+ * $PMCB200_DEVICES = comma-separated ordinals, used round-robin (an ordinal may repeat:
+ * several shards on one device, which is how the sharded path is tested on a one-GPU box);
+ * default list = $PMCB200_DEVICE (or 0), +1, ... modulo the device count.
+ * Like the reference (single-threaded, no locks anywhere) this layer keeps
+ * process-wide state: it is not re-entrant. */
 #define MAX_TARGETS 8
-static pmcb200_ctx *g_ctx = NULL;
+#define MAX_SHARDS 64
+static int g_ns = 0;
+static pmcb200_ctx *g_ctxs[MAX_SHARDS];
 static struct { posterior_log_pdf_func *f; void *data; pmcb200_target_t t; int used; } g_targets[MAX_TARGETS];
 static const void *g_active_target = NULL;
-/* device mirrors of the last psim (grow-only) */
-static struct { void *X, *idx, *flg, *w, *block; long cap; int d; long blen; } g_dev;
+/* device mirrors of each shard's slice of the last psim (grow-only) */
+typedef struct { void *X, *idx, *flg, *w, *block, *all; long cap; int d; long blen; } dev_mirror;
+static dev_mirror g_devs[MAX_SHARDS];
+/* page-locked staging of pmc_simu->indices (size_t on the host, int32 on the device) */
+static int32_t *g_idx32 = NULL;
+static long g_idx32_cap = 0;
 
 #define B200_OK(ctx, call, errcode, ret)                                                          \
    do { int rc__ = (call);                                                                        \
@@ -112,30 +135,73 @@ static struct { void *X, *idx, *flg, *w, *block; long cap; int d; long blen; } g
 
 pmcb200_ctx *pmc_b200_context(error **err)
 {
-   if (g_ctx) return g_ctx;
-   const char *e = getenv("PMCB200_DEVICE");
-   int dev = e ? atoi(e) : 0;
-   int rc = pmcb200_create(dev, NULL, &g_ctx);
-   if (rc != 0) {
-      g_ctx = NULL;
-      *err = addErrorVA(pmc_undef, "No usable CUDA device %d (pmcb200 code %d); the PMC iteration has no CPU path",
-                        *err, __LINE__, dev, rc);
+   if (g_ns > 0) return g_ctxs[0];
+   int ndev = pmcb200_device_count();
+   if (ndev < 1) {
+      *err = addError(pmc_undef, "No usable CUDA device; the PMC iteration has no CPU path", *err, __LINE__);
       return NULL;
    }
-   return g_ctx;
+   int ns = 1;
+   const char *e = getenv("PMCB200_NGPU");
+   if (e && *e) ns = (strcmp(e, "all") == 0) ? ndev : atoi(e);
+   testErrorRetVA(ns < 1 || ns > MAX_SHARDS, pmc_undef, "PMCB200_NGPU = %s (1..%d or 'all')", *err, __LINE__, NULL, e, MAX_SHARDS);
+   int list[MAX_SHARDS], nl = 0;
+   const char *dl = getenv("PMCB200_DEVICES");
+   if (dl && *dl) {
+      const char *q = dl;
+      while (*q && nl < MAX_SHARDS) {
+         char *end;
+         long v = strtol(q, &end, 10);
+         if (end == q) break;
+         list[nl++] = (int)v;
+         q = (*end == ',') ? end + 1 : end;
+      }
+   }
+   if (nl == 0) {
+      const char *d0 = getenv("PMCB200_DEVICE");
+      int first = d0 ? atoi(d0) : 0;
+      for (int r = 0; r < ns; r++) list[nl++] = (first + r) % ndev;
+   }
+   for (int r = 0; r < ns; r++) {
+      int dev = list[r % nl];
+      int rc = pmcb200_create(dev, NULL, &g_ctxs[r]);
+      if (rc != 0) {
+         for (int q = 0; q < r; q++) { pmcb200_destroy(g_ctxs[q]); g_ctxs[q] = NULL; }
+         *err = addErrorVA(pmc_undef, "No usable CUDA device %d (pmcb200 code %d); the PMC iteration has no CPU path",
+                           *err, __LINE__, dev, rc);
+         return NULL;
+      }
+   }
+   g_ns = ns;
+   return g_ctxs[0];
 }
+
+int pmc_b200_nshards(void) { return g_ns; }
 
 void pmc_b200_shutdown(void)
 {
-   if (!g_ctx) return;
-   if (g_dev.X) pmcb200_dev_free(g_ctx, g_dev.X);
-   if (g_dev.idx) pmcb200_dev_free(g_ctx, g_dev.idx);
-   if (g_dev.flg) pmcb200_dev_free(g_ctx, g_dev.flg);
-   if (g_dev.w) pmcb200_dev_free(g_ctx, g_dev.w);
-   if (g_dev.block) pmcb200_dev_free(g_ctx, g_dev.block);
-   memset(&g_dev, 0, sizeof(g_dev));
-   pmcb200_destroy(g_ctx);
-   g_ctx = NULL; g_active_target = NULL;
+   for (int r = 0; r < g_ns; r++) {
+      dev_mirror *m = &g_devs[r];
+      void *bufs[6] = { m->X, m->idx, m->flg, m->w, m->block, m->all };
+      for (int i = 0; i < 6; i++) if (bufs[i]) pmcb200_dev_free(g_ctxs[r], bufs[i]);
+      pmcb200_destroy(g_ctxs[r]);
+      g_ctxs[r] = NULL;
+   }
+   memset(g_devs, 0, sizeof(g_devs));
+   if (g_idx32) pmcb200_host_free(g_idx32);
+   g_idx32 = NULL; g_idx32_cap = 0;
+   g_ns = 0; g_active_target = NULL;
+}
+
+/* slice of an n-sample psim owned by shard r (same rule as pmcb200_iteration_host_multi) */
+static void shard_range(long n, int r, long *off, long *nr)
+{
+   long per = (n + g_ns - 1) / g_ns;
+   long o = (long)r * per;
+   if (o > n) o = n;
+   long m = n - o;
+   if (m > per) m = per;
+   *off = o; *nr = m;
 }
 
 void pmc_b200_register_target(posterior_log_pdf_func *f, void *data, const pmcb200_target_t *t, error **err)
@@ -149,12 +215,13 @@ void pmc_b200_register_target(posterior_log_pdf_func *f, void *data, const pmcb2
    *err = addError(pmc_outOfBound, "Too many registered device targets", *err, __LINE__);
 }
 
-static void activate_target(pmcb200_ctx *ctx, posterior_log_pdf_func *f, void *data, error **err)
+static void activate_target(posterior_log_pdf_func *f, void *data, error **err)
 {
    for (int i = 0; i < MAX_TARGETS; i++)
       if (g_targets[i].used && g_targets[i].f == f && g_targets[i].data == data) {
          if (g_active_target != &g_targets[i].t) {
-            B200_OK(ctx, pmcb200_set_target(ctx, &g_targets[i].t), pmc_incompat, );
+            for (int r = 0; r < g_ns; r++)
+               B200_OK(g_ctxs[r], pmcb200_set_target(g_ctxs[r], &g_targets[i].t), pmc_incompat, );
             g_active_target = &g_targets[i].t;
          }
          return;
@@ -167,7 +234,7 @@ static void activate_target(pmcb200_ctx *ctx, posterior_log_pdf_func *f, void *d
       if (bound) {
          pmc_b200_register_target(f, data, &t, err);
          forwardError(*err, __LINE__, );
-         activate_target(ctx, f, data, err);
+         activate_target(f, data, err);
          forwardError(*err, __LINE__, );
          return;
       }
@@ -177,28 +244,56 @@ static void activate_target(pmcb200_ctx *ctx, posterior_log_pdf_func *f, void *d
                    *err, __LINE__);
 }
 
-static void ensure_dev(pmcb200_ctx *ctx, long n, int d, long blen, error **err)
+/* mirrors of every shard's slice of an n-sample, d-dimensional psim; blen > 0 also sizes the
+ * statistics block and the gathered blocks of all shards */
+static void ensure_dev(long n, int d, long blen, error **err)
 {
-   if (n > g_dev.cap || d > g_dev.d) {
-      if (g_dev.X) { pmcb200_dev_free(ctx, g_dev.X); pmcb200_dev_free(ctx, g_dev.idx);
-                     pmcb200_dev_free(ctx, g_dev.flg); pmcb200_dev_free(ctx, g_dev.w); }
-      long cap = n > g_dev.cap ? n : g_dev.cap;
-      int dd = d > g_dev.d ? d : g_dev.d;
-      B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(double) * (size_t)cap * dd, &g_dev.X), pmc_allocate, );
-      B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(int32_t) * (size_t)cap, &g_dev.idx), pmc_allocate, );
-      B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(int16_t) * (size_t)cap, &g_dev.flg), pmc_allocate, );
-      B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(double) * (size_t)cap, &g_dev.w), pmc_allocate, );
-      g_dev.cap = cap; g_dev.d = dd;
-   }
-   if (blen > g_dev.blen) {
-      if (g_dev.block) pmcb200_dev_free(ctx, g_dev.block);
-      B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(double) * (size_t)blen, &g_dev.block), pmc_allocate, );
-      g_dev.blen = blen;
+   for (int r = 0; r < g_ns; r++) {
+      pmcb200_ctx *ctx = g_ctxs[r];
+      dev_mirror *m = &g_devs[r];
+      long off, nr;
+      shard_range(n, r, &off, &nr);
+      if (nr < 1) nr = 1;
+      if (nr > m->cap || d > m->d) {
+         if (m->X) { pmcb200_dev_free(ctx, m->X); pmcb200_dev_free(ctx, m->idx);
+                     pmcb200_dev_free(ctx, m->flg); pmcb200_dev_free(ctx, m->w); }
+         long cap = nr > m->cap ? nr : m->cap;
+         int dd = d > m->d ? d : m->d;
+         B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(double) * (size_t)cap * dd, &m->X), pmc_allocate, );
+         B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(int32_t) * (size_t)cap, &m->idx), pmc_allocate, );
+         B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(int16_t) * (size_t)cap, &m->flg), pmc_allocate, );
+         B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(double) * (size_t)cap, &m->w), pmc_allocate, );
+         m->cap = cap; m->d = dd;
+      }
+      if (blen > m->blen) {
+         if (m->block) { pmcb200_dev_free(ctx, m->block); pmcb200_dev_free(ctx, m->all); }
+         B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(double) * (size_t)blen, &m->block), pmc_allocate, );
+         B200_OK(ctx, pmcb200_dev_alloc(ctx, sizeof(double) * (size_t)blen * g_ns, &m->all), pmc_allocate, );
+         m->blen = blen;
+      }
    }
 }
 
-/* proposal (Cholesky-decomposed mix_mvdens) -> device */
-static void push_proposal(pmcb200_ctx *ctx, mix_mvdens *m, error **err)
+static int32_t *idx_staging(long n, error **err)
+{
+   if (n > g_idx32_cap) {
+      if (g_idx32) pmcb200_host_free(g_idx32);
+      g_idx32 = NULL; g_idx32_cap = 0;
+      void *p = NULL;
+      testErrorRet(pmcb200_host_alloc(sizeof(int32_t) * (size_t)n, &p) != 0, pmc_allocate, "Cannot allocate the index staging buffer",
+                   *err, __LINE__, NULL);
+      g_idx32 = (int32_t *)p; g_idx32_cap = n;
+   }
+   return g_idx32;
+}
+
+static void sync_all(error **err)
+{
+   for (int r = 0; r < g_ns; r++) B200_OK(g_ctxs[r], pmcb200_sync(g_ctxs[r]), pmc_badComm, );
+}
+
+/* proposal (Cholesky-decomposed mix_mvdens) -> every shard */
+static void push_proposal(mix_mvdens *m, error **err)
 {
    size_t K = m->ncomp, d = m->ndim;
    mix_mvdens_cholesky_decomp(m, err);
@@ -210,18 +305,25 @@ static void push_proposal(pmcb200_ctx *ctx, mix_mvdens *m, error **err)
       memcpy(mean + k * d, m->comp[k]->mean, d * sizeof(double));
       memcpy(chol + k * d * d, m->comp[k]->std, d * d * sizeof(double));
    }
-   int rc = pmcb200_set_proposal(ctx, (int)K, (int)d, m->comp[0]->df, m->wght, mean, chol);
+   for (int r = 0; r < g_ns; r++) {
+      int rc = pmcb200_set_proposal(g_ctxs[r], (int)K, (int)d, m->comp[0]->df, m->wght, mean, chol);
+      if (rc != 0) {
+         *err = addErrorVA(rc == PMCB200_ERR_CHOLESKY ? pmc_cholesky : pmc_incompat, "%s", *err, __LINE__,
+                           pmcb200_last_error(g_ctxs[r]));
+         break;
+      }
+   }
    free(mean);
-   if (rc != 0) *err = addErrorVA(rc == PMCB200_ERR_CHOLESKY ? pmc_cholesky : pmc_incompat, "%s", *err, __LINE__,
-                                  pmcb200_last_error(ctx));
 }
 
-/* updated proposal <- device.  As in pmclib, update_prop_rb leaves the COVARIANCE in comp[k]->std
- * (chol = 0; the Cholesky factor is recomputed on demand by the next use): the reference copies
- * std between components as a covariance (revive_comp, exec/cosmo_pmc.c:225).  Components that died
- * in the update (weight 0, cleanup_after_update) keep their previous mean and matrix. */
-static void pull_proposal(pmcb200_ctx *ctx, mix_mvdens *m, error **err)
+/* updated proposal <- device (shard 0; every shard holds the identical update).  As in pmclib,
+ * update_prop_rb leaves the COVARIANCE in comp[k]->std (chol = 0; the Cholesky factor is recomputed
+ * on demand by the next use): the reference copies std between components as a covariance
+ * (revive_comp, exec/cosmo_pmc.c:225).  Components that died in the update (weight 0,
+ * cleanup_after_update) keep their previous mean and matrix. */
+static void pull_proposal(mix_mvdens *m, error **err)
 {
+   pmcb200_ctx *ctx = g_ctxs[0];
    size_t K = m->ncomp, d = m->ndim;
    double *mean = (double *)malloc_err(sizeof(double) * K * d * (2 * d + 1), err);
    forwardError(*err, __LINE__, );
@@ -240,19 +342,27 @@ static void pull_proposal(pmcb200_ctx *ctx, mix_mvdens *m, error **err)
    if (rc != 0) *err = addErrorVA(pmc_incompat, "%s", *err, __LINE__, pmcb200_last_error(ctx));
 }
 
-static void push_samples(pmcb200_ctx *ctx, pmc_simu *p, int with_idx, int with_w, error **err)
+/* every shard's slice of the psim arrays -> its device mirror (queued, not waited for) */
+static void push_samples(pmc_simu *p, int with_X, int with_idx, int with_w, error **err)
 {
    long n = p->nsamples;
-   B200_OK(ctx, pmcb200_h2d(ctx, g_dev.X, p->X, sizeof(double) * (size_t)n * p->ndim), pmc_badComm, );
-   B200_OK(ctx, pmcb200_h2d(ctx, g_dev.flg, p->flg, sizeof(short) * (size_t)n), pmc_badComm, );
-   if (with_w) B200_OK(ctx, pmcb200_h2d(ctx, g_dev.w, p->weights, sizeof(double) * (size_t)n), pmc_badComm, );
+   int d = p->ndim;
+   int32_t *t = NULL;
    if (with_idx) {
-      int32_t *t = (int32_t *)malloc_err(sizeof(int32_t) * (size_t)n, err);
+      t = idx_staging(n, err);
       forwardError(*err, __LINE__, );
       for (long i = 0; i < n; i++) t[i] = (int32_t)p->indices[i];
-      int rc = pmcb200_h2d(ctx, g_dev.idx, t, sizeof(int32_t) * (size_t)n);
-      free(t);
-      B200_OK(ctx, rc, pmc_badComm, );
+   }
+   for (int r = 0; r < g_ns; r++) {
+      pmcb200_ctx *ctx = g_ctxs[r];
+      dev_mirror *m = &g_devs[r];
+      long off, nr;
+      shard_range(n, r, &off, &nr);
+      if (nr == 0) continue;
+      if (with_X) B200_OK(ctx, pmcb200_h2d_async(ctx, m->X, p->X + (size_t)off * d, sizeof(double) * (size_t)nr * d), pmc_badComm, );
+      B200_OK(ctx, pmcb200_h2d_async(ctx, m->flg, p->flg + off, sizeof(short) * (size_t)nr), pmc_badComm, );
+      if (with_w) B200_OK(ctx, pmcb200_h2d_async(ctx, m->w, p->weights + off, sizeof(double) * (size_t)nr), pmc_badComm, );
+      if (with_idx) B200_OK(ctx, pmcb200_h2d_async(ctx, m->idx, t + off, sizeof(int32_t) * (size_t)nr), pmc_badComm, );
    }
 }
 
@@ -296,36 +406,40 @@ double pmc_b200_single_loglike(const pmcb200_like_t *like, const double *x, erro
 /* ---- simulate_mix_mvdens (cosmo_pmc.c:320) -------------------------------------------- */
 size_t simulate_mix_mvdens(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, parabox *pb, error **err)
 {
-   pmcb200_ctx *ctx = pmc_b200_context(err);
+   pmc_b200_context(err);
    forwardError(*err, __LINE__, 0);
    testErrorRetVA((size_t)psim->ndim != proposal->ndim, pmc_dimension, "psim ndim %d != proposal ndim %zu", *err,
                   __LINE__, 0, psim->ndim, proposal->ndim);
    testErrorRet(pb != NULL && pb->ndim != psim->ndim, pmc_dimension, "parabox dimension mismatch", *err, __LINE__, 0);
    long n = psim->nsamples;
    int d = psim->ndim;
-   push_proposal(ctx, proposal, err);                       forwardError(*err, __LINE__, 0);
-   ensure_dev(ctx, n, d, 0, err);                           forwardError(*err, __LINE__, 0);
-   {
-      double lo[PMCB200_MAX_DIM], hi[PMCB200_MAX_DIM];
-      for (int j = 0; j < d; j++) { lo[j] = pb ? pb->min[j] : -HUGE_VAL; hi[j] = pb ? pb->max[j] : HUGE_VAL; }
-      B200_OK(ctx, pmcb200_set_box(ctx, d, lo, hi), pmc_incompat, 0);
-   }
+   push_proposal(proposal, err);                            forwardError(*err, __LINE__, 0);
+   ensure_dev(n, d, 0, err);                                forwardError(*err, __LINE__, 0);
+   int32_t *t = idx_staging(n, err);                        forwardError(*err, __LINE__, 0);
+   double lo[PMCB200_MAX_DIM], hi[PMCB200_MAX_DIM];
+   for (int j = 0; j < d; j++) { lo[j] = pb ? pb->min[j] : -HUGE_VAL; hi[j] = pb ? pb->max[j] : HUGE_VAL; }
    uint64_t seed = r ? r->seed : 0;
    uint32_t stream = r ? r->stream++ : 0;
-   B200_OK(ctx, pmcb200_simulate(ctx, n, seed, stream, 0, (double *)g_dev.X, (int32_t *)g_dev.idx, (int16_t *)g_dev.flg),
-           pmc_undef, 0);
-   int64_t nok = 0;
-   B200_OK(ctx, pmcb200_read_counts(ctx, &nok, NULL, NULL), pmc_badComm, 0);
-   B200_OK(ctx, pmcb200_d2h(ctx, psim->X, g_dev.X, sizeof(double) * (size_t)n * d), pmc_badComm, 0);
-   B200_OK(ctx, pmcb200_d2h(ctx, psim->flg, g_dev.flg, sizeof(short) * (size_t)n), pmc_badComm, 0);
-   {
-      int32_t *t = (int32_t *)malloc_err(sizeof(int32_t) * (size_t)n, err);
-      forwardError(*err, __LINE__, 0);
-      int rc = pmcb200_d2h(ctx, t, g_dev.idx, sizeof(int32_t) * (size_t)n);
-      for (long i = 0; i < n; i++) psim->indices[i] = (size_t)t[i];
-      free(t);
-      B200_OK(ctx, rc, pmc_badComm, 0);
+   for (int s = 0; s < g_ns; s++) {      /* queue every shard, then wait */
+      pmcb200_ctx *ctx = g_ctxs[s];
+      dev_mirror *m = &g_devs[s];
+      long off, ns;
+      shard_range(n, s, &off, &ns);
+      B200_OK(ctx, pmcb200_set_box(ctx, d, lo, hi), pmc_incompat, 0);
+      B200_OK(ctx, pmcb200_simulate(ctx, ns, seed, stream, off, (double *)m->X, (int32_t *)m->idx, (int16_t *)m->flg),
+              pmc_undef, 0);
+      if (ns == 0) continue;
+      B200_OK(ctx, pmcb200_d2h_async(ctx, psim->X + (size_t)off * d, m->X, sizeof(double) * (size_t)ns * d), pmc_badComm, 0);
+      B200_OK(ctx, pmcb200_d2h_async(ctx, psim->flg + off, m->flg, sizeof(short) * (size_t)ns), pmc_badComm, 0);
+      B200_OK(ctx, pmcb200_d2h_async(ctx, t + off, m->idx, sizeof(int32_t) * (size_t)ns), pmc_badComm, 0);
    }
+   int64_t nok = 0;
+   for (int s = 0; s < g_ns; s++) {
+      int64_t k = 0;
+      B200_OK(g_ctxs[s], pmcb200_read_counts(g_ctxs[s], &k, NULL, NULL), pmc_badComm, 0);    /* waits for the shard */
+      nok += k;
+   }
+   for (long i = 0; i < n; i++) psim->indices[i] = (size_t)t[i];
    psim->isLog = 0;
    return (size_t)nok;
 }
@@ -336,7 +450,7 @@ size_t generic_get_importance_weight_and_deduced_verb(pmc_simu *psim, const void
           retrieve_ded_func *retrieve_ded, void *target_data, double beta, int quiet, error **err)
 {
    (void)retrieve_ded; (void)quiet;
-   pmcb200_ctx *ctx = pmc_b200_context(err);
+   pmc_b200_context(err);
    forwardError(*err, __LINE__, 0);
    testErrorRet(proposal_log_pdf != mix_mvdens_log_pdf_void, pmc_undef,
                 "Only mix_mvdens_log_pdf_void proposals have a device path", *err, __LINE__, 0);
@@ -344,16 +458,28 @@ size_t generic_get_importance_weight_and_deduced_verb(pmc_simu *psim, const void
                 *err, __LINE__, 0);
    mix_mvdens *proposal = (mix_mvdens *)proposal_data;
    long n = psim->nsamples;
-   push_proposal(ctx, proposal, err);                              forwardError(*err, __LINE__, 0);
-   activate_target(ctx, posterior_log_pdf, target_data, err);      forwardError(*err, __LINE__, 0);
-   ensure_dev(ctx, n, psim->ndim, 0, err);                         forwardError(*err, __LINE__, 0);
-   push_samples(ctx, psim, 0, 0, err);                             forwardError(*err, __LINE__, 0);
-   B200_OK(ctx, pmcb200_importance_weights(ctx, n, (double *)g_dev.X, beta, (int16_t *)g_dev.flg, (double *)g_dev.w),
-           pmc_undef, 0);
-   int64_t nok = 0; double maxW = 0.0;
-   B200_OK(ctx, pmcb200_read_counts(ctx, NULL, &nok, &maxW), pmc_badComm, 0);
-   B200_OK(ctx, pmcb200_d2h(ctx, psim->weights, g_dev.w, sizeof(double) * (size_t)n), pmc_badComm, 0);
-   B200_OK(ctx, pmcb200_d2h(ctx, psim->flg, g_dev.flg, sizeof(short) * (size_t)n), pmc_badComm, 0);
+   push_proposal(proposal, err);                                   forwardError(*err, __LINE__, 0);
+   activate_target(posterior_log_pdf, target_data, err);           forwardError(*err, __LINE__, 0);
+   ensure_dev(n, psim->ndim, 0, err);                              forwardError(*err, __LINE__, 0);
+   push_samples(psim, 1, 0, 0, err);                               forwardError(*err, __LINE__, 0);
+   for (int s = 0; s < g_ns; s++) {
+      pmcb200_ctx *ctx = g_ctxs[s];
+      dev_mirror *m = &g_devs[s];
+      long off, ns;
+      shard_range(n, s, &off, &ns);
+      B200_OK(ctx, pmcb200_importance_weights(ctx, ns, (double *)m->X, beta, (int16_t *)m->flg, (double *)m->w), pmc_undef, 0);
+      if (ns == 0) continue;
+      B200_OK(ctx, pmcb200_d2h_async(ctx, psim->weights + off, m->w, sizeof(double) * (size_t)ns), pmc_badComm, 0);
+      B200_OK(ctx, pmcb200_d2h_async(ctx, psim->flg + off, m->flg, sizeof(short) * (size_t)ns), pmc_badComm, 0);
+   }
+   int64_t nok = 0;
+   double maxW = -HUGE_VAL;
+   for (int s = 0; s < g_ns; s++) {
+      int64_t k = 0; double mw = -HUGE_VAL;
+      B200_OK(g_ctxs[s], pmcb200_read_counts(g_ctxs[s], NULL, &k, &mw), pmc_badComm, 0);
+      nok += k;
+      if (mw > maxW) maxW = mw;
+   }
    psim->isLog = 1;
    psim->maxW = maxW;
    return (size_t)nok;
@@ -367,43 +493,99 @@ size_t generic_get_importance_weight_and_deduced(pmc_simu *psim, const void *pro
                                                          retrieve_ded, target_data, 1.0, 1, err);
 }
 
+/* {M, S, S2, T, n_flagged} of the weights held in the device mirrors (pmcb200_weight_stats per
+ * shard), combined over shards in shard order: log weights are re-based on the global maximum. */
+static void weight_stats_dev(long n, int is_log, double o[8], error **err)
+{
+   double part[MAX_SHARDS][8];
+   int have[MAX_SHARDS];
+   double M = -HUGE_VAL;
+   for (int s = 0; s < g_ns; s++) {
+      long off, ns;
+      shard_range(n, s, &off, &ns);
+      have[s] = 0;
+      if (ns == 0) continue;
+      B200_OK(g_ctxs[s], pmcb200_weight_stats(g_ctxs[s], ns, (int16_t *)g_devs[s].flg, (double *)g_devs[s].w, is_log, part[s]),
+              pmc_undef, );
+      if (!(part[s][1] > 0.0)) continue;          /* no flagged sample with a finite weight in this shard */
+      have[s] = 1;
+      if (part[s][0] > M) M = part[s][0];
+   }
+   memset(o, 0, 8 * sizeof(double));
+   o[0] = is_log ? M : 0.0;
+   for (int s = 0; s < g_ns; s++) {
+      long off, ns;
+      shard_range(n, s, &off, &ns);
+      if (ns > 0) o[4] += part[s][4];
+      if (!have[s]) continue;
+      const double *q = part[s];
+      if (is_log) {
+         double dM = q[0] - M, f = exp(dM);       /* dM = 0, f = 1 exactly for the shard holding the maximum */
+         o[1] += f * q[1];
+         o[2] += f * f * q[2];
+         o[3] += f * (q[3] + dM * q[1]);
+      } else {
+         o[1] += q[1]; o[2] += q[2]; o[3] += q[3];
+      }
+   }
+}
+
 /* ---- normalize_importance_weight (cosmo_pmc.c:378) --------------------------------------- */
 double normalize_importance_weight(pmc_simu *psim, error **err)
 {
-   pmcb200_ctx *ctx = pmc_b200_context(err);
+   pmc_b200_context(err);
    forwardError(*err, __LINE__, 0.0);
    testErrorRet(psim->isLog != 1, pmc_isLog, "Weights are not in log form", *err, __LINE__, 0.0);
    long n = psim->nsamples;
-   ensure_dev(ctx, n, psim->ndim, 0, err);                         forwardError(*err, __LINE__, 0.0);
-   B200_OK(ctx, pmcb200_h2d(ctx, g_dev.flg, psim->flg, sizeof(short) * (size_t)n), pmc_badComm, 0.0);
-   B200_OK(ctx, pmcb200_h2d(ctx, g_dev.w, psim->weights, sizeof(double) * (size_t)n), pmc_badComm, 0.0);
-   double sum = 0.0, logSum = 0.0, maxW = 0.0;
-   int rc = pmcb200_normalize_log_weights(ctx, n, (int16_t *)g_dev.flg, (double *)g_dev.w, &sum, &logSum, &maxW);
-   testErrorRetVA(rc == PMCB200_ERR_NOSAMPLE, pmc_nosamplep, "%s", *err, __LINE__, 0.0, pmcb200_last_error(ctx));
-   B200_OK(ctx, rc, pmc_undef, 0.0);
-   B200_OK(ctx, pmcb200_d2h(ctx, psim->weights, g_dev.w, sizeof(double) * (size_t)n), pmc_badComm, 0.0);
-   psim->isLog = 0; psim->logSum = logSum; psim->maxW = maxW;
-   return sum;
+   ensure_dev(n, psim->ndim, 0, err);                              forwardError(*err, __LINE__, 0.0);
+   push_samples(psim, 0, 0, 1, err);                               forwardError(*err, __LINE__, 0.0);
+   double o[8];
+   weight_stats_dev(n, 1, o, err);                                 forwardError(*err, __LINE__, 0.0);
+   testErrorRet(!(o[1] > 0.0), pmc_nosamplep, "normalize: no sample with finite weight", *err, __LINE__, 0.0);
+   for (int s = 0; s < g_ns; s++) {
+      pmcb200_ctx *ctx = g_ctxs[s];
+      long off, ns;
+      shard_range(n, s, &off, &ns);
+      if (ns == 0) continue;
+      B200_OK(ctx, pmcb200_normalize_with(ctx, ns, (int16_t *)g_devs[s].flg, (double *)g_devs[s].w, o[0], o[1]), pmc_undef, 0.0);
+      B200_OK(ctx, pmcb200_d2h_async(ctx, psim->weights + off, g_devs[s].w, sizeof(double) * (size_t)ns), pmc_badComm, 0.0);
+   }
+   sync_all(err);                                                  forwardError(*err, __LINE__, 0.0);
+   psim->isLog = 0; psim->logSum = log(o[1]) + o[0]; psim->maxW = o[0];
+   return o[1];
 }
 
 /* ---- update_prop_rb (cosmo_pmc.c:247) ------------------------------------------------------ */
 void update_prop_rb(mix_mvdens *proposal, pmc_simu *psim, error **err)
 {
-   pmcb200_ctx *ctx = pmc_b200_context(err);
+   pmc_b200_context(err);
    forwardError(*err, __LINE__, );
    testErrorRet(psim->isLog != 0, pmc_isLog, "update_prop_rb needs normalised (non-log) weights", *err, __LINE__, );
    long n = psim->nsamples;
-   push_proposal(ctx, proposal, err);                              forwardError(*err, __LINE__, );
-   long blen = (long)pmcb200_stat_block_len(ctx);
-   ensure_dev(ctx, n, psim->ndim, blen, err);                      forwardError(*err, __LINE__, );
-   push_samples(ctx, psim, 1, 1, err);                             forwardError(*err, __LINE__, );
-   B200_OK(ctx, pmcb200_em_local_linear(ctx, n, (double *)g_dev.X, (int32_t *)g_dev.idx, (int16_t *)g_dev.flg,
-                                        (double *)g_dev.w, (double *)g_dev.block), pmc_undef, );
-   pmcb200_stats_t st;
-   int rc = pmcb200_em_finish(ctx, 1, (double *)g_dev.block, n, &st);
-   testErrorRetVA(rc == PMCB200_ERR_NOSAMPLE, pmc_nosamplep, "%s", *err, __LINE__, , pmcb200_last_error(ctx));
-   B200_OK(ctx, rc, pmc_undef, );
-   pull_proposal(ctx, proposal, err);
+   push_proposal(proposal, err);                                   forwardError(*err, __LINE__, );
+   long blen = (long)pmcb200_stat_block_len(g_ctxs[0]);
+   ensure_dev(n, psim->ndim, blen, err);                           forwardError(*err, __LINE__, );
+   push_samples(psim, 1, 1, 1, err);                               forwardError(*err, __LINE__, );
+   double *blk[MAX_SHARDS], *all[MAX_SHARDS];
+   for (int s = 0; s < g_ns; s++) {
+      pmcb200_ctx *ctx = g_ctxs[s];
+      dev_mirror *m = &g_devs[s];
+      long off, ns;
+      shard_range(n, s, &off, &ns);
+      blk[s] = (double *)m->block; all[s] = (double *)m->all;
+      B200_OK(ctx, pmcb200_em_local_linear(ctx, ns, (double *)m->X, (int32_t *)m->idx, (int16_t *)m->flg,
+                                           (double *)m->w, blk[s]), pmc_undef, );
+   }
+   /* the one exchange per iteration (the reference gathers the weights on the master, cosmo_pmc.c:353-376):
+      statistics blocks to every shard by peer copies, then the identical combine + M-step everywhere */
+   if (g_ns > 1) B200_OK(g_ctxs[0], pmcb200_allgather_blocks(g_ctxs, g_ns, blk, all, blen), pmc_badComm, );
+   for (int s = 0; s < g_ns; s++) {
+      pmcb200_stats_t st;
+      int rc = pmcb200_em_finish(g_ctxs[s], g_ns, g_ns > 1 ? all[s] : blk[s], n, &st);
+      testErrorRetVA(rc == PMCB200_ERR_NOSAMPLE, pmc_nosamplep, "%s", *err, __LINE__, , pmcb200_last_error(g_ctxs[s]));
+      B200_OK(g_ctxs[s], rc, pmc_undef, );
+   }
+   pull_proposal(proposal, err);
    forwardError(*err, __LINE__, );
 }
 void update_prop_rb_void(void *proposal, pmc_simu *psim, error **err) { update_prop_rb((mix_mvdens *)proposal, psim, err); }
@@ -411,13 +593,12 @@ void update_prop_rb_void(void *proposal, pmc_simu *psim, error **err) { update_p
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 static void weight_stats(pmc_simu *psim, double o[8], error **err)
 {
-   pmcb200_ctx *ctx = pmc_b200_context(err);
+   pmc_b200_context(err);
    forwardError(*err, __LINE__, );
    long n = psim->nsamples;
-   ensure_dev(ctx, n, psim->ndim, 0, err);                         forwardError(*err, __LINE__, );
-   B200_OK(ctx, pmcb200_h2d(ctx, g_dev.flg, psim->flg, sizeof(short) * (size_t)n), pmc_badComm, );
-   B200_OK(ctx, pmcb200_h2d(ctx, g_dev.w, psim->weights, sizeof(double) * (size_t)n), pmc_badComm, );
-   B200_OK(ctx, pmcb200_weight_stats(ctx, n, (int16_t *)g_dev.flg, (double *)g_dev.w, psim->isLog, o), pmc_undef, );
+   ensure_dev(n, psim->ndim, 0, err);                              forwardError(*err, __LINE__, );
+   push_samples(psim, 0, 0, 1, err);                               forwardError(*err, __LINE__, );
+   weight_stats_dev(n, psim->isLog, o, err);                       forwardError(*err, __LINE__, );
 }
 
 /* perplexity = exp(-sum wbar log wbar)/N, ESS = 1/sum wbar^2 (manual.tex:555-590) */
@@ -535,23 +716,21 @@ pmc_simu *pmc_simu_from_file(FILE *F, int nsamples, int npar, int n_ded, mix_mvd
 size_t pmc_b200_iteration(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, double beta,
                           pmcb200_stats_t *stats, error **err)
 {
-   pmcb200_ctx *ctx = pmc_b200_context(err);
+   pmc_b200_context(err);
    forwardError(*err, __LINE__, 0);
    testErrorRet(g_active_target == NULL, pmc_undef, "Activate a device target first (a weight call, or "
                 "pmc_b200_register_target + generic_get_importance_weight...)", *err, __LINE__, 0);
    long n = psim->nsamples;
-   push_proposal(ctx, proposal, err);                              forwardError(*err, __LINE__, 0);
-   int32_t *idx = (int32_t *)malloc_err(sizeof(int32_t) * (size_t)n, err);
-   forwardError(*err, __LINE__, 0);
+   push_proposal(proposal, err);                                   forwardError(*err, __LINE__, 0);
+   int32_t *idx = idx_staging(n, err);                             forwardError(*err, __LINE__, 0);
    pmcb200_stats_t st;
-   int rc = pmcb200_iteration_host(ctx, n, r ? r->seed : 0, r ? r->stream++ : 0, beta, psim->X, idx,
-                                   (int16_t *)psim->flg, psim->weights, &st);
+   int rc = pmcb200_iteration_host_multi(g_ctxs, g_ns, n, r ? r->seed : 0, r ? r->stream++ : 0, beta, psim->X, idx,
+                                         (int16_t *)psim->flg, psim->weights, &st);
+   testErrorRetVA(rc == PMCB200_ERR_NOSAMPLE, pmc_nosamplep, "%s", *err, __LINE__, 0, pmcb200_last_error(g_ctxs[0]));
+   B200_OK(g_ctxs[0], rc, pmc_undef, 0);
    for (long i = 0; i < n; i++) psim->indices[i] = (size_t)idx[i];
-   free(idx);
-   testErrorRetVA(rc == PMCB200_ERR_NOSAMPLE, pmc_nosamplep, "%s", *err, __LINE__, 0, pmcb200_last_error(ctx));
-   B200_OK(ctx, rc, pmc_undef, 0);
    psim->isLog = 0; psim->logSum = st.logSum; psim->maxW = st.maxW;
-   pull_proposal(ctx, proposal, err);
+   pull_proposal(proposal, err);
    forwardError(*err, __LINE__, 0);
    if (stats) *stats = st;
    return (size_t)st.nok;

@@ -184,6 +184,23 @@ class PMC:
         self._ck(self.lib.pmcb200_sync(self.h))
 
 
+def iteration_host_multi(pmcs, N, seed, it, beta=1.0, hX=None, hidx=None, hflg=None, hw=None):
+    """pmcb200_iteration_host_multi: one iteration sharded over several contexts of THIS
+    process (one per GPU, or several on one GPU); statistics blocks travel by peer copies."""
+    def hp(a):
+        if a is None:
+            return None
+        return C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+    lib = pmcs[0].lib
+    arr = (C.c_void_p * len(pmcs))(*[p.h for p in pmcs])
+    st = A.Stats()
+    rc = lib.pmcb200_iteration_host_multi(arr, len(pmcs), N, seed, it, beta, hp(hX), hp(hidx), hp(hflg),
+                                          hp(hw), C.byref(st))
+    if rc:
+        raise PMCError(rc, lib.pmcb200_last_error(pmcs[0].h).decode())
+    return st.as_dict()
+
+
 def run_iteration_distributed(pmc, N_global, seed, it, beta, block, all_blocks, bufs=None,
                               rank=0, world=1):
     """One PMC iteration sharded over `world` ranks (one GPU each): contiguous

@@ -286,6 +286,39 @@ int pmcb200_iteration_host(pmcb200_ctx *ctx, int64_t N, uint64_t seed,
                            int32_t *hidx, int16_t *hflg, double *hw,
                            pmcb200_stats_t *stats);
 
+/* ---- several GPUs in ONE process (the reference shards the sample
+ * over MPI ranks, cosmo_pmc.c:323-376: send_simulation / receive_importance_weight)
+ * One context per shard; contexts may sit on different devices (or, for tests,
+ * on the same one).  Shard r of n owns the global sample indices
+ * [r*per, min(N,(r+1)*per)), per = ceil(N/n), and the Philox counter is the global
+ * index, so the result does not depend on n.  The only exchange per iteration is
+ * the statistics block, moved by peer copies (NVLink P2P between peer devices). */
+
+/* asynchronous copies on the context's stream (order them with pmcb200_sync);
+ * hptr should be page-locked (pmcb200_host_alloc) for the copy to overlap */
+int pmcb200_h2d_async(pmcb200_ctx *ctx, void *dptr, const void *hptr, size_t bytes);
+int pmcb200_d2h_async(pmcb200_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
+/* page-locked host memory, portable across devices (pmc_simu_init_plus_ded's
+ * lump: X, X_ded, weights, indices, flg); falls back to malloc without a device */
+int pmcb200_host_alloc(size_t bytes, void **hptr);
+int pmcb200_host_free(void *hptr);
+/* all-gather between the contexts of one process: for every q,
+ * dall[q][r*len .. (r+1)*len) = dblock[r][0..len), ordered after the work already
+ * queued on ctx[r]'s stream and before later work on ctx[q]'s stream.  Replaces
+ * the MPI gather of cosmo_pmc.c:353-376. */
+int pmcb200_allgather_blocks(pmcb200_ctx *const *ctx, int n, double *const *dblock,
+                             double *const *dall, int64_t len);
+/* pmcb200_iteration_host sharded over n contexts that hold the same proposal
+ * and target: every shard is queued before any is waited for; all contexts end
+ * with the identical updated proposal (fixed-order combine in pmcb200_em_finish). */
+int pmcb200_iteration_host_multi(pmcb200_ctx *const *ctx, int n, int64_t N, uint64_t seed,
+                                 uint32_t iter, double beta, double *hX, int32_t *hidx,
+                                 int16_t *hflg, double *hw, pmcb200_stats_t *stats);
+/* normalize_importance_weight (cosmo_pmc.c:378) with a max / sum that the caller
+ * combined over shards: w <- exp(w - maxW) / sum_shift for flagged samples */
+int pmcb200_normalize_with(pmcb200_ctx *ctx, int64_t N, const int16_t *dflg, double *dw,
+                           double maxW, double sum_shift);
+
 /* number of kernels launched by this context since creation (bench's
  * gpu_launches claim) */
 int64_t pmcb200_launch_count(const pmcb200_ctx *ctx);

@@ -89,8 +89,11 @@ void   estimate_param_covar_weight(size_t ndim, size_t nsamples, size_t nskip, c
  * for a (callback, data) pair once after reading the config.
  * generic_get_importance_weight_and_deduced_verb raises pmc_undef for a callback
  * that has no registered device target. */
-pmcb200_ctx *pmc_b200_context(error **err);          /* lazily created; device = $PMCB200_DEVICE or 0 */
+pmcb200_ctx *pmc_b200_context(error **err);          /* lazily created; shard 0 (device = $PMCB200_DEVICE or 0) */
 void pmc_b200_shutdown(void);
+/* number of shards (contexts) the host layer drives: $PMCB200_NGPU (default 1, "all" = every
+ * visible device), devices from $PMCB200_DEVICES (comma-separated, round-robin) */
+int pmc_b200_nshards(void);
 void pmc_b200_register_target(posterior_log_pdf_func *posterior_log_pdf, void *target_data,
                               const pmcb200_target_t *t, error **err);
 /* Auto-binding hook: called for a (callback, data) pair that has no registered

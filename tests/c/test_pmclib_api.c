@@ -102,7 +102,7 @@ int main(int argc, char **argv)
    F = fopen_err(name, "w", err);                                             quitOnError(*err, __LINE__, stderr);
    mix_mvdens_dump(F, proposal); fclose(F);
    size_t nok = simulate_mix_mvdens(psim, proposal, rng, pb, err);            quitOnError(*err, __LINE__, stderr);
-   printf("nok_box %zu\n", nok);
+   printf("nok_box %zu\nnshards %d\n", nok, pmc_b200_nshards());
    nok = generic_get_importance_weight_and_deduced_verb(psim, proposal, mix_mvdens_log_pdf_void, my_posterior, NULL,
                                                         &dummy_config, beta, 1, err);
    quitOnError(*err, __LINE__, stderr);

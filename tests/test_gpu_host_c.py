@@ -47,7 +47,8 @@ def read_mix(path):
     return np.array(w), np.array(mean), np.array(cov)
 
 
-def test_pmclib_named_iteration(oracle, tmp_path):
+@pytest.mark.parametrize("nshards", [1, 3])
+def test_pmclib_named_iteration(oracle, tmp_path, nshards):
     exe = tmp_path / "test_pmclib_api"
     libdir = os.path.join(ROOT, "cosmopmc_b200")
     gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
@@ -58,10 +59,13 @@ def test_pmclib_named_iteration(oracle, tmp_path):
     write_mix(tmp_path / "proposal_in", w, m, cov)
     N, seed, beta = 20000, 1234, 0.9
     out = subprocess.run([str(exe), T.SN_FIXTURE, str(tmp_path / "proposal_in"), str(N), str(seed), str(beta),
-                          str(tmp_path)], capture_output=True, text=True)
+                          str(tmp_path)], capture_output=True, text=True,
+                         env=dict(os.environ, PMCB200_NGPU=str(nshards), PMCB200_DEVICES="0"))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     r = parse(out.stdout)
     assert r["done"] == [1.0] and "MISMATCH" not in out.stdout
+    # the host layer shards every pmclib-named call over PMCB200_NGPU contexts (here all on device 0)
+    assert r["nshards"] == [float(nshards)]
     # oracle on the same seeded iteration (seed = gsl seed, iter = stream 0)
     spec = T.target_sn_demo()
     ch = oracle.cholesky_stack(cov)

@@ -393,6 +393,50 @@ def test_sharded_blocks_combine_like_one_rank(oracle, pmc_factory):
         assert np.allclose(a, b, rtol=1e-10, atol=1e-14)
 
 
+def test_iteration_host_multi_contexts(oracle, pmc_factory):
+    """(e) several contexts in one process (pmcb200_iteration_host_multi): 3 shards on one
+    device (uneven: 10001 = 3334 + 3334 + 3333) against the single-context call and the oracle.
+    Samples, indices and flags are bit-identical (Philox counter = global index); the update
+    agrees to the parity tolerance; every context ends with the identical proposal."""
+    from cosmopmc_b200.pmc import iteration_host_multi
+    spec = T.target_sn_demo()
+    w, m, cov = T.proposal_sn(10)
+    ch = oracle.cholesky_stack(cov)
+    N, seed = 10001, 77
+    one = pmc_factory(); one.set_target(spec); one.set_proposal(w, m, chol=ch)
+    X1 = np.empty((N, 5)); i1 = np.empty(N, np.int32); f1 = np.empty(N, np.int16); w1 = np.empty(N)
+    s1 = one.iteration_host(N, seed, 2, 0.8, X1, i1, f1, w1)
+    many = [pmc_factory() for _ in range(3)]
+    for p in many:
+        p.set_target(spec); p.set_proposal(w, m, chol=ch)
+    X2 = np.empty((N, 5)); i2 = np.empty(N, np.int32); f2 = np.empty(N, np.int16); w2 = np.empty(N)
+    s2 = iteration_host_multi(many, N, seed, 2, 0.8, X2, i2, f2, w2)
+    assert np.array_equal(X1, X2) and np.array_equal(i1, i2) and np.array_equal(f1, f2)
+    assert np.allclose(w1, w2, rtol=1e-12, atol=0)
+    for k in ("nok", "nok_box", "ndead", "nsamples"):
+        assert s1[k] == s2[k]
+    for k in ("maxW", "logSum", "perplexity", "ess", "enc", "ln_evidence"):
+        assert abs(s1[k] - s2[k]) <= 1e-12 * abs(s1[k]), k
+    ref = one.get_proposal()
+    props = [p.get_proposal() for p in many]
+    for a, b in zip(ref, props[0]):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-14)
+    for q in props[1:]:
+        for a, b in zip(props[0], q):
+            assert np.array_equal(a, b)          # fixed-order combine: bitwise identical on every shard
+    o = oracle.iteration(spec, N, seed, 2, 0.8, w, m, ch, nthreads=0)
+    assert np.array_equal(i2, o["idx"]) and np.array_equal(f2, o["flg"])
+    assert np.allclose(props[0][0], o["wght"], rtol=1e-8, atol=0)
+    assert np.allclose(props[0][1], o["mean"], rtol=1e-8, atol=0)
+    # more shards than samples: empty shards are legal
+    # (N = 2: fewer than MINCOUNT draws per component, so every component dies -- on every shard alike)
+    from cosmopmc_b200.pmc import PMCError
+    from cosmopmc_b200 import _abi as A
+    with pytest.raises(PMCError) as e:
+        iteration_host_multi(many, 2, seed, 3, 1.0)
+    assert e.value.code == A.ERR["NOSAMPLE"]
+
+
 def test_sn_fast_path_matches_libdevice_path(oracle, pmc_factory, tmp_path):
     """The SN kernel's table-based exp2 / MUFU-seeded rsqrt path against the same
     kernel forced through libdevice exp (PMCB200_SN_FORCE_SLOW=1, separate

@@ -63,6 +63,27 @@ def test_unchanged_reference_driver_runs_sn_demo(tmp_path):
     assert np.allclose(perp2[:, 2], perp[:, 2], rtol=2e-4)           # recomputed from the 9-digit text files
 
 
+@pytest.mark.skipif(not (os.path.exists(EXE) and os.path.isdir(DEMO)),
+                    reason="build_ref/cosmo_pmc not built (tools/build_ref_cosmo_pmc.py, container only)")
+def test_unchanged_reference_driver_sharded_over_contexts(tmp_path):
+    """(e) under the UNCHANGED driver: PMCB200_NGPU shards every pmclib-named call over several
+    contexts of the one process (here 3 contexts on device 0).  The Philox counter is the global
+    sample index, so the run must reproduce the one-context run: same sample counts, perplexity
+    and ENC histories equal to the files' printed precision."""
+    res = {}
+    for ns in (1, 3):
+        run = tmp_path / ("run%d" % ns)
+        shutil.copytree(DEMO, run, ignore=shutil.ignore_patterns("iter_*", "perplexity", "enc", "evidence*", "log_pmc",
+                                                                 "temperature", "proposal_fin", "run.log"))
+        write_fisher(run / "fisher")
+        out = subprocess.run([EXE, "-c", "config_pmc", "-s", "7", "-q"], cwd=run, capture_output=True, text=True,
+                             timeout=600, env=dict(os.environ, PMCB200_NGPU=str(ns), PMCB200_DEVICES="0"))
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+        res[ns] = (np.loadtxt(run / "perplexity"), np.loadtxt(run / "enc"), np.loadtxt(run / "evidence"))
+    for a, b in zip(res[1], res[3]):
+        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-5, atol=0)
+
+
 def _run_tempering_demo(name, fisher_mean, fisher_invcov, tmp_path, seed):
     demo = os.path.join(A.ROOT, "build_ref", "demo_" + name)
     if not (os.path.exists(EXE) and os.path.isdir(demo)):
