@@ -129,6 +129,9 @@ SYMBOLS = {
     "pmcb200_iteration_host_multi": (_i, [C.POINTER(_vp), _i, _i64, _u64, _u32, _d, _vp, _vp, _vp, _vp,
                                           C.POINTER(Stats)]),
     "pmcb200_normalize_with": (_i, [_vp, _i64, _vp, _vp, _d, _d]),
+    "pmcb200_post_moments": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pmcb200_post_sigma": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _d, _vp, _vp, C.POINTER(_d), C.POINTER(_i64)]),
+    "pmcb200_post_histogram": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -15,6 +15,7 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 # (object name, source, extra flags)
 UNITS = [("pmcb200.o", "pmcb200.cu", []),
          ("k_cosmo.o", "k_cosmo.cu", []),
+         ("k_post.o", "k_post.cu", []),
          ("k_mix0.o", "k_mix.cu", ["-DMIX_GROUP=0"]),
          ("k_mix1.o", "k_mix.cu", ["-DMIX_GROUP=1"]),
          ("k_mix2.o", "k_mix.cu", ["-DMIX_GROUP=2"]),

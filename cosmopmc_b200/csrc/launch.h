@@ -50,3 +50,14 @@ int pmc_init_sn_tables();   // per device, at context creation
 void pmc_launch_fp64_peak(double *out, const double *in, int blocks, int iters, cudaStream_t s);
 void pmc_launch_wstat(int64_t N, const int16_t *flg, const double *w, int is_log, int blocks, double *maxpart,
                       double *part, double *out8, cudaStream_t s);
+
+// weighted post-processing of a stored sample (k_post.cu)
+void pmc_launch_post_moments(int64_t N, int d, const double *X, const int16_t *flg, const double *w,
+                             const double *pivot, int blocks, double *partials, double *out, cudaStream_t s);
+int pmc_launch_post_hist(int64_t N, int d, const double *X, const int16_t *flg, const double *w, int nd,
+                         const int *pidx, const int *nbins, const double *limits, int blocks, double *out,
+                         cudaStream_t s);
+size_t pmc_post_sigma_temp_bytes(int64_t N);
+void pmc_launch_post_sigma(int64_t N, int d, int a, const double *X, const int16_t *flg, const double *w,
+                           double center, const double conf[3], double *work, void *temp, size_t temp_bytes,
+                           unsigned long long *nflag, double *out8, cudaStream_t s);

@@ -56,6 +56,7 @@ struct pmcb200_ctx {
   int sm_count = 148;
   // scratch for the host-buffer API
   DevBuf sX, sIdx, sFlg, sLogw, sLogpi, sErr, sBlock, sAll;
+  DevBuf sPost, sPostTmp;                 // post-processing work space
 };
 
 static int fail(pmcb200_ctx *c, int code, const char *fmt, ...) {
@@ -245,7 +246,7 @@ extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_target(c);
-  for (DevBuf *b : {&c->sX, &c->sIdx, &c->sFlg, &c->sLogw, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll})
+  for (DevBuf *b : {&c->sX, &c->sIdx, &c->sFlg, &c->sLogw, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll, &c->sPost, &c->sPostTmp})
     if (b->p) cudaFree(b->p);
   if (c->d_mix) cudaFree(c->d_mix);
   if (c->d_scal) cudaFree(c->d_scal);
@@ -1071,6 +1072,91 @@ extern "C" int pmcb200_em_local_linear(pmcb200_ctx *c, int64_t N, const double *
   if (N < 0 || !dblock || (N > 0 && (!dX || !didx || !dflg || !dwbar)))
     return fail(c, PMCB200_ERR_ARG, "em_local_linear: bad arguments");
   return launch_em_local(c, N, dX, didx, dflg, dwbar, dblock, 1);
+}
+
+// ---- weighted post-processing of a stored sample -----------------------------
+extern "C" int pmcb200_post_moments(pmcb200_ctx *c, int64_t N, int d, const double *dX, const int16_t *dflg,
+                                    const double *dw, double *mean, double *cov) {
+  int rc = need(c, false, false);
+  if (rc) return rc;
+  if (N < 1 || d < 1 || d > PMCB200_MAX_DIM || !dX || !mean) return fail(c, PMCB200_ERR_ARG, "post_moments: bad arguments");
+  const int M = 1 + d + d * (d + 1) / 2;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(2 * c->sm_count, (N + 255) / 256));
+  if ((rc = ensure(c, c->sPost, sizeof(double) * ((size_t)blocks * M + 2 * M + d)))) return rc;
+  double *part = (double *)c->sPost.p, *out = part + (size_t)blocks * M, *piv = out + 2 * M;
+  std::vector<double> h(M);
+  // pass 1 (pivot 0): S0 and the mean
+  pmc_launch_post_moments(N, d, dX, dflg, dw, nullptr, blocks, part, out, c->stream);
+  c->launches += 2;
+  CUDA_OK(c, cudaMemcpyAsync(h.data(), out, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (!(h[0] > 0.0)) return fail(c, PMCB200_ERR_NOSAMPLE, "post_moments: sum of weights is not positive");
+  for (int j = 0; j < d; j++) mean[j] = h[1 + j] / h[0];
+  if (!cov) return 0;
+  // pass 2: second moments about the mean (as estimate_param_covar_weight does)
+  CUDA_OK(c, cudaMemcpyAsync(piv, mean, sizeof(double) * d, cudaMemcpyHostToDevice, c->stream));
+  pmc_launch_post_moments(N, d, dX, dflg, dw, piv, blocks, part, out, c->stream);
+  c->launches += 2;
+  CUDA_OK(c, cudaMemcpyAsync(h.data(), out, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (int a = 0, t = 1 + d; a < d; a++)
+    for (int b = 0; b <= a; b++, t++) {
+      const double da = h[1 + a] / h[0], db = h[1 + b] / h[0];     // residual of the mean: O(1e-16)
+      cov[a * d + b] = cov[b * d + a] = h[t] / h[0] - da * db;
+    }
+  return 0;
+}
+
+extern "C" int pmcb200_post_sigma(pmcb200_ctx *c, int64_t N, int d, const double *dX, const int16_t *dflg,
+                                  const double *dw, int a, double center, const double conf[3], double sigma[6],
+                                  double *median, int64_t *nflagged) {
+  int rc = need(c, false, false);
+  if (rc) return rc;
+  if (N < 1 || d < 1 || a < 0 || a >= d || !dX || !conf || !sigma) return fail(c, PMCB200_ERR_ARG, "post_sigma: bad arguments");
+  const size_t tb = pmc_post_sigma_temp_bytes(N);
+  if ((rc = ensure(c, c->sPost, sizeof(double) * (4 * (size_t)N + 16)))) return rc;
+  if ((rc = ensure(c, c->sPostTmp, tb))) return rc;
+  double *work = (double *)c->sPost.p, *out8 = work + 4 * (size_t)N;
+  unsigned long long *nf = (unsigned long long *)(out8 + 8);
+  pmc_launch_post_sigma(N, d, a, dX, dflg, dw, center, conf, work, c->sPostTmp.p, tb, nf, out8, c->stream);
+  c->launches += 2;          // own kernels: gather + search (the sort and the scan are CUB's)
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, PMCB200_ERR_CUDA, "post_sigma launch: %s", cudaGetErrorString(e));
+  double h[8];
+  CUDA_OK(c, cudaMemcpyAsync(h, out8, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (int j = 0; j < 6; j++) sigma[j] = h[j];
+  if (median) *median = h[6];
+  if (nflagged) *nflagged = (int64_t)h[7];
+  return 0;
+}
+
+extern "C" int pmcb200_post_histogram(pmcb200_ctx *c, int64_t N, int d, const double *dX, const int16_t *dflg,
+                                      const double *dw, int nhdim, const int *pidx, const int *nbins,
+                                      const double *limits, double *count, double *sumw, double *sumw2) {
+  int rc = need(c, false, false);
+  if (rc) return rc;
+  if (N < 1 || d < 1 || !dX || (nhdim != 1 && nhdim != 2) || !pidx || !nbins || !limits || !count || !sumw || !sumw2)
+    return fail(c, PMCB200_ERR_ARG, "post_histogram: bad arguments");
+  size_t tdim = 1;
+  for (int i = 0; i < nhdim; i++) {
+    if (pidx[i] < 0 || pidx[i] >= d || nbins[i] < 1 || !(limits[2 * i + 1] > limits[2 * i]))
+      return fail(c, PMCB200_ERR_ARG, "post_histogram: bad axis %d", i);
+    tdim *= (size_t)nbins[i];
+  }
+  if (tdim * 3 * sizeof(double) > 200 * 1024) return fail(c, PMCB200_ERR_UNSUP, "post_histogram: %zu bins exceed the shared-memory copy (max 8533)", tdim);
+  if ((rc = ensure(c, c->sPost, sizeof(double) * 3 * tdim))) return rc;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(2 * c->sm_count, (N + 255) / 256));
+  if (pmc_launch_post_hist(N, d, dX, dflg, dw, nhdim, pidx, nbins, limits, blocks, (double *)c->sPost.p, c->stream))
+    return fail(c, PMCB200_ERR_UNSUP, "post_histogram: too many bins");
+  LAUNCH_OK(c);
+  std::vector<double> h(3 * tdim);
+  CUDA_OK(c, cudaMemcpyAsync(h.data(), c->sPost.p, sizeof(double) * 3 * tdim, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  memcpy(count, h.data(), sizeof(double) * tdim);
+  memcpy(sumw, h.data() + tdim, sizeof(double) * tdim);
+  memcpy(sumw2, h.data() + 2 * tdim, sizeof(double) * tdim);
+  return 0;
 }
 
 // ---- measurement helpers -------------------------------------------------------------------

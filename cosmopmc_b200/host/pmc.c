@@ -493,6 +493,50 @@ size_t generic_get_importance_weight_and_deduced(pmc_simu *psim, const void *pro
                                                          retrieve_ded, target_data, 1.0, 1, err);
 }
 
+/* ---- importance_sample (exec/importance_sample.c:26-91), batched ---------------------------
+ * The reference re-weights a stored sample under a second posterior with one host callback
+ * per point.  Here every point of psim goes through the device posterior in one launch per
+ * shard: weights[i] <- log pi(x_i), maxW, isLog = 1.  flg[i] = 1 for every evaluated point as in
+ * the reference, except that a point whose posterior raises an error or is not finite gets
+ * flg = 0 (the reference purges the error and keeps the callback's dummy return value; dropping
+ * the point is its documented policy, manual.tex:507-512).  Returns the number of flagged points. */
+size_t pmc_b200_importance_sample(pmc_simu *psim, posterior_log_pdf_func *posterior_log_pdf, void *target_data,
+                                  error **err)
+{
+   pmc_b200_context(err);
+   forwardError(*err, __LINE__, 0);
+   testErrorRet(psim->n_ded > 0, pmc_undef, "Deduced parameters (n_ded > 0) are not supported on the device path",
+                *err, __LINE__, 0);
+   long n = psim->nsamples;
+   activate_target(posterior_log_pdf, target_data, err);           forwardError(*err, __LINE__, 0);
+   ensure_dev(n, psim->ndim, 0, err);                              forwardError(*err, __LINE__, 0);
+   int32_t *e32 = idx_staging(n, err);                             forwardError(*err, __LINE__, 0);
+   push_samples(psim, 1, 0, 0, err);                               forwardError(*err, __LINE__, 0);
+   for (int s = 0; s < g_ns; s++) {
+      pmcb200_ctx *ctx = g_ctxs[s];
+      dev_mirror *m = &g_devs[s];
+      long off, ns;
+      shard_range(n, s, &off, &ns);
+      if (ns == 0) continue;
+      B200_OK(ctx, pmcb200_posterior_log_pdf(ctx, ns, (double *)m->X, (double *)m->w, (int32_t *)m->idx), pmc_undef, 0);
+      B200_OK(ctx, pmcb200_d2h_async(ctx, psim->weights + off, m->w, sizeof(double) * (size_t)ns), pmc_badComm, 0);
+      B200_OK(ctx, pmcb200_d2h_async(ctx, e32 + off, m->idx, sizeof(int32_t) * (size_t)ns), pmc_badComm, 0);
+   }
+   sync_all(err);                                                  forwardError(*err, __LINE__, 0);
+   size_t count = 0;
+   double MW = -1.0e30;
+   for (long i = 0; i < n; i++) {
+      int ok = (e32[i] == 0) && isfinite(psim->weights[i]);
+      psim->flg[i] = (short)ok;
+      if (!ok) { psim->weights[i] = 0.0; continue; }
+      if (count == 0 || psim->weights[i] > MW) MW = psim->weights[i];
+      count++;
+   }
+   psim->maxW = MW;
+   psim->isLog = 1;
+   return count;
+}
+
 /* {M, S, S2, T, n_flagged} of the weights held in the device mirrors (pmcb200_weight_stats per
  * shard), combined over shards in shard order: log weights are re-based on the global maximum. */
 static void weight_stats_dev(long n, int is_log, double o[8], error **err)

@@ -167,6 +167,35 @@ class PMC:
         p = C.c_void_p(hw.data_ptr() if isinstance(hw, torch.Tensor) else hw.ctypes.data)
         self._ck(self.lib.pmcb200_shard_weights_host(self.h, N, p))
 
+    # -- weighted post-processing of a stored sample (device tensors in, host results out) --
+    def post_moments(self, X, flg, w, with_cov=True):
+        N, d = X.shape
+        mean, cov = np.empty(d), np.empty((d, d))
+        self._ck(self.lib.pmcb200_post_moments(self.h, N, d, _dp(X), _dp(flg), _dp(w), mean.ctypes.data,
+                                               cov.ctypes.data if with_cov else None))
+        return (mean, cov) if with_cov else mean
+
+    def post_sigma(self, X, flg, w, a, center, conf):
+        N, d = X.shape
+        cf = np.ascontiguousarray(conf, dtype=np.float64)
+        sig = np.empty(6)
+        med, nf = C.c_double(), C.c_int64()
+        self._ck(self.lib.pmcb200_post_sigma(self.h, N, d, _dp(X), _dp(flg), _dp(w), a, center, cf.ctypes.data,
+                                             sig.ctypes.data, C.byref(med), C.byref(nf)))
+        return sig, med.value, nf.value
+
+    def post_histogram(self, X, flg, w, pidx, nbins, limits):
+        N, d = X.shape
+        pi = np.ascontiguousarray(pidx, dtype=np.int32)
+        nb = np.ascontiguousarray(nbins, dtype=np.int32)
+        lim = np.ascontiguousarray(limits, dtype=np.float64)
+        tdim = int(np.prod(nb))
+        cnt, sw, sw2 = np.empty(tdim), np.empty(tdim), np.empty(tdim)
+        self._ck(self.lib.pmcb200_post_histogram(self.h, N, d, _dp(X), _dp(flg), _dp(w), len(pi), pi.ctypes.data,
+                                                 nb.ctypes.data, lim.ctypes.data, cnt.ctypes.data, sw.ctypes.data,
+                                                 sw2.ctypes.data))
+        return cnt, sw, sw2
+
     def launch_count(self):
         return int(self.lib.pmcb200_launch_count(self.h))
 

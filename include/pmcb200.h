@@ -319,6 +319,31 @@ int pmcb200_iteration_host_multi(pmcb200_ctx *const *ctx, int n, int64_t N, uint
 int pmcb200_normalize_with(pmcb200_ctx *ctx, int64_t N, const int16_t *dflg, double *dw,
                            double maxW, double sum_shift);
 
+/* ---- weighted post-processing of a stored sample on the device --
+ * DEVICE inputs X[N*d], flg[N] (NULL = all samples), w[N] (NULL = unit weights);
+ * HOST outputs.  These replace the host loops and the per-parameter qsort that
+ * follow the last iteration (cosmo_pmc.c:441-461, meanvar_sample, histograms_sample). */
+/* mean_from_psim (exec_helper.c:79) and estimate_param_covar_weight
+ * (exec_helper.c:320-349): weighted mean[d] and covariance[d*d] (second moments
+ * about the mean, two passes); cov may be NULL */
+int pmcb200_post_moments(pmcb200_ctx *ctx, int64_t N, int d, const double *dX, const int16_t *dflg,
+                         const double *dw, double *mean, double *cov);
+/* sigma_from_psim (exec_helper.c:201-275) for parameter a around `center`:
+ * conf[3] = half confidence volumes (conf_68/2, conf_95/2, conf_99/2);
+ * sigma[0..3) upper, sigma[3..6) lower half-widths, -1 where the sample ends
+ * before the volume is reached.  *median = median_from_psim (exec_helper.c:164-199).
+ * The weights must be normalised (isLog = 0). */
+int pmcb200_post_sigma(pmcb200_ctx *ctx, int64_t N, int d, const double *dX, const int16_t *dflg,
+                       const double *dw, int a, double center, const double conf[3], double sigma[6],
+                       double *median, int64_t *nflagged);
+/* acc_histogram (tools/src/nhist.c:87-162) for nhdim = 1 or 2 parameters pidx[],
+ * nbins[] bins between limits[2*i], limits[2*i+1] (samples on or outside a limit
+ * are dropped; the last axis runs fastest): per bin the number of samples, sum w
+ * and sum w^2, from which the reference's data[] and var[] follow. */
+int pmcb200_post_histogram(pmcb200_ctx *ctx, int64_t N, int d, const double *dX, const int16_t *dflg,
+                           const double *dw, int nhdim, const int *pidx, const int *nbins,
+                           const double *limits, double *count, double *sumw, double *sumw2);
+
 /* number of kernels launched by this context since creation (bench's
  * gpu_launches claim) */
 int64_t pmcb200_launch_count(const pmcb200_ctx *ctx);

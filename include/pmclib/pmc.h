@@ -106,6 +106,11 @@ int pmc_b200_autobind(posterior_log_pdf_func *posterior_log_pdf, void *target_da
 /* one log-likelihood on the device (N = 1), used by the scalar nicaea-named
  * functions (chi2_SN, chi2_bao_*, chi2_cmbDP); x has like->npar entries */
 double pmc_b200_single_loglike(const pmcb200_like_t *like, const double *x, error **err);
+/* importance_sample() of exec/importance_sample.c:26-91 as one batched device evaluation:
+ * weights[i] <- log posterior(x_i) for every point of psim (isLog = 1, maxW set); flg = 0 for
+ * points whose posterior raised an error.  Returns the number of flagged points. */
+size_t pmc_b200_importance_sample(pmc_simu *psim, posterior_log_pdf_func *posterior_log_pdf, void *target_data,
+                                  error **err);
 /* whole iteration on a host psim + proposal in one call (the fast path used by
  * a binding that replaces the body of run_pmc_iteration_MPI) */
 size_t pmc_b200_iteration(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, double beta,

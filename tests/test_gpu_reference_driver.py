@@ -61,6 +61,27 @@ def test_unchanged_reference_driver_runs_sn_demo(tmp_path):
     assert out2.returncode == 0, out2.stdout[-2000:] + out2.stderr[-2000:]
     perp2 = np.loadtxt(run / "perplexity")
     assert np.allclose(perp2[:, 2], perp[:, 2], rtol=2e-4)           # recomputed from the 9-digit text files
+    # SURVEY 8f-1, importance_sample: the reference's unchanged tool (one scalar callback = one N=1 launch per
+    # point) against this repo's batched driver (one launch per shard) on the first 1500 points of the final
+    # sample, re-weighted under the same config: identical output files to the printed precision
+    imp_ref, imp_b200 = os.path.join(A.ROOT, "build_ref", "importance_sample"), os.path.join(A.ROOT, "build_ref", "importance_sample_b200")
+    if os.path.exists(imp_ref) and os.path.exists(imp_b200):
+        with open(run / "sub.pmcsim", "w") as f:
+            f.write("\n".join(lines[:3 + 1500]) + "\n")
+        cfg = open(run / "config_pmc").read().replace("nsamples        10000", "nsamples        750")   # x fsfinal 2 = 1500 slots
+        assert "nsamples        750" in cfg
+        open(run / "config_is", "w").write(cfg)
+        for exe, name, env in ((imp_ref, "ref.out", {}), (imp_b200, "b200.out", {}),
+                               (imp_b200, "b200_sharded.out", {"PMCB200_NGPU": "2", "PMCB200_DEVICES": "0"})):
+            o = subprocess.run([exe, "-c", "config_is", "-o", name, "-q", "sub.pmcsim"], cwd=run, capture_output=True,
+                               text=True, timeout=900, env=dict(os.environ, **env))
+            assert o.returncode == 0, o.stdout[-2000:] + o.stderr[-2000:]
+        ref, b2, b3 = (np.loadtxt(run / n) for n in ("ref.out", "b200.out", "b200_sharded.out"))
+        assert ref.shape == (1500, 7) and b2.shape == ref.shape and b3.shape == ref.shape
+        assert np.allclose(b2, ref, rtol=1e-8, atol=0) and np.allclose(b3, ref, rtol=1e-8, atol=0)
+        # log w_new - log w_old = log posterior: spot-check one row against the stored sample
+        old = np.loadtxt(run / "sub.pmcsim")
+        assert np.array_equal(old[:, 2:], ref[:, 2:]) and np.all(np.isfinite(ref[:, 0]))
 
 
 @pytest.mark.skipif(not (os.path.exists(EXE) and os.path.isdir(DEMO)),

@@ -66,6 +66,10 @@ def build():
         o = os.path.join(OUT, "obj", name + ".o")
         subprocess.check_call([GCC] + CFLAGS + INC + ["-c", src, "-o", o])
         subprocess.check_call([GCC, "-o", os.path.join(OUT, name), o] + common + link)
+    # this repo's batched counterpart of importance_sample (one device launch instead of one host callback per point)
+    o = os.path.join(OUT, "obj", "importance_sample_b200.o")
+    subprocess.check_call([GCC] + CFLAGS + INC + ["-c", os.path.join(ROOT, "cosmopmc_b200/exec/importance_sample_b200.c"), "-o", o])
+    subprocess.check_call([GCC, "-o", os.path.join(OUT, "importance_sample_b200"), o] + common + link)
     # the SN demo's inputs (Demo/MC_Demo/SN): config + data + parameter files, as bin/cosmo_pmc.pl stages them
     demo = os.path.join(OUT, "demo_SN")
     os.makedirs(demo, exist_ok=True)
