@@ -722,7 +722,81 @@ void estimate_param_covar_weight(size_t ndim, size_t nsamples, size_t nskip, con
       for (size_t b = 0; b <= a; b++) pvar[b * ndim + a] = pvar[a * ndim + b] = pvar[a * ndim + b] / s;
 }
 
-/* ---- pmcsim reader (restart path, cosmo_pmc.c:404-439; format exec_helper.c:351-424) ------- */
+/* ---- pmcsim files (restart path, cosmo_pmc.c:404-439; text format exec_helper.c:351-424) -----
+ * Text rows are `%16.9g` x (log w_unnormalised, -component, x[0..npar), x_ded[..]) for the flagged
+ * points.  At 1e7-1e8 samples the text file is the bottleneck of a restart and keeps only nine
+ * digits, so this layer also reads and writes a binary sidecar with the same content in exact
+ * doubles:
+ *   header  char magic[8] = "PMCSIMB1"; int32 npar, n_ded; int64 nsamples (draws), nrows; double logSum
+ *   rows    nrows x { double logw_unnormalised; double component; double x[npar]; double x_ded[n_ded] }
+ * pmc_simu_from_file recognises the magic, so a caller that opens either file gets the same psim. */
+static const char PMCSIM_MAGIC[8] = { 'P', 'M', 'C', 'S', 'I', 'M', 'B', '1' };
+typedef struct { char magic[8]; int32_t npar, n_ded; int64_t nsamples, nrows; double logSum; } pmcsim_bin_header;
+
+void pmc_simu_dump_binary(FILE *F, const pmc_simu *psim, error **err)
+{
+   pmcsim_bin_header h;
+   memcpy(h.magic, PMCSIM_MAGIC, 8);
+   h.npar = psim->ndim; h.n_ded = psim->n_ded; h.nsamples = psim->nsamples; h.nrows = 0; h.logSum = psim->logSum;
+   for (long i = 0; i < psim->nsamples; i++) h.nrows += psim->flg[i] != 0;
+   testErrorRet(fwrite(&h, sizeof(h), 1, F) != 1, io_file, "Cannot write the pmcsim header", *err, __LINE__, );
+   int nc = 2 + psim->ndim + psim->n_ded;
+   const long CH = 65536;
+   double *row = (double *)malloc_err(sizeof(double) * (size_t)nc * CH, err);
+   forwardError(*err, __LINE__, );
+   long k = 0;
+   for (long i = 0; i < psim->nsamples; i++) {
+      if (psim->flg[i]) {
+         double *q = row + (size_t)k * nc;
+         double lw = psim->weights[i];
+         q[0] = psim->isLog ? lw : log(lw) + psim->logSum;      /* as out_pmc_simu_cosmo_pmc, exec_helper.c:408-420 */
+         q[1] = (double)psim->indices[i];
+         memcpy(q + 2, psim->X + (size_t)i * psim->ndim, sizeof(double) * psim->ndim);
+         if (psim->n_ded) memcpy(q + 2 + psim->ndim, psim->X_ded + (size_t)i * psim->n_ded, sizeof(double) * psim->n_ded);
+         k++;
+      }
+      if (k == CH || (i == psim->nsamples - 1 && k > 0)) {
+         if (fwrite(row, sizeof(double) * nc, (size_t)k, F) != (size_t)k) {
+            free(row);
+            *err = addError(io_file, "Cannot write the pmcsim rows", *err, __LINE__);
+            return;
+         }
+         k = 0;
+      }
+   }
+   free(row);
+}
+
+static long read_pmcsim_binary(FILE *F, pmc_simu *p, long nsamples, int npar, int n_ded, double *maxW, error **err)
+{
+   pmcsim_bin_header h;
+   testErrorRet(fread(&h, sizeof(h), 1, F) != 1, io_eof, "Truncated binary pmcsim header", *err, __LINE__, 0);
+   testErrorRetVA(h.npar != npar || h.n_ded != n_ded, pmc_dimension, "Binary pmcsim holds npar=%d n_ded=%d, expected %d %d",
+                  *err, __LINE__, 0, h.npar, h.n_ded, npar, n_ded);
+   int nc = 2 + npar + n_ded;
+   long n = h.nrows < nsamples ? (long)h.nrows : nsamples;
+   double *row = (double *)malloc_err(sizeof(double) * (size_t)nc * 65536, err);
+   forwardError(*err, __LINE__, 0);
+   for (long i0 = 0; i0 < n; i0 += 65536) {
+      long m = n - i0 < 65536 ? n - i0 : 65536;
+      if (fread(row, sizeof(double) * nc, (size_t)m, F) != (size_t)m) {
+         free(row);
+         *err = addError(io_eof, "Truncated binary pmcsim file", *err, __LINE__);
+         return 0;
+      }
+      for (long k = 0; k < m; k++) {
+         const double *q = row + (size_t)k * nc;
+         long i = i0 + k;
+         p->weights[i] = q[0]; p->indices[i] = (size_t)q[1]; p->flg[i] = 1;
+         memcpy(p->X + (size_t)i * npar, q + 2, sizeof(double) * npar);
+         if (n_ded) memcpy(p->X_ded + (size_t)i * n_ded, q + 2 + npar, sizeof(double) * n_ded);
+         if (q[0] > *maxW) *maxW = q[0];
+      }
+   }
+   free(row);
+   return n;
+}
+
 pmc_simu *pmc_simu_from_file(FILE *F, int nsamples, int npar, int n_ded, mix_mvdens *proposal, int nclipw, error **err)
 {
    (void)proposal;
@@ -731,7 +805,12 @@ pmc_simu *pmc_simu_from_file(FILE *F, int nsamples, int npar, int n_ded, mix_mvd
    char line[16384];
    long n = 0;
    double maxW = -HUGE_VAL;
-   while (fgets(line, sizeof(line), F)) {
+   int c0 = fgetc(F);
+   if (c0 != EOF) ungetc(c0, F);
+   if (c0 == PMCSIM_MAGIC[0]) {          /* a text pmcsim starts with '#', a digit, a sign or blank */
+      n = read_pmcsim_binary(F, p, nsamples, npar, n_ded, &maxW, err);
+      forwardError(*err, __LINE__, NULL);
+   } else while (fgets(line, sizeof(line), F)) {
       char *s = line;
       while (*s == ' ' || *s == '\t') s++;
       if (*s == '#' || *s == '\n' || *s == 0) continue;

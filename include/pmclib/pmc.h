@@ -63,6 +63,10 @@ void      pmc_simu_free(pmc_simu **psim);
 pmc_simu *pmc_simu_from_file(FILE *PMCSIM, int nsamples, int npar, int n_ded, mix_mvdens *proposal,
                              int nclipw, error **err);
 
+/* binary sidecar of the pmcsim text file (same rows in exact doubles; pmc_simu_from_file reads
+ * either format): for samples of 1e7-1e8 points, where the %16.9g text file dominates a restart */
+void      pmc_simu_dump_binary(FILE *F, const pmc_simu *psim, error **err);
+
 /* ---- the four hot calls of run_pmc_iteration_MPI ----------------------------- */
 size_t simulate_mix_mvdens(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, parabox *pb, error **err);
 size_t generic_get_importance_weight_and_deduced_verb(pmc_simu *psim, const void *proposal_data,

@@ -133,6 +133,30 @@ int main(int argc, char **argv)
    F = fopen_err(name, "w", err);                                             quitOnError(*err, __LINE__, stderr);
    mix_mvdens_dump(F, proposal); fclose(F);
 
+   /* ---- binary pmcsim sidecar: dump, read back through pmc_simu_from_file, compare with the live psim ---- */
+   {
+      sprintf(name, "%s/pmcsim.bin", argv[6]);
+      F = fopen_err(name, "wb", err);                                         quitOnError(*err, __LINE__, stderr);
+      pmc_simu_dump_binary(F, psim, err);                                     quitOnError(*err, __LINE__, stderr);
+      fclose(F);
+      F = fopen_err(name, "rb", err);                                         quitOnError(*err, __LINE__, stderr);
+      pmc_simu *psim3 = pmc_simu_from_file(F, N, 5, 0, NULL, 0, err);         quitOnError(*err, __LINE__, stderr);
+      fclose(F);
+      long k = 0; double maxrel = 0.0; int bad = 0;
+      for (long i = 0; i < psim->nsamples; i++) {
+         if (!psim->flg[i]) continue;
+         if (!psim3->flg[k] || psim3->indices[k] != psim->indices[i] ||
+             memcmp(psim3->X + 5 * k, psim->X + 5 * i, 5 * sizeof(double)) != 0) bad++;
+         if (psim->weights[i] > 0) {
+            double r = fabs(psim3->weights[k] - psim->weights[i]) / psim->weights[i];
+            if (r > maxrel) maxrel = r;
+         }
+         k++;
+      }
+      printf("bin_roundtrip %ld %d %.3g %.17g %ld\n", k, bad, maxrel, psim3->logSum, psim3->nsamples);
+      pmc_simu_free(&psim3);
+   }
+
    /* ---- the same iteration through the fused call ---- */
    gsl_rng_set(rng, seed);
    pmc_simu *psim2 = pmc_simu_init_mpi(N, 5, 0, err);

@@ -90,6 +90,10 @@ def test_pmclib_named_iteration(oracle, tmp_path, nshards):
         assert np.allclose(chol @ chol.transpose(0, 2, 1), covo, rtol=1e-7, atol=1e-12)
     assert abs(r["fused_perplexity"][0] - so["perplexity"]) <= 1e-8 * so["perplexity"]
     assert r["fused_nok"][0] == so["nok"] and r["max_abs_dw"][0] < 1e-15
+    # binary pmcsim sidecar: every flagged row, exact parameters and indices, weights to rounding, same logSum
+    nrow, bad, maxrel, logsum3, ns3 = r["bin_roundtrip"]
+    assert nrow == so["nok"] and bad == 0 and maxrel < 1e-12 and ns3 == N
+    assert abs(logsum3 - so["logSum"]) <= 1e-8 * abs(so["logSum"])
     # an unregistered posterior callback is an error (no silent host fallback)
     assert r["unregistered_is_error"][0] == 1.0 and r["unregistered_is_error"][1] == -6008     # pmc_undef
     # file formats: proposal written before sampling (cosmo_pmc.c:316) round-trips at %g precision
