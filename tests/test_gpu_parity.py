@@ -437,6 +437,38 @@ def test_iteration_host_multi_contexts(oracle, pmc_factory):
     assert e.value.code == A.ERR["NOSAMPLE"]
 
 
+def test_iteration_host_multi_on_two_devices(oracle):
+    """the same on two physical GPUs (skipped on a one-GPU box): contexts on cuda:0 and cuda:1,
+    statistics blocks cross NVLink by cudaMemcpyPeerAsync; result identical to one context"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from cosmopmc_b200.pmc import PMC, iteration_host_multi
+    spec = T.target_sn_demo()
+    w, m, cov = T.proposal_sn(10)
+    ch = oracle.cholesky_stack(cov)
+    N, seed = 200001, 5
+    res = []
+    for devs in ((0,), (0, 1)):
+        pmcs = [PMC(g, use_torch_stream=False) for g in devs]
+        for p in pmcs:
+            p.set_target(spec); p.set_proposal(w, m, chol=ch)
+        hX = torch.empty((N, 5), dtype=torch.float64).pin_memory(); hi = torch.empty(N, dtype=torch.int32).pin_memory()
+        hf = torch.empty(N, dtype=torch.int16).pin_memory(); hw = torch.empty(N, dtype=torch.float64).pin_memory()
+        st = iteration_host_multi(pmcs, N, seed, 0, 1.0, hX, hi, hf, hw)
+        res.append((st, hX.numpy().copy(), hi.numpy().copy(), hf.numpy().copy(), hw.numpy().copy(),
+                    [p.get_proposal() for p in pmcs]))
+        for p in pmcs:
+            p.close()
+    (s1, X1, i1, f1, w1, p1), (s2, X2, i2, f2, w2, p2) = res
+    assert np.array_equal(X1, X2) and np.array_equal(i1, i2) and np.array_equal(f1, f2)
+    assert np.allclose(w1, w2, rtol=1e-12, atol=0) and s1["nok"] == s2["nok"]
+    assert abs(s1["perplexity"] - s2["perplexity"]) <= 1e-12 * s1["perplexity"]
+    for a, b in zip(p1[0], p2[0]):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-14)
+    for a, b in zip(p2[0], p2[1]):
+        assert np.array_equal(a, b)
+
+
 def test_sn_fast_path_matches_libdevice_path(oracle, pmc_factory, tmp_path):
     """The SN kernel's table-based exp2 / MUFU-seeded rsqrt path against the same
     kernel forced through libdevice exp (PMCB200_SN_FORCE_SLOW=1, separate
