@@ -78,18 +78,48 @@ def make_config(name):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons during the timed region: NVML (nvidia_ml_py, ~1 ms per sample)
+    when it loads, else the nvidia-smi query of the profiling recipe (~100 ms per sample)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.bits = [getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                         getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                         getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                         getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        return [str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for b in self.bits]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml:
+                    self.rows.append(self._sample_nvml())
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True,
                                      timeout=5).stdout.strip()
@@ -97,16 +127,16 @@ class ClockSampler(threading.Thread):
                     self.rows.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4)
+        reasons = sorted({self.NAMES[i] for r in self.rows for i in range(4)
                           if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_iteration_rate(spec, w, m, ch, seconds, nthreads):

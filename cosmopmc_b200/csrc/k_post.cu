@@ -9,6 +9,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -84,11 +86,94 @@ k_post_moments(int64_t N, int d, const double *__restrict__ X, const int16_t *__
   for (int j = tid; j < M; j += blockDim.x) partials[(size_t)blockIdx.x * M + j] = tot[j];
 }
 
-__global__ void k_post_reduce(const double *__restrict__ partials, int nblocks, int M, double *__restrict__ out) {
+// d <= 8: one sample per thread, the M = 1 + D + D(D+1)/2 running sums in registers (compile-time D),
+// grid-stride over the sample, warp-shuffle + shared-memory reduction per block.  HBM-bound: 8 D + 10
+// bytes per sample against ~3 M FP64 operations.
+template <int D>
+__global__ void __launch_bounds__(POST_BLOCK)
+k_post_moments_reg(int64_t N, const double *__restrict__ X, const int16_t *__restrict__ flg,
+                   const double *__restrict__ w, const double *__restrict__ pivot, double *__restrict__ partials) {
+  constexpr int M = 1 + D + D * (D + 1) / 2;
+  double acc[M];
+#pragma unroll
+  for (int j = 0; j < M; j++) acc[j] = 0.0;
+  double piv[D];
+#pragma unroll
+  for (int j = 0; j < D; j++) piv[j] = pivot ? pivot[j] : 0.0;
+  // a warp's 32 RPT rows are 32 RPT D contiguous doubles: loaded coalesced (lane + 32 k) into the
+  // warp's shared-memory slab (all loads of the step in flight together), then every lane reads
+  // its own rows (odd row stride: conflict-free)
+  constexpr int RPT = 2;                        // rows per thread and step
+  constexpr int DS = D | 1;
+  __shared__ double slab[POST_BLOCK / 32][32 * RPT * DS];
+  double *my = slab[threadIdx.x >> 5];
+  const int ln = threadIdx.x & 31;
+  const int64_t wstep = (int64_t)gridDim.x * (blockDim.x >> 5) * (32 * RPT);
+  for (int64_t n0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * RPT); n0 < N; n0 += wstep) {
+    const int64_t rem = (N - n0) * D;           // doubles left from the warp's first row
+    double v[RPT * D];
+#pragma unroll
+    for (int k = 0; k < RPT * D; k++) {
+      const int o = ln + 32 * k;
+      v[k] = (o < rem) ? X[n0 * D + o] : 0.0;
+    }
+    double ww[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+      const int64_t n = n0 + ln + 32 * r;
+      ww[r] = (n < N && (!flg || flg[n])) ? (w ? w[n] : 1.0) : 0.0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < RPT * D; k++) {
+      const int o = ln + 32 * k;
+      my[(o / D) * DS + (o % D)] = v[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+      if (ww[r] == 0.0) continue;               // unflagged rows may hold anything
+      double x[D];
+#pragma unroll
+      for (int j = 0; j < D; j++) x[j] = my[(ln + 32 * r) * DS + j] - piv[j];
+      acc[0] += ww[r];
+#pragma unroll
+      for (int a = 0, t = 1 + D; a < D; a++) {
+        const double wa = ww[r] * x[a];
+        acc[1 + a] += wa;
+#pragma unroll
+        for (int bb = 0; bb <= a; bb++, t++) acc[t] = fma(wa, x[bb], acc[t]);
+      }
+    }
+  }
+  __shared__ double red[POST_BLOCK / 32][M];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < M; j++) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][j] = v;
+  }
+  __syncthreads();
   for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < POST_BLOCK / 32; q++) v += red[q][j];
+    partials[(size_t)blockIdx.x * M + j] = v;
+  }
+}
+
+// block partials -> totals: one warp per feature, lanes stride over the blocks, fixed shuffle tree
+// (deterministic; a serial walk over ~1000 partials would cost more than the streaming pass itself)
+__global__ void k_post_reduce(const double *__restrict__ partials, int nblocks, int M, double *__restrict__ out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = wid; j < M; j += nw) {
     double s = 0.0;
-    for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * M + j];
-    out[j] = s;
+    for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * M + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[j] = s;
   }
 }
 
@@ -96,45 +181,74 @@ __global__ void k_post_reduce(const double *__restrict__ partials, int nblocks, 
 void pmc_launch_post_moments(int64_t N, int d, const double *X, const int16_t *flg, const double *w,
                              const double *pivot, int blocks, double *partials, double *out, cudaStream_t s) {
   const int M = 1 + d + d * (d + 1) / 2;
+  if (d <= 8) {
+    switch (d) {
+#define POST_CASE(D) case D: k_post_moments_reg<D><<<blocks, POST_BLOCK, 0, s>>>(N, X, flg, w, pivot, partials); break;
+      POST_CASE(1) POST_CASE(2) POST_CASE(3) POST_CASE(4) POST_CASE(5) POST_CASE(6) POST_CASE(7) POST_CASE(8)
+#undef POST_CASE
+    }
+    k_post_reduce<<<1, 1024, 0, s>>>(partials, blocks, M, out);
+    return;
+  }
   const int G = M > POST_BLOCK ? 1 : POST_BLOCK / M;
   const size_t smem = sizeof(double) * (POST_BLOCK * (d + 1) + d + M);
   cudaFuncSetAttribute(k_post_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_post_moments<<<blocks, POST_BLOCK, smem, s>>>(N, d, X, flg, w, pivot, M, G, partials);
-  k_post_reduce<<<1, POST_BLOCK, 0, s>>>(partials, blocks, M, out);
+  k_post_reduce<<<1, 1024, 0, s>>>(partials, blocks, M, out);
 }
 
 // ---- histogram: acc_histogram, tools/src/nhist.c:87-162 --------------------------------------------------
 // bins of 1 or 2 parameters; per bin {count, sum w, sum w^2}.  A sample on or outside a limit is
 // dropped (vp <= lo || vp >= hi), bin = (int)((vp - lo) / step) with the top bin protected.
 struct HistSpec { int nd; int pidx[2]; int nb[2]; double lo[2], hi[2], stp[2]; };
+// R private copies of the histogram per block (lane l adds into copy l % R): with few bins most
+// lanes of a warp hit the same bin and shared-memory atomics on one address serialise.
 __global__ void __launch_bounds__(POST_BLOCK)
 k_post_hist(int64_t N, int d, const double *__restrict__ X, const int16_t *__restrict__ flg,
-            const double *__restrict__ w, HistSpec h, int tdim, double *__restrict__ out /* [3][tdim] */) {
-  extern __shared__ double sh[];            // [3][tdim] private copy
-  for (int i = threadIdx.x; i < 3 * tdim; i += blockDim.x) sh[i] = 0.0;
+            const double *__restrict__ w, HistSpec h, int tdim, int R, double *__restrict__ out /* [3][tdim] */) {
+  extern __shared__ double sh[];            // [R][3][tdim]
+  for (int i = threadIdx.x; i < R * 3 * tdim; i += blockDim.x) sh[i] = 0.0;
   __syncthreads();
-  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
-    if (flg && !flg[n]) continue;
-    int pos = 0, mul = 1;
-    bool valid = true;
-    for (int ap = 0; ap < h.nd; ap++) {
-      const int ip = h.nd - ap - 1;
-      const double vp = X[n * d + h.pidx[ip]];
-      if (vp <= h.lo[ip] || vp >= h.hi[ip]) { valid = false; break; }
-      int nb = (int)((vp - h.lo[ip]) / h.stp[ip]);
-      if (nb == h.nb[ip]) nb--;
-      pos += nb * mul;
-      mul *= h.nb[ip];
+  double *mine = sh + (size_t)(threadIdx.x % R) * 3 * tdim;
+  constexpr int U = 4;                      // rows per thread and step: U independent strided loads in flight
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t n0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n0 < N; n0 += U * stride) {
+    double v0[U], v1[U], wg[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int64_t n = n0 + u * stride;
+      ok[u] = n < N && (!flg || flg[n]);
+      v0[u] = ok[u] ? X[n * d + h.pidx[0]] : 0.0;
+      v1[u] = (ok[u] && h.nd > 1) ? X[n * d + h.pidx[1]] : 0.0;
+      wg[u] = ok[u] ? (w ? w[n] : 1.0) : 0.0;
     }
-    if (!valid) continue;
-    const double wg = w ? w[n] : 1.0;
-    atomicAdd(&sh[pos], 1.0);
-    atomicAdd(&sh[tdim + pos], wg);
-    atomicAdd(&sh[2 * tdim + pos], wg * wg);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (!ok[u]) continue;
+      int pos = 0, mul = 1;
+      bool valid = true;
+      for (int ap = 0; ap < h.nd; ap++) {     // nhist.c:118-131: last axis first, it runs fastest
+        const int ip = h.nd - ap - 1;
+        const double vp = ip ? v1[u] : v0[u];
+        if (vp <= h.lo[ip] || vp >= h.hi[ip]) { valid = false; break; }
+        int nb = (int)((vp - h.lo[ip]) / h.stp[ip]);
+        if (nb == h.nb[ip]) nb--;
+        pos += nb * mul;
+        mul *= h.nb[ip];
+      }
+      if (!valid) continue;
+      atomicAdd(&mine[pos], 1.0);
+      atomicAdd(&mine[tdim + pos], wg[u]);
+      atomicAdd(&mine[2 * tdim + pos], wg[u] * wg[u]);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * tdim; i += blockDim.x)
-    if (sh[i] != 0.0) atomicAdd(&out[i], sh[i]);
+  for (int i = threadIdx.x; i < 3 * tdim; i += blockDim.x) {
+    double v = 0.0;
+    for (int r = 0; r < R; r++) v += sh[(size_t)r * 3 * tdim + i];
+    if (v != 0.0) atomicAdd(&out[i], v);
+  }
 }
 
 int pmc_launch_post_hist(int64_t N, int d, const double *X, const int16_t *flg, const double *w, int nd,
@@ -148,11 +262,15 @@ int pmc_launch_post_hist(int64_t N, int d, const double *X, const int16_t *flg, 
     h.stp[i] = (limits[2 * i + 1] - limits[2 * i]) / nbins[i];
     tdim *= nbins[i];
   }
-  const size_t smem = sizeof(double) * 3 * (size_t)tdim;
-  if (smem > 200 * 1024) return -1;
-  cudaMemsetAsync(out, 0, smem, s);
+  const size_t one = sizeof(double) * 3 * (size_t)tdim;
+  if (one > 200 * 1024) return -1;
+  int R = (int)std::min<size_t>(32, (48 * 1024) / one);      // copies within 48 KB
+  if (R < 1) R = 1;
+  while (R & (R - 1)) R &= R - 1;                             // power of two
+  const size_t smem = one * R;
+  cudaMemsetAsync(out, 0, one, s);
   cudaFuncSetAttribute(k_post_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_post_hist<<<blocks, POST_BLOCK, smem, s>>>(N, d, X, flg, w, h, tdim, out);
+  k_post_hist<<<blocks, POST_BLOCK, smem, s>>>(N, d, X, flg, w, h, tdim, R, out);
   return 0;
 }
 
@@ -162,11 +280,25 @@ __global__ void __launch_bounds__(POST_BLOCK)
 k_post_gather(int64_t N, int d, int a, const double *__restrict__ X, const int16_t *__restrict__ flg,
               const double *__restrict__ w, double *__restrict__ key, double *__restrict__ val,
               unsigned long long *__restrict__ nflag) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool ok = (n < N) && (!flg || flg[n]);
-  if (n < N) { key[n] = ok ? X[n * d + a] : INFINITY; val[n] = ok ? (w ? w[n] : 1.0) : 0.0; }
-  const unsigned m = __ballot_sync(0xffffffffu, ok);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(nflag, (unsigned long long)__popc(m));
+  constexpr int U = 4;                      // rows per thread: U independent strided loads in flight
+  const int64_t base = ((int64_t)blockIdx.x * U) * blockDim.x + threadIdx.x;
+  double xv[U], wv[U];
+  bool ok[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int64_t n = base + (int64_t)u * blockDim.x;
+    ok[u] = (n < N) && (!flg || flg[n]);
+    xv[u] = ok[u] ? X[n * d + a] : INFINITY;
+    wv[u] = ok[u] ? (w ? w[n] : 1.0) : 0.0;
+  }
+  unsigned cnt = 0;
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int64_t n = base + (int64_t)u * blockDim.x;
+    if (n < N) { key[n] = xv[u]; val[n] = wv[u]; }
+    cnt += __popc(__ballot_sync(0xffffffffu, ok[u]));
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(nflag, (unsigned long long)cnt);
 }
 
 // sigma_from_psim (exec_helper.c:201-275) and median_from_psim (:164-199) on the sorted sample.
@@ -227,7 +359,7 @@ void pmc_launch_post_sigma(int64_t N, int d, int a, const double *X, const int16
                            unsigned long long *nflag, double *out8, cudaStream_t s) {
   double *key = work, *val = work + N, *skey = work + 2 * N, *sval = work + 3 * N;
   cudaMemsetAsync(nflag, 0, sizeof(unsigned long long), s);
-  k_post_gather<<<(unsigned)((N + POST_BLOCK - 1) / POST_BLOCK), POST_BLOCK, 0, s>>>(N, d, a, X, flg, w, key, val, nflag);
+  k_post_gather<<<(unsigned)((N + 4 * POST_BLOCK - 1) / (4 * POST_BLOCK)), POST_BLOCK, 0, s>>>(N, d, a, X, flg, w, key, val, nflag);
   cub::DeviceRadixSort::SortPairs(temp, temp_bytes, key, skey, val, sval, N, 0, 64, s);
   cub::DeviceScan::InclusiveSum(temp, temp_bytes, sval, val, N, s);     // val <- prefix sums of the sorted weights
   k_post_sigma<<<1, 32, 0, s>>>(skey, val, nflag, center, conf[0], conf[1], conf[2], out8);

@@ -1081,7 +1081,8 @@ extern "C" int pmcb200_post_moments(pmcb200_ctx *c, int64_t N, int d, const doub
   if (rc) return rc;
   if (N < 1 || d < 1 || d > PMCB200_MAX_DIM || !dX || !mean) return fail(c, PMCB200_ERR_ARG, "post_moments: bad arguments");
   const int M = 1 + d + d * (d + 1) / 2;
-  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(2 * c->sm_count, (N + 255) / 256));
+  // d <= 8: register kernel, enough resident threads to cover the HBM latency; larger d: tile kernel
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((d <= 8 ? 8 : 2) * c->sm_count, (N + 255) / 256));
   if ((rc = ensure(c, c->sPost, sizeof(double) * ((size_t)blocks * M + 2 * M + d)))) return rc;
   double *part = (double *)c->sPost.p, *out = part + (size_t)blocks * M, *piv = out + 2 * M;
   std::vector<double> h(M);
@@ -1146,7 +1147,7 @@ extern "C" int pmcb200_post_histogram(pmcb200_ctx *c, int64_t N, int d, const do
   }
   if (tdim * 3 * sizeof(double) > 200 * 1024) return fail(c, PMCB200_ERR_UNSUP, "post_histogram: %zu bins exceed the shared-memory copy (max 8533)", tdim);
   if ((rc = ensure(c, c->sPost, sizeof(double) * 3 * tdim))) return rc;
-  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(2 * c->sm_count, (N + 255) / 256));
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((tdim <= 1024 ? 8 : 2) * c->sm_count, (N + 255) / 256));
   if (pmc_launch_post_hist(N, d, dX, dflg, dw, nhdim, pidx, nbins, limits, blocks, (double *)c->sPost.p, c->stream))
     return fail(c, PMCB200_ERR_UNSUP, "post_histogram: too many bins");
   LAUNCH_OK(c);
