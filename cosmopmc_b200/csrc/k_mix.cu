@@ -21,6 +21,35 @@
 
 static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
 
+// FP64 tensor-core EM statistics (d >= 10): persistent grid sized by the occupancy API
+template <int DD, int MT, bool STUDENT>
+static cudaError_t launch_em_mma(const MixArgs &a, cudaStream_t s) {
+  auto kern = k_em_stats_mma<DD, MT, STUDENT>;
+  const size_t smem = em_mma_smem_bytes(a.h.K, a.h.d, STUDENT);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 1, dev = 0, sms = 148;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PMC_BLOCK, smem);
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = std::max(1, std::min(a.blocks, std::max(1, per_sm) * sms));
+  if (a.nblocks_out) *a.nblocks_out = blocks;
+  kern<<<blocks, PMC_BLOCK, smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal, a.partials, a.linear);
+  return cudaGetLastError();
+}
+template <int DD>
+static cudaError_t run_em_mma(const MixArgs &a, cudaStream_t s) {
+  if constexpr (DD >= 10 && DD % 2 == 0) {
+    const int mt = em_mma_mt(a.h.K);
+    const bool st = a.h.df > 0;
+#define EMM(MTV) if (mt == MTV) { if constexpr (MTV * (((1 + DD + DD * (DD + 1) / 2 + 7) / 8 + 7) / 8) <= EM_MMA_MAXACC) \
+      return st ? launch_em_mma<DD, MTV, true>(a, s) : launch_em_mma<DD, MTV, false>(a, s); }
+    EMM(1) EMM(2) EMM(3) EMM(4)
+#undef EMM
+  }
+  return cudaErrorInvalidValue;
+}
+
 template <int DD>
 static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
   switch (op) {
@@ -43,6 +72,9 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
                                                     a.scal);
       break;
     case OP_EM: {
+      if constexpr (DD >= 10 && DD % 2 == 0) {
+        if (a.em_mma && em_mma_ok(a.h.K, a.h.d) && a.k0 == 0 && a.Kg == a.h.K) return run_em_mma<DD>(a, s);
+      }
       const bool reg = em_use_reg(a.Kg, a.h.d, a.h.df > 0);
       auto kern = reg ? k_em_stats<DD, true> : k_em_stats<DD, false>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);

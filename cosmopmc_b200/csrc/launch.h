@@ -23,6 +23,7 @@ struct MixArgs {
   int set = 0; double add_const = 0.0, beta = 1.0;
   double *logw = nullptr; const double *logwc = nullptr;
   double *partials = nullptr; int blocks = 0; size_t smem = 0; int linear = 0; int *nblocks_out = nullptr; int k0 = 0, Kg = 0;
+  int em_mma = 0;      // OP_EM: FP64 tensor-core kernel (host checked em_mma_ok)
 };
 
 bool pmc_mix_launch_g0(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e);

@@ -428,3 +428,184 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
     P[STAT_HDR + out] = s;
   }
 }
+
+// ---- K5, FP64 tensor-core variant (D >= 10, K <= 32) ---------------------------
+// ncu on C3 (d = 20, K = 10): k_em_stats is bound by the LSU data pipe (80 % of its
+// wavefront peak; one broadcast LDS per FMA of the K x tile x M' contraction) with the
+// FP64 pipe below a quarter busy.  tools/micro/dmma_probe.cu: DMMA.8x8x4 sustains 99.8 %
+// of the vector FP64 peak and a DFMA fed by one LDS runs at 49 %.  So phase 2 is issued
+// as mma.sync.m8n8k4.f64: M = 8 components, N = 8 features, K = 4 samples -- 256 FMA per
+// warp instruction for 1 + 2/MT shared-memory loads per lane.
+//   A fragment  a  = w rho gamma [component 8 mt + lane/4][sample s0 + lane%4]
+//   B fragment  b  = feature [sample s0 + lane%4][feature 8 tile + lane/4] = x_i x_j, with
+//                    a constant 1 stored in column D of the staged row, so that the G
+//                    statistic (1*1), the first moments (x_i * 1) and the second moments
+//                    are one expression (D even: the row stride D + 1 is odd)
+//   C fragment  c0,c1 = statistic [component 8 mt + lane/4][feature 8 tile + 2 (lane%4) + {0,1}]
+// Warp w owns the feature tiles w, w + 8, ... (NT per warp) for all MT component tiles;
+// the accumulators stay in registers across the tiles of the persistent block, and every
+// (component, feature) sum is owned by exactly one thread: no combine step, fixed order.
+// A = sum w rho equals G for a Gaussian proposal; for Student-t warp 0 accumulates it with
+// a second set of A fragments (w rho without gamma) against the ones column.
+#define EM_WSTRIDE (PMC_BLOCK + 4)     // row stride of s_wr / s_wg: the 8 rows of an A fragment fall on distinct banks
+#define EM_MMA_MAXACC 24               // MT x NT accumulator pairs per thread
+__host__ __device__ inline int em_mma_nt(int D) { return ((1 + D + mix_tri(D) + 7) / 8 + 7) / 8; }
+__host__ __device__ inline int em_mma_mt(int K) { return (K + 7) / 8; }
+__host__ __device__ inline bool em_mma_ok(int K, int d) {
+  const int D = pmc_pad_dim(d);
+  return D >= 10 && (D % 2) == 0 && K <= 32 && em_mma_mt(K) * em_mma_nt(D) <= EM_MMA_MAXACC;
+}
+__host__ __device__ inline size_t em_mma_smem_bytes(int K, int d, int student) {
+  const int D = pmc_pad_dim(d), KP = 8 * em_mma_mt(K);
+  return ((size_t)KP * EM_WSTRIDE * (student ? 2 : 1) + (size_t)PMC_BLOCK * (D + 1)) * sizeof(double) +
+         (size_t)K * sizeof(unsigned long long);
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int D, int MT, bool STUDENT>
+__global__ void __launch_bounds__(PMC_BLOCK, 2)
+k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
+               const double *__restrict__ X, const int32_t *__restrict__ idx,
+               const int16_t *__restrict__ flg, const double *__restrict__ logw,
+               const DevScal *__restrict__ scal, double *__restrict__ partials, int linear) {
+  extern __shared__ double sm[];
+  static_assert(D % 2 == 0, "the ones column needs the odd row stride D + 1");
+  constexpr int XS = D + 1;
+  constexpr int NT = ((1 + D + D * (D + 1) / 2 + 7) / 8 + 7) / 8;
+  constexpr int KP = 8 * MT;
+  const int K = h.K, d = h.d, M = stat_cs(d);
+  const int nfeat = 1 + d + mix_tri(d);       // G, B[d], C[tri] (stat block position: f = 0 -> 1, f >= 1 -> f + 2)
+  double *s_wr = sm;                                                        // [KP][EM_WSTRIDE] w rho
+  double *s_wg = STUDENT ? s_wr + (size_t)KP * EM_WSTRIDE : s_wr;           // w rho gamma
+  double *s_x = s_wg + (size_t)KP * EM_WSTRIDE;                             // [PMC_BLOCK][XS] x - pivot | 1
+  unsigned long long *s_cnt = (unsigned long long *)(s_x + (size_t)PMC_BLOCK * XS);   // [K]
+  __shared__ double red[32];
+  const double *pivot = mix + (size_t)K * h.stride;
+  const double M0 = linear ? 0.0 : dunkey(scal->max_key);
+  double tS = 0.0, tS2 = 0.0, tT = 0.0, tN = 0.0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  // this lane's B-fragment column of each owned feature tile: staged-row offsets (oi, oj)
+  int oi[NT], oj[NT];
+  int ntv = 0;                                 // owned tiles that hold a feature (warp-uniform)
+#pragma unroll
+  for (int q = 0; q < NT; q++) {
+    const int tile = warp + 8 * q;
+    if (tile * 8 < nfeat) ntv = q + 1;
+    const int f = tile * 8 + g;
+    int a = D, b = D;
+    if (f >= 1 && f < 1 + d) a = f - 1;
+    else if (f >= 1 + d && f < nfeat) {
+      const int qq = f - 1 - d;
+      int i = 0;
+      while ((i + 1) * (i + 2) / 2 <= qq) i++;
+      a = i; b = qq - i * (i + 1) / 2;
+    }
+    oi[q] = a; oj[q] = b;
+  }
+  double acc[MT][NT][2], accA[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    accA[m][0] = 0.0; accA[m][1] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NT; q++) { acc[m][q][0] = 0.0; acc[m][q][1] = 0.0; }
+  }
+  for (int k = K; k < KP; k++) { s_wr[k * EM_WSTRIDE + tid] = 0.0; if (STUDENT) s_wg[k * EM_WSTRIDE + tid] = 0.0; }
+  if (tid < K) s_cnt[tid] = 0ull;
+  const int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t n = tile * PMC_BLOCK + tid;
+    __syncthreads();
+    // ---- phase 1: weight and responsibilities of this thread's sample (as k_em_stats)
+    const bool ok = (n < N) && flg[n] && (!linear || logw[n] > 0.0);
+    if (ok) {
+      double x[D], y[D];
+      load_x<D>(X, n, d, x);
+      double lw, w;
+      if (linear) { w = logw[n]; lw = log(w); }
+      else { lw = logw[n] - M0; w = exp(lw); }
+      tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT); tN += 1.0;
+      double rt = 0.0;
+      for (int k = 0; k < K; k++) {
+        const double *comp = mix + (size_t)k * h.stride;
+        const double a = comp[0];
+        double r = 0.0, gam = 1.0;
+        if (a != 0.0) {
+          double m = comp_maha<D>(comp, d, x, y);
+          r = a * exp(comp_logpdf_from_maha(comp, d, h.df, m));
+          if (STUDENT) gam = (double)(h.df + d) / ((double)h.df + m);
+        }
+        rt += r;
+        s_wr[k * EM_WSTRIDE + tid] = r;
+        if (STUDENT) s_wg[k * EM_WSTRIDE + tid] = gam;
+      }
+      const double sc = w / rt;
+      for (int k = 0; k < K; k++) {
+        double r = s_wr[k * EM_WSTRIDE + tid] * sc;
+        s_wr[k * EM_WSTRIDE + tid] = r;
+        if (STUDENT) s_wg[k * EM_WSTRIDE + tid] *= r;
+      }
+#pragma unroll
+      for (int i = 0; i < D; i++) s_x[tid * XS + i] = x[i] - pivot[i];      // padded: 0 - 0
+    } else {
+      for (int k = 0; k < K; k++) { s_wr[k * EM_WSTRIDE + tid] = 0.0; if (STUDENT) s_wg[k * EM_WSTRIDE + tid] = 0.0; }
+#pragma unroll
+      for (int i = 0; i < D; i++) s_x[tid * XS + i] = 0.0;
+    }
+    s_x[tid * XS + D] = 1.0;
+    if ((n < N) && flg[n]) { const int c = idx[n]; if (c >= 0 && c < K) atomicAdd(&s_cnt[c], 1ull); }
+    __syncthreads();
+    // ---- phase 2: K x 256 x nfeat contraction on the FP64 tensor cores, 4 samples per step
+    const double *wa = s_wg + (size_t)g * EM_WSTRIDE + t;
+    const double *wr = s_wr + (size_t)g * EM_WSTRIDE + t;
+    const double *xr = s_x + (size_t)t * XS;
+#pragma unroll 2
+    for (int s0 = 0; s0 < PMC_BLOCK; s0 += 4, wa += 4, wr += 4, xr += 4 * XS) {
+      double a[MT];
+#pragma unroll
+      for (int m = 0; m < MT; m++) a[m] = wa[(size_t)m * 8 * EM_WSTRIDE];
+      double b0 = 0.0;
+#pragma unroll
+      for (int q = 0; q < NT; q++) {
+        if (q < ntv) {
+          const double b = xr[oi[q]] * xr[oj[q]];
+          if (q == 0) b0 = b;
+#pragma unroll
+          for (int m = 0; m < MT; m++) dmma884(acc[m][q][0], acc[m][q][1], a[m], b);
+        }
+      }
+      if (STUDENT && warp == 0) {
+#pragma unroll
+        for (int m = 0; m < MT; m++) dmma884(accA[m][0], accA[m][1], wr[(size_t)m * 8 * EM_WSTRIDE], b0);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- this block's partial
+  double *P0 = partials + (size_t)blockIdx.x * stat_len(K, d);
+  double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red), bN = block_sum(tN, red);
+  if (tid == 0) { P0[0] = M0; P0[1] = bS; P0[2] = bS2; P0[3] = bT; P0[4] = bN; P0[5] = 0; P0[6] = 0; P0[7] = 0; }
+  if (tid < K) P0[STAT_HDR + (size_t)tid * M + 2] = (double)s_cnt[tid];
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    const int k = m * 8 + g;
+    if (k >= K) continue;
+    double *Pk = P0 + STAT_HDR + (size_t)k * M;
+#pragma unroll
+    for (int q = 0; q < NT; q++) {
+      if (q >= ntv) continue;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int f = (warp + 8 * q) * 8 + 2 * t + c;
+        if (f >= nfeat) continue;
+        const double v = acc[m][q][c];
+        if (f == 0) { Pk[1] = v; if (!STUDENT) Pk[0] = v; }
+        else Pk[f + 2] = v;
+      }
+    }
+    if (STUDENT && warp == 0 && t == 0) Pk[0] = accA[m][0];
+  }
+}

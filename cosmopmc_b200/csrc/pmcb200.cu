@@ -53,6 +53,7 @@ struct pmcb200_ctx {
   double *d_work = nullptr, *d_result = nullptr; size_t work_cap = 0;
   double *h_result = nullptr;             // pinned
   int em_blocks = 0;
+  int em_no_mma = 0;        // PMCB200_EM_NO_MMA=1: keep the shared-memory EM kernel for d >= 10 (A/B measurements)
   int sm_count = 148;
   // scratch for the host-buffer API
   DevBuf sX, sIdx, sFlg, sLogw, sLogpi, sErr, sBlock, sAll;
@@ -322,6 +323,7 @@ static int install_proposal(pmcb200_ctx *c, int K, int d, int df, const double *
   if (rc) return rc;
   // EM work buffers
   int64_t len = stat_len(K, d);
+  { const char *ev = getenv("PMCB200_EM_NO_MMA"); c->em_no_mma = ev && *ev && *ev != '0'; }
   c->em_blocks = 4 * c->sm_count;     // capacity of the partials buffer; the launch uses the resident count
   size_t need = (size_t)c->em_blocks * len;
   if (c->partials_cap < need) {
@@ -647,14 +649,15 @@ static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const in
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->em_blocks, ntiles));
   // component groups: one launch unless the K x 256 shared-memory arrays exceed the budget
   int Kg = K;
-  while (Kg > 1 && em_smem_bytes(Kg, d, c->h.df > 0) > 200 * 1024) Kg = (Kg + 1) / 2;
+  const bool mma = em_mma_ok(K, d) && !c->em_no_mma;     // FP64 tensor-core kernel: all components in one launch
+  while (!mma && Kg > 1 && em_smem_bytes(Kg, d, c->h.df > 0) > 200 * 1024) Kg = (Kg + 1) / 2;
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.idxc = didx; a.flgc = dflg; a.logwc = dlogw;
-  a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.linear = linear;
+  a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.linear = linear; a.em_mma = mma;
   int used = blocks;
   a.nblocks_out = &used;
   for (int k0 = 0; k0 < K; k0 += Kg) {
     a.k0 = k0; a.Kg = std::min(Kg, K - k0);
-    a.smem = em_smem_bytes(a.Kg, d, c->h.df > 0);
+    a.smem = mma ? em_mma_smem_bytes(K, d, c->h.df > 0) : em_smem_bytes(a.Kg, d, c->h.df > 0);
     a.blocks = (k0 == 0) ? blocks : used;     // every group must use the same grid (shared partials layout)
     MIX_OK(c, OP_EM, a);
   }

@@ -335,6 +335,37 @@ def test_iteration_banana(oracle, pmc_factory):
     check_iteration(o, st, pmc, *h)
 
 
+@pytest.mark.parametrize("K,d,df,N", [(10, 20, -1, 30011), (20, 12, 5, 20000), (32, 11, -1, 25000),
+                                       (3, 18, 4, 9000), (8, 10, -1, 4096), (4, 32, 7, 12000)])
+def test_iteration_em_tensor_core_shapes(oracle, pmc_factory, K, d, df, N, monkeypatch):
+    """d >= 10 runs the EM statistics on the FP64 tensor cores (k_em_stats_mma): every component-tile
+    count MT = 1..4, padded dimensions (11 -> 12, 18 -> 20), Gaussian and Student-t, ragged last tile;
+    against the oracle, and against the shared-memory kernel (PMCB200_EM_NO_MMA=1) on the same sample."""
+    pmc = pmc_factory()
+    rng = np.random.default_rng(100 * K + d)
+    lo, hi = -6.0 * np.ones(d), 6.0 * np.ones(d)
+    tc = np.diag(0.5 + rng.random(d))
+    spec = T.TargetSpec(["dummy%d" % j for j in range(d)], lo, hi).add_mix([0.6, 0.4], [np.zeros(d), 0.5 * np.ones(d)],
+                                                                         [tc, 0.7 * tc])
+    mean = rng.normal(size=(K, d)) * 0.4
+    A_ = rng.normal(size=(K, d, d)) * 0.15
+    cov = np.einsum("kij,klj->kil", A_, A_) + np.eye(d)[None] * (1.0 + rng.random((K, 1, 1)))
+    w = rng.random(K) + 0.2; w /= w.sum()
+    ch = oracle.cholesky_stack(cov)
+    pmc.set_target(spec)
+    pmc.set_proposal(w, mean, chol=ch, df=df)
+    o, st, *h = run_both(oracle, pmc, spec, w, mean, ch, N, seed=11, df=df)
+    check_iteration(o, st, pmc, *h)
+    wg, mg, chg, covg = pmc.get_proposal()
+    monkeypatch.setenv("PMCB200_EM_NO_MMA", "1")
+    pmc.set_proposal(w, mean, chol=ch, df=df)
+    o2, st2, *h2 = run_both(oracle, pmc, spec, w, mean, ch, N, seed=11, df=df)
+    w2, m2, ch2, cov2 = pmc.get_proposal()
+    assert rel(wg, w2) < 1e-11 and rel(mg, m2, 1e-3) < 1e-10
+    assert np.max(np.abs(covg - cov2)) < 1e-10 * np.max(np.abs(cov2))
+    assert abs(st["perplexity"] - st2["perplexity"]) < 1e-12 * st2["perplexity"]
+
+
 def test_iteration_cmb_bao_sn(oracle, pmc_factory):
     pmc = pmc_factory()
     spec = T.target_cmb_bao_sn()
