@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <type_traits>
 #include "../../include/pmcb200.h"
 
 #define PMC_BLOCK 256
@@ -170,6 +171,46 @@ __device__ __forceinline__ double mix_logpdf(const double *__restrict__ mix, con
   return log(s);
 }
 
+// Compile-time loop: the body sees its index as a constant, so the register arrays it indexes can
+// never be demoted to local memory (nvcc gave up unrolling the triangular nest with #pragma unroll).
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+// S samples per thread, column-oriented: after y_k = t_k / L_kk every remaining row takes its update
+// t_i -= L_ik y_k at once.  Each t_i still receives its updates in ascending k and m its squares in
+// ascending i, so the result is bit-identical to comp_maha; but the D - k - 1 updates of a step are
+// independent (no serial FMA chain), and each L_ik fetched (a warp-uniform load: the LSU data pipe, not
+// the FP64 pipe, bounds these kernels -- tools/micro/dmma_probe.cu) feeds S FMAs.
+// t[s][i] holds x_i of sample s on entry and is destroyed.
+template <int D, int S>
+__device__ __forceinline__ void comp_maha_cols(const double *__restrict__ comp, double (&t)[S][D], double (&m)[S]) {
+  const double *mean = comp + 2, *L = comp + 2 + D, *rd = comp + 2 + D + D * (D + 1) / 2;
+  static_for<0, D>([&](auto ii) {
+    constexpr int i = decltype(ii)::value;
+    const double mu = mean[i];
+#pragma unroll
+    for (int s = 0; s < S; s++) t[s][i] -= mu;
+  });
+#pragma unroll
+  for (int s = 0; s < S; s++) m[s] = 0.0;
+  static_for<0, D>([&](auto kk) {
+    constexpr int k = decltype(kk)::value;
+    const double r = rd[k];
+    double y[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) { y[s] = t[s][k] * r; m[s] = fma(y[s], y[s], m[s]); }
+    static_for<k + 1, D>([&](auto ii) {
+      constexpr int i = decltype(ii)::value;
+      const double l = L[i * (i + 1) / 2 + k];
+#pragma unroll
+      for (int s = 0; s < S; s++) t[s][i] = fma(-l, y[s], t[s][i]);
+    });
+  });
+}
 // ---- Romberg (Numerical Recipes qromb, K = 5) ---------------------------------
 // Window y[0..4] of the last five trapezoid values (step ratio 1/4): Neville at
 // h = 0 with the constant ratios folded in.  Returns ss, sets dss.

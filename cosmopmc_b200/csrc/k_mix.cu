@@ -4,6 +4,10 @@
 #include "pmc_kernels.cuh"
 #include "launch.h"
 #include <algorithm>
+#include <cstdlib>
+#ifndef ESTEP_DEFAULT
+#define ESTEP_DEFAULT 0
+#endif
 
 #if MIX_GROUP == 0
 #define DLIST(X) X(2) X(3) X(4) X(5)
@@ -68,6 +72,21 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
                                                      a.logpi, a.err, a.set, a.add_const);
       break;
     case OP_WEIGHTS:
+      if constexpr (DD >= 10) {
+        // PMCB200_ESTEP: 0 = one sample per thread, row-oriented, mixture through L1 (k_weights);
+        // S = 1, 2, 3 = k_weights_multi with S samples per thread
+        static const int mode = getenv("PMCB200_ESTEP") ? atoi(getenv("PMCB200_ESTEP")) : ESTEP_DEFAULT;
+        const size_t mixbytes = (size_t)a.h.K * a.h.stride * sizeof(double);
+#define WM(SV) { auto kern = k_weights_multi<DD, SV>; const size_t sm = mixbytes + (size_t)DD * SV * PMC_BLOCK * sizeof(double); \
+          if (sm <= 200 * 1024) { \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
+            kern<<<(int)((a.N + PMC_BLOCK * SV - 1) / (PMC_BLOCK * SV)), PMC_BLOCK, sm, s>>>(a.mix, a.h, a.N, a.Xc, a.logpic, a.errc, a.beta, a.flg, a.logw, a.scal); \
+            return cudaGetLastError(); } }
+        if (mode == 1) WM(1)
+        if (mode == 2) WM(2)
+        if (mode == 3) WM(3)
+#undef WM
+      }
       k_weights<DD><<<nblk(a.N), PMC_BLOCK, 0, s>>>(a.mix, a.h, a.N, a.Xc, a.logpic, a.errc, a.beta, a.flg, a.logw,
                                                     a.scal);
       break;

@@ -186,6 +186,87 @@ k_weights(const double *__restrict__ mix, const MixHdr h, int64_t N,
   }
 }
 
+// K4 for d >= 10, where the K log-pdfs per sample make the kernel LSU-bound (one warp-uniform mixture load
+// per FMA; tools/micro/dmma_probe.cu: a DFMA fed by a broadcast LDG runs at 25 % of the FP64 peak, by a
+// broadcast LDS at 49 %).  The packed mixture is staged in shared memory; every thread owns S samples
+// (tile_base + s * PMC_BLOCK + tid: loads stay coalesced) which share each mixture load; the samples sit in
+// shared memory too ([i][s][tid], conflict-free) so that only the S x D working rows of the column-oriented
+// substitution live in registers.
+template <int D, int S>
+__global__ void __launch_bounds__(PMC_BLOCK, (S * D <= 48) ? 2 : 1)
+k_weights_multi(const double *__restrict__ mixg, const MixHdr h, int64_t N,
+                const double *__restrict__ X, const double *__restrict__ logpi,
+                const int32_t *__restrict__ err, double beta, int16_t *__restrict__ flg,
+                double *__restrict__ logw, DevScal *scal) {
+  __shared__ double red[32];
+  __shared__ int cnt[32];
+  extern __shared__ double s_buf[];
+  double *s_xt = s_buf;                                    // [D][S][PMC_BLOCK]
+  double *s_mix = s_buf + (size_t)D * S * PMC_BLOCK;       // packed mixture
+  const int nmix = h.K * h.stride;
+  for (int i = threadIdx.x; i < nmix; i += PMC_BLOCK) s_mix[i] = mixg[i];
+  const int64_t base = (int64_t)blockIdx.x * (PMC_BLOCK * S) + threadIdx.x;
+  bool live[S];
+#pragma unroll
+  for (int s = 0; s < S; s++) {
+    const int64_t n = base + (int64_t)s * PMC_BLOCK;
+    live[s] = (n < N) && flg[n];
+#pragma unroll
+    for (int i = 0; i < D; i++)
+      s_xt[((size_t)i * S + s) * PMC_BLOCK + threadIdx.x] = (live[s] && i < h.d) ? X[n * h.d + i] : 0.0;
+  }
+  __syncthreads();
+  double acc[S], m[S], t[S][D];
+#pragma unroll
+  for (int s = 0; s < S; s++) acc[s] = 0.0;
+  for (int k = 0; k < h.K; k++) {
+    const double *comp = s_mix + (size_t)k * h.stride;
+    const double w = comp[0];
+    if (w == 0.0) continue;
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+      for (int s = 0; s < S; s++) t[s][i] = s_xt[((size_t)i * S + s) * PMC_BLOCK + threadIdx.x];
+    comp_maha_cols<D, S>(comp, t, m);
+#pragma unroll
+    for (int s = 0; s < S; s++) acc[s] = fma(w, exp(comp_logpdf_from_maha(comp, h.d, h.df, m[s])), acc[s]);
+  }
+  double lwmax = -INFINITY;
+  int nok = 0;
+#pragma unroll
+  for (int s = 0; s < S; s++) {
+    const int64_t n = base + (int64_t)s * PMC_BLOCK;
+    if (n < N) {
+      int ok = 0;
+      double lw = 0.0;
+      if (live[s]) {
+        const double lq = log(acc[s]);
+        const double v = beta * logpi[n] - lq;
+        ok = (err[n] == 0) && isfinite(lq) && isfinite(v);
+        if (ok) { lw = v; lwmax = fmax(lwmax, v); nok++; } else flg[n] = 0;
+      }
+      logw[n] = ok ? lw : 0.0;
+    }
+  }
+  double wm = warp_max(lwmax);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nok += __shfl_xor_sync(0xffffffffu, nok, o);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { red[w] = wm; cnt[w] = nok; }
+  __syncthreads();
+  if (w == 0) {
+    double v = (lane < (PMC_BLOCK >> 5)) ? red[lane] : -INFINITY;
+    int c = (lane < (PMC_BLOCK >> 5)) ? cnt[lane] : 0;
+    v = warp_max(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0 && c > 0) {
+      atomicMax(&scal->max_key, dkey(v));
+      atomicAdd(&scal->nok, (unsigned long long)c);
+    }
+  }
+}
+
 // ---- K5: Rao-Blackwellised EM sufficient statistics (update_prop_rb,
 // cosmo_pmc.c:247).  Stat block layout (doubles):
 //   [0] M = local max log w  [1] S = sum e^(lw-M)  [2] S2 = sum e^2(lw-M)
@@ -458,7 +539,7 @@ __host__ __device__ inline bool em_mma_ok(int K, int d) {
 __host__ __device__ inline size_t em_mma_smem_bytes(int K, int d, int student) {
   const int D = pmc_pad_dim(d), KP = 8 * em_mma_mt(K);
   return ((size_t)KP * EM_WSTRIDE * (student ? 2 : 1) + (size_t)PMC_BLOCK * (D + 1)) * sizeof(double) +
-         (size_t)K * sizeof(unsigned long long);
+         (size_t)K * sizeof(unsigned long long) + ((size_t)K * mix_stride(d) + D) * sizeof(double);   // + staged mixture, pivot
 }
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -482,8 +563,10 @@ k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
   double *s_wg = STUDENT ? s_wr + (size_t)KP * EM_WSTRIDE : s_wr;           // w rho gamma
   double *s_x = s_wg + (size_t)KP * EM_WSTRIDE;                             // [PMC_BLOCK][XS] x - pivot | 1
   unsigned long long *s_cnt = (unsigned long long *)(s_x + (size_t)PMC_BLOCK * XS);   // [K]
+  double *s_mix = (double *)(s_cnt + K);      // packed mixture + pivot: broadcast LDS instead of LDG in phase 1
   __shared__ double red[32];
-  const double *pivot = mix + (size_t)K * h.stride;
+  for (int i = threadIdx.x; i < K * h.stride + D; i += PMC_BLOCK) s_mix[i] = mix[i];
+  const double *pivot = s_mix + (size_t)K * h.stride;
   const double M0 = linear ? 0.0 : dunkey(scal->max_key);
   double tS = 0.0, tS2 = 0.0, tT = 0.0, tN = 0.0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -519,22 +602,28 @@ k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t n = tile * PMC_BLOCK + tid;
     __syncthreads();
-    // ---- phase 1: weight and responsibilities of this thread's sample (as k_em_stats)
+    // ---- phase 1: weight and responsibilities of this thread's sample (as k_em_stats; the sample sits in
+    // its s_x row -- odd stride, conflict-free -- and each component runs the column-oriented substitution)
     const bool ok = (n < N) && flg[n] && (!linear || logw[n] > 0.0);
+    double *xrow = s_x + (size_t)tid * XS;
     if (ok) {
-      double x[D], y[D];
-      load_x<D>(X, n, d, x);
+#pragma unroll
+      for (int i = 0; i < D; i++) xrow[i] = (i < d) ? X[n * d + i] : 0.0;
       double lw, w;
       if (linear) { w = logw[n]; lw = log(w); }
       else { lw = logw[n] - M0; w = exp(lw); }
       tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT); tN += 1.0;
       double rt = 0.0;
       for (int k = 0; k < K; k++) {
-        const double *comp = mix + (size_t)k * h.stride;
+        const double *comp = s_mix + (size_t)k * h.stride;
         const double a = comp[0];
         double r = 0.0, gam = 1.0;
         if (a != 0.0) {
-          double m = comp_maha<D>(comp, d, x, y);
+          double tt[1][D], m1[1];
+#pragma unroll
+          for (int i = 0; i < D; i++) tt[0][i] = xrow[i];
+          comp_maha_cols<D, 1>(comp, tt, m1);
+          const double m = m1[0];
           r = a * exp(comp_logpdf_from_maha(comp, d, h.df, m));
           if (STUDENT) gam = (double)(h.df + d) / ((double)h.df + m);
         }
@@ -549,11 +638,11 @@ k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
         if (STUDENT) s_wg[k * EM_WSTRIDE + tid] *= r;
       }
 #pragma unroll
-      for (int i = 0; i < D; i++) s_x[tid * XS + i] = x[i] - pivot[i];      // padded: 0 - 0
+      for (int i = 0; i < D; i++) xrow[i] -= pivot[i];      // padded: 0 - 0
     } else {
       for (int k = 0; k < K; k++) { s_wr[k * EM_WSTRIDE + tid] = 0.0; if (STUDENT) s_wg[k * EM_WSTRIDE + tid] = 0.0; }
 #pragma unroll
-      for (int i = 0; i < D; i++) s_x[tid * XS + i] = 0.0;
+      for (int i = 0; i < D; i++) xrow[i] = 0.0;
     }
     s_x[tid * XS + D] = 1.0;
     if ((n < N) && flg[n]) { const int c = idx[n]; if (c >= 0 && c < K) atomicAdd(&s_cnt[c], 1ull); }
