@@ -6,7 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #ifndef ESTEP_DEFAULT
-#define ESTEP_DEFAULT 0
+#define ESTEP_DEFAULT 2
 #endif
 
 #if MIX_GROUP == 0
@@ -43,7 +43,7 @@ static cudaError_t launch_em_mma(const MixArgs &a, cudaStream_t s) {
 }
 template <int DD>
 static cudaError_t run_em_mma(const MixArgs &a, cudaStream_t s) {
-  if constexpr (DD >= 10 && DD % 2 == 0) {
+  {
     const int mt = em_mma_mt(a.h.K);
     const bool st = a.h.df > 0;
 #define EMM(MTV) if (mt == MTV) { if constexpr (MTV * (((1 + DD + DD * (DD + 1) / 2 + 7) / 8 + 7) / 8) <= EM_MMA_MAXACC) \
@@ -72,9 +72,10 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
                                                      a.logpi, a.err, a.set, a.add_const);
       break;
     case OP_WEIGHTS:
-      if constexpr (DD >= 10) {
+      if constexpr (DD >= 5) {
         // PMCB200_ESTEP: 0 = one sample per thread, row-oriented, mixture through L1 (k_weights);
-        // S = 1, 2, 3 = k_weights_multi with S samples per thread
+        // 1, 3 = k_weights_multi with that many samples per thread; 2 (default) = 4 samples for d <= 8, else 2
+        // (measured, C3 d = 20 K = 10, 1e7 samples: 5.78 / 3.89 / 3.00 / 3.33 ms for modes 0 / 1 / 2 / 3)
         static const int mode = getenv("PMCB200_ESTEP") ? atoi(getenv("PMCB200_ESTEP")) : ESTEP_DEFAULT;
         const size_t mixbytes = (size_t)a.h.K * a.h.stride * sizeof(double);
 #define WM(SV) { auto kern = k_weights_multi<DD, SV>; const size_t sm = mixbytes + (size_t)DD * SV * PMC_BLOCK * sizeof(double); \
@@ -83,7 +84,7 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
             kern<<<(int)((a.N + PMC_BLOCK * SV - 1) / (PMC_BLOCK * SV)), PMC_BLOCK, sm, s>>>(a.mix, a.h, a.N, a.Xc, a.logpic, a.errc, a.beta, a.flg, a.logw, a.scal); \
             return cudaGetLastError(); } }
         if (mode == 1) WM(1)
-        if (mode == 2) WM(2)
+        if (mode == 2) { if constexpr (DD <= 8) WM(4) else WM(2) }
         if (mode == 3) WM(3)
 #undef WM
       }
@@ -91,7 +92,7 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
                                                     a.scal);
       break;
     case OP_EM: {
-      if constexpr (DD >= 10 && DD % 2 == 0) {
+      {
         if (a.em_mma && em_mma_ok(a.h.K, a.h.d) && a.k0 == 0 && a.Kg == a.h.K) return run_em_mma<DD>(a, s);
       }
       const bool reg = em_use_reg(a.Kg, a.h.d, a.h.df > 0);

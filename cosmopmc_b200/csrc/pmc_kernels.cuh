@@ -510,7 +510,7 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
   }
 }
 
-// ---- K5, FP64 tensor-core variant (D >= 10, K <= 32) ---------------------------
+// ---- K5, FP64 tensor-core variant (K <= 32; the default) ------------------------
 // ncu on C3 (d = 20, K = 10): k_em_stats is bound by the LSU data pipe (80 % of its
 // wavefront peak; one broadcast LDS per FMA of the K x tile x M' contraction) with the
 // FP64 pipe below a quarter busy.  tools/micro/dmma_probe.cu: DMMA.8x8x4 sustains 99.8 %
@@ -521,7 +521,7 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
 //   B fragment  b  = feature [sample s0 + lane%4][feature 8 tile + lane/4] = x_i x_j, with
 //                    a constant 1 stored in column D of the staged row, so that the G
 //                    statistic (1*1), the first moments (x_i * 1) and the second moments
-//                    are one expression (D even: the row stride D + 1 is odd)
+//                    are one expression
 //   C fragment  c0,c1 = statistic [component 8 mt + lane/4][feature 8 tile + 2 (lane%4) + {0,1}]
 // Warp w owns the feature tiles w, w + 8, ... (NT per warp) for all MT component tiles;
 // the accumulators stay in registers across the tiles of the persistent block, and every
@@ -534,11 +534,11 @@ __host__ __device__ inline int em_mma_nt(int D) { return ((1 + D + mix_tri(D) + 
 __host__ __device__ inline int em_mma_mt(int K) { return (K + 7) / 8; }
 __host__ __device__ inline bool em_mma_ok(int K, int d) {
   const int D = pmc_pad_dim(d);
-  return D >= 10 && (D % 2) == 0 && K <= 32 && em_mma_mt(K) * em_mma_nt(D) <= EM_MMA_MAXACC;
+  return K <= 32 && em_mma_mt(K) * em_mma_nt(D) <= EM_MMA_MAXACC;
 }
 __host__ __device__ inline size_t em_mma_smem_bytes(int K, int d, int student) {
   const int D = pmc_pad_dim(d), KP = 8 * em_mma_mt(K);
-  return ((size_t)KP * EM_WSTRIDE * (student ? 2 : 1) + (size_t)PMC_BLOCK * (D + 1)) * sizeof(double) +
+  return ((size_t)KP * EM_WSTRIDE * (student ? 2 : 1) + (size_t)PMC_BLOCK * ((D + 1) | 1)) * sizeof(double) +
          (size_t)K * sizeof(unsigned long long) + ((size_t)K * mix_stride(d) + D) * sizeof(double);   // + staged mixture, pivot
 }
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -553,8 +553,7 @@ k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
                const int16_t *__restrict__ flg, const double *__restrict__ logw,
                const DevScal *__restrict__ scal, double *__restrict__ partials, int linear) {
   extern __shared__ double sm[];
-  static_assert(D % 2 == 0, "the ones column needs the odd row stride D + 1");
-  constexpr int XS = D + 1;
+  constexpr int XS = (D + 1) | 1;           // odd row stride (conflict-free rows); column D holds the constant 1
   constexpr int NT = ((1 + D + D * (D + 1) / 2 + 7) / 8 + 7) / 8;
   constexpr int KP = 8 * MT;
   const int K = h.K, d = h.d, M = stat_cs(d);
