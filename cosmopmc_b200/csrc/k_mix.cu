@@ -26,9 +26,9 @@
 static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
 
 // FP64 tensor-core EM statistics (d >= 10): persistent grid sized by the occupancy API
-template <int DD, int MT, bool STUDENT>
+template <int DD, int MT, bool STUDENT, bool RHO>
 static cudaError_t launch_em_mma(const MixArgs &a, cudaStream_t s) {
-  auto kern = k_em_stats_mma<DD, MT, STUDENT>;
+  auto kern = k_em_stats_mma<DD, MT, STUDENT, RHO>;
   const size_t smem = em_mma_smem_bytes(a.h.K, a.h.d, STUDENT);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -38,7 +38,8 @@ static cudaError_t launch_em_mma(const MixArgs &a, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int blocks = std::max(1, std::min(a.blocks, std::max(1, per_sm) * sms));
   if (a.nblocks_out) *a.nblocks_out = blocks;
-  kern<<<blocks, PMC_BLOCK, smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal, a.partials, a.linear);
+  kern<<<blocks, PMC_BLOCK, smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal, a.partials, a.linear,
+                                       a.rho_in);
   return cudaGetLastError();
 }
 template <int DD>
@@ -47,7 +48,8 @@ static cudaError_t run_em_mma(const MixArgs &a, cudaStream_t s) {
     const int mt = em_mma_mt(a.h.K);
     const bool st = a.h.df > 0;
 #define EMM(MTV) if (mt == MTV) { if constexpr (MTV * (((1 + DD + DD * (DD + 1) / 2 + 7) / 8 + 7) / 8) <= EM_MMA_MAXACC) \
-      return st ? launch_em_mma<DD, MTV, true>(a, s) : launch_em_mma<DD, MTV, false>(a, s); }
+      { if constexpr (DD >= 10) { if (a.rho_in && !st) return launch_em_mma<DD, MTV, false, true>(a, s); } \
+        return st ? launch_em_mma<DD, MTV, true, false>(a, s) : launch_em_mma<DD, MTV, false, false>(a, s); } }
     EMM(1) EMM(2) EMM(3) EMM(4)
 #undef EMM
   }
@@ -81,7 +83,8 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
 #define WM(SV) { auto kern = k_weights_multi<DD, SV>; const size_t sm = mixbytes + (size_t)DD * SV * PMC_BLOCK * sizeof(double); \
           if (sm <= 200 * 1024) { \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; \
-            kern<<<(int)((a.N + PMC_BLOCK * SV - 1) / (PMC_BLOCK * SV)), PMC_BLOCK, sm, s>>>(a.mix, a.h, a.N, a.Xc, a.logpic, a.errc, a.beta, a.flg, a.logw, a.scal); \
+            kern<<<(int)((a.N + PMC_BLOCK * SV - 1) / (PMC_BLOCK * SV)), PMC_BLOCK, sm, s>>>(a.mix, a.h, a.N, a.Xc, a.logpic, a.errc, a.beta, a.flg, a.logw, a.scal, a.rho); \
+            if (a.rho && a.rho_written) *a.rho_written = 1; \
             return cudaGetLastError(); } }
         if (mode == 1) WM(1)
         if (mode == 2) { if constexpr (DD <= 8) WM(4) else WM(2) }
@@ -93,7 +96,7 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
       break;
     case OP_EM: {
       {
-        if (a.em_mma && em_mma_ok(a.h.K, a.h.d) && a.k0 == 0 && a.Kg == a.h.K) return run_em_mma<DD>(a, s);
+        if (a.em_mma && em_mma_ok(a.h.K, a.h.d, a.h.df > 0) && a.k0 == 0 && a.Kg == a.h.K) return run_em_mma<DD>(a, s);
       }
       const bool reg = em_use_reg(a.Kg, a.h.d, a.h.df > 0);
       auto kern = reg ? k_em_stats<DD, true> : k_em_stats<DD, false>;

@@ -24,6 +24,9 @@ struct MixArgs {
   double *logw = nullptr; const double *logwc = nullptr;
   double *partials = nullptr; int blocks = 0; size_t smem = 0; int linear = 0; int *nblocks_out = nullptr; int k0 = 0, Kg = 0;
   int em_mma = 0;      // OP_EM: FP64 tensor-core kernel (host checked em_mma_ok)
+  // E-step cache: OP_WEIGHTS stores r_k(x_n) = alpha_k phi_k(x_n) at rho[k * N + n] (and sets *rho_written when the
+  // kernel it chose does so); OP_EM reads them (rho_in) instead of repeating the K whitenings
+  double *rho = nullptr; int *rho_written = nullptr; const double *rho_in = nullptr;
 };
 
 bool pmc_mix_launch_g0(int op, const MixArgs &a, cudaStream_t s, cudaError_t *e);

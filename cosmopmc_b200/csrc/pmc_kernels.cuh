@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(PMC_BLOCK, (S * D <= 48) ? 2 : 1)
 k_weights_multi(const double *__restrict__ mixg, const MixHdr h, int64_t N,
                 const double *__restrict__ X, const double *__restrict__ logpi,
                 const int32_t *__restrict__ err, double beta, int16_t *__restrict__ flg,
-                double *__restrict__ logw, DevScal *scal) {
+                double *__restrict__ logw, DevScal *scal, double *__restrict__ rho) {
   __shared__ double red[32];
   __shared__ int cnt[32];
   extern __shared__ double s_buf[];
@@ -222,14 +222,25 @@ k_weights_multi(const double *__restrict__ mixg, const MixHdr h, int64_t N,
   for (int k = 0; k < h.K; k++) {
     const double *comp = s_mix + (size_t)k * h.stride;
     const double w = comp[0];
-    if (w == 0.0) continue;
+    if (w == 0.0) {
+      if (rho) {
+#pragma unroll
+        for (int s = 0; s < S; s++) if (live[s]) rho[(size_t)k * N + base + (int64_t)s * PMC_BLOCK] = 0.0;
+      }
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < D; i++)
 #pragma unroll
       for (int s = 0; s < S; s++) t[s][i] = s_xt[((size_t)i * S + s) * PMC_BLOCK + threadIdx.x];
     comp_maha_cols<D, S>(comp, t, m);
 #pragma unroll
-    for (int s = 0; s < S; s++) acc[s] = fma(w, exp(comp_logpdf_from_maha(comp, h.d, h.df, m[s])), acc[s]);
+    for (int s = 0; s < S; s++) {
+      const double e = exp(comp_logpdf_from_maha(comp, h.d, h.df, m[s]));
+      acc[s] = fma(w, e, acc[s]);
+      // E-step cache: alpha_k phi_k(x) exactly as the EM kernel forms it (k_em_stats_mma, phase 1)
+      if (rho && live[s]) rho[(size_t)k * N + base + (int64_t)s * PMC_BLOCK] = w * e;
+    }
   }
   double lwmax = -INFINITY;
   int nok = 0;
@@ -528,30 +539,36 @@ k_em_stats(const double *__restrict__ mix, const MixHdr h, int64_t N,
 // (component, feature) sum is owned by exactly one thread: no combine step, fixed order.
 // A = sum w rho equals G for a Gaussian proposal; for Student-t warp 0 accumulates it with
 // a second set of A fragments (w rho without gamma) against the ones column.
+// RHO: phase 1 reads alpha_k phi_k(x_n) from the E-step cache the weight kernel of the same iteration
+// filled (same expression, same operands: bit-identical statistics) instead of repeating the whitenings.
 #define EM_WSTRIDE (PMC_BLOCK + 4)     // row stride of s_wr / s_wg: the 8 rows of an A fragment fall on distinct banks
 #define EM_MMA_MAXACC 24               // MT x NT accumulator pairs per thread
 __host__ __device__ inline int em_mma_nt(int D) { return ((1 + D + mix_tri(D) + 7) / 8 + 7) / 8; }
 __host__ __device__ inline int em_mma_mt(int K) { return (K + 7) / 8; }
-__host__ __device__ inline bool em_mma_ok(int K, int d) {
-  const int D = pmc_pad_dim(d);
-  return K <= 32 && em_mma_mt(K) * em_mma_nt(D) <= EM_MMA_MAXACC;
-}
 __host__ __device__ inline size_t em_mma_smem_bytes(int K, int d, int student) {
   const int D = pmc_pad_dim(d), KP = 8 * em_mma_mt(K);
   return ((size_t)KP * EM_WSTRIDE * (student ? 2 : 1) + (size_t)PMC_BLOCK * ((D + 1) | 1)) * sizeof(double) +
          (size_t)K * sizeof(unsigned long long) + ((size_t)K * mix_stride(d) + D) * sizeof(double);   // + staged mixture, pivot
+}
+// accumulators within the register budget and everything staged within the shared-memory budget;
+// otherwise the shared-memory kernel (component groups) takes the update
+__host__ __device__ inline bool em_mma_ok(int K, int d, int student) {
+  const int D = pmc_pad_dim(d);
+  return K <= 32 && em_mma_mt(K) * em_mma_nt(D) <= EM_MMA_MAXACC && em_mma_smem_bytes(K, d, student) <= 200 * 1024;
 }
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int D, int MT, bool STUDENT>
+template <int D, int MT, bool STUDENT, bool RHO>
 __global__ void __launch_bounds__(PMC_BLOCK, 2)
 k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
                const double *__restrict__ X, const int32_t *__restrict__ idx,
                const int16_t *__restrict__ flg, const double *__restrict__ logw,
-               const DevScal *__restrict__ scal, double *__restrict__ partials, int linear) {
+               const DevScal *__restrict__ scal, double *__restrict__ partials, int linear,
+               const double *__restrict__ rho) {
+  static_assert(!(RHO && STUDENT), "the E-step cache holds no Mahalanobis distances (Student-t gamma)");
   extern __shared__ double sm[];
   constexpr int XS = (D + 1) | 1;           // odd row stride (conflict-free rows); column D holds the constant 1
   constexpr int NT = ((1 + D + D * (D + 1) / 2 + 7) / 8 + 7) / 8;
@@ -617,7 +634,8 @@ k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
         const double *comp = s_mix + (size_t)k * h.stride;
         const double a = comp[0];
         double r = 0.0, gam = 1.0;
-        if (a != 0.0) {
+        if (RHO) r = rho[(size_t)k * N + n];      // alpha_k phi_k(x_n) left by the weight kernel of this iteration
+        else if (a != 0.0) {
           double tt[1][D], m1[1];
 #pragma unroll
           for (int i = 0; i < D; i++) tt[0][i] = xrow[i];

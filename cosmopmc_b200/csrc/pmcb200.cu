@@ -55,6 +55,12 @@ struct pmcb200_ctx {
   int em_blocks = 0;
   int em_no_mma = 0;        // PMCB200_EM_NO_MMA=1: keep the shared-memory EM kernel for d >= 10 (A/B measurements)
   int sm_count = 148;
+  // E-step cache (d >= 10, Gaussian proposal): the weight kernel leaves alpha_k phi_k(x_n) here and the EM statistics
+  // kernel of the same iteration reads it back instead of repeating the K whitenings per sample.  Valid for exactly
+  // one (sample array, N, proposal version); consumed by the next em_local.  PMCB200_EM_NO_RHO=1 disables it.
+  DevBuf sRho;
+  const double *rho_X = nullptr; int64_t rho_N = 0; uint64_t rho_ver = 0, prop_ver = 0; bool rho_valid = false;
+  int em_no_rho = 0;
   // scratch for the host-buffer API
   DevBuf sX, sIdx, sFlg, sLogw, sLogpi, sErr, sBlock, sAll;
   DevBuf sPost, sPostTmp;                 // post-processing work space
@@ -247,7 +253,7 @@ extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_target(c);
-  for (DevBuf *b : {&c->sX, &c->sIdx, &c->sFlg, &c->sLogw, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll, &c->sPost, &c->sPostTmp})
+  for (DevBuf *b : {&c->sX, &c->sIdx, &c->sFlg, &c->sLogw, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll, &c->sPost, &c->sPostTmp, &c->sRho})
     if (b->p) cudaFree(b->p);
   if (c->d_mix) cudaFree(c->d_mix);
   if (c->d_scal) cudaFree(c->d_scal);
@@ -324,6 +330,8 @@ static int install_proposal(pmcb200_ctx *c, int K, int d, int df, const double *
   // EM work buffers
   int64_t len = stat_len(K, d);
   { const char *ev = getenv("PMCB200_EM_NO_MMA"); c->em_no_mma = ev && *ev && *ev != '0'; }
+  { const char *ev = getenv("PMCB200_EM_NO_RHO"); c->em_no_rho = ev && *ev && *ev != '0'; }
+  c->prop_ver++; c->rho_valid = false;
   c->em_blocks = 4 * c->sm_count;     // capacity of the partials buffer; the launch uses the resident count
   size_t need = (size_t)c->em_blocks * len;
   if (c->partials_cap < need) {
@@ -637,7 +645,22 @@ static int launch_weights(pmcb200_ctx *c, int64_t N, const double *dX, const dou
   if (N <= 0) return 0;
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.logpic = dlogpi; a.errc = derr; a.beta = beta;
   a.flg = dflg; a.logw = dlogw; a.scal = c->d_scal;
+  // E-step cache: worth its 16 K bytes of HBM traffic per sample where the K whitenings cost more (d >= 10)
+  c->rho_valid = false;
+  int written = 0;
+  const int K = c->h.K, d = c->h.d;
+  if (!c->em_no_rho && !c->em_no_mma && pmc_pad_dim(d) >= 10 && c->h.df <= 0 && em_mma_ok(K, d, 0)) {
+    const size_t bytes = (size_t)N * K * sizeof(double);
+    if (c->sRho.cap < bytes) {        // soft: without the buffer the EM kernel simply recomputes
+      if (c->sRho.p) cudaFree(c->sRho.p);
+      c->sRho.p = nullptr; c->sRho.cap = 0;
+      if (cudaMalloc(&c->sRho.p, bytes) == cudaSuccess) c->sRho.cap = bytes;
+      else { c->sRho.p = nullptr; cudaGetLastError(); }
+    }
+    if (c->sRho.p) { a.rho = (double *)c->sRho.p; a.rho_written = &written; }
+  }
   MIX_OK(c, OP_WEIGHTS, a);
+  if (written) { c->rho_valid = true; c->rho_X = dX; c->rho_N = N; c->rho_ver = c->prop_ver; }
   return 0;
 }
 
@@ -649,10 +672,13 @@ static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const in
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->em_blocks, ntiles));
   // component groups: one launch unless the K x 256 shared-memory arrays exceed the budget
   int Kg = K;
-  const bool mma = em_mma_ok(K, d) && !c->em_no_mma;     // FP64 tensor-core kernel: all components in one launch
+  const bool mma = em_mma_ok(K, d, c->h.df > 0) && !c->em_no_mma;     // FP64 tensor-core kernel: all components in one launch
   while (!mma && Kg > 1 && em_smem_bytes(Kg, d, c->h.df > 0) > 200 * 1024) Kg = (Kg + 1) / 2;
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.idxc = didx; a.flgc = dflg; a.logwc = dlogw;
   a.scal = c->d_scal; a.partials = c->d_partials; a.blocks = blocks; a.linear = linear; a.em_mma = mma;
+  if (mma && !linear && c->rho_valid && c->rho_X == dX && c->rho_N == N && c->rho_ver == c->prop_ver)
+    a.rho_in = (const double *)c->sRho.p;
+  c->rho_valid = false;      // one weight pass feeds one update
   int used = blocks;
   a.nblocks_out = &used;
   for (int k0 = 0; k0 < K; k0 += Kg) {
