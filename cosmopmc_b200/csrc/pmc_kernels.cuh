@@ -80,6 +80,53 @@ k_simulate(const double *__restrict__ mix, const MixHdr h, const double *__restr
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(&scal->nok_box, (unsigned long long)__popc(b));
 }
 
+// Staged variant (the default): every lane transforms with ITS OWN component's Cholesky factor, so the factor
+// loads are a gather over up to K addresses, and every lane stores its own 8d-byte row (32 sectors per store).
+// Here the packed mixture sits in shared memory with an odd component stride (lanes of different components
+// fall on different banks) and the tile of samples is assembled in shared memory (odd row stride) and written
+// out with fully coalesced stores.  Same arithmetic, same results.
+template <int D>
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_simulate_staged(const double *__restrict__ mixg, const MixHdr h, const double *__restrict__ box,
+                  int64_t N, uint64_t seed, uint32_t iter, int64_t offset,
+                  double *__restrict__ X, int32_t *__restrict__ idx, int16_t *__restrict__ flg,
+                  DevScal *scal) {
+  extern __shared__ double s_sim[];
+  const int sstride = h.stride | 1, xs = h.d | 1;
+  double *s_out = s_sim;                                   // [PMC_BLOCK][xs]
+  double *s_mix = s_sim + (size_t)PMC_BLOCK * xs;          // [K][sstride]
+  for (int i = threadIdx.x; i < h.K * h.stride; i += PMC_BLOCK) {
+    const int k = i / h.stride;
+    s_mix[k * sstride + (i - k * h.stride)] = mixg[i];
+  }
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * PMC_BLOCK;
+  const int64_t n = base + threadIdx.x;
+  int inbox = 0;
+  if (n < N) {
+    double u, z[D], ts;
+    draw_normals<D>(seed, iter, (uint64_t)(offset + n), h.d, h.df, u, z, ts);
+    MixHdr hs = h; hs.stride = sstride;
+    int k = select_component(s_mix, hs, u);
+    transform_store<D>(s_mix + (size_t)k * sstride, h.d, z, ts, box, box + h.d, s_out + (size_t)threadIdx.x * xs, inbox);
+    idx[n] = k;
+    flg[n] = (int16_t)inbox;
+  }
+  unsigned b = __ballot_sync(0xffffffffu, inbox);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&scal->nok_box, (unsigned long long)__popc(b));
+  __syncthreads();
+  const int rows = (int)min((int64_t)PMC_BLOCK, N - base);
+  double *Xt = X + base * h.d;
+  // the tile is rows * d contiguous doubles of X: element e = r d + c, advanced by PMC_BLOCK per step
+  const int tot = rows * h.d, qd = PMC_BLOCK / h.d, rd = PMC_BLOCK - qd * h.d;
+  int r = threadIdx.x / h.d, c = threadIdx.x - r * h.d;
+  for (int e = threadIdx.x; e < tot; e += PMC_BLOCK) {
+    Xt[e] = s_out[(size_t)r * xs + c];
+    r += qd; c += rd;
+    if (c >= h.d) { c -= h.d; r++; }
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(PMC_BLOCK)
 k_simulate_from_draws(const double *__restrict__ mix, const MixHdr h,
