@@ -233,7 +233,13 @@ int pmcb200_normalize_weights(pmcb200_ctx *ctx, int64_t N, const int16_t *dflg,
  * [nranks * len] and calls pmcb200_em_finish on every rank, which combines
  * them in rank order (bit-identical on all ranks), performs the M-step, the
  * dead-component rule and the Cholesky on the device, installs the new
- * proposal in ctx and fills *stats.  nranks==1: dall == dblock. */
+ * proposal in ctx and fills *stats.  nranks==1: dall == dblock.
+ * E-step cache: for ndim >= 10 and a Gaussian proposal pmcb200_importance_weights
+ * leaves alpha_k phi_k(x_n) of its samples in a context-owned buffer, and the NEXT
+ * pmcb200_em_local on the same dX, N and proposal reads it instead of repeating the
+ * K whitenings per sample (bit-identical statistics).  The caller must therefore not
+ * modify dX between the two calls (the reference's iteration never does:
+ * cosmo_pmc.c:343-378 only reads psim->X).  Any other call order recomputes. */
 int64_t pmcb200_stat_block_len(const pmcb200_ctx *ctx);
 int pmcb200_em_local(pmcb200_ctx *ctx, int64_t N, const double *dX,
                      const int32_t *didx, const int16_t *dflg,
