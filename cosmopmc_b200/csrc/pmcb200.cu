@@ -610,6 +610,7 @@ static int launch_simulate(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t it
   if (!c->d_box) return fail(c, PMCB200_ERR_STATE, "simulate needs the target's box (pmcb200_set_target)");
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.box = c->d_box; a.N = N; a.seed = seed; a.iter = iter;
   a.offset = offset; a.X = dX; a.idx = didx; a.flg = dflg; a.scal = c->d_scal;
+  c->rho_valid = false;      // the sample array is being rewritten
   MIX_OK(c, OP_SIMULATE, a);
   return 0;
 }
@@ -712,6 +713,7 @@ extern "C" int pmcb200_simulate_from_draws(pmcb200_ctx *c, int64_t N, const doub
   if (N == 0) return 0;
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.box = c->d_box; a.N = N; a.U = du; a.Z = dz; a.X = dX; a.idx = didx;
   a.flg = dflg;
+  c->rho_valid = false;
   MIX_OK(c, OP_SIMULATE_DRAWS, a);
   return 0;
 }
