@@ -132,6 +132,7 @@ SYMBOLS = {
     "pmcb200_post_moments": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "pmcb200_post_sigma": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _d, _vp, _vp, C.POINTER(_d), C.POINTER(_i64)]),
     "pmcb200_post_histogram": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pmcb200_fisher_host": (_i, [_vp, _vp, _vp, _i, _vp, C.POINTER(_i)]),
 }
 
 _lib = None

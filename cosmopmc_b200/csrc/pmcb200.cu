@@ -736,6 +736,61 @@ extern "C" int pmcb200_posterior_log_pdf(pmcb200_ctx *c, int64_t N, const double
   return launch_posterior(c, N, dX, nullptr, dlogpi, derr);
 }
 
+// Fisher matrix at a point: go_fishing.c:37-85, all stencil points in one posterior launch.
+extern "C" int pmcb200_fisher_host(pmcb200_ctx *c, const double *pos, const double *h, int diag_only,
+                                   double *F, int *nbad) {
+  int rc = need(c, false, true);
+  if (rc) return rc;
+  if (!pos || !h || !F) return fail(c, PMCB200_ERR_ARG, "fisher_host: bad arguments");
+  const int d = c->tgt.npar;
+  for (int a = 0; a < d; a++)
+    if (!(h[a] >= 1.0e-20) || !std::isfinite(h[a])) return fail(c, PMCB200_ERR_ARG, "fisher_host: h[%d] too small", a);
+  static const int diff[4][2] = {{+1, +1}, {+1, -1}, {-1, +1}, {-1, -1}};
+  // stencil: per element (a, b >= a) the points j = 0..3 (j = 2 of a diagonal element repeats j = 1)
+  std::vector<double> pts;
+  std::vector<int> first;           // index of point j = 0 of each element, elements in (a, b) order
+  for (int a = 0; a < d; a++)
+    for (int b = a; b < d; b++) {
+      if (diag_only && a != b) continue;
+      first.push_back((int)(pts.size() / d));
+      for (int j = 0; j < 4; j++) {
+        if (j == 2 && a == b) continue;
+        const size_t o = pts.size();
+        pts.insert(pts.end(), pos, pos + d);
+        pts[o + a] += diff[j][0] * h[a];        // two separate additions, as the reference's loop over k
+        pts[o + b] += diff[j][1] * h[b];
+      }
+    }
+  const int64_t np = (int64_t)(pts.size() / d);
+  if ((rc = ensure(c, c->sX, (size_t)np * d * sizeof(double)))) return rc;
+  if ((rc = ensure(c, c->sLogpi, (size_t)np * sizeof(double)))) return rc;
+  if ((rc = ensure(c, c->sErr, (size_t)np * sizeof(int32_t)))) return rc;
+  CUDA_OK(c, cudaMemcpyAsync(c->sX.p, pts.data(), (size_t)np * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->rho_valid = false;
+  if ((rc = launch_posterior(c, np, (const double *)c->sX.p, nullptr, (double *)c->sLogpi.p, (int32_t *)c->sErr.p))) return rc;
+  std::vector<double> lp(np);
+  std::vector<int32_t> er(np);
+  CUDA_OK(c, cudaMemcpyAsync(lp.data(), c->sLogpi.p, (size_t)np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(er.data(), c->sErr.p, (size_t)np * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  int bad = 0;
+  for (int64_t i = 0; i < np; i++) bad += (er[i] != 0) || !std::isfinite(lp[i]);
+  if (nbad) *nbad = bad;
+  if (bad) return fail(c, PMCB200_ERR_ARG, "fisher_host: likelihood error at %d of %lld stencil points", bad, (long long)np);
+  for (int i = 0; i < d * d; i++) F[i] = 0.0;
+  size_t e = 0;
+  for (int a = 0; a < d; a++)
+    for (int b = a; b < d; b++) {
+      if (diag_only && a != b) continue;
+      const double *q = lp.data() + first[e++];
+      const double c0 = q[0], c1 = q[1], c2 = (a == b) ? q[1] : q[2], c3 = (a == b) ? q[2] : q[3];
+      const double f = -(c0 - c1 - c2 + c3) / (4.0 * h[a] * h[b]);
+      F[a * d + b] = f;
+      F[b * d + a] = f;
+    }
+  return 0;
+}
+
 extern "C" int pmcb200_importance_weights(pmcb200_ctx *c, int64_t N, const double *dX, double beta,
                                           int16_t *dflg, double *dlogw) {
   int rc = need(c, true, true);

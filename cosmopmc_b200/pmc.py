@@ -196,6 +196,17 @@ class PMC:
                                                  sw2.ctypes.data))
         return cnt, sw, sw2
 
+    def fisher_matrix(self, pos, h, diag_only=False):
+        """go_fishing.c fisher_element over all (a, b): one batched posterior launch."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        d = pos.size
+        F = np.empty((d, d))
+        nbad = C.c_int(0)
+        self._ck(self.lib.pmcb200_fisher_host(self.h, pos.ctypes.data, h.ctypes.data, int(bool(diag_only)),
+                                              F.ctypes.data, C.byref(nbad)))
+        return F
+
     def launch_count(self):
         return int(self.lib.pmcb200_launch_count(self.h))
 

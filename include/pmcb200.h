@@ -350,6 +350,21 @@ int pmcb200_post_histogram(pmcb200_ctx *ctx, int64_t N, int d, const double *dX,
                            const double *dw, int nhdim, const int *pidx, const int *nbins,
                            const double *limits, double *count, double *sumw, double *sumw2);
 
+/* ---- Fisher matrix at a point ------------------------------
+ * go_fishing.c:37-85 fisher_element / :124-156 fisher_matrix_part: the second
+ * derivatives of -log posterior by Numerical Recipes (5.7.10),
+ *   F_ab = -(P(+a,+b) - P(+a,-b) - P(-a,+b) + P(-a,-b)) / (4 h_a h_b),
+ * h_a = fh (max_a - min_a) supplied by the caller (mkmax.h:33), with the
+ * reference's diagonal shortcut (the two mixed points coincide with the centre
+ * and are evaluated once).  The reference evaluates the 4 d(d+1)/2 stencil
+ * points one host call at a time (MPI-split over elements); here they are ONE
+ * batched posterior launch.  pos, h: host [npar]; F: host [npar*npar], symmetric;
+ * diag_only != 0 computes the diagonal only (mcmcini_fisher_diag,
+ * go_fishing.c:100,134) and zeroes the rest.  A likelihood error at any stencil
+ * point fails the call (the reference forwards the error), *nbad = their number. */
+int pmcb200_fisher_host(pmcb200_ctx *ctx, const double *pos, const double *h, int diag_only,
+                        double *F, int *nbad);
+
 /* number of kernels launched by this context since creation (bench's
  * gpu_launches claim) */
 int64_t pmcb200_launch_count(const pmcb200_ctx *ctx);

@@ -533,3 +533,69 @@ def test_sn_fast_path_matches_libdevice_path(oracle, pmc_factory, tmp_path):
     ok = err == 0
     assert ok.sum() > 2000
     assert rel(lp[ok], slow[0][ok]) < 1e-12
+
+
+# ------------------------------------------------- Fisher matrix (go_fishing.c) -------
+def _fisher_stencil(pos, h, diag_only):
+    """The reference's stencil order (go_fishing.c:37-85, elements (a, b >= a))."""
+    diff = [(+1, +1), (+1, -1), (-1, +1), (-1, -1)]
+    pts, elems = [], []
+    d = len(pos)
+    for a in range(d):
+        for b in range(a, d):
+            if diag_only and a != b:
+                continue
+            idx = []
+            for j in range(4):
+                if j == 2 and a == b:
+                    idx.append(idx[1]); continue
+                p = np.array(pos, dtype=np.float64)
+                p[a] += diff[j][0] * h[a]
+                p[b] += diff[j][1] * h[b]
+                idx.append(len(pts)); pts.append(p)
+            elems.append((a, b, idx))
+    return np.array(pts), elems
+
+
+@pytest.mark.parametrize("diag_only", [False, True])
+def test_fisher_matrix_batched(oracle, pmc_factory, diag_only):
+    """pmcb200_fisher_host: all 4 d(d+1)/2 stencil points of go_fishing.c's fisher_element in one launch.
+    (1) Gaussian target: F = Sigma^-1 (central differences are exact on a quadratic); (2) SN Ia demo at the
+    test suite's fiducial, fh = 0.001 (mkmax.h:33): against the same stencil evaluated by the oracle."""
+    pmc = pmc_factory()
+    d = 6
+    rng = np.random.default_rng(5)
+    A_ = rng.normal(size=(d, d)) * 0.3
+    cov = A_ @ A_.T + np.eye(d)
+    lo, hi = -8.0 * np.ones(d), 8.0 * np.ones(d)
+    spec = T.TargetSpec(["dummy%d" % j for j in range(d)], lo, hi).add_mix([1.0], [0.2 * np.ones(d)], [cov])
+    pmc.set_target(spec)
+    pos, h = 0.1 * np.arange(d), 0.01 * (hi - lo)
+    F = pmc.fisher_matrix(pos, h, diag_only)
+    ref = np.linalg.inv(cov)
+    if diag_only:
+        ref = np.diag(np.diag(ref))
+    assert np.allclose(F, F.T, rtol=0, atol=0)
+    assert np.max(np.abs(F - ref)) < 1e-6 * np.max(np.abs(ref))
+    # SN Ia
+    spec = T.target_sn_demo()
+    pmc.set_target(spec)
+    pos = np.array([0.27, -1.0, 19.31, 1.6, -1.8])
+    lo, hi = spec.box
+    h = 0.001 * (hi - lo)
+    F = pmc.fisher_matrix(pos, h, diag_only)
+    pts, elems = _fisher_stencil(pos, h, diag_only)
+    lp, err = oracle.posterior_log_pdf(spec, pts)
+    assert not err.any()
+    ref = np.zeros((5, 5))
+    for a, b, idx in elems:
+        c = lp[idx]
+        ref[a, b] = ref[b, a] = -(c[0] - c[1] - c[2] + c[3]) / (4.0 * h[a] * h[b])
+    scale = np.sqrt(np.abs(np.outer(np.diag(ref), np.diag(ref))))
+    assert np.max(np.abs(F - ref) / scale) < 1e-5
+    assert np.all(np.diag(F) > 0)
+    # a stencil point outside the physical region fails loudly, as the reference forwards the error
+    from cosmopmc_b200.pmc import PMCError
+    bad = pos.copy(); bad[1] = 2.9
+    with pytest.raises(PMCError):
+        pmc.fisher_matrix(bad, h * 500.0, diag_only)
