@@ -99,7 +99,6 @@ static int fail(pmcb200_ctx *c, int code, const char *fmt, ...) {
                   cudaGetErrorString(e__), __FILE__, __LINE__);                     \
   } while (0)
 
-static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
 
 static int ensure(pmcb200_ctx *c, DevBuf &b, size_t bytes) {
   if (b.cap >= bytes) return 0;
