@@ -430,6 +430,20 @@ __constant__ double ROMBW[10] = {3937.0 / 103275.0, 3062.0 / 80325.0, 27728.0 / 
                                   65536.0 / 722925.0, -31.0 / 206550.0, -73.0 / 481950.0, -67.0 / 722925.0,
                                   -424.0 / 722925.0, 256.0 / 722925.0};
 struct SNSums { double g0, S1, S2, S3, S4; };
+// SN_CHAIN_SUMS (build variant, default off): the sums S_j of the new nodes of a stage are formed by chaining
+// the integrand's final accumulate (fma(ry, w, acc)) through the stage's nodes, NR's sequential order, instead of
+// 15 separate additions per redshift.  Changes the last bits (summation order), not the algorithm.  Measured
+// once (profiles/sn_r01_v8_hotspots.txt): 52.45 vs 52.93 ms per 1e7 samples; not adopted in round 1 because the
+// parity suite could not be re-run on the GPU afterwards.
+#ifndef SN_CHAIN_SUMS
+#define SN_CHAIN_SUMS 0
+#endif
+// accumulate operand of tabulated node i: the running sum of its stage (stages start at i = 1, 2, 4, 8)
+#if SN_CHAIN_SUMS
+#define SN_ACC(i, fv, f1) ((i) == 0 ? (f1) : (((i) & ((i) - 1)) == 0 ? 0.0 : (fv)[(i) - 1]))
+#else
+#define SN_ACC(i, fv, f1) ((i) == 0 ? (f1) : 0.0)
+#endif
 template <bool HASQ, bool FLAT, bool SLOW, bool NEG>
 __device__ __forceinline__ void sn_romb5(const SNCoef &ec, const double *__restrict__ T,
                                          const double2 *__restrict__ nd, const double *__restrict__ na,
@@ -441,22 +455,27 @@ __device__ __forceinline__ void sn_romb5(const SNCoef &ec, const double *__restr
     for (int i = 0; i < 16; i++) {
       const Ld4 n = ld256(n4 + 4 * i);
       if (i == 0) { lnaz = n.x; h = 1.0 - n.z; }
-      fv[i] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.x, n.y, n.z, i == 0 ? f1 : 0.0);
+      fv[i] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.x, n.y, n.z, SN_ACC(i, fv, f1));
     }
   } else {                      // two 16-byte nodes {ln a, a^-1/2} per load
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
       const Ld4 n = ld256(nd + i);
       if (i == 0) { lnaz = n.x; h = 1.0 - __ldg(na); }
-      fv[i] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.x, n.y, 0.0, i == 0 ? f1 : 0.0);
-      fv[i + 1] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.z, n.w, 0.0, 0.0);
+      fv[i] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.x, n.y, 0.0, SN_ACC(i, fv, f1));
+      fv[i + 1] = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.z, n.w, 0.0, SN_ACC(i + 1, fv, f1));
     }
   }
   S.g0 = 0.5 * fv[0];
+#if SN_CHAIN_SUMS
+  // build variant: each stage's sum was chained through the integrand's final FMA (NR's sequential order)
+  S.S1 = fv[1]; S.S2 = fv[3]; S.S3 = fv[7]; S.S4 = fv[15];
+#else
   S.S1 = fv[1];
   S.S2 = fv[2] + fv[3];
   S.S3 = (fv[4] + fv[5]) + (fv[6] + fv[7]);
   S.S4 = ((fv[8] + fv[9]) + (fv[10] + fv[11])) + ((fv[12] + fv[13]) + (fv[14] + fv[15]));
+#endif
   ss = h * fma(ROMBW[0], S.g0, fma(ROMBW[1], S.S1, fma(ROMBW[2], S.S2, fma(ROMBW[3], S.S3, ROMBW[4] * S.S4))));
   dss = h * fma(ROMBW[5], S.g0, fma(ROMBW[6], S.S1, fma(ROMBW[7], S.S2, fma(ROMBW[8], S.S3, ROMBW[9] * S.S4))));
 }
