@@ -291,6 +291,74 @@ def test_em_update_recovers_gaussian(oracle):
     assert nd3 == 1 and w3[1] == 0.0 and abs(w3[0] - 1) < 1e-15
 
 
+@pytest.mark.parametrize("df", [-1, 4])
+def test_em_update_against_independent_numpy(oracle, df):
+    """The oracle's Rao-Blackwellised update (the checker of the GPU EM kernels) against a plain numpy / scipy
+    restatement of Cappe et al. 2008 eqs. 12-14 (Student-t: gamma = (nu + d) / (nu + m), mu' = B / G,
+    Sigma' = sum w rho gamma (x - mu')(x - mu')^T / alpha'): multi-component, non-uniform weights."""
+    rng = np.random.default_rng(17 + df)
+    N, K, d = 6000, 4, 3
+    mean = rng.normal(size=(K, d)) * 1.5
+    Aa = rng.normal(size=(K, d, d)) * 0.4
+    cov = np.einsum("kij,klj->kil", Aa, Aa) + 0.5 * np.eye(d)
+    alpha = np.array([0.4, 0.3, 0.2, 0.1])
+    comp = rng.choice(K, size=N, p=alpha)
+    X = np.stack([rng.multivariate_normal(mean[k], cov[k]) for k in comp]) + 0.3
+    wbar = rng.random(N) ** 3
+    flg = (rng.random(N) > 0.05).astype(np.int16)
+    wbar[flg == 0] = 0.0
+    wbar /= wbar.sum()
+    ch = oracle.cholesky_stack(cov)
+    w2, m2, ch2, cov2, nd = oracle.update_prop_rb(X, comp.astype(np.int32), flg, wbar, alpha, mean, ch, df=df)
+    assert nd == 0
+    if df > 0:
+        pdf = np.stack([stats.multivariate_t(mean[k], cov[k], df=df).pdf(X) for k in range(K)], 1)
+        icov = np.linalg.inv(cov)
+        dx = X[:, None, :] - mean[None]
+        maha = np.einsum("nki,kij,nkj->nk", dx, icov, dx)
+        gam = (df + d) / (df + maha)
+    else:
+        pdf = np.stack([stats.multivariate_normal(mean[k], cov[k]).pdf(X) for k in range(K)], 1)
+        gam = np.ones((N, K))
+    rho = alpha * pdf
+    rho /= rho.sum(1, keepdims=True)
+    wr = wbar[:, None] * rho
+    A_ = wr.sum(0)
+    G_ = (wr * gam).sum(0)
+    mu = np.einsum("nk,ni->ki", wr * gam, X) / G_[:, None]
+    dxn = X[:, None, :] - mu[None]
+    Sig = np.einsum("nk,nki,nkj->kij", wr * gam, dxn, dxn) / A_[:, None, None]
+    assert np.allclose(w2, A_ / A_.sum(), rtol=1e-11)
+    assert np.allclose(m2, mu, rtol=1e-10, atol=1e-12)
+    assert np.allclose(cov2, Sig, rtol=1e-9, atol=1e-12)
+
+
+def test_fisher_stencil_of_a_gaussian_posterior(oracle):
+    """go_fishing.c:37-85 restated (the checker of pmcb200_fisher_host): NR (5.7.10) central second differences of
+    the oracle's posterior, with the reference's diagonal shortcut, recover Sigma^-1 of a Gaussian target."""
+    d = 4
+    rng = np.random.default_rng(2)
+    Aa = rng.normal(size=(d, d)) * 0.4
+    cov = Aa @ Aa.T + np.eye(d)
+    lo, hi = -6.0 * np.ones(d), 6.0 * np.ones(d)
+    spec = T.TargetSpec(["dummy%d" % j for j in range(d)], lo, hi).add_mix([1.0], [0.1 * np.ones(d)], [cov])
+    pos, h = 0.05 * np.arange(d), 0.01 * (hi - lo)
+    diff = [(+1, +1), (+1, -1), (-1, +1), (-1, -1)]
+    F = np.zeros((d, d))
+    for a in range(d):
+        for b in range(a, d):
+            c = []
+            for j in range(4):
+                if j == 2 and a == b:
+                    c.append(c[1]); continue
+                p = pos.copy(); p[a] += diff[j][0] * h[a]; p[b] += diff[j][1] * h[b]
+                lp, err = oracle.posterior_log_pdf(spec, p[None])
+                assert not err.any()
+                c.append(lp[0])
+            F[a, b] = F[b, a] = -(c[0] - c[1] - c[2] + c[3]) / (4.0 * h[a] * h[b])
+    assert np.max(np.abs(F - np.linalg.inv(cov))) < 1e-8
+
+
 def test_evidence_known_answer_tempering_demo(oracle):
     """Demo/tempering/README.md:11-36: Gaussian target on the unit square => evidence ~ 1."""
     spec = T.target_gauss2d()
