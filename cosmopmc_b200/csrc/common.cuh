@@ -134,7 +134,7 @@ __device__ __forceinline__ int select_component(const double *__restrict__ mix, 
 // ---- Gaussian / Student-t component log-pdf: forward substitution
 // y = L^-1 (x - mu), m = y.y (the "batched triangular contraction") ------------
 template <int D>
-__device__ __forceinline__ double comp_maha(const double *__restrict__ comp, int d,
+__host__ __device__ __forceinline__ double comp_maha(const double *__restrict__ comp, int d,
                                             const double (&x)[D], double (&y)[D]) {
   (void)d;       // the packed layout is padded to D: all offsets are compile-time constants
   const double *mean = comp + 2, *L = comp + 2 + D, *rd = comp + 2 + D + D * (D + 1) / 2;
@@ -149,7 +149,7 @@ __device__ __forceinline__ double comp_maha(const double *__restrict__ comp, int
   }
   return m;
 }
-__device__ __forceinline__ double comp_logpdf_from_maha(const double *__restrict__ comp, int d,
+__host__ __device__ __forceinline__ double comp_logpdf_from_maha(const double *__restrict__ comp, int d,
                                                         int df, double m) {
   if (df <= 0) return fma(-0.5, m, comp[1]);
   return comp[1] - 0.5 * (double)(df + d) * log1p(m / (double)df);
@@ -174,7 +174,7 @@ __device__ __forceinline__ double mix_logpdf(const double *__restrict__ mix, con
 // Compile-time loop: the body sees its index as a constant, so the register arrays it indexes can
 // never be demoted to local memory (nvcc gave up unrolling the triangular nest with #pragma unroll).
 template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F &&f) {
+__host__ __device__ __forceinline__ void static_for(F &&f) {
   if constexpr (I < N) {
     f(std::integral_constant<int, I>{});
     static_for<I + 1, N>(f);
@@ -187,7 +187,7 @@ __device__ __forceinline__ void static_for(F &&f) {
 // the FP64 pipe, bounds these kernels -- tools/micro/dmma_probe.cu) feeds S FMAs.
 // t[s][i] holds x_i of sample s on entry and is destroyed.
 template <int D, int S>
-__device__ __forceinline__ void comp_maha_cols(const double *__restrict__ comp, double (&t)[S][D], double (&m)[S]) {
+__host__ __device__ __forceinline__ void comp_maha_cols(const double *__restrict__ comp, double (&t)[S][D], double (&m)[S]) {
   const double *mean = comp + 2, *L = comp + 2 + D, *rd = comp + 2 + D + D * (D + 1) / 2;
   static_for<0, D>([&](auto ii) {
     constexpr int i = decltype(ii)::value;

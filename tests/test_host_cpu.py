@@ -150,3 +150,16 @@ def test_pmclib_named_host_api_cpu(tmp_path):
     out = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("ok ") and int(out.stdout.split()[1]) > 100
+
+
+def test_device_math_helpers_on_host(tmp_path):
+    """tests/c/test_device_math.cu (nvcc, runs on the CPU): the column-oriented multi-sample whitening of
+    k_weights_multi / k_em_stats_mma is bit-identical to the row-oriented forward substitution and agrees with a
+    long-double reference; the tensor-core kernel's feature enumeration covers the statistics block exactly once."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    exe = str(tmp_path / "test_device_math")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "--extended-lambda", "-o", exe, os.path.join(ROOT, "tests", "c", "test_device_math.cu")],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "device math host check ok" in out.stdout, out.stdout + out.stderr
