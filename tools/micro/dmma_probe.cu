@@ -37,6 +37,32 @@ __global__ void __launch_bounds__(256) k_dmma(double *out, const double *in, int
   if (s == 123.456) out[0] = s;
 }
 
+// DFMA and DMMA interleaved (NF DFMAs per DMMA): do the vector FP64 lanes and the FP64 tensor path share one
+// datapath (combined rate <= 100 % of the vector peak) or run side by side?
+template <int NF>
+__global__ void __launch_bounds__(256) k_both(double *out, const double *in, int iters) {
+  double a = in[threadIdx.x & 7], b = in[8 + (threadIdx.x & 7)], y = in[threadIdx.x & 3];
+  double c[4][2], x[8];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { c[i][0] = i; c[i][1] = -i; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      dmma(c[i][0], c[i][1], a, b);
+#pragma unroll
+      for (int j = 0; j < NF; j++) x[(i * NF + j) & 7] = fma(x[(i * NF + j) & 7], y, 1e-9);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) s += c[i][0] + c[i][1];
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += x[i];
+  if (s == 123.456) out[0] = s;
+}
+
 __constant__ double CT[1024];
 // MODE 0: 8 DFMA; 1: 8 DFMA + 8 IMAD; 2: 8 DFMA + 8 broadcast LDS feeding them; 3: 8 DFMA + 8 uniform-indexed
 // constant loads feeding them; 4: 8 DFMA + 4 IMAD; 5: 8 DFMA fed by 8 broadcast LDG (L1-resident)
@@ -121,6 +147,15 @@ int main() {
     ms = best_ms(k_dmma<4>, blocks, d, in, iters);
     fma = 256.0 * 4 * iters * 8.0 * blocks;
     printf("DMMA m8n8k4 x4 acc   blocks/SM %d: %.2f TFLOP/s (%.1f%%)\n", b, 2 * fma / ms * 1e-9, 100 * fma / (ms * 1e-3) / peak);
+  }
+  for (int b : {2, 4}) {     // 1 DMMA = 8 warp-DFMAs of work: NF = 8 asks for equal shares
+    const int blocks = 148 * b, iters = 4096;
+    float ms = best_ms(k_both<8>, blocks, d, in, iters);
+    double fma = (256.0 + 32.0 * 8) * 4 * iters * 8.0 * blocks;
+    printf("4 x (1 DMMA + 8 DFMA)  blocks/SM %d: %.3f ms, combined %.1f%% of the vector FP64 peak\n", b, ms, 100 * fma / (ms * 1e-3) / peak);
+    ms = best_ms(k_both<2>, blocks, d, in, iters);
+    fma = (256.0 + 32.0 * 2) * 4 * iters * 8.0 * blocks;
+    printf("4 x (1 DMMA + 2 DFMA)  blocks/SM %d: %.3f ms, combined %.1f%% of the vector FP64 peak\n", b, ms, 100 * fma / (ms * 1e-3) / peak);
   }
   const char *names[6] = {"8 DFMA", "8 DFMA + 8 IMAD", "8 DFMA + 8 LDS.64 bcast", "8 DFMA + 8 const idx", "8 DFMA + 4 IMAD", "8 DFMA + 8 LDG bcast"};
   for (int b : {2, 4}) {
