@@ -211,6 +211,75 @@ __host__ __device__ __forceinline__ void comp_maha_cols(const double *__restrict
     });
   });
 }
+// Column-packed copy of one component for the staged E-step (built by cp_fill_component): every section
+// starts on a 16-byte boundary so that two doubles travel per shared-memory load (LDS.128) --
+//   [0] wght  [1] lognorm | mean[Dp] | 1/L_ii [Dp] | for k = 0 .. D-2: column k of L below the diagonal,
+//   L[k+1..D-1][k], padded to an even length;  Dp = D rounded up to even.
+template <int D> struct CpLayout {
+  static constexpr int Dp = (D + 1) & ~1;
+  static constexpr int o_mean = 2, o_rd = 2 + Dp, o_L = 2 + 2 * Dp;
+  __host__ __device__ static constexpr int coff(int k) {      // offset of column k inside the L section
+    int o = 0;
+    for (int j = 0; j < k; j++) o += ((D - 1 - j) + 1) & ~1;
+    return o;
+  }
+  static constexpr int stride = o_L + coff(D - 1);            // column D-1 is empty
+};
+// dst (CpLayout<D>::stride doubles, zeroed by the caller: padding must be finite) from the row-packed component src
+template <int D>
+__host__ __device__ inline void cp_fill_component(const double *__restrict__ src, double *__restrict__ dst, int lane,
+                                                  int nlanes) {
+  using CL = CpLayout<D>;
+  const double *mean = src + 2, *L = src + 2 + D, *rd = src + 2 + D + D * (D + 1) / 2;
+  if (lane == 0) { dst[0] = src[0]; dst[1] = src[1]; }
+  for (int i = lane; i < D; i += nlanes) { dst[CL::o_mean + i] = mean[i]; dst[CL::o_rd + i] = rd[i]; }
+  for (int e = lane; e < D * (D + 1) / 2; e += nlanes) {      // e = i (i + 1) / 2 + k, k <= i
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= e) i++;
+    const int k = e - i * (i + 1) / 2;
+    if (k < i) dst[CL::o_L + CL::coff(k) + (i - k - 1)] = L[e];
+  }
+}
+// comp_maha_cols on the column-packed copy: identical operations in identical order (bit-identical result),
+// half the shared-memory load instructions.
+template <int D, int S>
+__host__ __device__ __forceinline__ void comp_maha_cols_cp(const double *__restrict__ cp, double (&t)[S][D],
+                                                           double (&m)[S]) {
+  using CL = CpLayout<D>;
+  const double2 *mean2 = reinterpret_cast<const double2 *>(cp + CL::o_mean);
+  const double *rd = cp + CL::o_rd;
+  static_for<0, CL::Dp / 2>([&](auto jj) {
+    constexpr int i = 2 * decltype(jj)::value;
+    const double2 mu = mean2[i / 2];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      t[s][i] -= mu.x;
+      if constexpr (i + 1 < D) t[s][i + 1] -= mu.y;
+    }
+  });
+#pragma unroll
+  for (int s = 0; s < S; s++) m[s] = 0.0;
+  static_for<0, D>([&](auto kk) {
+    constexpr int k = decltype(kk)::value;
+    const double r = rd[k];
+    double y[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) { y[s] = t[s][k] * r; m[s] = fma(y[s], y[s], m[s]); }
+    constexpr int n = D - 1 - k;                               // rows below the diagonal
+    const double2 *col = reinterpret_cast<const double2 *>(cp + CL::o_L + CL::coff(k));
+    static_for<0, (n + 1) / 2>([&](auto jj) {
+      constexpr int j = decltype(jj)::value;
+      const double2 l = col[j];
+      constexpr int i0 = k + 1 + 2 * j;
+#pragma unroll
+      for (int s = 0; s < S; s++) {
+        t[s][i0] = fma(-l.x, y[s], t[s][i0]);
+        if constexpr (i0 + 1 < D) t[s][i0 + 1] = fma(-l.y, y[s], t[s][i0 + 1]);
+      }
+    });
+  });
+}
+
 // ---- Romberg (Numerical Recipes qromb, K = 5) ---------------------------------
 // Window y[0..4] of the last five trapezoid values (step ratio 1/4): Neville at
 // h = 0 with the constant ratios folded in.  Returns ss, sets dss.

@@ -102,6 +102,17 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
         if (mode == 1) WM(1)
         if (mode == 2) { if constexpr (DD <= 8) WM(4) else WM(2) }
         if (mode == 3) WM(3)
+        if (mode == 4) {      // experimental: column-packed staged mixture (two doubles per LDS)
+          auto kern = k_weights_multi<DD, (DD <= 8 ? 4 : 2), true>;
+          constexpr int SV = (DD <= 8 ? 4 : 2);
+          const size_t sm = (size_t)a.h.K * CpLayout<DD>::stride * sizeof(double) + (size_t)DD * SV * PMC_BLOCK * sizeof(double);
+          if (sm <= 200 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e;
+            kern<<<(int)((a.N + PMC_BLOCK * SV - 1) / (PMC_BLOCK * SV)), PMC_BLOCK, sm, s>>>(a.mix, a.h, a.N, a.Xc, a.logpic, a.errc, a.beta, a.flg, a.logw, a.scal, a.rho);
+            if (a.rho && a.rho_written) *a.rho_written = 1;
+            return cudaGetLastError();
+          }
+        }
 #undef WM
       }
       k_weights<DD><<<nblk(a.N), PMC_BLOCK, 0, s>>>(a.mix, a.h, a.N, a.Xc, a.logpic, a.errc, a.beta, a.flg, a.logw,

@@ -239,7 +239,9 @@ k_weights(const double *__restrict__ mix, const MixHdr h, int64_t N,
 // (tile_base + s * PMC_BLOCK + tid: loads stay coalesced) which share each mixture load; the samples sit in
 // shared memory too ([i][s][tid], conflict-free) so that only the S x D working rows of the column-oriented
 // substitution live in registers.
-template <int D, int S>
+// CP (experimental, PMCB200_ESTEP=4): the staged mixture is the column-packed copy (CpLayout, common.cuh), read
+// two doubles per LDS; same operations in the same order.
+template <int D, int S, bool CP = false>
 __global__ void __launch_bounds__(PMC_BLOCK, (S * D <= 48) ? 2 : 1)
 k_weights_multi(const double *__restrict__ mixg, const MixHdr h, int64_t N,
                 const double *__restrict__ X, const double *__restrict__ logpi,
@@ -250,8 +252,16 @@ k_weights_multi(const double *__restrict__ mixg, const MixHdr h, int64_t N,
   extern __shared__ double s_buf[];
   double *s_xt = s_buf;                                    // [D][S][PMC_BLOCK]
   double *s_mix = s_buf + (size_t)D * S * PMC_BLOCK;       // packed mixture
-  const int nmix = h.K * h.stride;
-  for (int i = threadIdx.x; i < nmix; i += PMC_BLOCK) s_mix[i] = mixg[i];
+  if constexpr (CP) {
+    const int ncp = h.K * CpLayout<D>::stride;
+    for (int i = threadIdx.x; i < ncp; i += PMC_BLOCK) s_mix[i] = 0.0;
+    __syncthreads();
+    for (int k = 0; k < h.K; k++)
+      cp_fill_component<D>(mixg + (size_t)k * h.stride, s_mix + (size_t)k * CpLayout<D>::stride, threadIdx.x, PMC_BLOCK);
+  } else {
+    const int nmix = h.K * h.stride;
+    for (int i = threadIdx.x; i < nmix; i += PMC_BLOCK) s_mix[i] = mixg[i];
+  }
   const int64_t base = (int64_t)blockIdx.x * (PMC_BLOCK * S) + threadIdx.x;
   bool live[S];
 #pragma unroll
@@ -267,7 +277,7 @@ k_weights_multi(const double *__restrict__ mixg, const MixHdr h, int64_t N,
 #pragma unroll
   for (int s = 0; s < S; s++) acc[s] = 0.0;
   for (int k = 0; k < h.K; k++) {
-    const double *comp = s_mix + (size_t)k * h.stride;
+    const double *comp = s_mix + (size_t)k * (CP ? CpLayout<D>::stride : h.stride);
     const double w = comp[0];
     if (w == 0.0) {
       if (rho) {
@@ -280,7 +290,8 @@ k_weights_multi(const double *__restrict__ mixg, const MixHdr h, int64_t N,
     for (int i = 0; i < D; i++)
 #pragma unroll
       for (int s = 0; s < S; s++) t[s][i] = s_xt[((size_t)i * S + s) * PMC_BLOCK + threadIdx.x];
-    comp_maha_cols<D, S>(comp, t, m);
+    if constexpr (CP) comp_maha_cols_cp<D, S>(comp, t, m);
+    else comp_maha_cols<D, S>(comp, t, m);
 #pragma unroll
     for (int s = 0; s < S; s++) {
       const double e = exp(comp_logpdf_from_maha(comp, h.d, h.df, m[s]));

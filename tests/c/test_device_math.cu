@@ -2,7 +2,8 @@
 // __host__ __device__ and use only IEEE add / mul / fma, so the host results equal the device's bit for bit).
 //  1. comp_maha_cols<D, S> (column-oriented, S samples per thread: k_weights_multi, k_em_stats_mma phase 1) is
 //     BIT-IDENTICAL to comp_maha<D> (row-oriented forward substitution: k_weights, k_logq, k_em_stats), and both
-//     agree with a long-double forward substitution.
+//     agree with a long-double forward substitution; so is comp_maha_cols_cp on the column-packed copy built by
+//     cp_fill_component (experimental variant).
 //  2. the packed-mixture layout helpers (mix_stride, pmc_pad_dim) and the EM feature enumeration used by the
 //     tensor-core kernel (f = 0 -> G, 1..d -> B, then the lower triangle by rows) cover the statistics block once.
 #include <cstdio>
@@ -33,9 +34,18 @@ static int check_maha(int d) {
     for (int s = 0; s < S; s++)
       for (int i = 0; i < D; i++) { x[s][i] = (i < d) ? 6.0 * urand() - 3.0 : 0.0; t[s][i] = x[s][i]; }
     comp_maha_cols<D, S>(comp.data(), t, m_cols);
+    // column-packed copy (experimental k_weights_multi<.., CP = true>): same operations, same order
+    alignas(16) double cp[CpLayout<D>::stride + 2];
+    for (int e = 0; e < CpLayout<D>::stride; e++) cp[e] = 0.0;
+    for (int lane = 0; lane < 7; lane++) cp_fill_component<D>(comp.data(), cp, lane, 7);
+    double t2[S][D], m_cp[S];
+    for (int s = 0; s < S; s++) for (int i = 0; i < D; i++) t2[s][i] = x[s][i];
+    comp_maha_cols_cp<D, S>(cp, t2, m_cp);
+    if (cp[0] != comp[0] || cp[1] != comp[1]) { printf("D=%d: cp header\n", D); bad++; }
     for (int s = 0; s < S; s++) {
       const double m_row = comp_maha<D>(comp.data(), d, x[s], y);
       if (memcmp(&m_row, &m_cols[s], 8) != 0) { printf("D=%d S=%d: row %.17g != cols %.17g\n", D, S, m_row, m_cols[s]); bad++; }
+      if (memcmp(&m_row, &m_cp[s], 8) != 0) { printf("D=%d S=%d: row %.17g != column-packed %.17g\n", D, S, m_row, m_cp[s]); bad++; }
       long double yl[D], ml = 0.0L;       // reference
       for (int i = 0; i < D; i++) {
         long double tt = (long double)x[s][i] - mean[i];
