@@ -63,9 +63,9 @@ __device__ inline int apply_params(const DevLike &L, const double *__restrict__ 
       bad = 1;
   } else {
     if (h100 < 0) bad = 1;
-    double h2 = h100 * h100;
-    Omegam = omegam / h2; Omegab = omegab / h2; Omegade = omegade / h2;
-    Omeganumass = omeganumass / h2; Omegac = omegac / h2; OmegaK = omegaK / h2;
+    // two divisions each, as param.c:1567-1572 writes them (x/h/h and x/(h*h) differ in the last bit)
+    Omegam = omegam / h100 / h100; Omegab = omegab / h100 / h100; Omegade = omegade / h100 / h100;
+    Omeganumass = omeganumass / h100 / h100; Omegac = omegac / h100 / h100; OmegaK = omegaK / h100 / h100;
     iOmegade = iomegade; iOmegaK = iomegaK;
   }
   if (Omegam > 0 && iOmegade == 1 && iOmegaK == 1) bad = 1;
@@ -84,7 +84,8 @@ __device__ inline int apply_params(const DevLike &L, const double *__restrict__ 
 }
 
 // nicaea test_range_de_conservative (sn.c:265, bao.c:156, wmap.c:1029): w(a) outside [-1, -1/3]
-// at a = 1 or a = a_acc.  A violating model gets log L = 0 from the probe (reference behaviour).
+// at a = 1 or a = a_acc.  A violating model gets log L = 0 from the SN and BAO probes (sn.c:263-274,
+// bao.c:154-176); likeli_CMBDistPrior raises wmap_de_prior instead (wmap.c:1041-1044), which drops the point.
 __device__ __forceinline__ bool de_conservative_violated(const pmcb200_cosmo_t &c) {
   const double w_now = c.w0_de;
   double w_acc = w_now;
@@ -591,7 +592,7 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   int e = 0;
   if (active) e = apply_params(L, X + n * d, m);
   const bool cut = active && !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c);
-  if (!active || e || cut) {   // keep the warp's control flow uniform on a benign model
+  if (!active || e) {   // keep the warp's control flow uniform on a benign model
     m.c = L.model;
 #pragma unroll
     for (int i = 0; i < 4; i++) m.Theta2[i] = L.Theta2[i];
@@ -629,8 +630,10 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   else sn_zloop<HASQ, FLAT, false, false>(L, ec, T, pm, f1s, R_HUBBLE * ec.scale, chi2, logdet, e, nev);
   double res = -0.5 * chi2;
   if (L.sn_add_logdetCov) res -= 0.5 * logdet;
-  if (!isfinite(res)) e = 1;
-  if (cut) { res = 0.0; e = 0; }     // de_conservative: log L = 0, sn.c:263-274
+  // de_conservative: log L = 0 without evaluating chi2_SN (sn.c:263-274); SetDl has already run (sn.c:260), so a
+  // distance error of a violating model is still an error
+  if (cut) res = 0.0;
+  else if (!isfinite(res)) e = 1;
   if (active) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
   else if (n < N && set) { logpi[n] = 0.0; if (err) err[n] = 0; }
   if (cnt) {   // measurement only: one atomic pair per warp
@@ -697,8 +700,9 @@ k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   double res = 0.0;
   const pmcb200_cosmo_t &c = m.c;
   const bool cut = !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(c);
-  if (!e && !cut && (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0))) e = 1;
-  if (!e && !cut) {
+  if (cut) e = 1;      // wmap.c:1041-1044: wmap_de_prior error, the point gets zero weight
+  if (!e && (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0))) e = 1;
+  if (!e) {
     double model[4];
     double zs = z_star(c), as = 1.0 / (1.0 + zs);
     double ww = w_generic(c, as, 1, e, T);

@@ -292,6 +292,7 @@ extern "C" int pmcb200_dev_free(pmcb200_ctx *c, void *dptr) {
 }
 extern "C" int pmcb200_h2d(pmcb200_ctx *c, void *dptr, const void *hptr, size_t bytes) {
   if (!c) return PMCB200_ERR_ARG;
+  c->rho_valid = false;      // the caller may be rewriting the sample or flag array the E-step cache was computed from
   CUDA_OK(c, cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -949,6 +950,7 @@ extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, 
 extern "C" int pmcb200_h2d_async(pmcb200_ctx *c, void *dptr, const void *hptr, size_t bytes) {
   if (!c) return PMCB200_ERR_ARG;
   CUDA_OK(c, cudaSetDevice(c->device));
+  c->rho_valid = false;
   if (bytes) CUDA_OK(c, cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
   return 0;
 }

@@ -193,7 +193,9 @@ k_wstat_sums(int64_t N, const int16_t *__restrict__ flg, const double *__restric
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
     if (!flg[n]) continue;
     double v, lw;
-    if (is_log) { lw = w[n] - M; v = exp(lw); }
+    // a flagged sample whose weight is zero / whose log weight is not finite (a stored log(0) read back by
+    // pmc_simu_from_file) counts as a draw but contributes nothing: 0 * -inf must not reach the sums
+    if (is_log) { lw = w[n] - M; v = exp(lw); if (!(v > 0.0) || !isfinite(lw)) { tN += 1.0; continue; } }
     else { v = w[n]; if (!(v > 0.0)) { tN += 1.0; continue; } lw = log(v); }
     tS += v; tS2 = fma(v, v, tS2); tT = fma(v, lw, tT); tN += 1.0;
   }

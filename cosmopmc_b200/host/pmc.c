@@ -92,9 +92,10 @@ void pmc_simu_realloc(pmc_simu *p, long nsamples, error **err)
 {
    if (nsamples <= p->nsamples_alloc && nsamples == p->nsamples) return;
    testErrorRetVA(nsamples < 1, pmc_dimension, "Invalid number of samples %ld", *err, __LINE__, , nsamples);
-   pmcb200_host_free(p->buf);
-   p->buf = psim_lump(psim_bytes(nsamples, p->ndim, p->n_ded), err);
+   void *nb = psim_lump(psim_bytes(nsamples, p->ndim, p->n_ded), err);     /* the old lump survives a failed allocation */
    forwardError(*err, __LINE__, );
+   pmcb200_host_free(p->buf);
+   p->buf = nb;
    p->nsamples = p->nsamples_alloc = nsamples;
    psim_carve(p, nsamples);
    p->isLog = 0;
@@ -749,7 +750,7 @@ void pmc_simu_dump_binary(FILE *F, const pmc_simu *psim, error **err)
       if (psim->flg[i]) {
          double *q = row + (size_t)k * nc;
          double lw = psim->weights[i];
-         q[0] = psim->isLog ? lw : log(lw) + psim->logSum;      /* as out_pmc_simu_cosmo_pmc, exec_helper.c:408-420 */
+         q[0] = (psim->isLog ? lw : log(lw)) + psim->logSum;    /* as out_pmc_simu_cosmo_pmc, exec_helper.c:408-420: logSum is always added */
          q[1] = (double)psim->indices[i];
          memcpy(q + 2, psim->X + (size_t)i * psim->ndim, sizeof(double) * psim->ndim);
          if (psim->n_ded) memcpy(q + 2 + psim->ndim, psim->X_ded + (size_t)i * psim->n_ded, sizeof(double) * psim->n_ded);

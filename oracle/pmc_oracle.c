@@ -430,9 +430,9 @@ static int apply_params(const pmcb200_like_t *L, const double *x, model_t *m)
          return 1;                         /* mixing physical / non-physical */
    } else {
       if (h100 < 0) return 1;
-      double h2 = h100 * h100;
-      Omegam = omegam / h2; Omegab = omegab / h2; Omegade = omegade / h2;
-      Omeganumass = omeganumass / h2; Omegac = omegac / h2; OmegaK = omegaK / h2;
+      /* param.c:1567-1572 divides twice (x/h100/h100) */
+      Omegam = omegam / h100 / h100; Omegab = omegab / h100 / h100; Omegade = omegade / h100 / h100;
+      Omeganumass = omeganumass / h100 / h100; Omegac = omegac / h100 / h100; OmegaK = omegaK / h100 / h100;
       iOmegade = iomegade; iOmegaK = iomegaK;
    }
    if (Omegam > 0 && iOmegade == 1 && iOmegaK == 1) return 1;  /* overdetermined */
@@ -628,12 +628,18 @@ static int de_conservative_violated(const pmcb200_cosmo_t *c)
 double orc_loglike(const pmcb200_like_t *L, const double *x, int *err)
 {
    model_t m;
-   /* hard cut of the de_conservative prior inside each probe: the reference returns log L = 0
-    * (not -inf) for a violating model, sn.c:263-274, bao.c:154-176, wmap.c:1027-1039 */
+   /* hard cut of the de_conservative prior inside each probe: SN and BAO return log L = 0
+    * (not -inf) for a violating model, sn.c:263-274, bao.c:154-176; likeli_CMBDistPrior computes 0
+    * and then raises wmap_de_prior (wmap.c:1027-1044), so the point is dropped */
    if (L->special == PMCB200_SPECIAL_de_conservative &&
        (L->kind == PMCB200_LIKE_SNIa || L->kind == PMCB200_LIKE_BAO || L->kind == PMCB200_LIKE_CMBDistPrior)) {
       if (apply_params(L, x, &m)) { *err = 1; return 0.0; }
-      if (de_conservative_violated(&m.c)) return 0.0;
+      if (de_conservative_violated(&m.c)) {
+         if (L->kind == PMCB200_LIKE_CMBDistPrior) *err = 1;
+         /* sn.c:260 runs SetDl before the test of sn.c:263-274: a distance error still counts */
+         if (L->kind == PMCB200_LIKE_SNIa) loglike_sn(L, &m, err, NULL);
+         return 0.0;
+      }
    }
    switch (L->kind) {
       case PMCB200_LIKE_Mvdens:

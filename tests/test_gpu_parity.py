@@ -194,13 +194,13 @@ def test_posterior_sn_bao_w0wa(oracle, pmc_factory):
 
 
 def test_posterior_de_conservative(oracle, pmc_factory):
-    """special prior de_conservative on every probe: volume term (param.c:1072-1094) and the
-    log L = 0 cut for violating models (sn.c:263-274, bao.c:154-176, wmap.c:1027-1039)."""
+    """special prior de_conservative on every probe: volume term (param.c:1072-1094); the SN and BAO probes
+    return log L = 0 for a violating model (sn.c:263-274, bao.c:154-176), likeli_CMBDistPrior raises
+    wmap_de_prior (wmap.c:1041-1044) so the point is dropped with zero weight."""
     pmc = pmc_factory()
-    spec = (T.TargetSpec(["Omega_b", "Omega_m", "Omega_de", "h_100", "w_0_de", "w_1_de", "M", "alpha", "beta"],
-                         [0.02, 0.1, 0.3, 0.5, -1.5, -1.5, 19.1, 0.5, -3.5],
-                         [0.08, 0.6, 1.1, 0.9, 0.0, 1.5, 19.8, 2.6, -0.8])
-            .add_cmbdp(special="de_conservative").add_bao(T.BAO_BOSS12_DZ, special="de_conservative")
+    names = ["Omega_b", "Omega_m", "Omega_de", "h_100", "w_0_de", "w_1_de", "M", "alpha", "beta"]
+    lo, hi = [0.02, 0.1, 0.3, 0.5, -1.5, -1.5, 19.1, 0.5, -3.5], [0.08, 0.6, 1.1, 0.9, 0.0, 1.5, 19.8, 2.6, -0.8]
+    spec = (T.TargetSpec(names, lo, hi).add_bao(T.BAO_BOSS12_DZ, special="de_conservative")
             .add_snia(cosmo=T.COSMO_DP, special="de_conservative"))
     pmc.set_target(spec)
     X = box_samples(spec, 1500, 21)
@@ -209,8 +209,18 @@ def test_posterior_de_conservative(oracle, pmc_factory):
     assert 0.2 < cutm.mean() < 0.95
     check_posterior(oracle, pmc, spec, X)
     got, err = pmc.posterior_log_pdf(dev(X))
-    got = got.cpu().numpy()
-    assert np.ptp(got[cutm]) < 1e-12            # every probe returned 0: only the constant prior is left
+    got, err = got.cpu().numpy(), err.cpu().numpy()
+    assert np.ptp(got[cutm & (err == 0)]) < 1e-12   # both probes returned 0: only the constant prior is left
+    assert (cutm & (err == 0)).sum() > 0.9 * cutm.sum()
+    # with the CMB distance priors in the set a violating model is an error (flag 0), never log L = 0
+    spec3 = (T.TargetSpec(names, lo, hi).add_cmbdp(special="de_conservative")
+             .add_bao(T.BAO_BOSS12_DZ, special="de_conservative").add_snia(cosmo=T.COSMO_DP, special="de_conservative"))
+    pmc.set_target(spec3)
+    ref, eref = oracle.posterior_log_pdf(spec3, X)
+    got, err = pmc.posterior_log_pdf(dev(X))
+    got, err = got.cpu().numpy(), err.cpu().numpy()
+    assert np.array_equal(err != 0, eref != 0) and np.all(err[cutm] != 0) and (err[~cutm] == 0).sum() > 50
+    assert rel(got[eref == 0], ref[eref == 0]) < RTOL_LOG
     # narrower w0 range than the prior: refused like the reference does
     bad = T.TargetSpec(["Omega_m", "w_0_de", "M", "alpha", "beta"], [0.0, -0.8, 19.1, 0.5, -3.5],
                        [1.2, 0.5, 19.8, 2.6, -0.8]).add_snia(special="de_conservative")
@@ -232,6 +242,22 @@ def test_posterior_bao_A_and_prior(oracle, pmc_factory):
     spec.set_prior([0.3, 0.72], [[0.01, 0.0002], [0.0002, 0.0064]], indprior=[1, 0, 1])   # (Omega_m, h_100)
     pmc.set_target(spec)
     check_posterior(oracle, pmc, spec, box_samples(spec, 1500, 16))
+
+
+def test_posterior_bao_D_V_ratio(oracle, pmc_factory):
+    """distance_D_V_ratio (bao.c:56,170-171): model_i = D_V(z_2i) / D_V(z_2i+1) against a 2-point Gaussian
+    (Percival et al. 2010-like ratios D_V(0.35)/D_V(0.2) and D_V(0.57)/D_V(0.35)), curved w0 cosmology."""
+    pmc = pmc_factory()
+    spec = T.TargetSpec(["Omega_m", "Omega_de", "w_0_de", "h_100"], [0.05, 0.2, -2.0, 0.5], [0.8, 1.2, -0.4, 0.9])
+    spec.add_bao(dict(method="distance_D_V_ratio", mean=[1.736, 1.52], covinv=[[260.0, -40.0], [-40.0, 400.0]],
+                      z=[0.35, 0.2, 0.57, 0.35]))
+    pmc.set_target(spec)
+    r = check_posterior(oracle, pmc, spec, box_samples(spec, 2000, 22))
+    # the ratio is scale free: h_100 must not matter (property of the reference formula)
+    X = box_samples(spec, 200, 23)
+    X2 = X.copy(); X2[:, 3] = 0.55
+    a, _ = pmc.posterior_log_pdf(dev(X)); b, _ = pmc.posterior_log_pdf(dev(X2))
+    assert rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-12
 
 
 def test_posterior_banana_and_mixture(oracle, pmc_factory):
@@ -380,6 +406,20 @@ def test_iteration_cmb_bao_sn(oracle, pmc_factory):
     pmc.set_proposal(w, m, chol=ch)
     o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 6000, seed=4)
     check_iteration(o, st, pmc, *h)
+
+
+def test_iteration_sn_bao_w0wa(oracle, pmc_factory):
+    """C4 (BASELINE.json configs[3]): SN Ia + BAO d_z, w0-wa, d = 7, K = 10 -- the bench's proposal, full iteration."""
+    pmc = pmc_factory()
+    spec = T.target_sn_bao_w0wa()
+    w, m, cov = T.proposal_generic(spec, 10, 4, [0.28, 0.72, -1.0, 0.0, 19.31, 1.4, -2.4],
+                                   [0.04, 0.06, 0.15, 0.2, 0.03, 0.1, 0.1])
+    ch = oracle.cholesky_stack(cov)
+    pmc.set_target(spec)
+    pmc.set_proposal(w, m, chol=ch)
+    o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 8000, seed=6)
+    check_iteration(o, st, pmc, *h)
+    assert st["nok"] > 7000
 
 
 def test_multi_iteration_convergence_gauss2d(pmc_factory):

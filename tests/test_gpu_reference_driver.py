@@ -199,10 +199,22 @@ def test_reference_pipeline_wmap_distance_priors(tmp_path):
     with open(run / "config_fish", "w") as fo:
         subprocess.check_call(["perl", need[3], "-F", "-p", "maxlogP", "-c", "config_pmc"], cwd=run, stdout=fo)
     sh([need[2], "-q", "-f"])                     # 3 data, 4 parameters: force a positive (diagonal) Fisher matrix
-    sh([need[0], "-c", "config_pmc", "-s", "1", "-q"])
+    r = sh([need[0], "-c", "config_pmc", "-s", "1", "-q"])
     perp = np.loadtxt(run / "perplexity")
     assert perp.shape[0] == 10 and perp[-1, 2] > 0.3 and perp[-1, 2] > perp[0, 2]
     rows = [l.split() for l in open(run / "iter_9" / "mean") if not l.startswith("#")]
     mean = np.array([float(r[2]) for r in rows])
     assert 0.03 < mean[0] < 0.07 and 0.2 < mean[1] < 0.45 and 0.55 < mean[2] < 0.85 and 0.5 < mean[3] < 0.85
-    assert "Clipping point" in open(run / "log_pmc").read() or True
+    # clip_weights (cosmo_pmc.c:396-399, nclipw 5, reports on stderr): five points per iteration, and the mean
+    # of the final iteration is the one of the CLIPPED sample -- recomputed here from the unclipped pmcsim file
+    # (written at cosmo_pmc.c:392, before the clipping) with its five largest weights removed
+    assert r.stderr.count("Clipping point") == 5 * 10, r.stderr[-2000:]
+    sim = np.loadtxt(run / "iter_9" / "pmcsim")
+    lw, X = sim[:, 0], sim[:, 2:6]
+    w = np.exp(lw - lw.max())
+    keep = np.ones(len(w), bool)
+    keep[np.argsort(w)[-5:]] = False
+    m_clip = (w[keep, None] * X[keep]).sum(0) / w[keep].sum()
+    m_all = (w[:, None] * X).sum(0) / w.sum()
+    assert np.allclose(mean, m_clip, rtol=2e-5), (mean, m_clip, m_all)       # text files carry 9 / 5 digits
+    assert np.abs(m_all - m_clip).max() > 0.0

@@ -240,6 +240,43 @@ def test_bao_cmb_sanity(oracle):
     assert err2.sum() == 0 and lp2[0] > lp2[1]
 
 
+def test_bao_D_V_ratio_against_quad(oracle):
+    """distance_D_V_ratio (bao.c:56,170-171): D_V(z_2i) / D_V(z_2i+1), D_V = [f_K^2 c z / H]^(1/3)
+    (Manual/manual.tex:1707-1735), against scipy quadrature for a curved w0 model."""
+    from scipy.integrate import quad
+    data = dict(method="distance_D_V_ratio", mean=[1.736, 1.52], covinv=[[260.0, -40.0], [-40.0, 400.0]],
+                z=[0.35, 0.2, 0.57, 0.35])
+    spec = T.TargetSpec(["Omega_m", "Omega_de", "w_0_de"], [0.05, 0.2, -2.0], [0.8, 1.2, -0.4]).add_bao(data)
+    x = np.array([[0.3, 0.6, -0.9], [0.25, 0.85, -1.2]])
+    lp, err = oracle.posterior_log_pdf(spec, x)
+    assert err.sum() == 0
+    cov = np.linalg.inv(np.array(data["covinv"]))
+    for i, (Om, Ode, w0) in enumerate(x):
+        OK = 1.0 - Om - Ode
+        E = lambda z: np.sqrt(Om * (1 + z) ** 3 + OK * (1 + z) ** 2 + Ode * (1 + z) ** (3 * (1 + w0)))
+        def DV(z):
+            w = quad(lambda t: 1.0 / E(t), 0.0, z, epsabs=1e-13, epsrel=1e-13)[0]
+            sk = np.sqrt(abs(OK))
+            fk = np.sinh(sk * w) / sk if OK > 0 else np.sin(sk * w) / sk
+            return (fk * fk * z / E(z)) ** (1.0 / 3.0)
+        model = np.array([DV(0.35) / DV(0.2), DV(0.57) / DV(0.35)])
+        r = model - np.array(data["mean"])
+        ref = (-0.5 * r @ np.array(data["covinv"]) @ r - 0.5 * (2 * np.log(2 * np.pi) + np.linalg.slogdet(cov)[1])
+               - np.sum(np.log(spec.box[1] - spec.box[0])))
+        assert abs(lp[i] - ref) < 2e-5 * max(1.0, abs(ref))      # Romberg EPS 1e-6 on each distance
+
+
+def test_cmbdp_de_conservative_is_an_error(oracle):
+    """wmap.c:1041-1044: a model outside the de_conservative range raises wmap_de_prior (point dropped),
+    unlike SN / BAO which return log L = 0 (sn.c:263-274, bao.c:154-176)."""
+    names, lo, hi = ["Omega_b", "Omega_m", "Omega_de", "h_100", "w_0_de"], [0.02, 0.1, 0.3, 0.5, -1.5], [0.08, 0.6, 1.1, 0.9, 0.0]
+    x = np.array([[0.045, 0.27, 0.73, 0.71, -0.8], [0.045, 0.27, 0.73, 0.71, -1.2], [0.045, 0.27, 0.73, 0.71, -0.2]])
+    lp, err = oracle.posterior_log_pdf(T.TargetSpec(names, lo, hi).add_cmbdp(special="de_conservative"), x)
+    assert list(err != 0) == [False, True, True]
+    lp, err = oracle.posterior_log_pdf(T.TargetSpec(names, lo, hi).add_bao(T.BAO_BOSS12_DZ, special="de_conservative"), x)
+    assert err.sum() == 0 and lp[1] == lp[2] and lp[0] != lp[1]
+
+
 def test_weights_normalisation_perplexity_ess(oracle):
     rng = np.random.default_rng(3)
     N = 5000
