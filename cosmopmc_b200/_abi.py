@@ -21,7 +21,10 @@ SPAR = {"Omega_m": P["Omegam"], "Omega_b": P["Omegab"], "Omega_de": P["Omegade"]
         "100_omega_b": P["omegab100"], "omega_de": P["omegade"], "omega_c": P["omegac"],
         "omega_K": P["omegaK"], "w_0_de": P["w0de"], "w_1_de": P["w1de"],
         "M": P["M"], "alpha": P["alpha"], "beta": P["beta"], "logbeta": P["logbeta"],
-        "beta_z": P["beta_z"]}
+        "beta_z": P["beta_z"],
+        # the reference's own spellings (tools/include/par.h:36-149)
+        "log_beta": P["logbeta"], "omega_nu_mass": P["omeganumass"], "N_eff_nu_mass": P["Neffnumass"],
+        "stretch": P["stretch"], "color": P["color"]}
 
 LIKE = dict(Mvdens=0, MixMvdens=1, SNIa=3, CMBDistPrior=6, BAO=7, BANANA=100)
 SPECIAL = dict(none=0, unity=1, de_conservative=2)
@@ -100,6 +103,7 @@ SYMBOLS = {
     "pmcb200_simulate_from_draws": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "pmcb200_proposal_log_pdf": (_i, [_vp, _i64, _vp, _vp]),
     "pmcb200_posterior_log_pdf": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "pmcb200_map_params": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "pmcb200_importance_weights": (_i, [_vp, _i64, _vp, _d, _vp, _vp]),
     "pmcb200_normalize_weights": (_i, [_vp, _i64, _vp, _vp]),
     "pmcb200_stat_block_len": (_i64, [_vp]),

@@ -718,6 +718,25 @@ k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
 }
 
+// Parity probe: the mapped model of one data set per sample (the device's apply_params), so that the parameter
+// mapping can be compared bit for bit with the reference's own switch + set_base_parameters.
+// out[n*16 ..] = Omega_m Omega_de w0 w1 h_100 Omega_b Omega_nu_mass Neff_nu_mass de_param Theta2[4] stretch color 0
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_map_params(const DevLike L, int64_t N, const double *__restrict__ X, int d, double *__restrict__ out,
+             int32_t *__restrict__ err) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  Model m;
+  const int e = apply_params(L, X + n * d, m);
+  double *o = out + n * 16;
+  o[0] = m.c.Omega_m; o[1] = m.c.Omega_de; o[2] = m.c.w0_de; o[3] = m.c.w1_de; o[4] = m.c.h_100;
+  o[5] = m.c.Omega_b; o[6] = m.c.Omega_nu_mass; o[7] = m.c.Neff_nu_mass; o[8] = (double)m.c.de_param;
+#pragma unroll
+  for (int i = 0; i < 4; i++) o[9 + i] = m.Theta2[i];
+  o[13] = m.stretch; o[14] = m.color; o[15] = 0.0;
+  if (err) err[n] = e;
+}
+
 __global__ void __launch_bounds__(PMC_BLOCK)
 k_like_banana(const DevLike L, int64_t N, const double *__restrict__ X, int d,
               const int16_t *__restrict__ flg, double *__restrict__ logpi,

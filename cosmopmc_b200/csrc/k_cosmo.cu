@@ -54,6 +54,9 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
   }
 }
 
+void pmc_launch_map_params(const DevLike &L, int64_t N, const double *X, int d, double *out, int32_t *err, cudaStream_t s) {
+  k_map_params<<<nblk(N), PMC_BLOCK, 0, s>>>(L, N, X, d, out, err);
+}
 void pmc_launch_normalize(int64_t N, const int16_t *flg, double *w, double M, double invS, cudaStream_t s) {
   k_normalize<<<nblk(N), PMC_BLOCK, 0, s>>>(N, flg, w, M, invS);
 }

@@ -44,6 +44,7 @@ static inline cudaError_t pmc_mix_launch(int op, const MixArgs &a, cudaStream_t 
 // cosmology / analytic likelihood kernels (k_cosmo.cu)
 void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const int16_t *flg, double *logpi,
                      int32_t *err, int set, double add_const, DevCount *cnt, cudaStream_t s);
+void pmc_launch_map_params(const DevLike &L, int64_t N, const double *X, int d, double *out, int32_t *err, cudaStream_t s);
 // small kernels (k_cosmo.cu)
 void pmc_launch_normalize(int64_t N, const int16_t *flg, double *w, double M, double invS, cudaStream_t s);
 void pmc_launch_em_reduce(const double *partials, int nblocks, int64_t len, const DevScal *scal, int64_t N_local,

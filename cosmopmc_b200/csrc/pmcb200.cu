@@ -736,6 +736,20 @@ extern "C" int pmcb200_posterior_log_pdf(pmcb200_ctx *c, int64_t N, const double
   return launch_posterior(c, N, dX, nullptr, dlogpi, derr);
 }
 
+extern "C" int pmcb200_map_params(pmcb200_ctx *c, int idata, int64_t N, const double *dX, double *dout, int32_t *derr) {
+  int rc = need(c, false, true);
+  if (rc) return rc;
+  if (idata < 0 || idata >= c->tgt.ndata || N < 0 || (N > 0 && (!dX || !dout)))
+    return fail(c, PMCB200_ERR_ARG, "map_params: bad arguments");
+  const int kind = c->like[idata].kind;
+  if (kind != PMCB200_LIKE_SNIa && kind != PMCB200_LIKE_BAO && kind != PMCB200_LIKE_CMBDistPrior)
+    return fail(c, PMCB200_ERR_UNSUP, "map_params: data set %d has no cosmological parameters", idata);
+  if (N == 0) return 0;
+  pmc_launch_map_params(c->like[idata], N, dX, c->tgt.npar, dout, derr, c->stream);
+  LAUNCH_OK(c);
+  return 0;
+}
+
 // Fisher matrix at a point: go_fishing.c:37-85, all stencil points in one posterior launch.
 extern "C" int pmcb200_fisher_host(pmcb200_ctx *c, const double *pos, const double *h, int diag_only,
                                    double *F, int *nbad) {

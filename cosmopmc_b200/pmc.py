@@ -118,6 +118,14 @@ class PMC:
         self._ck(self.lib.pmcb200_posterior_log_pdf(self.h, N, _dp(X), _dp(out), _dp(err)))
         return out[:N], err[:N]
 
+    def map_params(self, idata, X):
+        """device apply_params of data set idata (parity probe): (N, 16) models + error flags"""
+        N = X.shape[0]
+        out = torch.zeros((max(N, 1), 16), dtype=torch.float64, device=self.device)
+        err = torch.zeros(max(N, 1), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.pmcb200_map_params(self.h, idata, N, _dp(X), _dp(out), _dp(err)))
+        return out[:N], err[:N]
+
     def get_importance_weight(self, X, flg, logw, beta=1.0):
         self._ck(self.lib.pmcb200_importance_weights(self.h, X.shape[0], _dp(X), beta, _dp(flg), _dp(logw)))
 

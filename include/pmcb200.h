@@ -217,6 +217,14 @@ int pmcb200_proposal_log_pdf(pmcb200_ctx *ctx, int64_t N, const double *dX,
  * NULL. */
 int pmcb200_posterior_log_pdf(pmcb200_ctx *ctx, int64_t N, const double *dX,
                               double *dlogpi, int32_t *derr);
+/* The parameter mapping alone, for parity checks against the reference's compiled code: the
+ * `switch (like->par[i])` of likeli_SNIa / likeli_BAO / likeli_CMBDistPrior (sn.c:167-224,
+ * bao.c:100-147, wmap.c:966-1019) followed by set_base_parameters (param.c:1544-1661) for data
+ * set idata.  dout[n*16 ..] = Omega_m Omega_de w0_de w1_de h_100 Omega_b Omega_nu_mass
+ * Neff_nu_mass de_param Theta2[0..3] stretch color 0; derr[n] != 0 where the reference raises
+ * tls_cosmo_par / ce_infnan (derr may be NULL). */
+int pmcb200_map_params(pmcb200_ctx *ctx, int idata, int64_t N, const double *dX,
+                       double *dout, int32_t *derr);
 /* generic_get_importance_weight_and_deduced_verb, cosmo_pmc.c:343-345:
  * log w = beta*log pi - log q for flagged samples; clears flg on error or
  * non-finite weight; tracks max log w and nok on the device. */

@@ -53,6 +53,7 @@ def lib():
             "orc_posterior_log_pdf": (_d, [C.POINTER(A.Target), _vp, _pi]),
             "orc_posterior_log_pdf_batch": (None, [C.POINTER(A.Target), _i64, _vp, _vp, _vp, _i]),
             "orc_sn_mean_stages": (_d, [C.POINTER(A.Like), _vp]),
+            "orc_map_params": (_i, [C.POINTER(A.Like), _vp, _vp]),
             "orc_importance_weights": (_i64, [C.POINTER(A.Target), _i64, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _vp, _vp, _pd, _i]),
             "orc_normalize_weights": (_d, [_i64, _vp, _vp, _d, _pd]),
             "orc_perplexity_and_ess": (_d, [_i64, _vp, _vp, _pd]),
@@ -126,6 +127,18 @@ def posterior_log_pdf(spec, X, nthreads=0):
     out = np.empty(N)
     err = np.zeros(N, dtype=np.int32)
     lib().orc_posterior_log_pdf_batch(C.byref(spec.t), N, _p(X), _p(out), _p(err), nthreads)
+    return out, err
+
+
+def map_params(spec, idata, X):
+    """mapped model of data set idata for every row of X: (N, 16) array + error flags"""
+    X = f64(X)
+    out = np.zeros((X.shape[0], 16))
+    err = np.zeros(X.shape[0], dtype=np.int32)
+    for n in range(X.shape[0]):
+        row = np.zeros(16)
+        err[n] = lib().orc_map_params(C.byref(spec.t.like[idata]), _p(np.ascontiguousarray(X[n])), _p(row))
+        out[n] = row
     return out, err
 
 

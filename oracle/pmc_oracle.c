@@ -662,6 +662,20 @@ double orc_loglike(const pmcb200_like_t *L, const double *x, int *err)
    }
 }
 
+/* the mapped model of one probe, for the bit-level comparison with the reference's own
+ * switch + set_base_parameters (oracle/_ref/libref_param.so):
+ * out = Omega_m Omega_de w0 w1 h_100 Omega_b Omega_nu_mass Neff_nu_mass de_param Theta2[4] stretch color */
+int orc_map_params(const pmcb200_like_t *L, const double *x, double out[16])
+{
+   model_t m;
+   int e = apply_params(L, x, &m);
+   out[0] = m.c.Omega_m; out[1] = m.c.Omega_de; out[2] = m.c.w0_de; out[3] = m.c.w1_de; out[4] = m.c.h_100;
+   out[5] = m.c.Omega_b; out[6] = m.c.Omega_nu_mass; out[7] = m.c.Neff_nu_mass; out[8] = (double)m.c.de_param;
+   for (int i = 0; i < 4; i++) out[9 + i] = m.Theta2[i];
+   out[13] = m.stretch; out[14] = m.color; out[15] = 0.0;
+   return e;
+}
+
 double orc_sn_mean_stages(const pmcb200_like_t *L, const double *x)
 {
    model_t m; int err = 0; double ms = 0.0;

@@ -64,6 +64,7 @@ void   orc_posterior_log_pdf_batch(const pmcb200_target_t *t, int64_t N,
                                    const double *X, double *out, int32_t *err,
                                    int nthreads);
 double orc_sn_mean_stages(const pmcb200_like_t *L, const double *x);
+int    orc_map_params(const pmcb200_like_t *L, const double *x, double out[16]);
 /* ---- weights (pmclib pmc.c; call sites cosmo_pmc.c:343,378,46,62,84) ------ */
 int64_t orc_importance_weights(const pmcb200_target_t *t, int64_t N,
                      const double *X, int K, int d, int df, const double *wght,
