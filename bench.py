@@ -328,6 +328,7 @@ def main():
                         "h2d_bytes_per_step": int(w_pin.numel() + m_pin.numel() + ch_pin.numel()) * 8,
                         "d2h_bytes_per_step": int(n_loc * (8 * d + 4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d)))},
                 "gpu_launches": launches, "clocks": clocks,
+                "counters_timed_region": cnt,
                 "stats": {k: st[k] for k in ("perplexity", "ess", "nok", "enc", "ndead")} if st else None}
         if roof:
             line["roofline"] = roof

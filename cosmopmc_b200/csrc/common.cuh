@@ -58,7 +58,8 @@ struct DevScal {
 struct DevCount {
   unsigned long long sn_evals;  // SN integrand evaluations
   unsigned long long sn_zsteps; // (sample, redshift) pairs integrated
-  unsigned long long pad[2];
+  unsigned long long gen_evals;      // integrand evaluations of the BAO / CMB kernels (on-the-fly nodes)
+  unsigned long long gen_integrals;  // their integrals
 };
 
 __device__ __forceinline__ unsigned long long dkey(double x) {

@@ -351,6 +351,168 @@ __device__ inline double gauss_comp_logpdf(const double *__restrict__ comp, int 
   return fma(-0.5, m, comp[1]);
 }
 
+// ---- lean integrand of the BAO / CMB integrals (k_like_bao, k_like_cmbdp) ------------------------------
+// These integrals have sample-dependent limits (a_star, a_drag, a(z_BAO)), so their Romberg nodes cannot
+// be tabulated the way the SN kernel's are: every node needs ln a.  The comoving distance to a_star alone
+// takes 11 stages = 1025 evaluations per sample (oracle stage histogram), so the
+// per-evaluation instruction count IS the kernel.  Per interior node (a > 0):
+//   ln a   1024-entry {1/c_i, -ln(1/c_i)} table on the top ten mantissa bits, r = m/c_i - 1 (|r| < 2^-11),
+//          degree-4 log1p (truncation r^5/5 < 6e-18): 6 FP64 + 1 I2F (the 32-entry version: 12)
+//   2^s    the SN kernel's pre-biased 1024-entry table + degree-3 polynomial: 6 FP64 + 1 IMAD (was 9 + LDS)
+//   no per-node range / sign tests: the bound on |s| over the whole interval is checked once per sample,
+//   and a non-positive radicand turns into NaN through MUFU.RSQ64H and reaches the Romberg result
+#define LOG1K_N 1024
+__device__ double2 g_log1k[LOG1K_N];       // filled by pmc_init_sn_tables()
+__constant__ double LOG1KP[4] = {-0.25, 1.0 / 3.0, -0.5, 0.693147180559945309417};
+struct GLean {
+  double Om, OK, Or, p2, q2, lg, lgq;      // lg = log2|Ode|, lgq = lg + q2 (linder: s = p2 ln a - q2 a + lgq)
+  unsigned sgn;
+  int jassal, ok;
+};
+__device__ __forceinline__ GLean make_glean(const ECoefF &f) {
+  GLean g;
+  g.Om = f.e.Om; g.OK = f.e.OK; g.Or = f.e.Or; g.p2 = f.p2; g.q2 = f.q2; g.lg = f.lg; g.lgq = f.lg + f.q2;
+  g.sgn = f.sgn; g.jassal = f.e.jassal; g.ok = f.ok;
+  return g;
+}
+// fast path valid for every node a >= amin of the interval: |s| stays inside the table-based exp2's range
+__device__ __forceinline__ bool glean_in_range(const GLean &g, double amin) {
+  return g.ok && g.sgn == 0u && (fabs(g.p2) * fabs(log(amin)) + 2.0 * fabs(g.q2) + fabs(g.lg) < 990.0);
+}
+__device__ __forceinline__ double lean_log(double x, const double2 *__restrict__ LT) {
+  const int hi = __double2hiint(x);
+  const double2 tc = LT[(hi >> 10) & (LOG1K_N - 1)];
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double r = fma(m, tc.x, -1.0);
+  double q = fma(LOG1KP[0], r, LOG1KP[1]);
+  q = fma(q, r, LOG1KP[2]);
+  q = fma(q, r, 1.0);
+  const double e = (double)((hi >> 20) - 1023);
+  return fma(e, LOG1KP[3], fma(q, r, tc.y));
+}
+// a^4 E^2(a) at an interior node; ET = the pre-biased 2^(j/1024) table (g_sn_exp2)
+template <bool HASQ>
+__device__ __forceinline__ double a4E2_lean(const GLean &g, const double2 *__restrict__ LT, const double *__restrict__ ET,
+                                            double a) {
+  const double lna = lean_log(a, LT);
+  double s;
+  if (HASQ) {
+    if (g.jassal) { const double oma = 1.0 - a; s = fma(g.q2 * oma, oma, fma(g.p2, lna, g.lg)); }
+    else s = fma(g.p2, lna, fma(-g.q2, a, g.lgq));
+  } else s = fma(g.p2, lna, g.lg);
+  const double kf = s + EXP2D3[3];
+  const int k32 = __double2loint(kf);
+  const double f = s - (kf - EXP2D3[3]);
+  double p = EXP2D3[2];
+  p = fma(p, f, EXP2D3[1]);
+  p = fma(p, f, EXP2D3[0]);
+  p = fma(p, f, 1.0);
+  const double tj = ET[k32 & (SN_EXP2_N - 1)];
+  const int hi = __double2hiint(tj) + k32 * SN_EXP2_N;      // Ode > 0 on this path (glean_in_range)
+  return fma(__hiloint2double(hi, __double2loint(tj)), p, fma(a, fma(g.OK, a, g.Om), g.Or));
+}
+// acc + 1/sqrt(v): MUFU.RSQ64H seed + third-order correction (as sn_f); v <= 0 gives NaN
+__device__ __forceinline__ double rsqrt_acc(double v, double acc) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+  const double t = v * y;
+  const double er = fma(-t, y, 1.0);
+  const double c = fma(0.375, er, 0.5);
+  const double w = fma(er, c, 1.0);
+  return fma(y, w, acc);
+}
+// NR qromb with the interior nodes of a stage evaluated four at a time into four partial sums
+// (independent chains; the reference sums sequentially: the difference is O(1e-16)).  f(x, acc) returns
+// acc + integrand(x); fa, fb = integrand at the two end points.  nev counts evaluations.
+template <class F>
+__device__ __forceinline__ double romberg4(F f, double fa, double fb, double a, double b, int &err, unsigned &nev) {
+  double y[5];
+  const double h = b - a;
+  double st = 0.5 * h * (fa + fb);
+  y[0] = st;
+  double ss = st, dss;
+  nev += 2;
+  for (int j = 1; j < ROMB_JMAX; j++) {
+    const int it = 1 << (j - 1);
+    const double tnm = (double)it, del = h / tnm;
+    double sum;
+    if (it < 4) {
+      sum = 0.0;
+      for (int i = 0; i < it; i++) sum = f(fma((double)i + 0.5, del, a), sum);
+    } else {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      // x += 4 del per chain, as NR's trapzd steps x += del (one rounding per step either way)
+      double x0 = fma(0.5, del, a), x1 = fma(1.5, del, a), x2 = fma(2.5, del, a), x3 = fma(3.5, del, a);
+      const double d4 = 4.0 * del;
+      for (int i = 0; i < it; i += 4) {
+        s0 = f(x0, s0); s1 = f(x1, s1); s2 = f(x2, s2); s3 = f(x3, s3);
+        x0 += d4; x1 += d4; x2 += d4; x3 += d4;
+      }
+      sum = (s0 + s1) + (s2 + s3);
+    }
+    nev += it;
+    st = 0.5 * (st + h * sum / tnm);
+    if (j < 5) y[j] = st;
+    else { y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4]; y[4] = st; }
+    if (j >= 4) {
+      ss = romb_extrap(y, dss);
+      if (!isfinite(ss)) { err = 1; return ss; }
+      if (fabs(dss) <= ROMB_EPS * fabs(ss)) return ss;
+    }
+  }
+  err = 1;
+  return ss;
+}
+struct LeanTabs { const double *T; const double2 *LT; const double *ET; };
+// comoving distance [Mpc/h], a .. 1
+template <bool HASQ>
+__device__ __forceinline__ double w_lean(const pmcb200_cosmo_t &c, double a, int wOmegar, int &err, const LeanTabs &tb,
+                                         unsigned &nev) {
+  const ECoefF f = make_ecoef_fast(c, wOmegar);
+  const GLean g = make_glean(f);
+  if (!(a > 0.0) || !glean_in_range(g, a)) return w_generic(c, a, wOmegar, err, tb.T);
+  const double fa = rsqrt_acc(a4E2_fast(f, a, tb.T), 0.0), fb = rsqrt_acc(a4E2_fast(f, 1.0, tb.T), 0.0);
+  const double r = romberg4([&](double x, double acc) { return rsqrt_acc(a4E2_lean<HASQ>(g, tb.LT, tb.ET, x), acc); },
+                            fa, fb, a, 1.0, err, nev);
+  return R_HUBBLE * r;
+}
+// comoving sound horizon [Mpc/h], 0 .. a (radiation included)
+template <bool HASQ>
+__device__ __forceinline__ double r_sound_lean(const pmcb200_cosmo_t &c, double a, int &err, const LeanTabs &tb,
+                                               unsigned &nev) {
+  const ECoefF f = make_ecoef_fast(c, 1);
+  const GLean g = make_glean(f);
+  // smallest interior node of a stage <= 12 (deeper stages, never seen, restart on the general path)
+  if (!(a > 0.0) || !glean_in_range(g, a * (1.0 / 8192.0))) return r_sound(c, a, err, tb.T);
+  const double Rfac = 0.75 * c.Omega_b * c.h_100 * c.h_100 / OMEGA_GAMMA_H2, R3 = 3.0 * Rfac;
+  const double fa = rsqrt_acc(f.e.Or * 3.0, 0.0);
+  const double fb = rsqrt_acc(a4E2_fast(f, a, tb.T) * fma(R3, a, 3.0), 0.0);
+  int e2 = 0;
+  unsigned n2 = 0;
+  const double r = romberg4([&](double x, double acc) {
+    return rsqrt_acc(a4E2_lean<HASQ>(g, tb.LT, tb.ET, x) * fma(R3, x, 3.0), acc); }, fa, fb, 0.0, a, e2, n2);
+  if (n2 > 2u + 4096u) return r_sound(c, a, err, tb.T);     // beyond stage 12: the range check no longer covers the nodes
+  nev += n2;
+  if (e2) err = 1;
+  return R_HUBBLE * r;
+}
+template <bool HASQ>
+__device__ __forceinline__ double D_V_lean(const pmcb200_cosmo_t &c, double z, int &err, const LeanTabs &tb, unsigned &nev) {
+  const double a = 1.0 / (1.0 + z);
+  const double ww = w_lean<HASQ>(c, a, 0, err, tb, nev);
+  const double fK = f_K(c, ww);
+  const ECoefF f = make_ecoef_fast(c, 0);
+  const double a2 = a * a;
+  const double EE = a4E2_fast(f, a, tb.T) / (a2 * a2);
+  if (!(EE > 0.0)) { err = 1; return NAN; }
+  return cbrt(fK * fK * R_HUBBLE * z / sqrt(EE));
+}
+// stage the three tables: T[96] (general path), LT[1024] (log), ET[1024] (exp2); blockDim.x >= 96
+__device__ __forceinline__ void load_lean_tables(double *T, double2 *LT, double *ET) {
+  for (int i = threadIdx.x; i < LOG1K_N; i += blockDim.x) { LT[i] = g_log1k[i]; ET[i] = g_sn_exp2[i]; }
+  load_fast_tables(T);
+}
+
 // write/accumulate one likelihood term
 __device__ __forceinline__ void put_loglike(double *logpi, int32_t *err, int64_t n, int set,
                                             double add_const, double res, int e) {
@@ -650,11 +812,109 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   }
 }
 
-// ---- BAO / CMB distance priors / analytic targets: one sample per thread -----
+// ---- BAO / CMB distance priors: one sample per thread, lean integrand (HASQ: w1 != 0 or jassal possible) -----
+// cnt->gen_evals / gen_integrals: integrand evaluations and integrals of these two kernels (measurement)
+__device__ __forceinline__ void count_gen(DevCount *cnt, unsigned nev, unsigned nint) {
+  if (!cnt) return;
+  unsigned long long tot = nev, ni = nint;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, o); ni += __shfl_xor_sync(0xffffffffu, ni, o); }
+  if ((threadIdx.x & 31) == 0 && ni) { atomicAdd(&cnt->gen_evals, tot); atomicAdd(&cnt->gen_integrals, ni); }
+}
+template <bool HASQ>
 __global__ void __launch_bounds__(PMC_BLOCK)
 k_like_bao(const DevLike L, int64_t N, const double *__restrict__ X, int d,
            const int16_t *__restrict__ flg, double *__restrict__ logpi,
-           int32_t *__restrict__ err, int set, double add_const) {
+           int32_t *__restrict__ err, int set, double add_const, DevCount *cnt) {
+  __shared__ double T[96];
+  __shared__ double2 LT[LOG1K_N];
+  __shared__ double ET[SN_EXP2_N];
+  load_lean_tables(T, LT, ET);
+  const LeanTabs tb{T, LT, ET};
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned nev = 0, nint = 0;
+  if (n < N && flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } }
+  else if (n < N) {
+    Model m;
+    int e = apply_params(L, X + n * d, m);
+    double res = 0.0;
+    if (!e && !(L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c))) {
+      double model[4];
+      const int nd = L.g_ndim;
+      const pmcb200_cosmo_t &c = m.c;
+      if (L.bao_method == PMCB200_BAO_distance_A) {
+        if (!(c.Omega_m > 0.0)) e = 1;
+        else for (int i = 0; i < nd; i++) {
+          model[i] = D_V_lean<HASQ>(c, L.g_z[i], e, tb, nev) * sqrt(c.Omega_m) / (L.g_z[i] * R_HUBBLE);
+          nint++;
+        }
+      } else if (L.bao_method == PMCB200_BAO_distance_d_z) {
+        if (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0)) e = 1;
+        else {
+          const double rs = r_sound_lean<HASQ>(c, 1.0 / (1.0 + z_drag(c)), e, tb, nev);
+          nint++;
+          for (int i = 0; i < nd; i++) { model[i] = rs / D_V_lean<HASQ>(c, L.g_z[i], e, tb, nev); nint++; }
+        }
+      } else {
+        for (int i = 0; i < nd; i++) {
+          model[i] = D_V_lean<HASQ>(c, L.g_z[2 * i], e, tb, nev) / D_V_lean<HASQ>(c, L.g_z[2 * i + 1], e, tb, nev);
+          nint += 2;
+        }
+      }
+      if (!e) res = gauss_comp_logpdf(L.g_comp, nd, model);
+      if (!isfinite(res)) e = 1;
+    }
+    put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  }
+  count_gen(cnt, nev, nint);
+}
+
+template <bool HASQ>
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+             const int16_t *__restrict__ flg, double *__restrict__ logpi,
+             int32_t *__restrict__ err, int set, double add_const, DevCount *cnt) {
+  __shared__ double T[96];
+  __shared__ double2 LT[LOG1K_N];
+  __shared__ double ET[SN_EXP2_N];
+  load_lean_tables(T, LT, ET);
+  const LeanTabs tb{T, LT, ET};
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned nev = 0, nint = 0;
+  if (n < N && flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } }
+  else if (n < N) {
+    Model m;
+    int e = apply_params(L, X + n * d, m);
+    double res = 0.0;
+    const pmcb200_cosmo_t &c = m.c;
+    const bool cut = !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(c);
+    if (cut) e = 1;      // wmap.c:1041-1044: wmap_de_prior error, the point gets zero weight
+    if (!e && (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0))) e = 1;
+    if (!e) {
+      double model[4];
+      const double zs = z_star(c), as = 1.0 / (1.0 + zs);
+      const double ww = w_lean<HASQ>(c, as, 1, e, tb, nev);
+      const double fK = f_K(c, ww);
+      const double rs = r_sound_lean<HASQ>(c, as, e, tb, nev);
+      nint += 2;
+      model[0] = M_PI * fK / rs;
+      model[1] = sqrt(c.Omega_m) * fK / R_HUBBLE;
+      model[2] = zs;
+      model[3] = 100.0 * c.Omega_b * c.h_100 * c.h_100;
+      if (!e) res = gauss_comp_logpdf(L.g_comp, L.g_ndim, model);
+      if (!isfinite(res)) e = 1;
+    }
+    put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  }
+  count_gen(cnt, nev, nint);
+}
+
+// round-1 versions (general integrand with per-node checks, sequential sums): kept for A/B measurements
+// (PMCB200_LIKE_V1=1) and as the cross-check of the lean path in the parity suite
+__global__ void __launch_bounds__(PMC_BLOCK)
+k_like_bao_v1(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+              const int16_t *__restrict__ flg, double *__restrict__ logpi,
+              int32_t *__restrict__ err, int set, double add_const) {
   __shared__ double T[96];
   load_fast_tables(T);
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -687,9 +947,9 @@ k_like_bao(const DevLike L, int64_t N, const double *__restrict__ X, int d,
 }
 
 __global__ void __launch_bounds__(PMC_BLOCK)
-k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
-             const int16_t *__restrict__ flg, double *__restrict__ logpi,
-             int32_t *__restrict__ err, int set, double add_const) {
+k_like_cmbdp_v1(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+                const int16_t *__restrict__ flg, double *__restrict__ logpi,
+                int32_t *__restrict__ err, int set, double add_const) {
   __shared__ double T[96];
   load_fast_tables(T);
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -700,7 +960,7 @@ k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   double res = 0.0;
   const pmcb200_cosmo_t &c = m.c;
   const bool cut = !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(c);
-  if (cut) e = 1;      // wmap.c:1041-1044: wmap_de_prior error, the point gets zero weight
+  if (cut) e = 1;
   if (!e && (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0))) e = 1;
   if (!e) {
     double model[4];

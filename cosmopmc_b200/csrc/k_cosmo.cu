@@ -21,6 +21,15 @@ int pmc_init_sn_tables() {
     }
     have = true;
   }
+  // lean_log's table: c_i = 1 + (i + 1/2)/1024, {rc = double(1/c_i), -ln(rc)} (of the ROUNDED reciprocal)
+  static double ltab[2 * LOG1K_N];
+  if (ltab[0] == 0.0)
+    for (int i = 0; i < LOG1K_N; i++) {
+      const double rc = (double)(1.0L / (1.0L + ((long double)i + 0.5L) / LOG1K_N));
+      ltab[2 * i] = rc;
+      ltab[2 * i + 1] = (double)(-logl((long double)rc));
+    }
+  if (cudaMemcpyToSymbol(g_log1k, ltab, sizeof(ltab)) != cudaSuccess) return 1;
   return cudaMemcpyToSymbol(g_sn_exp2, tab, sizeof(tab)) == cudaSuccess ? 0 : 1;
 }
 
@@ -33,6 +42,9 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
   // PMCB200_SN_FORCE_SLOW=1 routes every warp through libdevice exp (used by the
   // tests to validate the fast path against it)
   static const int force_slow = getenv("PMCB200_SN_FORCE_SLOW") ? atoi(getenv("PMCB200_SN_FORCE_SLOW")) : 0;
+  // PMCB200_LIKE_V1=1: round-1 BAO / CMB kernels (A/B measurements, cross-check of the lean integrand); read per call
+  const char *ev1 = getenv("PMCB200_LIKE_V1");
+  const int like_v1 = ev1 && *ev1 && *ev1 != '0';
   switch (L.kind) {
     case PMCB200_LIKE_SNIa:
       if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
@@ -41,10 +53,14 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
       else k_like_sn<false, false><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
       break;
     case PMCB200_LIKE_BAO:
-      k_like_bao<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
+      if (like_v1) k_like_bao_v1<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
+      else if (L.sn_hasq) k_like_bao<true><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt);
+      else k_like_bao<false><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt);
       break;
     case PMCB200_LIKE_CMBDistPrior:
-      k_like_cmbdp<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
+      if (like_v1) k_like_cmbdp_v1<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
+      else if (L.sn_hasq) k_like_cmbdp<true><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt);
+      else k_like_cmbdp<false><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt);
       break;
     case PMCB200_LIKE_BANANA:
       k_like_banana<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);

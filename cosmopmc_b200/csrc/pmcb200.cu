@@ -527,6 +527,11 @@ extern "C" int pmcb200_set_target(pmcb200_ctx *c, const pmcb200_target_t *t) {
     D.kind = L.kind; D.npar = L.npar; D.special = L.special; D.model = L.model;
     if (L.npar != d) return fail(c, PMCB200_ERR_DIM, "like %d: npar %d != %d", i, L.npar, d);
     for (int j = 0; j < d; j++) D.par[j] = L.par[j];
+    {   // launch-uniform specialisation: the second exponent term exists only if w1 can be non-zero
+      bool has_w1 = L.model.w1_de != 0.0 || L.model.de_param == PMCB200_DE_jassal;
+      for (int j = 0; j < L.npar; j++) if (L.par[j] == PMCB200_P_w1de) has_w1 = true;
+      D.sn_hasq = has_w1 ? 1 : 0;
+    }
     switch (L.kind) {
       case PMCB200_LIKE_SNIa:
         if ((rc = build_sn(c, L, D))) return rc;
@@ -1268,7 +1273,7 @@ extern "C" int pmcb200_counters(pmcb200_ctx *c, int64_t out[4]) {
   CUDA_OK(c, cudaMemcpyAsync(&h, c->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCount), c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  out[0] = (int64_t)h.sn_evals; out[1] = (int64_t)h.sn_zsteps; out[2] = 0; out[3] = 0;
+  out[0] = (int64_t)h.sn_evals; out[1] = (int64_t)h.sn_zsteps; out[2] = (int64_t)h.gen_evals; out[3] = (int64_t)h.gen_integrals;
   return 0;
 }
 

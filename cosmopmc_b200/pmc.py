@@ -221,7 +221,7 @@ class PMC:
     def counters(self):
         out = (C.c_int64 * 4)()
         self._ck(self.lib.pmcb200_counters(self.h, C.byref(out)))
-        return dict(sn_evals=int(out[0]), sn_zsteps=int(out[1]))
+        return dict(sn_evals=int(out[0]), sn_zsteps=int(out[1]), gen_evals=int(out[2]), gen_integrals=int(out[3]))
 
     def fp64_peak_tflops(self):
         v = C.c_double()

@@ -379,7 +379,8 @@ int64_t pmcb200_launch_count(const pmcb200_ctx *ctx);
 /* measurement helpers (not part of the reference's API):
  * counters[0] = SN integrand evaluations summed over all posterior launches
  * since the last call (resets on read), counters[1] = samples x redshifts
- * walked by the SN kernel; fp64_peak runs a DFMA-only kernel and returns the
+ * walked by the SN kernel, counters[2] / [3] = integrand evaluations / integrals of
+ * the BAO and CMB kernels; fp64_peak runs a DFMA-only kernel and returns the
  * measured vector-FP64 peak in TFLOP/s (the roofline denominator that
  * MEASURED_PEAKS.json does not carry). */
 int pmcb200_counters(pmcb200_ctx *ctx, int64_t out[4]);

@@ -519,14 +519,17 @@ static double int_for_r_sound(double a, void *p)
    return 1.0 / sqrt(dd);
 }
 
-static double r_sound(const pmcb200_cosmo_t *c, double a, int *err)
+double orc_r_sound(const pmcb200_cosmo_t *c, double a, int *nstage, int *err)
 {  /* comoving sound horizon [Mpc/h] at scale factor a */
    rsint_t q = {c, 0};
    int e = 0;
-   double r = orc_qromberg(int_for_r_sound, &q, 0.0, a, ORC_ROMB_EPS, NULL, &e);
+   double r = orc_qromberg(int_for_r_sound, &q, 0.0, a, ORC_ROMB_EPS, nstage, &e);
    if (e || q.bad) *err = 1;
    return ORC_R_HUBBLE * r;
 }
+static double r_sound(const pmcb200_cosmo_t *c, double a, int *err) { return orc_r_sound(c, a, NULL, err); }
+double orc_z_star(const pmcb200_cosmo_t *c);
+double orc_z_drag(const pmcb200_cosmo_t *c);
 
 static double z_drag(const pmcb200_cosmo_t *c)
 {
@@ -543,6 +546,9 @@ static double z_star(const pmcb200_cosmo_t *c)
    double g2 = 0.560 / (1.0 + 21.1 * pow(omb, 1.81));
    return 1048.0 * (1.0 + 0.00124 * pow(omb, -0.738)) * (1.0 + g1 * pow(omm, g2));
 }
+
+double orc_z_star(const pmcb200_cosmo_t *c) { return z_star(c); }
+double orc_z_drag(const pmcb200_cosmo_t *c) { return z_drag(c); }
 
 static double D_V(const pmcb200_cosmo_t *c, double z, int *err)
 {  /* [f_K^2(w) c z / H(z)]^(1/3), Mpc/h */

@@ -58,6 +58,9 @@ double orc_Esqr(const pmcb200_cosmo_t *c, double a, int wOmegar);
 double orc_w(const pmcb200_cosmo_t *c, double a, int wOmegar, int *nstage, int *err);
 double orc_f_K(const pmcb200_cosmo_t *c, double w, int wOmegar);
 double orc_D_lum(const pmcb200_cosmo_t *c, double a, int *err);
+double orc_r_sound(const pmcb200_cosmo_t *c, double a, int *nstage, int *err);
+double orc_z_star(const pmcb200_cosmo_t *c);
+double orc_z_drag(const pmcb200_cosmo_t *c);
 double orc_loglike(const pmcb200_like_t *L, const double *x, int *err);
 double orc_posterior_log_pdf(const pmcb200_target_t *t, const double *x, int *err);
 void   orc_posterior_log_pdf_batch(const pmcb200_target_t *t, int64_t N,

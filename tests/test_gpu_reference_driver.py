@@ -218,3 +218,30 @@ def test_reference_pipeline_wmap_distance_priors(tmp_path):
     m_all = (w[:, None] * X).sum(0) / w.sum()
     assert np.allclose(mean, m_clip, rtol=2e-5), (mean, m_clip, m_all)       # text files carry 9 / 5 digits
     assert np.abs(m_all - m_clip).max() > 0.0
+
+
+SUITE_DIR = os.path.join(A.ROOT, "build_ref", "test_suite")
+
+
+@pytest.mark.parametrize("name", ["SN", "BAO_distance_A", "BAO_distance_d_z", "WMAP_Distance_Priors", "SN+BAO"])
+def test_reference_test_suite_log_posterior_at_fiducial(tmp_path, name):
+    """The reference's own regression recipe (bin/test_suite_cosmo_pmc.pl:51-58,321-367,431-452): `max_post -m n`
+    evaluates the log-posterior at the suite's fiducial point.  The UNCHANGED max_post binary (reference
+    exec/max_post.c + wrappers/ + tools/, linked against this library: the likelihood is one N = 1 launch of the
+    batched CUDA kernels) must print the golden value (tests/golden/test_suite_logpost.json, oracle-made: the
+    reference stores none) to the 6 digits of its `%g` (max_post.c:253)."""
+    import json
+    exe = os.path.join(A.ROOT, "build_ref", "max_post")
+    src = os.path.join(SUITE_DIR, name)
+    if not (os.path.exists(exe) and os.path.isdir(src)):
+        pytest.skip("build_ref/max_post or build_ref/test_suite not built (container only)")
+    gold = json.load(open(os.path.join(A.ROOT, "tests", "golden", "test_suite_logpost.json")))["cases"][name]
+    run = tmp_path / "ts"
+    shutil.copytree(src, run)
+    r = subprocess.run([exe, "-m", "n", "-c", "config_max_test_suite"], cwd=run, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and (run / "maxlogP").exists(), r.stdout[-2000:] + r.stderr[-2000:]
+    tok = open(run / "maxlogP").read().split()
+    val = float(tok[tok.index("=") + 1])
+    p = np.array([float(v) for v in tok[-len(gold["fid"]):]])
+    assert np.allclose(p, gold["fid"], rtol=1e-6)                    # -m n: the point is not moved
+    assert abs(val - gold["logpost"]) <= 6e-6 * abs(gold["logpost"]), (val, gold["logpost"])

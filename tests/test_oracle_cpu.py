@@ -155,6 +155,19 @@ def test_golden_logposterior(oracle):
     assert np.allclose(got, g["logpost"], rtol=1e-13, atol=0)
 
 
+def test_golden_test_suite_fiducials(oracle):
+    """the fiducial points of bin/test_suite_cosmo_pmc.pl:51-58 for SN, BAO (A, d_z), WMAP distance priors and the
+    joint SN + BAO set against the committed goldens (generator: tests/golden/make_test_suite_fixture.py)"""
+    import importlib.util
+    spec_ = importlib.util.spec_from_file_location("mk", os.path.join(HERE, "golden", "make_test_suite_fixture.py"))
+    mk = importlib.util.module_from_spec(spec_); spec_.loader.exec_module(mk)
+    gold = json.load(open(os.path.join(HERE, "golden", "test_suite_logpost.json")))["cases"]
+    for name, (spec, fid) in mk.suite().items():
+        lp, err = oracle.posterior_log_pdf(spec, np.array([fid]))
+        assert err[0] == 0 and fid == gold[name]["fid"]
+        assert abs(lp[0] - gold[name]["logpost"]) <= 1e-12 * abs(gold[name]["logpost"]), name
+
+
 def test_parameter_mapping_rules(oracle):
     """set_base_parameters (param.c:1544-1661): flat closure, physical densities, error cases."""
     spec = T.target_sn_demo()

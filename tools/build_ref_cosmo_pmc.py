@@ -102,6 +102,51 @@ def build():
         with open(os.path.join(dst, "config_max"), "w") as fo:
             subprocess.check_call(["perl", os.path.join(REF, "bin/config_pmc_to_max_and_fish.pl"), "-M", "-f", fid,
                                    "-c", os.path.join(dst, "config_pmc")], stdout=fo)
+    # the reference's own regression recipe, bin/test_suite_cosmo_pmc.pl:51-58,321-367,431-452: `max_post -m n`
+    # (no maximisation: the log-posterior at a fixed fiducial point) for the in-scope demo directories
+    ts = os.path.join(OUT, "test_suite")
+    SUITE = (("SN", "Demo/MC_Demo/SN", ["data/Sn/Union/sne_union_marek.list", "par_files/cosmo_SN.par", "par_files/cosmo.par"],
+              "0.27 -1.0 19.31 1.6 -1.8"),
+             ("BAO_distance_A", "Demo/MC_Demo/BAO/distance_A", ["data/BAO/bao_Reid10_A_0.35", "par_files/cosmoDP.par"], "0.27 0.73"),
+             ("BAO_distance_d_z", "Demo/MC_Demo/BAO/distance_d_z", ["data/BAO/bao_BOSS12_d_z_0.57", "par_files/cosmoDP.par"], "0.27 0.73"),
+             ("WMAP_Distance_Priors", "Demo/MC_Demo/WMAP_Distance_Priors",
+              ["data/WMAP_Distance_Priors/wmap7DistPrior_ML_covinv", "par_files/cosmoDP.par"], "0.045 0.27 0.73 0.71"))
+    for name, cfgdir, files, fid in SUITE:
+        dst = os.path.join(ts, name)
+        os.makedirs(dst, exist_ok=True)
+        shutil.copy(os.path.join(REF, cfgdir, "config_pmc"), dst)
+        for f in files:
+            shutil.copy(os.path.join(REF, f), dst)
+        with open(os.path.join(dst, "config_max_test_suite"), "w") as fo:
+            subprocess.check_call(["perl", os.path.join(REF, "bin/config_pmc_to_max_and_fish.pl"), "-M", "-f", fid,
+                                   "-c", os.path.join(dst, "config_pmc")], stdout=fo)
+    # the joint set of the test suite (COSMOS-S10+SN+BAO, fid :56) without its out-of-scope lensing probe:
+    # the SN and BAO sections of that config file, the lensing-only parameters (sigma_8, z_rescale) dropped
+    dst = os.path.join(ts, "SN+BAO")
+    os.makedirs(dst, exist_ok=True)
+    for f in ["data/Sn/Union/sne_union_marek.list", "par_files/cosmo_SN.par", "par_files/cosmo.par",
+              "data/BAO/bao_Reid10_A_0.35", "par_files/cosmoDP.par"]:
+        shutil.copy(os.path.join(REF, f), dst)
+    src = open(os.path.join(REF, "Demo/MC_Demo/COSMOS-S10+SN+BAO/config_pmc")).read().split("\n")
+    keep, skip = [], False
+    for line in src:
+        t = line.split()
+        if t[:1] == ["#"] and t[1:2] == ["Lensing"]:
+            skip = True
+        elif t[:1] == ["#"] and t[1:2] == ["BAO"]:
+            skip = False
+        if skip or t[:2] == ["sdata", "Lensing"]:
+            continue
+        if t[:1] == ["npar"]: line = "npar            6"
+        if t[:1] == ["spar"]: line = "spar            Omega_m w_0_de h_100 M     alpha  beta"
+        if t[:1] == ["min"]: line = "min             0.0   -3.5     0.4   19.1  0.5   -3.5"
+        if t[:1] == ["max"]: line = "max             1.2    0.5     1.0   19.8  2.6   -0.8"
+        if t[:1] == ["ndata"]: line = "ndata           2"
+        keep.append(line)
+    open(os.path.join(dst, "config_pmc"), "w").write("\n".join(keep))
+    with open(os.path.join(dst, "config_max_test_suite"), "w") as fo:
+        subprocess.check_call(["perl", os.path.join(REF, "bin/config_pmc_to_max_and_fish.pl"), "-M", "-f",
+                               "0.27 -1.0 0.7 19.31 1.6 -1.8", "-c", os.path.join(dst, "config_pmc")], stdout=fo)
     # the tempering demos (Demo/tempering/README.md: evidence known answers)
     for sub in ["1_mvnorm_2D_temp_none", "2_mixmvnorm_2D_temp_none"]:
         dst = os.path.join(OUT, "demo_" + sub)
