@@ -354,7 +354,7 @@ __device__ inline double gauss_comp_logpdf(const double *__restrict__ comp, int 
 // ---- lean integrand of the BAO / CMB integrals (k_like_bao, k_like_cmbdp) ------------------------------
 // These integrals have sample-dependent limits (a_star, a_drag, a(z_BAO)), so their Romberg nodes cannot
 // be tabulated the way the SN kernel's are: every node needs ln a.  The comoving distance to a_star alone
-// takes 11 stages = 1025 evaluations per sample (oracle stage histogram), so the
+// takes 11 stages = 1025 evaluations per sample (measured stage histogram), so the
 // per-evaluation instruction count IS the kernel.  Per interior node (a > 0):
 //   ln a   1024-entry {1/c_i, -ln(1/c_i)} table on the top ten mantissa bits, r = m/c_i - 1 (|r| < 2^-11),
 //          degree-4 log1p (truncation r^5/5 < 6e-18): 6 FP64 + 1 I2F (the 32-entry version: 12)
