@@ -78,11 +78,11 @@ void pmc_launch_normalize(int64_t N, const int16_t *flg, double *w, double M, do
 }
 void pmc_launch_em_reduce(const double *partials, int nblocks, int64_t len, const DevScal *scal, int64_t N_local,
                           double *block, cudaStream_t s) {
-  k_em_reduce<<<1, PMC_BLOCK, 0, s>>>(partials, nblocks, len, scal, N_local, block);
+  k_em_reduce<<<(int)((len + PMC_BLOCK - 1) / PMC_BLOCK), PMC_BLOCK, 0, s>>>(partials, nblocks, len, scal, N_local, block);
 }
 void pmc_launch_em_finish(const double *mix, MixHdr h, int nranks, const double *all, int64_t N_global,
-                          double *work, double *result, cudaStream_t s) {
-  k_em_finish<<<1, 64, 0, s>>>(mix, h, nranks, all, N_global, work, result);
+                          double *work, double *result, unsigned *done_cnt, cudaStream_t s) {
+  k_em_finish<<<h.K, 32, 0, s>>>(mix, h, nranks, all, N_global, work, result, done_cnt);
 }
 void pmc_launch_fp64_peak(double *out, const double *in, int blocks, int iters, cudaStream_t s) {
   k_fp64_peak<<<blocks, 256, 0, s>>>(out, in, iters);

@@ -50,7 +50,7 @@ void pmc_launch_normalize(int64_t N, const int16_t *flg, double *w, double M, do
 void pmc_launch_em_reduce(const double *partials, int nblocks, int64_t len, const DevScal *scal, int64_t N_local,
                           double *block, cudaStream_t s);
 void pmc_launch_em_finish(const double *mix, MixHdr h, int nranks, const double *all, int64_t N_global,
-                          double *work, double *result, cudaStream_t s);
+                          double *work, double *result, unsigned *done_cnt, cudaStream_t s);
 int pmc_init_sn_tables();   // per device, at context creation
 void pmc_launch_fp64_peak(double *out, const double *in, int blocks, int iters, cudaStream_t s);
 void pmc_launch_wstat(int64_t N, const int16_t *flg, const double *w, int is_log, int blocks, double *maxpart,

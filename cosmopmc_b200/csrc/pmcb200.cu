@@ -49,6 +49,7 @@ struct pmcb200_ctx {
   // per-iteration device state
   DevScal *d_scal = nullptr;
   DevCount *d_cnt = nullptr;
+  unsigned *d_fin_cnt = nullptr;          // blocks of k_em_finish that are done (self-resetting)
   double *d_partials = nullptr; size_t partials_cap = 0;
   double *d_work = nullptr, *d_result = nullptr; size_t work_cap = 0;
   double *h_result = nullptr;             // pinned
@@ -221,6 +222,8 @@ static int create_impl(pmcb200_ctx *c, int device, void *stream) {
   if (pmc_init_sn_tables()) return fail(c, PMCB200_ERR_CUDA, "SN table upload failed");
   CUDA_OK(c, cudaMalloc((void **)&c->d_cnt, sizeof(DevCount)));
   CUDA_OK(c, cudaMemset(c->d_cnt, 0, sizeof(DevCount)));
+  CUDA_OK(c, cudaMalloc((void **)&c->d_fin_cnt, sizeof(unsigned)));
+  CUDA_OK(c, cudaMemset(c->d_fin_cnt, 0, sizeof(unsigned)));
   CUDA_OK(c, cudaMallocHost((void **)&c->h_result, sizeof(double) * (RES_HDR + PMCB200_MAX_COMP * (1 + PMCB200_MAX_DIM + PMCB200_MAX_DIM * PMCB200_MAX_DIM))));
   return 0;
 }
@@ -257,6 +260,7 @@ extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
   if (c->d_mix) cudaFree(c->d_mix);
   if (c->d_scal) cudaFree(c->d_scal);
   if (c->d_cnt) cudaFree(c->d_cnt);
+  if (c->d_fin_cnt) cudaFree(c->d_fin_cnt);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_work) cudaFree(c->d_work);
   if (c->d_result) cudaFree(c->d_result);
@@ -856,7 +860,7 @@ extern "C" int pmcb200_em_finish(pmcb200_ctx *c, int nranks, const double *dall,
   if (rc) return rc;
   if (nranks < 1 || nranks > 64 || !dall || N_global < 1) return fail(c, PMCB200_ERR_ARG, "em_finish: bad arguments");
   const int K = c->h.K, d = c->h.d;
-  pmc_launch_em_finish(c->d_mix, c->h, nranks, dall, N_global, c->d_work, c->d_result, c->stream);
+  pmc_launch_em_finish(c->d_mix, c->h, nranks, dall, N_global, c->d_work, c->d_result, c->d_fin_cnt, c->stream);
   LAUNCH_OK(c);
   size_t rlen = RES_HDR + (size_t)K * (1 + d + (size_t)d * d);
   CUDA_OK(c, cudaMemcpyAsync(c->h_result, c->d_result, rlen * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

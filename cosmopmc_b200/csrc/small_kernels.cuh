@@ -11,129 +11,149 @@ k_normalize(int64_t N, const int16_t *__restrict__ flg, double *__restrict__ w, 
   w[n] = flg[n] ? exp(w[n] - M) * invS : 0.0;
 }
 
-// fixed-order sum of the block partials -> this rank's stat block
+// fixed-order sum of the block partials -> this rank's stat block.  One thread per entry of the block, every
+// thread sums its entry over the blocks in ascending order (the order the one-block version of round 1 used:
+// identical results), with eight loads in flight; adjacent threads read adjacent addresses.
 __global__ void __launch_bounds__(PMC_BLOCK)
 k_em_reduce(const double *__restrict__ partials, int nblocks, int64_t len,
             const DevScal *__restrict__ scal, int64_t N_local, double *__restrict__ block) {
-  for (int64_t o = threadIdx.x; o < len; o += blockDim.x) {
-    double s = 0.0;
-    if (o >= 1 && o != 5 && o != 6 && o != 7)
-      for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * len + o];
-    if (o == 0) s = partials[0];          // the shift every block used
-    if (o == 5) s = (double)scal->nok_box;
-    if (o == 6) s = (double)N_local;
-    block[o] = s;
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= len) return;
+  double s = 0.0;
+  if (o >= 1 && o != 5 && o != 6 && o != 7) {
+    const double *p = partials + o;
+    int b = 0;
+    for (; b + 8 <= nblocks; b += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = p[(size_t)(b + u) * len];
+#pragma unroll
+      for (int u = 0; u < 8; u++) s += v[u];
+    }
+    for (; b < nblocks; b++) s += p[(size_t)b * len];
   }
+  if (o == 0) s = partials[0];          // the shift every block used
+  if (o == 5) s = (double)scal->nok_box;
+  if (o == 6) s = (double)N_local;
+  block[o] = s;
 }
 
 // ---- M-step: combine the rank blocks in rank order, update alpha/mu/Sigma,
 // dead-component rule (manual.tex:482-490), Cholesky, diagnostics ---------------
 // result layout (doubles): [0..16) stats, then wght[K], mean[K*d], chol[K*d*d]
-__global__ void __launch_bounds__(64)
+// One block (one warp) per component: lanes over the entries of the component's statistics for the
+// combine, over the rows of the covariance for the Cholesky (left-looking; row i's inner product runs over
+// q < j in ascending order, as the one-thread version did).  The block that finishes last (device counter)
+// normalises the weights and writes the diagnostics.  Every rank runs this on identical input, so the
+// updated proposal is bitwise identical across ranks.
+// work: [0..K) unnormalised alpha, [K..2K) newly-dead flags (scratch between the blocks)
+__global__ void __launch_bounds__(32)
 k_em_finish(const double *__restrict__ mix, const MixHdr h, int nranks,
-            const double *__restrict__ all, int64_t N_global, double *__restrict__ work,
-            double *__restrict__ result) {
+            const double *__restrict__ all, int64_t N_global, double *work,
+            double *__restrict__ result, unsigned *done_cnt) {
   const int K = h.K, d = h.d, tri = mix_tri(d), cs = stat_cs(d);
   const int64_t len = stat_len(K, d);
   const double *pivot = mix + (size_t)K * h.stride;
-  __shared__ double sh[8];
   __shared__ double s_scale[64];
-  __shared__ int s_dead[PMCB200_MAX_COMP];
-  __shared__ double s_alpha[PMCB200_MAX_COMP];
-  const int tid = threadIdx.x;
+  __shared__ double s_hdr[8];
+  __shared__ double s_st[3 + PMCB200_MAX_DIM + PMCB200_MAX_DIM * (PMCB200_MAX_DIM + 1) / 2];
+  __shared__ double s_L[PMCB200_MAX_DIM][PMCB200_MAX_DIM + 1];
+  __shared__ int s_last;
+  const int lane = threadIdx.x, k = blockIdx.x;
   // global max and per-rank rescale
-  if (tid == 0) {
-    double M = -INFINITY;
-    for (int g = 0; g < nranks; g++) M = fmax(M, all[g * len]);
-    sh[0] = M;
-  }
-  __syncthreads();
-  const double M = sh[0];
-  for (int g = tid; g < nranks; g += blockDim.x) {
-    double Mg = all[g * len];
+  double M = -INFINITY;
+  for (int g = 0; g < nranks; g++) M = fmax(M, all[g * len]);
+  for (int g = lane; g < nranks; g += 32) {
+    const double Mg = all[g * len];
     s_scale[g] = (Mg == -INFINITY) ? 0.0 : exp(Mg - M);
   }
-  __syncthreads();
-  // combined block into work[len] (fixed rank order)
-  for (int64_t o = tid; o < len; o += blockDim.x) {
+  __syncwarp();
+  // header sums (fixed rank order; every block computes the same values)
+  if (lane < 7) {
+    const int o = lane;
     double s = 0.0;
     if (o == 0) s = M;
-    else if (o == 1 || o >= STAT_HDR) {
-      bool is_count = (o >= STAT_HDR) && (((o - STAT_HDR) % cs) == 2);
-      for (int g = 0; g < nranks; g++) s += all[g * len + o] * (is_count ? 1.0 : s_scale[g]);
-    } else if (o == 2) {
-      for (int g = 0; g < nranks; g++) s += all[g * len + o] * s_scale[g] * s_scale[g];
-    } else if (o == 3) {   // T_g shifts: sum w_g (lw - M) = e^(Mg-M) [T_g + (Mg-M) S_g]
+    else if (o == 1) { for (int g = 0; g < nranks; g++) s += all[g * len + 1] * s_scale[g]; }
+    else if (o == 2) { for (int g = 0; g < nranks; g++) s += all[g * len + 2] * s_scale[g] * s_scale[g]; }
+    else if (o == 3) {   // T_g shifts: sum w_g (lw - M) = e^(Mg-M) [T_g + (Mg-M) S_g]
       for (int g = 0; g < nranks; g++) {
-        double Mg = all[g * len];
+        const double Mg = all[g * len];
         if (s_scale[g] > 0.0) s += s_scale[g] * (all[g * len + 3] + (Mg - M) * all[g * len + 1]);
       }
-    } else {
-      for (int g = 0; g < nranks; g++) s += all[g * len + o];
-    }
-    work[o] = s;
+    } else { for (int g = 0; g < nranks; g++) s += all[g * len + o]; }
+    s_hdr[o] = s;
   }
-  __syncthreads();
-  const double S = work[1], S2 = work[2], T = work[3];
-  // per-component M-step, one thread per component
-  for (int k = tid; k < K; k += blockDim.x) {
-    const double *st = work + STAT_HDR + (size_t)k * cs;
-    const double *comp = mix + (size_t)k * h.stride;
-    double *o_mean = result + RES_HDR + K + (size_t)k * d;
-    double *o_chol = result + RES_HDR + K + (size_t)K * d + (size_t)k * d * d;
-    const double A = st[0], G = st[1], count = st[2];
-    const double alpha = A / S;
-    int was_alive = comp[0] != 0.0;
-    int dead = !was_alive || !(alpha >= 1.0 / (double)N_global) || count < (double)PMCB200_MINCOUNT;
-    if (!dead) {
-      // delta = B/G, mu' = p + delta, Sigma' = (C - G delta delta^T)/A; Cholesky in place
-      const double *B = st + 3, *Cc = st + 3 + d;
-      for (int i = 0; i < d; i++)
-        for (int j = 0; j <= i; j++) {
-          double di = B[i] / G, dj = B[j] / G;
-          o_chol[i * d + j] = (Cc[i * (i + 1) / 2 + j] - G * di * dj) / A;
-        }
-      for (int j = 0; j < d && !dead; j++) {
-        double s = o_chol[j * d + j];
-        for (int q = 0; q < j; q++) s -= o_chol[j * d + q] * o_chol[j * d + q];
-        if (!(s > 0.0) || !isfinite(s)) { dead = 1; break; }
-        double ljj = sqrt(s);
-        o_chol[j * d + j] = ljj;
-        for (int i = j + 1; i < d; i++) {
-          double t = o_chol[i * d + j];
-          for (int q = 0; q < j; q++) t -= o_chol[i * d + q] * o_chol[j * d + q];
-          o_chol[i * d + j] = t / ljj;
-        }
-      }
-      if (!dead) {
-        for (int i = 0; i < d; i++) {
-          o_mean[i] = pivot[i] + B[i] / G;
-          for (int j = i + 1; j < d; j++) o_chol[i * d + j] = 0.0;
-        }
-      }
-    }
-    if (dead) {   // keep the old mean / factor, weight 0
-      const int Dp = pmc_pad_dim(d);
-      const double *mean = comp + 2, *L = comp + 2 + Dp;
-      for (int i = 0; i < d; i++) {
-        o_mean[i] = mean[i];
-        for (int j = 0; j < d; j++) o_chol[i * d + j] = (j <= i) ? L[i * (i + 1) / 2 + j] : 0.0;
-      }
-    }
-    s_dead[k] = dead && was_alive;
-    s_alpha[k] = dead ? 0.0 : alpha;
+  // this component's statistics, combined over the ranks
+  for (int o = lane; o < cs; o += 32) {
+    const int64_t off = STAT_HDR + (int64_t)k * cs + o;
+    double s = 0.0;
+    for (int g = 0; g < nranks; g++) s += all[g * len + off] * (o == 2 ? 1.0 : s_scale[g]);
+    s_st[o] = s;
   }
-  __syncthreads();
-  if (tid == 0) {
+  __syncwarp();
+  const double S = s_hdr[1];
+  const double *comp = mix + (size_t)k * h.stride;
+  double *o_mean = result + RES_HDR + K + (size_t)k * d;
+  double *o_chol = result + RES_HDR + K + (size_t)K * d + (size_t)k * d * d;
+  const double A = s_st[0], G = s_st[1], count = s_st[2];
+  const double alpha = A / S;
+  const int was_alive = comp[0] != 0.0;
+  int dead = !was_alive || !(alpha >= 1.0 / (double)N_global) || count < (double)PMCB200_MINCOUNT;
+  if (!dead) {
+    // delta = B/G, mu' = p + delta, Sigma' = (C - G delta delta^T)/A; Cholesky in shared memory
+    const double *B = s_st + 3, *Cc = s_st + 3 + d;
+    for (int e = lane; e < tri; e += 32) {
+      int i = 0;
+      while ((i + 1) * (i + 2) / 2 <= e) i++;
+      const int j = e - i * (i + 1) / 2;
+      const double di = B[i] / G, dj = B[j] / G;
+      s_L[i][j] = (Cc[e] - G * di * dj) / A;
+    }
+    __syncwarp();
+    for (int j = 0; j < d; j++) {
+      double sjj = s_L[j][j];
+      for (int q = 0; q < j; q++) sjj -= s_L[j][q] * s_L[j][q];
+      if (!(sjj > 0.0) || !isfinite(sjj)) { dead = 1; break; }       // warp-uniform
+      const double ljj = sqrt(sjj);
+      for (int i = j + 1 + lane; i < d; i += 32) {
+        double t = s_L[i][j];
+        for (int q = 0; q < j; q++) t -= s_L[i][q] * s_L[j][q];
+        s_L[i][j] = t / ljj;
+      }
+      __syncwarp();
+      if (lane == 0) s_L[j][j] = ljj;
+      __syncwarp();
+    }
+  }
+  if (!dead) {
+    const double *B = s_st + 3;
+    for (int i = lane; i < d; i += 32) o_mean[i] = pivot[i] + B[i] / G;
+    for (int e = lane; e < d * d; e += 32) { const int i = e / d, j = e - i * d; o_chol[e] = (j <= i) ? s_L[i][j] : 0.0; }
+  } else {   // keep the old mean / factor, weight 0
+    const int Dp = pmc_pad_dim(d);
+    const double *mean = comp + 2, *L = comp + 2 + Dp;
+    for (int i = lane; i < d; i += 32) o_mean[i] = mean[i];
+    for (int e = lane; e < d * d; e += 32) { const int i = e / d, j = e - i * d; o_chol[e] = (j <= i) ? L[i * (i + 1) / 2 + j] : 0.0; }
+  }
+  if (lane == 0) { work[k] = dead ? 0.0 : alpha; work[K + k] = (dead && was_alive) ? 1.0 : 0.0; }
+  // ---- last block: normalise the weights, diagnostics
+  __threadfence();
+  if (lane == 0) s_last = (atomicAdd(done_cnt, 1u) == (unsigned)(K - 1));
+  __syncwarp();
+  if (!s_last) return;
+  __threadfence();
+  if (lane == 0) {
+    *done_cnt = 0u;                                  // ready for the next launch
+    const volatile double *wk = work;
     double wsum = 0.0, enc = 0.0;
     int ndead = 0;
-    for (int k = 0; k < K; k++) { wsum += s_alpha[k]; ndead += s_dead[k]; }
-    for (int k = 0; k < K; k++) {
-      double a = (wsum > 0.0) ? s_alpha[k] / wsum : 0.0;
-      result[RES_HDR + k] = a;
+    for (int q = 0; q < K; q++) { wsum += wk[q]; ndead += (int)wk[K + q]; }
+    for (int q = 0; q < K; q++) {
+      const double a = (wsum > 0.0) ? wk[q] / wsum : 0.0;
+      result[RES_HDR + q] = a;
       enc = fma(a, a, enc);
     }
-    const double Ng = (double)N_global;
+    const double Ng = (double)N_global, S2 = s_hdr[2], T = s_hdr[3];
     result[0] = M;                                   // maxW
     result[1] = S;                                   // sum_shift
     result[2] = log(S) + M;                          // logSum
@@ -142,11 +162,10 @@ k_em_finish(const double *__restrict__ mix, const MixHdr h, int nranks,
     result[5] = log(S) + M - log(Ng);                // ln evidence
     result[6] = 1.0 / enc;                           // ENC (updated proposal)
     result[7] = (double)ndead;
-    result[8] = work[4];                             // nok
-    result[9] = work[5];                             // nok_box
-    result[10] = work[6];                            // N summed over ranks
+    result[8] = s_hdr[4];                            // nok
+    result[9] = s_hdr[5];                            // nok_box
+    result[10] = s_hdr[6];                           // N summed over ranks
   }
-  (void)tri;
 }
 
 // DFMA-only kernel: 8 independent chains per thread, 2 register operands + 1

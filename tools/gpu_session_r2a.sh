@@ -20,6 +20,8 @@ for cfg in cmb_bao_sn sn_bao; do
   PMCB200_LIKE_V1=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/launches_${cfg}_v1.csv \
     python bench.py --config $cfg --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_bench_${cfg}_v1.log 2>&1
 done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/launches_banana.csv \
+  python bench.py --config banana --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_bench_banana.log 2>&1
 timeout 300 python bench.py > $O/bench_sn.json 2> $O/bench_sn.err
 timeout 300 python bench.py --config cmb_bao_sn --no-cpu-baseline > $O/bench_c5.json 2> $O/bench_c5.err
 timeout 300 python bench.py --config sn_bao --no-cpu-baseline > $O/bench_c4.json 2> $O/bench_c4.err
