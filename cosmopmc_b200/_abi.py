@@ -113,6 +113,9 @@ SYMBOLS = {
     "pmcb200_iteration_shard_host": (_i, [_vp, _i64, _u64, _u32, _i64, _d, _vp, _vp, _vp, _vp]),
     "pmcb200_shard_weights_host": (_i, [_vp, _i64, _vp]),
     "pmcb200_iteration_host": (_i, [_vp, _i64, _u64, _u32, _d, _vp, _vp, _vp, _vp, C.POINTER(Stats)]),
+    "pmcb200_iteration_host_begin": (_i, [_vp, _i64, _u64, _u32, _d, _vp, _vp, _vp, _vp, C.POINTER(Stats)]),
+    "pmcb200_shard_weights_host_begin": (_i, [_vp, _i64, _vp]),
+    "pmcb200_host_wait": (_i, [_vp, _i]),
     "pmcb200_launch_count": (_i64, [_vp]),
     "pmcb200_set_box": (_i, [_vp, _i, _vp, _vp]),
     "pmcb200_read_counts": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),

@@ -62,8 +62,18 @@ struct pmcb200_ctx {
   DevBuf sRho;
   const double *rho_X = nullptr; int64_t rho_N = 0; uint64_t rho_ver = 0, prop_ver = 0; bool rho_valid = false;
   int em_no_rho = 0;
-  // scratch for the host-buffer API
-  DevBuf sX, sIdx, sFlg, sLogw, sLogpi, sErr, sBlock, sAll;
+  // scratch for the host-buffer API.  The sample arrays exist twice so that the device-to-host copies of one
+  // iteration can drain while the next one computes (pmcb200_iteration_host_begin / pmcb200_host_wait); the
+  // second set is only allocated if a caller actually leaves copies in flight.
+  struct ScratchSet {
+    DevBuf X, Idx, Flg, Logw;
+    cudaEvent_t copied = nullptr;         // recorded on copy_stream after the set's last queued copy
+    bool busy = false;                    // copies queued and not yet waited for
+    uint64_t seq = 0;                     // order of the iterations that used the set
+  } set[2];
+  int cur = 0;
+  uint64_t seq = 0;
+  DevBuf sFish, sLogpi, sErr, sBlock, sAll;
   DevBuf sPost, sPostTmp;                 // post-processing work space
 };
 
@@ -214,6 +224,7 @@ static int create_impl(pmcb200_ctx *c, int device, void *stream) {
   CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
   CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
   CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_blk, cudaEventDisableTiming));
+  for (auto &t : c->set) CUDA_OK(c, cudaEventCreateWithFlags(&t.copied, cudaEventDisableTiming));
   cudaDeviceProp prop;
   CUDA_OK(c, cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -255,7 +266,12 @@ extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_target(c);
-  for (DevBuf *b : {&c->sX, &c->sIdx, &c->sFlg, &c->sLogw, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll, &c->sPost, &c->sPostTmp, &c->sRho})
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (auto &t : c->set) {
+    for (DevBuf *b : {&t.X, &t.Idx, &t.Flg, &t.Logw}) if (b->p) cudaFree(b->p);
+    if (t.copied) cudaEventDestroy(t.copied);
+  }
+  for (DevBuf *b : {&c->sFish, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll, &c->sPost, &c->sPostTmp, &c->sRho})
     if (b->p) cudaFree(b->p);
   if (c->d_mix) cudaFree(c->d_mix);
   if (c->d_scal) cudaFree(c->d_scal);
@@ -785,12 +801,12 @@ extern "C" int pmcb200_fisher_host(pmcb200_ctx *c, const double *pos, const doub
       }
     }
   const int64_t np = (int64_t)(pts.size() / d);
-  if ((rc = ensure(c, c->sX, (size_t)np * d * sizeof(double)))) return rc;
+  if ((rc = ensure(c, c->sFish, (size_t)np * d * sizeof(double)))) return rc;
   if ((rc = ensure(c, c->sLogpi, (size_t)np * sizeof(double)))) return rc;
   if ((rc = ensure(c, c->sErr, (size_t)np * sizeof(int32_t)))) return rc;
-  CUDA_OK(c, cudaMemcpyAsync(c->sX.p, pts.data(), (size_t)np * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMemcpyAsync(c->sFish.p, pts.data(), (size_t)np * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   c->rho_valid = false;
-  if ((rc = launch_posterior(c, np, (const double *)c->sX.p, nullptr, (double *)c->sLogpi.p, (int32_t *)c->sErr.p))) return rc;
+  if ((rc = launch_posterior(c, np, (const double *)c->sFish.p, nullptr, (double *)c->sLogpi.p, (int32_t *)c->sErr.p))) return rc;
   std::vector<double> lp(np);
   std::vector<int32_t> er(np);
   CUDA_OK(c, cudaMemcpyAsync(lp.data(), c->sLogpi.p, (size_t)np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -897,10 +913,26 @@ static int iteration_core(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t ite
   int rc;
   const int d = c->h.d;
   const size_t n1 = (size_t)std::max<int64_t>(N, 1), n = (size_t)N;
-  if (!dX) { if ((rc = ensure(c, c->sX, n1 * d * sizeof(double)))) return rc; dX = (double *)c->sX.p; }
-  if (!didx) { if ((rc = ensure(c, c->sIdx, n1 * sizeof(int32_t)))) return rc; didx = (int32_t *)c->sIdx.p; }
-  if (!dflg) { if ((rc = ensure(c, c->sFlg, n1 * sizeof(int16_t)))) return rc; dflg = (int16_t *)c->sFlg.p; }
-  if (!dlogw) { if ((rc = ensure(c, c->sLogw, n1 * sizeof(double)))) return rc; dlogw = (double *)c->sLogw.p; }
+  if (!dX || !didx || !dflg || !dlogw) {
+    // library scratch: stay on the current set unless an earlier iteration's copies are still draining from it
+    if (c->set[c->cur].busy) {
+      if (cudaEventQuery(c->set[c->cur].copied) == cudaSuccess) c->set[c->cur].busy = false;
+      else {
+        c->cur ^= 1;
+        if (c->set[c->cur].busy) {            // both in flight: the kernels wait for the older set's copies
+          CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->set[c->cur].copied, 0));
+          c->set[c->cur].busy = false;
+        }
+      }
+      cudaGetLastError();
+    }
+    c->set[c->cur].seq = ++c->seq;
+  }
+  pmcb200_ctx::ScratchSet &t = c->set[c->cur];
+  if (!dX) { if ((rc = ensure(c, t.X, n1 * d * sizeof(double)))) return rc; dX = (double *)t.X.p; }
+  if (!didx) { if ((rc = ensure(c, t.Idx, n1 * sizeof(int32_t)))) return rc; didx = (int32_t *)t.Idx.p; }
+  if (!dflg) { if ((rc = ensure(c, t.Flg, n1 * sizeof(int16_t)))) return rc; dflg = (int16_t *)t.Flg.p; }
+  if (!dlogw) { if ((rc = ensure(c, t.Logw, n1 * sizeof(double)))) return rc; dlogw = (double *)t.Logw.p; }
   if ((rc = ensure(c, c->sLogpi, n1 * sizeof(double)))) return rc;
   if ((rc = ensure(c, c->sErr, n1 * sizeof(int32_t)))) return rc;
   if ((rc = reset_scal(c))) return rc;
@@ -939,22 +971,50 @@ extern "C" int pmcb200_iteration_shard_host(pmcb200_ctx *c, int64_t N, uint64_t 
   return iteration_core(c, N, seed, iter, offset, beta, nullptr, nullptr, nullptr, nullptr, dblock, hX, hidx, hflg);
 }
 
-extern "C" int pmcb200_shard_weights_host(pmcb200_ctx *c, int64_t N, double *hw) {
+// normalised weights of the current scratch set to the host, queued behind the set's other copies; marks the
+// set as draining (pmcb200_host_wait, or the next-but-one iteration, waits for it)
+extern "C" int pmcb200_shard_weights_host_begin(pmcb200_ctx *c, int64_t N, double *hw) {
   int rc = need(c, true, false);
   if (rc) return rc;
-  if (N < 0 || !hw || (size_t)N * sizeof(double) > c->sLogw.cap) return fail(c, PMCB200_ERR_ARG, "shard_weights_host: bad arguments");
-  if (N > 0) {
-    if ((rc = pmcb200_normalize_weights(c, N, (int16_t *)c->sFlg.p, (double *)c->sLogw.p))) return rc;
-    CUDA_OK(c, cudaMemcpyAsync(hw, c->sLogw.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  pmcb200_ctx::ScratchSet &t = c->set[c->cur];
+  if (N < 0 || (hw && (size_t)N * sizeof(double) > t.Logw.cap)) return fail(c, PMCB200_ERR_ARG, "shard_weights_host: bad arguments");
+  if (N > 0 && hw) {
+    if ((rc = pmcb200_normalize_weights(c, N, (int16_t *)t.Flg.p, (double *)t.Logw.p))) return rc;
+    CUDA_OK(c, cudaEventRecord(c->ev_b, c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_b, 0));
+    CUDA_OK(c, cudaMemcpyAsync(hw, t.Logw.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
   }
-  cudaStreamSynchronize(c->copy_stream);
-  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  CUDA_OK(c, cudaEventRecord(t.copied, c->copy_stream));
+  t.busy = true;
   return 0;
 }
 
-extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, double beta,
-                                      double *hX, int32_t *hidx, int16_t *hflg, double *hw,
-                                      pmcb200_stats_t *stats) {
+// wait for the host arrays: lag = 0 all iterations begun so far, lag = 1 all but the most recent one
+extern "C" int pmcb200_host_wait(pmcb200_ctx *c, int lag) {
+  if (!c || lag < 0) return PMCB200_ERR_ARG;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  for (auto &t : c->set)
+    if (t.busy && t.seq + (uint64_t)lag <= c->seq) {
+      CUDA_OK(c, cudaEventSynchronize(t.copied));
+      t.busy = false;
+    }
+  if (lag == 0) {
+    CUDA_OK(c, cudaStreamSynchronize(c->copy_stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+extern "C" int pmcb200_shard_weights_host(pmcb200_ctx *c, int64_t N, double *hw) {
+  if (!hw) return fail(c, PMCB200_ERR_ARG, "shard_weights_host: bad arguments");
+  int rc = pmcb200_shard_weights_host_begin(c, N, hw);
+  if (rc) return rc;
+  return pmcb200_host_wait(c, 0);
+}
+
+extern "C" int pmcb200_iteration_host_begin(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, double beta,
+                                            double *hX, int32_t *hidx, int16_t *hflg, double *hw,
+                                            pmcb200_stats_t *stats) {
   int rc = need(c, true, true);
   if (rc) return rc;
   if (N < 1) return fail(c, PMCB200_ERR_ARG, "iteration_host: N = %lld", (long long)N);
@@ -962,10 +1022,16 @@ extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, 
   double *dblock = (double *)c->sBlock.p;
   if ((rc = iteration_core(c, N, seed, iter, 0, beta, nullptr, nullptr, nullptr, nullptr, dblock, hX, hidx, hflg))) return rc;
   rc = pmcb200_em_finish(c, 1, dblock, N, stats);
-  if (rc == 0 && hw) rc = pmcb200_shard_weights_host(c, N, hw);
-  cudaStreamSynchronize(c->copy_stream);
-  CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  return rc;
+  int rc2 = pmcb200_shard_weights_host_begin(c, N, rc == 0 ? hw : nullptr);
+  return rc ? rc : rc2;
+}
+
+extern "C" int pmcb200_iteration_host(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, double beta,
+                                      double *hX, int32_t *hidx, int16_t *hflg, double *hw,
+                                      pmcb200_stats_t *stats) {
+  int rc = pmcb200_iteration_host_begin(c, N, seed, iter, beta, hX, hidx, hflg, hw, stats);
+  int rc2 = c ? pmcb200_host_wait(c, 0) : 0;
+  return rc ? rc : rc2;
 }
 
 
@@ -1095,8 +1161,8 @@ extern "C" int pmcb200_iteration_host_multi(pmcb200_ctx *const *ctx, int n, int6
     pmcb200_ctx *c = ctx[r];
     const int64_t off = std::min<int64_t>(N, r * per), nr = std::max<int64_t>(0, std::min<int64_t>(per, N - off));
     if (nr == 0) continue;
-    if ((rc = pmcb200_normalize_weights(c, nr, (int16_t *)c->sFlg.p, (double *)c->sLogw.p))) { if (r) fail(c0, rc, "shard %d: %s", r, c->errmsg); return rc; }
-    CUDA_OK(c, cudaMemcpyAsync(hw + off, c->sLogw.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = pmcb200_normalize_weights(c, nr, (int16_t *)c->set[c->cur].Flg.p, (double *)c->set[c->cur].Logw.p))) { if (r) fail(c0, rc, "shard %d: %s", r, c->errmsg); return rc; }
+    CUDA_OK(c, cudaMemcpyAsync(hw + off, c->set[c->cur].Logw.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
   for (int r = 0; r < n; r++) {
     pmcb200_ctx *c = ctx[r];

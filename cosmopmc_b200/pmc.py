@@ -165,6 +165,23 @@ class PMC:
         self._ck(rc)
         return self.last_stats
 
+    def iteration_host_begin(self, N, seed, it, beta=1.0, hX=None, hidx=None, hflg=None, hw=None):
+        """as iteration_host, but returns with the host copies still draining (host_wait)"""
+        def hp(a):
+            return None if a is None else C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+        st = A.Stats()
+        rc = self.lib.pmcb200_iteration_host_begin(self.h, N, seed, it, beta, hp(hX), hp(hidx), hp(hflg), hp(hw), C.byref(st))
+        self.last_stats = st.as_dict()
+        self._ck(rc)
+        return self.last_stats
+
+    def shard_weights_host_begin(self, N, hw):
+        p = C.c_void_p(hw.data_ptr() if isinstance(hw, torch.Tensor) else hw.ctypes.data)
+        self._ck(self.lib.pmcb200_shard_weights_host_begin(self.h, N, p))
+
+    def host_wait(self, lag=0):
+        self._ck(self.lib.pmcb200_host_wait(self.h, lag))
+
     def iteration_shard_host(self, N, seed, it, offset, beta, block, hX=None, hidx=None, hflg=None):
         def hp(a):
             return None if a is None else C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)

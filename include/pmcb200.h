@@ -300,6 +300,20 @@ int pmcb200_iteration_host(pmcb200_ctx *ctx, int64_t N, uint64_t seed,
                            int32_t *hidx, int16_t *hflg, double *hw,
                            pmcb200_stats_t *stats);
 
+/* Pipelined delivery of the host arrays: _begin returns as soon as the update is done (stats filled, new
+ * proposal installed) with the device-to-host copies of X / idx / flg / w still draining on the library's
+ * copy stream; the NEXT iteration may be begun at once (the sample arrays exist twice on the device) and its
+ * kernels overlap those copies.  pmcb200_host_wait(ctx, 1) returns when the arrays of every iteration but the
+ * most recent one are complete on the host, pmcb200_host_wait(ctx, 0) when all are.  Consecutive _begin calls
+ * must be given different host arrays.  This is what lets the driver write iteration i's pmcsim file
+ * (cosmo_pmc.c:392) while iteration i + 1 computes; pmcb200_iteration_host == _begin + pmcb200_host_wait(ctx, 0). */
+int pmcb200_iteration_host_begin(pmcb200_ctx *ctx, int64_t N, uint64_t seed,
+                                 uint32_t iter, double beta, double *hX,
+                                 int32_t *hidx, int16_t *hflg, double *hw,
+                                 pmcb200_stats_t *stats);
+int pmcb200_shard_weights_host_begin(pmcb200_ctx *ctx, int64_t N, double *hw);
+int pmcb200_host_wait(pmcb200_ctx *ctx, int lag);
+
 /* ---- several GPUs in ONE process (the reference shards the sample
  * over MPI ranks, cosmo_pmc.c:323-376: send_simulation / receive_importance_weight)
  * One context per shard; contexts may sit on different devices (or, for tests,
