@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--config", default="sn", choices=["sn", "banana", "sn_bao", "cmb_bao_sn"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
     return ap.parse_args()
 
 
@@ -57,6 +57,10 @@ def make_config(name):
         spec = T.target_sn_demo()
         w, m, cov = T.proposal_sn(10)
         label = "SN Ia (Union 307 SNe, flat wCDM): Omega_m w0 M alpha beta, K=10 Gaussian proposal"
+    elif name == "sn_curved":       # C2's curved variant (BASELINE.json text: Omega_m Omega_de M alpha beta); tools/ only
+        spec = T.target_sn_curved()
+        w, m, cov = T.proposal_generic(spec, 10, 4, [0.3, 0.75, 19.33, 1.4, -2.4], [0.06, 0.12, 0.03, 0.1, 0.1])
+        label = "SN Ia (Union 307 SNe, curved LCDM): Omega_m Omega_de M alpha beta, K=10"
     elif name == "banana":
         spec = T.target_banana(20)
         w, m, cov = T.proposal_banana(10, 20)
@@ -139,18 +143,18 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def cpu_iteration_rate(spec, w, m, ch, seconds, nthreads):
+def cpu_iteration_rate(spec, w, m, ch, seconds, nthreads, mode_b=False):
     """Times the CPU oracle (kind 'port': restatement of pmclib+nicaea, the
     reference binary cannot be built here) on a bounded sample of the workload."""
     from oracle import oracle_lib as O
     O.build()
     n0 = 2000
     t = time.perf_counter()
-    O.iteration(spec, n0, SEED, 0, 1.0, w, m, ch, nthreads=nthreads)
+    O.iteration(spec, n0, SEED, 0, 1.0, w, m, ch, nthreads=nthreads, mode_b=mode_b)
     dt = max(time.perf_counter() - t, 1e-3)
     n = int(min(max(n0, n0 * seconds / dt), 2_000_000))
     t = time.perf_counter()
-    O.iteration(spec, n, SEED, 0, 1.0, w, m, ch, nthreads=nthreads)
+    O.iteration(spec, n, SEED, 0, 1.0, w, m, ch, nthreads=nthreads, mode_b=mode_b)
     dt = time.perf_counter() - t
     return n / dt, n, dt
 
@@ -173,12 +177,19 @@ def run_reference(args):
         O.iteration(spec, per_step, SEED, args.warmup + i, 1.0, w, m, ch, nthreads=cores)
     dt = time.perf_counter() - t
     val = per_step * args.steps / dt
+    tb = time.perf_counter()
+    O.iteration(spec, per_step, SEED, 99, 1.0, w, m, ch, nthreads=cores, mode_b=True)
+    val_b = per_step / (time.perf_counter() - tb)
     sample = "%d samples/step of the %s workload (full iteration: sample+likelihood+weights+EM)" % (per_step, args.config)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": label, "samples_per_step": per_step},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "mode": "A: reference-shaped (serial sampling / normalisation / EM as on the reference's rank 0, "
+                                     "weights over all cores like its MPI scatter)",
+                             "mode_b": {"value": val_b, "unit": UNIT, "cores": cores,
+                                        "mode": "B: every stage parallel over samples (OpenMP); one step of the same sample"}},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "CPU oracle (C restatement of pmclib+nicaea, OpenMP over samples in the weight stage); "
@@ -219,11 +230,10 @@ def main():
     blen = pmc.stat_block_len()
     block = torch.zeros(blen, dtype=torch.float64, device="cuda")
     allb = torch.zeros((world, blen), dtype=torch.float64, device="cuda")
-    # pinned host buffers for the end-to-end path
-    hX = torch.empty((n_loc, d), dtype=torch.float64).pin_memory()
-    hidx = torch.empty(n_loc, dtype=torch.int32).pin_memory()
-    hflg = torch.empty(n_loc, dtype=torch.int16).pin_memory()
-    hw = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+    # pinned host buffers for the end-to-end path: two sets, the copies of one iteration drain while the next computes
+    hsets = [(torch.empty((n_loc, d), dtype=torch.float64).pin_memory(), torch.empty(n_loc, dtype=torch.int32).pin_memory(),
+              torch.empty(n_loc, dtype=torch.int16).pin_memory(), torch.empty(n_loc, dtype=torch.float64).pin_memory())
+             for _ in range(2)]
     w_pin = torch.from_numpy(w.copy()).pin_memory()
     m_pin = torch.from_numpy(m.copy()).pin_memory()
     ch_pin = torch.from_numpy(ch.copy()).pin_memory()
@@ -233,30 +243,44 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(it):
-        """hot path, inputs resident in HBM: the proposal is re-installed every
-        step so that every step does identical work"""
-        pmc.set_proposal(w, m, chol=ch)
-        pmc.iteration_local(n_loc, SEED, it, off, 1.0, block, bufs)
-        if world > 1:
-            dist.all_gather_into_tensor(allb, block)
-            return pmc.update_prop_rb(world, allb, n_glob)
-        return pmc.update_prop_rb(1, block, n_glob)
+    def make_steps(nl):
+        """step functions for nl samples on this rank (global nl * world, this rank's offset rank * nl)"""
+        ng, of = nl * world, rank * nl
 
-    def step_e2e(it):
-        """the reference-facing call: host proposal in, host pmc_simu arrays out"""
-        pmc.set_proposal(w_pin.numpy(), m_pin.numpy(), chol=ch_pin.numpy())
-        if world == 1:
-            return pmc.iteration_host(n_loc, SEED, it, 1.0, hX, hidx, hflg, hw)
-        pmc.iteration_shard_host(n_loc, SEED, it, off, 1.0, block, hX, hidx, hflg)
-        dist.all_gather_into_tensor(allb, block)
-        st = pmc.update_prop_rb(world, allb, n_glob)
-        pmc.shard_weights_host(n_loc, hw)
-        return st
+        def step_device(it):
+            """hot path, inputs resident in HBM: the proposal is re-installed every
+            step so that every step does identical work"""
+            pmc.set_proposal(w, m, chol=ch)
+            pmc.iteration_local(nl, SEED, it, of, 1.0, block, bufs)
+            if world > 1:
+                dist.all_gather_into_tensor(allb, block)
+                return pmc.update_prop_rb(world, allb, ng)
+            return pmc.update_prop_rb(1, block, ng)
 
-    def timed(fn, steps, warmup, sampler=None):
+        def step_e2e(it):
+            """the reference-facing call: host proposal in, host pmc_simu arrays out (X, indices, flags, normalised
+            weights).  Pipelined delivery (pmcb200_iteration_host_begin / pmcb200_host_wait): the call returns when
+            the update is done; this step then waits for the PREVIOUS iteration's host arrays, whose copies drained
+            while this iteration's kernels ran -- what a driver writing iteration i's pmcsim file during iteration
+            i + 1 does.  Every array of every timed iteration is complete on the host before the clock stops."""
+            hX, hidx, hflg, hw = hsets[it % 2]
+            pmc.set_proposal(w_pin.numpy(), m_pin.numpy(), chol=ch_pin.numpy())
+            if world == 1:
+                st = pmc.iteration_host_begin(nl, SEED, it, 1.0, hX[:nl], hidx[:nl], hflg[:nl], hw[:nl])
+            else:
+                pmc.iteration_shard_host(nl, SEED, it, of, 1.0, block, hX[:nl], hidx[:nl], hflg[:nl])
+                dist.all_gather_into_tensor(allb, block)
+                st = pmc.update_prop_rb(world, allb, ng)
+                pmc.shard_weights_host_begin(nl, hw[:nl])
+            pmc.host_wait(1)
+            return st
+        return step_device, step_e2e
+
+    def timed(fn, steps, warmup, sampler=None, drain=False):
         for i in range(warmup):
             fn(i)
+        if drain:
+            pmc.host_wait(0)
         barrier()
         pmc.counters()
         l0 = pmc.launch_count()
@@ -267,6 +291,8 @@ def main():
         st = None
         for i in range(steps):
             st = fn(warmup + i)
+        if drain:
+            pmc.host_wait(0)          # the last iteration's host arrays, inside the timed region
         e1.record()
         barrier()
         if sampler:
@@ -277,10 +303,27 @@ def main():
         return ms.item(), st, pmc.launch_count() - l0, pmc.counters()
 
     sampler = ClockSampler(local) if rank == 0 else None
+    step_device, step_e2e = make_steps(n_loc)
     ms, st, launches, cnt = timed(step_device, args.steps, args.warmup, sampler)
-    ms_e2e, st_e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    ms_e2e, st_e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1), drain=True)
     value = n_glob * args.steps / (ms * 1e-3)
     e2e = n_glob * args.steps / (ms_e2e * 1e-3)
+
+    # strong scaling beside the weak run: the SAME global sample count as one GPU's (BASELINE.json's target is
+    # "10^7 samples in < 100 ms on 8 GPUs"), sharded over the ranks, same steps
+    strong = None
+    if args.scaling == "weak" and world > 1:
+        nl_s = (args.nsamples + world - 1) // world
+        sd, se = make_steps(nl_s)
+        ms_s, _, _, _ = timed(sd, args.steps, args.warmup)
+        ms_se, _, _, _ = timed(se, args.steps, max(1, args.warmup - 1), drain=True)
+        strong = {"n_gpus": world, "samples_global": nl_s * world, "samples_per_gpu": nl_s, "ms_per_step": ms_s / args.steps,
+                  "value": nl_s * world * args.steps / (ms_s * 1e-3), "unit": UNIT,
+                  "e2e": {"value": nl_s * world * args.steps / (ms_se * 1e-3), "ms_per_step": ms_se / args.steps}}
+
+    elif args.scaling == "weak":
+        strong = {"n_gpus": 1, "samples_global": n_glob, "samples_per_gpu": n_loc, "ms_per_step": ms / args.steps, "value": value,
+                  "unit": UNIT, "e2e": {"value": e2e, "ms_per_step": ms_e2e / args.steps}}
 
     # dominant kernel alone (SN likelihood), CUDA events on the launching stream
     roof = None
@@ -325,8 +368,13 @@ def main():
                            "l2": "inputs larger than L2 (sample array %.0f MB per GPU)" % (n_loc * d * 8 / 1e6),
                            "parallelism": "samples sharded over %d GPU(s); one NCCL all-gather of %d doubles per iteration" % (world, blen)},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "api": "pmcb200_iteration_host_begin + pmcb200_host_wait (pipelined host delivery; all host arrays of "
+                               "all timed iterations complete inside the timed region)" if world == 1 else
+                               "pmcb200_iteration_shard_host + NCCL all-gather + pmcb200_em_finish + pmcb200_shard_weights_host_begin "
+                               "+ pmcb200_host_wait (pipelined host delivery)",
                         "h2d_bytes_per_step": int(w_pin.numel() + m_pin.numel() + ch_pin.numel()) * 8,
                         "d2h_bytes_per_step": int(n_loc * (8 * d + 4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d)))},
+                "strong": strong,
                 "gpu_launches": launches, "clocks": clocks,
                 "counters_timed_region": cnt,
                 "stats": {k: st[k] for k in ("perplexity", "ess", "nok", "enc", "ndead")} if st else None}
@@ -335,8 +383,14 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             rate, n, dt = cpu_iteration_rate(spec, w, m, ch, args.cpu_seconds, cores)
+            rate_b, n_b, dt_b = cpu_iteration_rate(spec, w, m, ch, args.cpu_seconds, cores, mode_b=True)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d samples, one full iteration of the same workload, %.1f s" % (n, dt)}
+                                    "mode": "A: reference-shaped (sampling, normalisation and EM serial as on the reference's rank 0; "
+                                            "weights over all cores like its MPI scatter)",
+                                    "sample": "%d samples, one full iteration of the same workload, %.1f s" % (n, dt),
+                                    "mode_b": {"value": rate_b, "unit": UNIT, "cores": cores,
+                                               "mode": "B: every stage parallel over samples (OpenMP)",
+                                               "sample": "%d samples, %.1f s" % (n_b, dt_b)}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -421,85 +421,142 @@ __device__ __forceinline__ double rsqrt_acc(double v, double acc) {
   const double w = fma(er, c, 1.0);
   return fma(y, w, acc);
 }
-// NR qromb with the interior nodes of a stage evaluated four at a time into four partial sums
-// (independent chains; the reference sums sequentially: the difference is O(1e-16)).  f(x, acc) returns
-// acc + integrand(x); fa, fb = integrand at the two end points.  nev counts evaluations.
-template <class F>
-__device__ __forceinline__ double romberg4(F f, double fa, double fb, double a, double b, int &err, unsigned &nev) {
+// One integral of the BAO / CMB kernels: comoving distance (RS = false) or sound horizon (RS = true: the radicand
+// is multiplied by 3 (1 + R a), R3 = 3 R_fac)
+struct GInt { GLean g; double R3; };
+template <bool HASQ, bool RS>
+__device__ __forceinline__ double gint_acc(const GInt &q, const double2 *__restrict__ LT, const double *__restrict__ ET,
+                                           double x, double acc) {
+  double v = a4E2_lean<HASQ>(q.g, LT, ET, x);
+  if (RS) v *= fma(q.R3, x, 3.0);
+  return rsqrt_acc(v, acc);
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// the fields gint_acc reads, from lane src
+__device__ __forceinline__ GInt gint_from_lane(const GInt &q, int src) {
+  GInt r;
+  r.g.Om = shfl_d(q.g.Om, src); r.g.OK = shfl_d(q.g.OK, src); r.g.Or = shfl_d(q.g.Or, src);
+  r.g.p2 = shfl_d(q.g.p2, src); r.g.q2 = shfl_d(q.g.q2, src); r.g.lg = shfl_d(q.g.lg, src); r.g.lgq = shfl_d(q.g.lgq, src);
+  r.g.sgn = 0u; r.g.jassal = __shfl_sync(0xffffffffu, q.g.jassal, src); r.g.ok = 1;
+  r.R3 = shfl_d(q.R3, src);
+  return r;
+}
+// NR qromb, warp-synchronous: EVERY lane of the warp calls this together (lanes without an integral pass
+// active = false).  Stages with fewer than ROMB_COOP_MIN new nodes: every lane evaluates its own nodes, four at a
+// time into four partial sums (independent chains; the reference sums sequentially: the difference is O(1e-16)).
+// Deeper stages -- the rare integral that needs them (dark energy dominating the early universe makes the
+// sound-horizon integrand singular and the rule runs to 2^19 nodes; round 1 let one lane grind through them while
+// 31 waited and the kernel waited for that warp: 137 ms for 1e7 BAO samples that need 2 ms) -- are evaluated by
+// the WHOLE WARP for one lane at a time: the owner's coefficients travel by shuffles, lane l takes the nodes
+// l, l + 32, ... and a butterfly sum hands the stage sum back (the same bits in every lane, and a function of
+// the owner's sample alone: results do not depend on the warp's other samples).
+#define ROMB_COOP_MIN 1024
+template <bool HASQ, bool RS>
+__device__ double romberg_warp(const GInt &q, const double2 *__restrict__ LT, const double *__restrict__ ET, double fa,
+                               double fb, double a, double b, bool active, int &err, unsigned &nev) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   double y[5];
   const double h = b - a;
   double st = 0.5 * h * (fa + fb);
   y[0] = st;
   double ss = st, dss;
-  nev += 2;
-  for (int j = 1; j < ROMB_JMAX; j++) {
+  bool done = !active;
+  if (active) nev += 2;
+  for (int j = 1;; j++) {                         // j is warp-uniform: a lane only ever stops early
     const int it = 1 << (j - 1);
     const double tnm = (double)it, del = h / tnm;
-    double sum;
-    if (it < 4) {
-      sum = 0.0;
-      for (int i = 0; i < it; i++) sum = f(fma((double)i + 0.5, del, a), sum);
-    } else {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      // x += 4 del per chain, as NR's trapzd steps x += del (one rounding per step either way)
-      double x0 = fma(0.5, del, a), x1 = fma(1.5, del, a), x2 = fma(2.5, del, a), x3 = fma(3.5, del, a);
-      const double d4 = 4.0 * del;
-      for (int i = 0; i < it; i += 4) {
-        s0 = f(x0, s0); s1 = f(x1, s1); s2 = f(x2, s2); s3 = f(x3, s3);
-        x0 += d4; x1 += d4; x2 += d4; x3 += d4;
+    double sum = 0.0;
+    if (it < ROMB_COOP_MIN) {
+      if (!done) {
+        if (it < 4) {
+          for (int i = 0; i < it; i++) sum = gint_acc<HASQ, RS>(q, LT, ET, fma((double)i + 0.5, del, a), sum);
+        } else {
+          // x += 4 del per chain, as NR's trapzd steps x += del (one rounding per step either way)
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          double x0 = fma(0.5, del, a), x1 = fma(1.5, del, a), x2 = fma(2.5, del, a), x3 = fma(3.5, del, a);
+          const double d4 = 4.0 * del;
+          for (int i = 0; i < it; i += 4) {
+            s0 = gint_acc<HASQ, RS>(q, LT, ET, x0, s0); s1 = gint_acc<HASQ, RS>(q, LT, ET, x1, s1);
+            s2 = gint_acc<HASQ, RS>(q, LT, ET, x2, s2); s3 = gint_acc<HASQ, RS>(q, LT, ET, x3, s3);
+            x0 += d4; x1 += d4; x2 += d4; x3 += d4;
+          }
+          sum = (s0 + s1) + (s2 + s3);
+        }
       }
-      sum = (s0 + s1) + (s2 + s3);
+    } else {
+      unsigned mask = __ballot_sync(FULL, !done);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const GInt qs = gint_from_lane(q, src);
+        const double as = shfl_d(a, src), dels = shfl_d(del, src);
+        const double step = 32.0 * dels, d4 = 4.0 * step;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        double x0 = fma((double)lane + 0.5, dels, as), x1 = x0 + step, x2 = x1 + step, x3 = x2 + step;
+        for (int k = 0; k < (it >> 5); k += 4) {
+          s0 = gint_acc<HASQ, RS>(qs, LT, ET, x0, s0); s1 = gint_acc<HASQ, RS>(qs, LT, ET, x1, s1);
+          s2 = gint_acc<HASQ, RS>(qs, LT, ET, x2, s2); s3 = gint_acc<HASQ, RS>(qs, LT, ET, x3, s3);
+          x0 += d4; x1 += d4; x2 += d4; x3 += d4;
+        }
+        const double tot = warp_sum((s0 + s1) + (s2 + s3));
+        if (lane == src) sum = tot;
+      }
     }
-    nev += it;
-    st = 0.5 * (st + h * sum / tnm);
-    if (j < 5) y[j] = st;
-    else { y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4]; y[4] = st; }
-    if (j >= 4) {
-      ss = romb_extrap(y, dss);
-      if (!isfinite(ss)) { err = 1; return ss; }
-      if (fabs(dss) <= ROMB_EPS * fabs(ss)) return ss;
+    if (!done) {
+      nev += it;
+      st = 0.5 * (st + h * sum / tnm);
+      if (j < 5) y[j] = st;
+      else { y[0] = y[1]; y[1] = y[2]; y[2] = y[3]; y[3] = y[4]; y[4] = st; }
+      if (j >= 4) {
+        ss = romb_extrap(y, dss);
+        if (!isfinite(ss)) { err = 1; done = true; }
+        else if (fabs(dss) <= ROMB_EPS * fabs(ss)) done = true;
+      }
+      if (!done && j + 1 >= ROMB_JMAX) { err = 1; done = true; }      // too many steps
     }
+    if (__all_sync(FULL, done)) break;
   }
-  err = 1;
   return ss;
 }
 struct LeanTabs { const double *T; const double2 *LT; const double *ET; };
-// comoving distance [Mpc/h], a .. 1
+// comoving distance [Mpc/h], a .. 1.  Warp-synchronous: all lanes call it; act = this lane wants the value.
 template <bool HASQ>
-__device__ __forceinline__ double w_lean(const pmcb200_cosmo_t &c, double a, int wOmegar, int &err, const LeanTabs &tb,
-                                         unsigned &nev) {
+__device__ __forceinline__ double w_lean(const pmcb200_cosmo_t &c, double a, int wOmegar, bool act, int &err,
+                                         const LeanTabs &tb, unsigned &nev) {
   const ECoefF f = make_ecoef_fast(c, wOmegar);
-  const GLean g = make_glean(f);
-  if (!(a > 0.0) || !glean_in_range(g, a)) return w_generic(c, a, wOmegar, err, tb.T);
-  const double fa = rsqrt_acc(a4E2_fast(f, a, tb.T), 0.0), fb = rsqrt_acc(a4E2_fast(f, 1.0, tb.T), 0.0);
-  const double r = romberg4([&](double x, double acc) { return rsqrt_acc(a4E2_lean<HASQ>(g, tb.LT, tb.ET, x), acc); },
-                            fa, fb, a, 1.0, err, nev);
-  return R_HUBBLE * r;
+  GInt q;
+  q.g = make_glean(f); q.R3 = 0.0;
+  const bool fast = act && (a > 0.0) && glean_in_range(q.g, a);
+  double fa = 0.0, fb = 0.0;
+  if (fast) { fa = rsqrt_acc(a4E2_fast(f, a, tb.T), 0.0); fb = rsqrt_acc(a4E2_fast(f, 1.0, tb.T), 0.0); }
+  double r = R_HUBBLE * romberg_warp<HASQ, false>(q, tb.LT, tb.ET, fa, fb, a, 1.0, fast, err, nev);
+  if (act && !fast) r = w_generic(c, a, wOmegar, err, tb.T);      // outside the table-based exp2's range: general path
+  return r;
 }
-// comoving sound horizon [Mpc/h], 0 .. a (radiation included)
+// comoving sound horizon [Mpc/h], 0 .. a (radiation included); warp-synchronous like w_lean
 template <bool HASQ>
-__device__ __forceinline__ double r_sound_lean(const pmcb200_cosmo_t &c, double a, int &err, const LeanTabs &tb,
+__device__ __forceinline__ double r_sound_lean(const pmcb200_cosmo_t &c, double a, bool act, int &err, const LeanTabs &tb,
                                                unsigned &nev) {
   const ECoefF f = make_ecoef_fast(c, 1);
-  const GLean g = make_glean(f);
-  // smallest interior node of a stage <= 12 (deeper stages, never seen, restart on the general path)
-  if (!(a > 0.0) || !glean_in_range(g, a * (1.0 / 8192.0))) return r_sound(c, a, err, tb.T);
-  const double Rfac = 0.75 * c.Omega_b * c.h_100 * c.h_100 / OMEGA_GAMMA_H2, R3 = 3.0 * Rfac;
-  const double fa = rsqrt_acc(f.e.Or * 3.0, 0.0);
-  const double fb = rsqrt_acc(a4E2_fast(f, a, tb.T) * fma(R3, a, 3.0), 0.0);
-  int e2 = 0;
-  unsigned n2 = 0;
-  const double r = romberg4([&](double x, double acc) {
-    return rsqrt_acc(a4E2_lean<HASQ>(g, tb.LT, tb.ET, x) * fma(R3, x, 3.0), acc); }, fa, fb, 0.0, a, e2, n2);
-  if (n2 > 2u + 4096u) return r_sound(c, a, err, tb.T);     // beyond stage 12: the range check no longer covers the nodes
-  nev += n2;
-  if (e2) err = 1;
-  return R_HUBBLE * r;
+  GInt q;
+  q.g = make_glean(f);
+  const double Rfac = 0.75 * c.Omega_b * c.h_100 * c.h_100 / OMEGA_GAMMA_H2;
+  q.R3 = 3.0 * Rfac;
+  // the smallest interior node of the deepest stage (ROMB_JMAX = 20) is a 2^-20
+  const bool fast = act && (a > 0.0) && glean_in_range(q.g, a * (1.0 / 1048576.0));
+  double fa = 0.0, fb = 0.0;
+  if (fast) { fa = rsqrt_acc(f.e.Or * 3.0, 0.0); fb = rsqrt_acc(a4E2_fast(f, a, tb.T) * fma(q.R3, a, 3.0), 0.0); }
+  double r = R_HUBBLE * romberg_warp<HASQ, true>(q, tb.LT, tb.ET, fa, fb, 0.0, a, fast, err, nev);
+  if (act && !fast) r = r_sound(c, a, err, tb.T);
+  return r;
 }
 template <bool HASQ>
-__device__ __forceinline__ double D_V_lean(const pmcb200_cosmo_t &c, double z, int &err, const LeanTabs &tb, unsigned &nev) {
+__device__ __forceinline__ double D_V_lean(const pmcb200_cosmo_t &c, double z, bool act, int &err, const LeanTabs &tb,
+                                           unsigned &nev) {
   const double a = 1.0 / (1.0 + z);
-  const double ww = w_lean<HASQ>(c, a, 0, err, tb, nev);
+  const double ww = w_lean<HASQ>(c, a, 0, act, err, tb, nev);
+  if (!act) return 1.0;
   const double fK = f_K(c, ww);
   const ECoefF f = make_ecoef_fast(c, 0);
   const double a2 = a * a;
@@ -831,41 +888,44 @@ k_like_bao(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   __shared__ double ET[SN_EXP2_N];
   load_lean_tables(T, LT, ET);
   const LeanTabs tb{T, LT, ET};
-  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned nev = 0, nint = 0;
-  if (n < N && flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } }
-  else if (n < N) {
-    Model m;
-    int e = apply_params(L, X + n * d, m);
-    double res = 0.0;
-    if (!e && !(L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c))) {
-      double model[4];
-      const int nd = L.g_ndim;
-      const pmcb200_cosmo_t &c = m.c;
-      if (L.bao_method == PMCB200_BAO_distance_A) {
-        if (!(c.Omega_m > 0.0)) e = 1;
-        else for (int i = 0; i < nd; i++) {
-          model[i] = D_V_lean<HASQ>(c, L.g_z[i], e, tb, nev) * sqrt(c.Omega_m) / (L.g_z[i] * R_HUBBLE);
-          nint++;
-        }
-      } else if (L.bao_method == PMCB200_BAO_distance_d_z) {
-        if (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0)) e = 1;
-        else {
-          const double rs = r_sound_lean<HASQ>(c, 1.0 / (1.0 + z_drag(c)), e, tb, nev);
-          nint++;
-          for (int i = 0; i < nd; i++) { model[i] = rs / D_V_lean<HASQ>(c, L.g_z[i], e, tb, nev); nint++; }
-        }
-      } else {
-        for (int i = 0; i < nd; i++) {
-          model[i] = D_V_lean<HASQ>(c, L.g_z[2 * i], e, tb, nev) / D_V_lean<HASQ>(c, L.g_z[2 * i + 1], e, tb, nev);
-          nint += 2;
-        }
-      }
-      if (!e) res = gauss_comp_logpdf(L.g_comp, nd, model);
-      if (!isfinite(res)) e = 1;
+  const bool live = (n < N) && (!flg || flg[n]);
+  Model m;
+  int e = 0;
+  if (live) e = apply_params(L, X + n * d, m);
+  const bool cut = live && !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c);
+  const int nd = L.g_ndim, method = L.bao_method;
+  // the integrals are warp-synchronous (romberg_warp): every lane walks the same calls, act says whose count
+  bool act = live && !e && !cut;
+  if (act && method != PMCB200_BAO_distance_D_V_ratio && !(m.c.Omega_m > 0.0)) { e = 1; act = false; }
+  if (act && method == PMCB200_BAO_distance_d_z && !(m.c.Omega_b > 0.0)) { e = 1; act = false; }
+  if (!act) m.c = L.model;
+  const pmcb200_cosmo_t &c = m.c;
+  double model[4] = {0.0, 0.0, 0.0, 0.0};
+  if (method == PMCB200_BAO_distance_A) {
+    for (int i = 0; i < nd; i++) {
+      model[i] = D_V_lean<HASQ>(c, L.g_z[i], act, e, tb, nev) * sqrt(c.Omega_m) / (L.g_z[i] * R_HUBBLE);
+      nint += act;
     }
-    put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  } else if (method == PMCB200_BAO_distance_d_z) {
+    const double rs = r_sound_lean<HASQ>(c, 1.0 / (1.0 + z_drag(c)), act, e, tb, nev);
+    nint += act;
+    for (int i = 0; i < nd; i++) { model[i] = rs / D_V_lean<HASQ>(c, L.g_z[i], act, e, tb, nev); nint += act; }
+  } else {
+    for (int i = 0; i < nd; i++) {
+      const double num = D_V_lean<HASQ>(c, L.g_z[2 * i], act, e, tb, nev);
+      model[i] = num / D_V_lean<HASQ>(c, L.g_z[2 * i + 1], act, e, tb, nev);
+      nint += 2 * act;
+    }
   }
+  double res = 0.0;
+  if (act) {
+    if (!e) res = gauss_comp_logpdf(L.g_comp, nd, model);
+    if (!isfinite(res)) e = 1;
+  }
+  if (live) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);      // cut: log L = 0, no error (bao.c:154-176)
+  else if (n < N && set) { logpi[n] = 0.0; if (err) err[n] = 0; }
   count_gen(cnt, nev, nint);
 }
 
@@ -879,33 +939,35 @@ k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   __shared__ double ET[SN_EXP2_N];
   load_lean_tables(T, LT, ET);
   const LeanTabs tb{T, LT, ET};
-  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned nev = 0, nint = 0;
-  if (n < N && flg && !flg[n]) { if (set) { logpi[n] = 0.0; if (err) err[n] = 0; } }
-  else if (n < N) {
-    Model m;
-    int e = apply_params(L, X + n * d, m);
-    double res = 0.0;
-    const pmcb200_cosmo_t &c = m.c;
-    const bool cut = !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(c);
-    if (cut) e = 1;      // wmap.c:1041-1044: wmap_de_prior error, the point gets zero weight
-    if (!e && (!(c.Omega_m > 0.0) || !(c.Omega_b > 0.0))) e = 1;
-    if (!e) {
-      double model[4];
-      const double zs = z_star(c), as = 1.0 / (1.0 + zs);
-      const double ww = w_lean<HASQ>(c, as, 1, e, tb, nev);
-      const double fK = f_K(c, ww);
-      const double rs = r_sound_lean<HASQ>(c, as, e, tb, nev);
-      nint += 2;
-      model[0] = M_PI * fK / rs;
-      model[1] = sqrt(c.Omega_m) * fK / R_HUBBLE;
-      model[2] = zs;
-      model[3] = 100.0 * c.Omega_b * c.h_100 * c.h_100;
-      if (!e) res = gauss_comp_logpdf(L.g_comp, L.g_ndim, model);
-      if (!isfinite(res)) e = 1;
-    }
-    put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  const bool live = (n < N) && (!flg || flg[n]);
+  Model m;
+  int e = 0;
+  if (live) e = apply_params(L, X + n * d, m);
+  if (live && !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c))
+    e = 1;               // wmap.c:1041-1044: wmap_de_prior error, the point gets zero weight
+  if (live && !e && (!(m.c.Omega_m > 0.0) || !(m.c.Omega_b > 0.0))) e = 1;
+  const bool act = live && !e;
+  if (!act) m.c = L.model;
+  const pmcb200_cosmo_t &c = m.c;
+  const double zs = z_star(c), as = 1.0 / (1.0 + zs);
+  const double ww = w_lean<HASQ>(c, as, 1, act, e, tb, nev);
+  const double rs = r_sound_lean<HASQ>(c, as, act, e, tb, nev);
+  nint += 2 * act;
+  double res = 0.0;
+  if (act) {
+    double model[4];
+    const double fK = f_K(c, ww);
+    model[0] = M_PI * fK / rs;
+    model[1] = sqrt(c.Omega_m) * fK / R_HUBBLE;
+    model[2] = zs;
+    model[3] = 100.0 * c.Omega_b * c.h_100 * c.h_100;
+    if (!e) res = gauss_comp_logpdf(L.g_comp, L.g_ndim, model);
+    if (!isfinite(res)) e = 1;
   }
+  if (live) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  else if (n < N && set) { logpi[n] = 0.0; if (err) err[n] = 0; }
   count_gen(cnt, nev, nint);
 }
 

@@ -94,6 +94,7 @@ void pmc_simu_realloc(pmc_simu *p, long nsamples, error **err)
    testErrorRetVA(nsamples < 1, pmc_dimension, "Invalid number of samples %ld", *err, __LINE__, , nsamples);
    void *nb = psim_lump(psim_bytes(nsamples, p->ndim, p->n_ded), err);     /* the old lump survives a failed allocation */
    forwardError(*err, __LINE__, );
+   pmc_b200_invalidate_mirror(p);
    pmcb200_host_free(p->buf);
    p->buf = nb;
    p->nsamples = p->nsamples_alloc = nsamples;
@@ -104,6 +105,7 @@ void pmc_simu_realloc(pmc_simu *p, long nsamples, error **err)
 void pmc_simu_free(pmc_simu **p)
 {
    if (!p || !*p) return;
+   pmc_b200_invalidate_mirror(*p);
    pmcb200_host_free((*p)->buf); free(*p); *p = NULL;
 }
 
@@ -128,6 +130,70 @@ static dev_mirror g_devs[MAX_SHARDS];
 /* page-locked staging of pmc_simu->indices (size_t on the host, int32 on the device) */
 static int32_t *g_idx32 = NULL;
 static long g_idx32_cap = 0;
+
+/* ---- what the device mirrors hold --------------------------------------------
+ * The reference calls simulate / weights / normalise / update one after the other on the same psim and never
+ * writes the sample arrays in between (exec/cosmo_pmc.c:320-399 only pokes psim->nsamples).  Round 1 re-uploaded
+ * every array on every call (2 x 400 MB of X per iteration at 1e7 samples).  Now each entry point records which
+ * arrays it left identical on host and device, with a fingerprint (MIRROR_NFP sampled elements + size) of the host
+ * copy; the next entry point skips the upload of an array whose record is intact AND whose fingerprint still
+ * matches the host array.  A caller that rewrites an array wholesale (pmc_simu_from_file, a copy, a new draw) is
+ * caught by the fingerprint; one that edits single elements must call pmc_b200_invalidate_mirror(psim).
+ * PMCB200_ALWAYS_UPLOAD=1 restores the unconditional uploads. */
+#define MV_X 1u
+#define MV_IDX 2u
+#define MV_FLG 4u
+#define MV_W 8u
+#define MIRROR_NFP 256
+static struct {
+   const pmc_simu *owner; long n; int d, ns; unsigned valid;
+   double fpX[MIRROR_NFP], fpW[MIRROR_NFP]; short fpF[MIRROR_NFP]; size_t fpI[MIRROR_NFP];
+} g_mir;
+static long g_mir_skipped_bytes = 0, g_mir_uploaded_bytes = 0;
+static inline long fp_pos(long j, long n) { return (long)(((unsigned long long)j * 2654435761ull + (j == 1 ? (unsigned long long)(n - 1) : 0ull)) % (unsigned long long)n); }
+static void mirror_mark(const pmc_simu *p, unsigned bits)
+{
+   if (g_mir.owner != p || g_mir.n != p->nsamples || g_mir.d != p->ndim || g_mir.ns != g_ns) {
+      g_mir.owner = p; g_mir.n = p->nsamples; g_mir.d = p->ndim; g_mir.ns = g_ns; g_mir.valid = 0;
+   }
+   long n = p->nsamples;
+   size_t nx = (size_t)n * p->ndim;
+   for (long j = 0; j < MIRROR_NFP && n > 0; j++) {
+      long i = fp_pos(j, n);
+      if (bits & MV_X) g_mir.fpX[j] = p->X[fp_pos(j, (long)nx)];
+      if (bits & MV_W) g_mir.fpW[j] = p->weights[i];
+      if (bits & MV_FLG) g_mir.fpF[j] = p->flg[i];
+      if (bits & MV_IDX) g_mir.fpI[j] = p->indices[i];
+   }
+   g_mir.valid |= bits;
+}
+static void mirror_clear(const pmc_simu *p, unsigned bits) { if (g_mir.owner == p) g_mir.valid &= ~bits; }
+void pmc_b200_invalidate_mirror(const pmc_simu *p) { if (!p || g_mir.owner == p) g_mir.valid = 0; }
+/* arrays whose device mirror may be trusted for this call */
+static unsigned mirror_fresh(const pmc_simu *p)
+{
+   static int always = -1;
+   if (always < 0) { const char *e = getenv("PMCB200_ALWAYS_UPLOAD"); always = e && *e && *e != '0'; }
+   if (always || g_mir.owner != p || g_mir.n != p->nsamples || g_mir.d != p->ndim || g_mir.ns != g_ns) return 0;
+   unsigned ok = g_mir.valid;
+   long n = p->nsamples;
+   size_t nx = (size_t)n * p->ndim;
+   for (long j = 0; j < MIRROR_NFP && n > 0 && ok; j++) {
+      long i = fp_pos(j, n);
+      /* bit patterns, not values: NaN == NaN here */
+      if ((ok & MV_X) && memcmp(&g_mir.fpX[j], &p->X[fp_pos(j, (long)nx)], sizeof(double)) != 0) ok &= ~MV_X;
+      if ((ok & MV_W) && memcmp(&g_mir.fpW[j], &p->weights[i], sizeof(double)) != 0) ok &= ~MV_W;
+      if ((ok & MV_FLG) && g_mir.fpF[j] != p->flg[i]) ok &= ~MV_FLG;
+      if ((ok & MV_IDX) && g_mir.fpI[j] != p->indices[i]) ok &= ~MV_IDX;
+   }
+   g_mir.valid = ok;
+   return ok;
+}
+void pmc_b200_mirror_traffic(long *uploaded_bytes, long *skipped_bytes)
+{
+   if (uploaded_bytes) *uploaded_bytes = g_mir_uploaded_bytes;
+   if (skipped_bytes) *skipped_bytes = g_mir_skipped_bytes;
+}
 
 #define B200_OK(ctx, call, errcode, ret)                                                          \
    do { int rc__ = (call);                                                                        \
@@ -192,6 +258,7 @@ void pmc_b200_shutdown(void)
    if (g_idx32) pmcb200_host_free(g_idx32);
    g_idx32 = NULL; g_idx32_cap = 0;
    g_ns = 0; g_active_target = NULL;
+   memset(&g_mir, 0, sizeof(g_mir));
 }
 
 /* slice of an n-sample psim owned by shard r (same rule as pmcb200_iteration_host_multi) */
@@ -256,6 +323,7 @@ static void ensure_dev(long n, int d, long blen, error **err)
       shard_range(n, r, &off, &nr);
       if (nr < 1) nr = 1;
       if (nr > m->cap || d > m->d) {
+         g_mir.valid = 0;                           /* the mirrors are being replaced */
          if (m->X) { pmcb200_dev_free(ctx, m->X); pmcb200_dev_free(ctx, m->idx);
                      pmcb200_dev_free(ctx, m->flg); pmcb200_dev_free(ctx, m->w); }
          long cap = nr > m->cap ? nr : m->cap;
@@ -349,6 +417,14 @@ static void push_samples(pmc_simu *p, int with_X, int with_idx, int with_w, erro
    long n = p->nsamples;
    int d = p->ndim;
    int32_t *t = NULL;
+   int with_flg = 1;
+   const unsigned fresh = mirror_fresh(p);
+   if (with_X && (fresh & MV_X)) { with_X = 0; g_mir_skipped_bytes += (long)sizeof(double) * n * d; }
+   if (with_idx && (fresh & MV_IDX)) { with_idx = 0; g_mir_skipped_bytes += (long)sizeof(int32_t) * n; }
+   if (with_w && (fresh & MV_W)) { with_w = 0; g_mir_skipped_bytes += (long)sizeof(double) * n; }
+   if (fresh & MV_FLG) { with_flg = 0; g_mir_skipped_bytes += (long)sizeof(short) * n; }
+   g_mir_uploaded_bytes += (with_X ? (long)sizeof(double) * n * d : 0) + (with_idx ? (long)sizeof(int32_t) * n : 0) +
+                           (with_w ? (long)sizeof(double) * n : 0) + (with_flg ? (long)sizeof(short) * n : 0);
    if (with_idx) {
       t = idx_staging(n, err);
       forwardError(*err, __LINE__, );
@@ -361,10 +437,11 @@ static void push_samples(pmc_simu *p, int with_X, int with_idx, int with_w, erro
       shard_range(n, r, &off, &nr);
       if (nr == 0) continue;
       if (with_X) B200_OK(ctx, pmcb200_h2d_async(ctx, m->X, p->X + (size_t)off * d, sizeof(double) * (size_t)nr * d), pmc_badComm, );
-      B200_OK(ctx, pmcb200_h2d_async(ctx, m->flg, p->flg + off, sizeof(short) * (size_t)nr), pmc_badComm, );
+      if (with_flg) B200_OK(ctx, pmcb200_h2d_async(ctx, m->flg, p->flg + off, sizeof(short) * (size_t)nr), pmc_badComm, );
       if (with_w) B200_OK(ctx, pmcb200_h2d_async(ctx, m->w, p->weights + off, sizeof(double) * (size_t)nr), pmc_badComm, );
       if (with_idx) B200_OK(ctx, pmcb200_h2d_async(ctx, m->idx, t + off, sizeof(int32_t) * (size_t)nr), pmc_badComm, );
    }
+   mirror_mark(p, (with_X ? MV_X : 0u) | (with_idx ? MV_IDX : 0u) | (with_w ? MV_W : 0u) | (with_flg ? MV_FLG : 0u));
 }
 
 __attribute__((weak)) int pmc_b200_autobind(posterior_log_pdf_func *f, void *data, pmcb200_target_t *t, error **err)
@@ -442,6 +519,8 @@ size_t simulate_mix_mvdens(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, par
    }
    for (long i = 0; i < n; i++) psim->indices[i] = (size_t)t[i];
    psim->isLog = 0;
+   pmc_b200_invalidate_mirror(psim);
+   mirror_mark(psim, MV_X | MV_IDX | MV_FLG);       /* the draw is identical on host and device; the weights are stale */
    return (size_t)nok;
 }
 
@@ -483,6 +562,7 @@ size_t generic_get_importance_weight_and_deduced_verb(pmc_simu *psim, const void
    }
    psim->isLog = 1;
    psim->maxW = maxW;
+   mirror_mark(psim, MV_W | MV_FLG);                /* log weights and the cleared flags, both sides */
    return (size_t)nok;
 }
 
@@ -535,6 +615,7 @@ size_t pmc_b200_importance_sample(pmc_simu *psim, posterior_log_pdf_func *poster
    }
    psim->maxW = MW;
    psim->isLog = 1;
+   mirror_clear(psim, MV_IDX | MV_FLG | MV_W);      /* the index mirror served as the error array; host flags / weights were edited */
    return count;
 }
 
@@ -597,6 +678,7 @@ double normalize_importance_weight(pmc_simu *psim, error **err)
    }
    sync_all(err);                                                  forwardError(*err, __LINE__, 0.0);
    psim->isLog = 0; psim->logSum = log(o[1]) + o[0]; psim->maxW = o[0];
+   mirror_mark(psim, MV_W);
    return o[1];
 }
 
@@ -691,6 +773,7 @@ void clip_weights(pmc_simu *psim, int nclipw, FILE *OUT, error **err)
    double s = 0.0;
    for (long i = 0; i < psim->nsamples; i++) if (psim->flg[i]) s += psim->weights[i];
    testErrorRet(!(s > 0.0), pmc_negWeight, "All weights clipped", *err, __LINE__, );
+   mirror_clear(psim, MV_W | MV_FLG);               /* host-side edit of weights and flags */
    for (long i = 0; i < psim->nsamples; i++) psim->weights[i] = psim->flg[i] ? psim->weights[i] / s : 0.0;
    psim->logSum += log(s);
 }
@@ -854,6 +937,7 @@ size_t pmc_b200_iteration(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, doub
    B200_OK(g_ctxs[0], rc, pmc_undef, 0);
    for (long i = 0; i < n; i++) psim->indices[i] = (size_t)idx[i];
    psim->isLog = 0; psim->logSum = st.logSum; psim->maxW = st.maxW;
+   pmc_b200_invalidate_mirror(psim);               /* the fused call works on library scratch, not on the mirrors */
    pull_proposal(proposal, err);
    forwardError(*err, __LINE__, 0);
    if (stats) *stats = st;

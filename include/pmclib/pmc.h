@@ -98,6 +98,12 @@ void pmc_b200_shutdown(void);
 /* number of shards (contexts) the host layer drives: $PMCB200_NGPU (default 1, "all" = every
  * visible device), devices from $PMCB200_DEVICES (comma-separated, round-robin) */
 int pmc_b200_nshards(void);
+/* Device mirrors of a psim's arrays are reused between the pmclib-named calls of one iteration instead of being
+ * re-uploaded (host/pmc.c "what the device mirrors hold").  A caller that edits single elements of X / weights /
+ * flg / indices between two calls must say so; wholesale rewrites are detected.  psim == NULL: forget everything. */
+void pmc_b200_invalidate_mirror(const pmc_simu *psim);
+/* bytes uploaded / uploads avoided by the mirror bookkeeping since start (diagnostic) */
+void pmc_b200_mirror_traffic(long *uploaded_bytes, long *skipped_bytes);
 void pmc_b200_register_target(posterior_log_pdf_func *posterior_log_pdf, void *target_data,
                               const pmcb200_target_t *t, error **err);
 /* Auto-binding hook: called for a (callback, data) pair that has no registered

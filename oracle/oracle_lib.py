@@ -60,6 +60,7 @@ def lib():
             "orc_enc": (_d, [_i, _vp]),
             "orc_update_prop_rb": (_i, [_i64, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
             "orc_iteration": (_i, [C.POINTER(A.Target), _i64, _u64, _u32, _d, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(A.Stats), _i]),
+            "orc_iteration_mode_b": (_i, [C.POINTER(A.Target), _i64, _u64, _u32, _d, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(A.Stats), _i]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
@@ -180,7 +181,7 @@ def update_prop_rb(X, idx, flg, wbar, wght, mean, chol, df=-1):
     return wght, mean, chol, cov, nd
 
 
-def iteration(spec, N, seed, it, beta, wght, mean, chol, df=-1, nthreads=0):
+def iteration(spec, N, seed, it, beta, wght, mean, chol, df=-1, nthreads=0, mode_b=False):
     wght, mean, chol = f64(wght).copy(), f64(mean).copy(), f64(chol).copy()
     K, d = mean.shape
     X = np.empty((N, d))
@@ -188,7 +189,8 @@ def iteration(spec, N, seed, it, beta, wght, mean, chol, df=-1, nthreads=0):
     flg = np.empty(N, dtype=np.int16)
     w = np.empty(N)
     st = A.Stats()
-    rc = lib().orc_iteration(C.byref(spec.t), N, seed, it, beta, K, d, df, _p(wght), _p(mean),
+    fn = lib().orc_iteration_mode_b if mode_b else lib().orc_iteration
+    rc = fn(C.byref(spec.t), N, seed, it, beta, K, d, df, _p(wght), _p(mean),
                              _p(chol), _p(X), _p(idx), _p(flg), _p(w), C.byref(st), nthreads)
     return dict(rc=rc, wght=wght, mean=mean, chol=chol, X=X, idx=idx, flg=flg, w=w,
                 stats=st.as_dict())

@@ -830,22 +830,50 @@ double orc_enc(int K, const double *wght)
  * in place (chol = Cholesky of the new covariance); cov_out (may be NULL)
  * receives the new covariances.  Returns the number of components killed.
  * ========================================================================== */
+static int update_prop_rb_impl(int64_t N, const double *X, const int32_t *idx,
+                       const int16_t *flg, const double *wbar, int K, int d,
+                       int df, double *wght, double *mean, double *chol,
+                       double *cov_out, int nthreads);
 int orc_update_prop_rb(int64_t N, const double *X, const int32_t *idx,
                        const int16_t *flg, const double *wbar, int K, int d,
                        int df, double *wght, double *mean, double *chol,
                        double *cov_out)
 {
+   return update_prop_rb_impl(N, X, idx, flg, wbar, K, d, df, wght, mean, chol, cov_out, 1);
+}
+
+/* nthreads == 1: the serial loops of the reference's rank 0 (what the parity tests check).  nthreads > 1
+ * ("mode B" of the CPU baseline): contiguous chunks of samples per thread with thread-private sums, combined in
+ * thread order -- same sums up to the association of the additions. */
+static int update_prop_rb_impl(int64_t N, const double *X, const int32_t *idx,
+                       const int16_t *flg, const double *wbar, int K, int d,
+                       int df, double *wght, double *mean, double *chol,
+                       double *cov_out, int nthreads)
+{
    const size_t dd = (size_t)d * d;
-   double *A = calloc(K, sizeof(double)), *G = calloc(K, sizeof(double));
-   double *B = calloc((size_t)K * d, sizeof(double));
-   double *C = calloc((size_t)K * dd, sizeof(double));
+   int nt = nthreads > 1 ? nthreads : 1;
+   double *A = calloc((size_t)nt * K, sizeof(double)), *G = calloc((size_t)nt * K, sizeof(double));
+   double *B = calloc((size_t)nt * K * d, sizeof(double));
+   double *C = calloc((size_t)nt * K * dd, sizeof(double));
    double *rho = malloc(((size_t)N * K) * sizeof(double));   /* rho*gamma cached */
-   int64_t *count = calloc(K, sizeof(int64_t));
+   int64_t *count = calloc((size_t)nt * K, sizeof(int64_t));
    int64_t Nall = N;
    int ndead = 0;
 
    /* E-step + first moments */
-   for (int64_t n = 0; n < N; n++) {
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nt)
+#endif
+   {
+#ifdef _OPENMP
+   const int th = omp_get_thread_num();
+#else
+   const int th = 0;
+#endif
+   const int64_t n0 = N * th / nt, n1 = N * (th + 1) / nt;
+   double *At = A + (size_t)th * K, *Gt = G + (size_t)th * K, *Bt = B + (size_t)th * K * d;
+   int64_t *ct = count + (size_t)th * K;
+   for (int64_t n = n0; n < n1; n++) {
       if (!flg[n]) continue;
       const double *x = X + n * d;
       double r[PMCB200_MAX_COMP], gam[PMCB200_MAX_COMP], rt = 0.0;
@@ -865,22 +893,39 @@ int orc_update_prop_rb(int64_t N, const double *X, const int32_t *idx,
             gam[k] = (df + d) / (df + m);
          }
       }
-      count[idx[n]]++;
+      ct[idx[n]]++;
       for (int k = 0; k < K; k++) {
          double rk = r[k] / rt;
          rho[n * K + k] = rk * gam[k];
          double wr = wbar[n] * rk;
-         A[k] += wr;
-         G[k] += wr * gam[k];
-         for (int i = 0; i < d; i++) B[k * d + i] += wr * gam[k] * x[i];
+         At[k] += wr;
+         Gt[k] += wr * gam[k];
+         for (int i = 0; i < d; i++) Bt[k * d + i] += wr * gam[k] * x[i];
       }
    }
+   }
+   for (int th = 1; th < nt; th++)
+      for (int k = 0; k < K; k++) {
+         A[k] += A[(size_t)th * K + k]; G[k] += G[(size_t)th * K + k]; count[k] += count[(size_t)th * K + k];
+         for (int i = 0; i < d; i++) B[k * d + i] += B[((size_t)th * K + k) * d + i];
+      }
    /* M-step: alpha' = A, mu' = B/G, Sigma' = sum w rho gamma (x-mu')(x-mu')^T / A */
    for (int k = 0; k < K; k++) {
       if (wght[k] == 0.0 || !(A[k] > 0.0)) continue;
       for (int i = 0; i < d; i++) B[k * d + i] /= G[k];
    }
-   for (int64_t n = 0; n < N; n++) {
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nt)
+#endif
+   {
+#ifdef _OPENMP
+   const int th = omp_get_thread_num();
+#else
+   const int th = 0;
+#endif
+   const int64_t n0 = N * th / nt, n1 = N * (th + 1) / nt;
+   double *Ct = C + (size_t)th * K * dd;
+   for (int64_t n = n0; n < n1; n++) {
       if (!flg[n]) continue;
       const double *x = X + n * d;
       for (int k = 0; k < K; k++) {
@@ -890,10 +935,13 @@ int orc_update_prop_rb(int64_t N, const double *X, const int32_t *idx,
          for (int i = 0; i < d; i++) {
             double di = x[i] - B[k * d + i];
             for (int j = 0; j <= i; j++)
-               C[k * dd + i * d + j] += wr * di * (x[j] - B[k * d + j]);
+               Ct[k * dd + i * d + j] += wr * di * (x[j] - B[k * d + j]);
          }
       }
    }
+   }
+   for (int th = 1; th < nt; th++)
+      for (size_t e = 0; e < (size_t)K * dd; e++) C[e] += C[(size_t)th * K * dd + e];
    /* install + cleanup_after_update: dead if alpha < 1/N or fewer than
     * MINCOUNT points sampled from it, or the new covariance is not PD */
    double wsum = 0.0;
@@ -941,6 +989,41 @@ int orc_update_prop_rb(int64_t N, const double *X, const int32_t *idx,
  * reference's MPI scatter; sampling, normalisation and EM stay serial as on
  * the reference's rank 0.
  * ========================================================================== */
+/* "Mode B" of the CPU baseline: every stage parallel over samples -- what a CPU port
+ * would do given the freedom this repository took on the GPU.  Sampling is the same Philox stream (identical
+ * draws); the EM sums are combined per thread. */
+int orc_iteration_mode_b(const pmcb200_target_t *t, int64_t N, uint64_t seed,
+                  uint32_t iter, double beta, int K, int d, int df,
+                  double *wght, double *mean, double *chol, double *X,
+                  int32_t *idx, int16_t *flg, double *w,
+                  pmcb200_stats_t *st, int nthreads)
+{
+   memset(st, 0, sizeof(*st));
+   st->nsamples = N;
+   int nt = nthreads > 0 ? nthreads : 1;
+#ifdef _OPENMP
+   if (nthreads <= 0) nt = omp_get_max_threads();
+#endif
+   int64_t nok = 0;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nt) reduction(+ : nok) schedule(static)
+#endif
+   for (int64_t c = 0; c < (N + 4095) / 4096; c++) {
+      int64_t n0 = c * 4096, n1 = n0 + 4096 < N ? n0 + 4096 : N;
+      nok += orc_simulate(n1 - n0, seed, iter, n0, K, d, df, wght, mean, chol, t->min, t->max, X + n0 * d, idx + n0, flg + n0);
+   }
+   st->nok_box = nok;
+   if (st->nok_box == 0) return PMCB200_ERR_NOSAMPLE;
+   st->nok = orc_importance_weights(t, N, X, K, d, df, wght, mean, chol, beta, flg, w, &st->maxW, nt);
+   if (st->nok == 0) return PMCB200_ERR_NOSAMPLE;
+   st->sum_shift = orc_normalize_weights(N, flg, w, st->maxW, &st->logSum);
+   st->perplexity = orc_perplexity_and_ess(N, flg, w, &st->ess);
+   st->ln_evidence = st->logSum - log((double)N);
+   st->ndead = update_prop_rb_impl(N, X, idx, flg, w, K, d, df, wght, mean, chol, NULL, nt);
+   st->enc = orc_enc(K, wght);
+   return 0;
+}
+
 int orc_iteration(const pmcb200_target_t *t, int64_t N, uint64_t seed,
                   uint32_t iter, double beta, int K, int d, int df,
                   double *wght, double *mean, double *chol, double *X,

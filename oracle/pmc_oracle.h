@@ -90,6 +90,12 @@ int    orc_iteration(const pmcb200_target_t *t, int64_t N, uint64_t seed,
                      int32_t *idx, int16_t *flg, double *w,
                      pmcb200_stats_t *st, int nthreads);
 
+int    orc_iteration_mode_b(const pmcb200_target_t *t, int64_t N, uint64_t seed,
+                     uint32_t iter, double beta, int K, int d, int df,
+                     double *wght, double *mean, double *chol, double *X,
+                     int32_t *idx, int16_t *flg, double *w,
+                     pmcb200_stats_t *st, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -181,6 +181,20 @@ int main(int argc, char **argv)
    printf("unregistered_is_error %d %d\n", isError(*err), getErrorValue(*err));
    purgeError(err);
 
+   {  /* mirror bookkeeping: X went up at most once in the staged iteration above (never, in fact: simulate leaves it
+         on the device), and a host-side edit of single elements followed by pmc_b200_invalidate_mirror is seen */
+      long up = 0, skipped = 0;
+      pmc_b200_mirror_traffic(&up, &skipped);
+      printf("mirror_uploaded %ld\nmirror_skipped %ld\n", up, skipped);
+      double before, ess_b;
+      before = perplexity_and_ess(psim, MC_UNORM, &ess_b, err);               quitOnError(*err, __LINE__, stderr);
+      long imax = 0;
+      for (long i = 1; i < psim->nsamples; i++) if (psim->weights[i] > psim->weights[imax]) imax = i;
+      psim->weights[imax] = 0.0;                                              /* single-element edit */
+      pmc_b200_invalidate_mirror(psim);
+      double after = perplexity_and_ess(psim, MC_UNORM, &ess_b, err);         quitOnError(*err, __LINE__, stderr);
+      printf("perplexity_edit_seen %d\n", after != before);
+   }
    pmc_simu_free(&psim); pmc_simu_free(&psim2);
    mix_mvdens_free(&proposal); mix_mvdens_free(&proposal2);
    free_parabox(&pb); gsl_rng_free(rng);

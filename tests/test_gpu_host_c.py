@@ -90,6 +90,20 @@ def test_pmclib_named_iteration(oracle, tmp_path, nshards):
         assert np.allclose(chol @ chol.transpose(0, 2, 1), covo, rtol=1e-7, atol=1e-12)
     assert abs(r["fused_perplexity"][0] - so["perplexity"]) <= 1e-8 * so["perplexity"]
     assert r["fused_nok"][0] == so["nok"] and r["max_abs_dw"][0] < 1e-15
+    # mirror bookkeeping of the pmclib-named layer: simulate leaves X / idx / flg on the device and the weight,
+    # normalisation, update and diagnostics calls reuse the mirrors: the sample array itself (N x 5 doubles) is
+    # never uploaded, and most of the other uploads are skipped; an announced host-side edit is honoured.
+    # PMCB200_ALWAYS_UPLOAD=1 (the round-1 behaviour) must give identical results.
+    assert r["mirror_uploaded"][0] < 8 * N * 5 and r["mirror_skipped"][0] >= 2 * 8 * N * 5
+    assert r["perplexity_edit_seen"] == [1.0]
+    out2 = subprocess.run([str(exe), T.SN_FIXTURE, str(tmp_path / "proposal_in"), str(N), str(seed), str(beta),
+                           str(tmp_path)], capture_output=True, text=True,
+                          env=dict(os.environ, PMCB200_NGPU=str(nshards), PMCB200_DEVICES="0", PMCB200_ALWAYS_UPLOAD="1"))
+    assert out2.returncode == 0
+    r2 = parse(out2.stdout)
+    assert r2["mirror_skipped"] == [0.0] and r2["mirror_uploaded"][0] >= 2 * 8 * N * 5
+    for key in ("nok", "maxW", "logSum", "norm", "perplexity", "ess", "ln_evidence", "enc", "staged_wght", "staged_mean", "staged_chol"):
+        assert r2[key] == r[key], key
     # binary pmcsim sidecar: every flagged row, exact parameters and indices, weights to rounding, same logSum
     nrow, bad, maxrel, logsum3, ns3 = r["bin_roundtrip"]
     assert nrow == so["nok"] and bad == 0 and maxrel < 1e-12 and ns3 == N

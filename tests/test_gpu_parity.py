@@ -260,6 +260,31 @@ def test_posterior_bao_D_V_ratio(oracle, pmc_factory):
     assert rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-12
 
 
+def test_posterior_bao_deep_romberg_stages(oracle, pmc_factory):
+    """w0 + w1 > 1/3: dark energy dominates the early universe, the sound-horizon integrand is singular at a -> 0
+    and the Romberg rule runs deep (up to 2^19 nodes, or 'too many steps').  On the device those stages are
+    evaluated by the whole warp for one lane at a time (romberg_warp); values and error flags must still be the
+    oracle's, for the stragglers and for their well-behaved warp neighbours."""
+    pmc = pmc_factory()
+    spec = T.target_sn_bao_w0wa()
+    pmc.set_target(spec)
+    rng = np.random.default_rng(31)
+    N = 96
+    X = np.array([0.28, 0.72, -1.0, 0.0, 19.31, 1.4, -2.4])[None, :] + rng.normal(size=(N, 7)) * np.array([0.04, 0.06, 0.15, 0.2, 0.03, 0.1, 0.1])
+    hard = [3, 17, 40, 41, 77]                      # a few lanes of three different warps
+    X[hard, 2] = [-0.4, -0.2, -0.6, -0.3, -0.1]
+    X[hard, 3] = [0.9, 0.7, 1.2, 1.5, 0.5]
+    ref, eref = oracle.posterior_log_pdf(spec, X)
+    got, egot = pmc.posterior_log_pdf(dev(X))
+    got, egot = got.cpu().numpy(), egot.cpu().numpy()
+    assert np.array_equal(egot != 0, eref != 0)
+    ok = eref == 0
+    assert ok.sum() >= N - len(hard)
+    assert rel(got[ok], ref[ok]) < RTOL_LOG
+    c = pmc.counters()
+    assert c["gen_evals"] > 2 * N * 17              # the deep stages were walked (and counted)
+
+
 def test_posterior_banana_and_mixture(oracle, pmc_factory):
     pmc = pmc_factory()
     spec = T.target_banana(20)
@@ -420,6 +445,39 @@ def test_iteration_sn_bao_w0wa(oracle, pmc_factory):
     o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 8000, seed=6)
     check_iteration(o, st, pmc, *h)
     assert st["nok"] > 7000
+
+
+def test_pipelined_host_delivery_matches_blocking_call(oracle, pmc_factory):
+    """pmcb200_iteration_host_begin / pmcb200_host_wait: three chained iterations with the copies of one draining
+    under the next give the same host arrays, statistics and proposals as three blocking pmcb200_iteration_host calls."""
+    spec = T.target_sn_demo()
+    w, m, cov = T.proposal_sn(10)
+    ch = oracle.cholesky_stack(cov)
+    N = 30000
+    def host():
+        return (torch.empty((N, 5), dtype=torch.float64).pin_memory(), torch.empty(N, dtype=torch.int32).pin_memory(),
+                torch.empty(N, dtype=torch.int16).pin_memory(), torch.empty(N, dtype=torch.float64).pin_memory())
+    a = pmc_factory(); a.set_target(spec); a.set_proposal(w, m, chol=ch)
+    ref = []
+    for it in range(3):
+        h = host()
+        st = a.iteration_host(N, 77, it, 1.0, *h)
+        ref.append((st, [t.clone() for t in h], a.get_proposal()))
+    b = pmc_factory(); b.set_target(spec); b.set_proposal(w, m, chol=ch)
+    hs, sts = [host() for _ in range(3)], []
+    for it in range(3):
+        sts.append(b.iteration_host_begin(N, 77, it, 1.0, *hs[it]))
+        b.host_wait(1)                               # everything but the iteration just begun is on the host
+        if it > 0:
+            for t, r in zip(hs[it - 1], ref[it - 1][1]):
+                assert torch.equal(t, r)
+    b.host_wait(0)
+    for it in range(3):
+        assert sts[it] == ref[it][0]
+        for t, r in zip(hs[it], ref[it][1]):
+            assert torch.equal(t, r)
+    for x, y in zip(b.get_proposal(), ref[2][2]):
+        assert np.array_equal(x, y)
 
 
 def test_multi_iteration_convergence_gauss2d(pmc_factory):

@@ -44,7 +44,11 @@ def test_device_parameter_mapping_bitwise(pmc_factory, tmp_path, case):
         assert np.array_equal(ed != 0, E != 0), (case[0], i)
         ok = E == 0
         nc = 15 if spec.t.like[i].kind == A.LIKE["SNIa"] else 9
-        assert np.array_equal(bits(md[ok][:, :nc]), bits(M[ok][:, :nc])), (case[0], i)
+        cols = np.arange(nc)
+        if "log_beta" in case[1]:      # Theta2[2] = -exp(x): libdevice's exp against glibc's, one ulp apart at most
+            assert np.max(np.abs(md[ok][:, 11] - M[ok][:, 11]) / np.abs(M[ok][:, 11])) < 3e-16
+            cols = cols[cols != 11]
+        assert np.array_equal(bits(md[ok][:, cols]), bits(M[ok][:, cols])), (case[0], i)
     ref.close()
 
 
