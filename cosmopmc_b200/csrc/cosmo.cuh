@@ -791,12 +791,169 @@ __device__ __forceinline__ void sn_zloop(const DevLike &L, const SNCoef &ec, con
   }
 }
 
+// One redshift for ONE lane (the warp-per-sample kernel below): sn_zloop's body with lane-local control flow --
+// the rare integral that does not converge at stage 5 continues in its own lane.
+template <bool HASQ, bool FLAT, bool SLOW, bool NEG>
+__device__ __forceinline__ void sn_zone(const DevLike &L, const SNCoef &ec, const double *__restrict__ T,
+                                        const SNPer &m_, double f1, double rh, int iz, double &chi2, double &logdet,
+                                        int &e, unsigned &nev) {
+  const bool flat = fabs(ec.OK) < FLAT_EPS;
+  const int mode = L.sn_chi2mode;
+  const double2 *__restrict__ nd = L.nodes + (size_t)iz * SN_NODES;
+  const double *__restrict__ na = L.nodes_a + (size_t)iz * SN_NODES;
+  SNSums S;
+  double ss, dss, lnaz, h;
+  sn_romb5<HASQ, FLAT, SLOW, NEG>(ec, T, nd, na, L.nodes4 + (size_t)iz * (4 * 16), f1, S, ss, dss, lnaz, h);
+  bool done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
+  nev += 17;
+  if (!done) {        // rare: rebuild the tableau row of stage 5 and continue (as sn_zloop)
+    const double g0 = S.g0, S1 = S.S1, S2 = S.S2, S3 = S.S3, S4 = S.S4;
+    const double T1 = h * g0, T2 = 0.5 * h * (g0 + S1), T3 = 0.25 * h * (g0 + S1 + S2),
+                 T4 = 0.125 * h * (g0 + S1 + S2 + S3), T5 = 0.0625 * h * (g0 + S1 + S2 + S3 + S4);
+    double a1 = fma(T2 - T1, 1.0 / 3.0, T2);
+    double b1 = fma(T3 - T2, 1.0 / 3.0, T3), b2 = fma(b1 - a1, 1.0 / 15.0, b1);
+    double c1 = fma(T4 - T3, 1.0 / 3.0, T4), c2 = fma(c1 - b1, 1.0 / 15.0, c1);
+    double d1 = fma(T5 - T4, 1.0 / 3.0, T5), d2 = fma(d1 - c1, 1.0 / 15.0, d1), d3 = fma(d2 - c2, 1.0 / 63.0, d2);
+    (void)b2;
+    double st = T5, R0 = T5, R1 = d1, R2 = d2, R3 = d3;
+    int j = 5;
+    while (!done) {
+      if (j >= ROMB_JMAX) { ss = NAN; break; }
+      const int it = 1 << (j - 1);
+      double s = 0.0;
+      if (2 * it <= SN_NODES) {
+        for (int i = it; i < 2 * it; i++) {
+          const double2 n = __ldg(&nd[i]);
+          s = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, n.x, n.y, (HASQ || !FLAT) ? __ldg(&na[i]) : 0.0, s);
+        }
+      } else {
+        const double del = h / (double)it, az = __ldg(na);
+        for (int i = 0; i < it; i++) {
+          double a = fma((double)i + 0.5, del, az);
+          s = sn_f<HASQ, FLAT, SLOW, NEG>(ec, T, log(a), rsqrt(a), a, s);
+        }
+      }
+      nev += it;
+      st = 0.5 * (st + h * s / (double)it);
+      double n1 = fma(st - R0, 1.0 / 3.0, st), n2 = fma(n1 - R1, 1.0 / 15.0, n1), n3 = fma(n2 - R2, 1.0 / 63.0, n2);
+      dss = (n3 - R3) * (1.0 / 255.0);
+      ss = n3 + dss;
+      R0 = st; R1 = n1; R2 = n2; R3 = n3;
+      done = !isfinite(ss) || (fabs(dss) <= ROMB_EPS * fabs(ss));
+      j++;
+    }
+  }
+  double ww = rh * ss;
+  double fk = (FLAT || flat) ? ww : f_K_from(ec.OK, ww);
+  if (!(fk > 0.0)) e = 1;
+  const double mu_th = fma(5.0 / M_LN10, (SLOW ? log(fk) : fast_log(fk, T)) - lnaz, SN_MU0);
+  const int i0 = __ldg(&L.first[iz]), i1 = __ldg(&L.first[iz + 1]);
+  for (int i = i0; i < i1; i++) {
+    const double2 *__restrict__ r = reinterpret_cast<const double2 *>(L.sn + (size_t)i * SN_ROW);
+    const double2 ms = __ldg(&r[0]), cz = __ldg(&r[1]), w01 = __ldg(&r[2]), w23 = __ldg(&r[3]), w45 = __ldg(&r[4]);
+    double mu_obs, sig2;
+    if (mode == PMCB200_CHI2_betaz) {
+      const double t2 = fma(m_.Theta3, cz.y, m_.t2base);
+      mu_obs = ms.x + m_.Theta0 + m_.t1 * (ms.y - m_.stretch) + t2 * (cz.x - m_.color);
+      sig2 = w01.x + m_.d1 * m_.d1 * w01.y + t2 * t2 * w23.x + 2.0 * (m_.d1 * w23.y + t2 * w45.x + m_.d1 * t2 * w45.y);
+    } else {
+      mu_obs = fma(m_.t1, ms.y, fma(m_.t2base, cz.x, ms.x + m_.base0));
+      sig2 = fma(m_.k1, w01.y, fma(m_.k2, w23.x, fma(m_.k3, w23.y, fma(m_.k4, w45.x, fma(m_.k5, w45.y, w01.x)))));
+    }
+    const double res = mu_obs - mu_th;
+    chi2 = fma(res * res, fast_rcp(sig2), chi2);
+    if (L.sn_add_logdetCov) logdet += log(sig2);
+  }
+}
+
 #ifndef SN_MIN_BLOCKS
 #define SN_MIN_BLOCKS 2
 #endif
 #ifndef SN_BLOCK
 #define SN_BLOCK 256
 #endif
+// per-sample constants of the SN likelihood: integrand coefficients in both normalisations, chi^2 terms
+__device__ __forceinline__ void sn_setup(const DevLike &L, const Model &m, int force_slow, SNCoef &ec, SNPer &pm,
+                                         double &f1, double &f1s) {
+  {
+    const ECoef g = make_ecoef(m.c, 0);
+    ec.Om = g.Om; ec.OK = g.OK; ec.Ode = g.Ode; ec.p = g.p - 1.0; ec.q = g.q; ec.jassal = g.jassal;
+    ec.p2 = ec.p * M_LOG2E; ec.q2 = g.q * M_LOG2E;
+    const double aO = fabs(g.Ode);
+    const double lg = log2(aO);
+    ec.sgn = (g.Ode < 0.0) ? 0x80000000u : 0u;
+    ec.Oms = g.Om / aO; ec.OKs = g.OK / aO; ec.scale = rsqrt(aO);
+    // bound on |s| over a in [a_min, 1]; outside the fast path's range (or Ode = 0,
+    // non-finite input) the warp takes the libdevice path
+    const double lna_min = -__ldg(&L.nodes[(size_t)(L.sn_nz - 1) * SN_NODES]).x;
+    ec.slow = force_slow || !(fabs(ec.p2) * lna_min + fabs(ec.q2) + fabs(lg) < 990.0);
+  }
+  // integrand at a = 1 (a^-1/2 = 1, 2^0 = 1), in both normalisations
+  f1 = rsqrt(ec.Om + ec.OK + ec.Ode);
+  f1s = rsqrt(ec.Oms + ec.OKs + (ec.sgn ? -1.0 : 1.0));
+  pm.Theta0 = m.Theta2[0]; pm.Theta3 = m.Theta2[3]; pm.t1 = m.Theta2[1]; pm.t2base = m.Theta2[2];
+  pm.d1 = pm.t1; pm.d2 = pm.t2base; pm.stretch = m.stretch; pm.color = m.color;
+  if (L.sn_chi2mode == PMCB200_CHI2_no_sc) { pm.d1 = 0.0; pm.d2 = 0.0; pm.t1 = 0.0; pm.t2base = 0.0; }
+  if (L.sn_chi2mode == PMCB200_CHI2_Theta2_denom_fixed) { pm.d1 = L.Theta2_denom[1]; pm.d2 = L.Theta2_denom[2]; }
+  pm.base0 = pm.Theta0 - pm.t1 * pm.stretch - pm.t2base * pm.color;
+  pm.k1 = pm.d1 * pm.d1; pm.k2 = pm.d2 * pm.d2; pm.k3 = 2.0 * pm.d1; pm.k4 = 2.0 * pm.d2;
+  pm.k5 = 2.0 * pm.d1 * pm.d2;
+}
+
+// ---- SN Ia for small batches: ONE SAMPLE PER WARP, lanes across the redshifts ------------------------------
+// The thread-per-sample kernel needs N >= 2 x 148 x 256 samples to fill the machine; the reference's own demo
+// draws 10^4 per iteration (Demo/MC_Demo/SN/config_pmc), where it occupies 40 of 148 SMs with 8 warps each.
+// Here lane l of the warp owns the redshifts l, l + 32, ...: the 16 tabulated nodes, the Romberg combination, the
+// distance modulus and the chi^2 terms of the supernovae at that redshift are all lane-local (sn_zone); the
+// sample's chi^2 is one butterfly sum.  Same per-redshift arithmetic as k_like_sn; the sum over redshifts is
+// associated differently (per lane, then across lanes), an O(1e-16) relative difference.
+template <bool HASQ, bool FLAT>
+__global__ void __launch_bounds__(SN_BLOCK, 2)
+k_like_sn_warp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+               const int16_t *__restrict__ flg, double *__restrict__ logpi,
+               int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow) {
+  __shared__ double T[96 + SN_EXP2_N];
+  load_fast_tables_sn(T);
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (SN_BLOCK / 32) + (threadIdx.x >> 5);     // this warp's sample
+  if (n >= N) return;
+  const bool active = !flg || flg[n];
+  if (!active) { if (lane == 0 && set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
+  Model m;
+  int e = apply_params(L, X + n * d, m);
+  const bool cut = !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c);
+  unsigned nev = 0;
+  double chi2 = 0.0, logdet = 0.0;
+  if (!e) {
+    SNCoef ec;
+    SNPer pm;
+    double f1, f1s;
+    sn_setup(L, m, force_slow, ec, pm, f1, f1s);
+    for (int iz = lane; iz < L.sn_nz; iz += 32) {
+      if (ec.slow) sn_zone<HASQ, FLAT, true, false>(L, ec, T, pm, f1, R_HUBBLE, iz, chi2, logdet, e, nev);
+      else if (ec.sgn != 0u) sn_zone<HASQ, FLAT, false, true>(L, ec, T, pm, f1s, R_HUBBLE * ec.scale, iz, chi2, logdet, e, nev);
+      else sn_zone<HASQ, FLAT, false, false>(L, ec, T, pm, f1s, R_HUBBLE * ec.scale, iz, chi2, logdet, e, nev);
+    }
+    chi2 = warp_sum(chi2);
+    if (L.sn_add_logdetCov) logdet = warp_sum(logdet);
+    e = __any_sync(0xffffffffu, e);
+  }
+  double res = -0.5 * chi2;
+  if (L.sn_add_logdetCov) res -= 0.5 * logdet;
+  if (cut) res = 0.0;                      // sn.c:260-274: SetDl ran, chi2_SN did not
+  else if (!isfinite(res)) e = 1;
+  if (lane == 0) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  if (cnt) {
+    unsigned tot = nev;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) {
+      atomicAdd(&cnt->sn_evals, (unsigned long long)tot);
+      atomicAdd(&cnt->sn_zsteps, (unsigned long long)L.sn_nz);
+    }
+  }
+}
+
 template <bool HASQ, bool FLAT>
 __global__ void __launch_bounds__(SN_BLOCK, SN_MIN_BLOCKS)
 k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
@@ -818,30 +975,9 @@ k_like_sn(const DevLike L, int64_t N, const double *__restrict__ X, int d,
     m.stretch = 1.0; m.color = 0.0;
   }
   SNCoef ec;
-  {
-    const ECoef g = make_ecoef(m.c, 0);
-    ec.Om = g.Om; ec.OK = g.OK; ec.Ode = g.Ode; ec.p = g.p - 1.0; ec.q = g.q; ec.jassal = g.jassal;
-    ec.p2 = ec.p * M_LOG2E; ec.q2 = g.q * M_LOG2E;
-    const double aO = fabs(g.Ode);
-    const double lg = log2(aO);
-    ec.sgn = (g.Ode < 0.0) ? 0x80000000u : 0u;
-    ec.Oms = g.Om / aO; ec.OKs = g.OK / aO; ec.scale = rsqrt(aO);
-    // bound on |s| over a in [a_min, 1]; outside the fast path's range (or Ode = 0,
-    // non-finite input) the warp takes the libdevice path
-    const double lna_min = -__ldg(&L.nodes[(size_t)(L.sn_nz - 1) * SN_NODES]).x;
-    ec.slow = force_slow || !(fabs(ec.p2) * lna_min + fabs(ec.q2) + fabs(lg) < 990.0);
-  }
-  // integrand at a = 1 (a^-1/2 = 1, 2^0 = 1), in both normalisations
-  const double f1 = rsqrt(ec.Om + ec.OK + ec.Ode);
-  const double f1s = rsqrt(ec.Oms + ec.OKs + (ec.sgn ? -1.0 : 1.0));
   SNPer pm;
-  pm.Theta0 = m.Theta2[0]; pm.Theta3 = m.Theta2[3]; pm.t1 = m.Theta2[1]; pm.t2base = m.Theta2[2];
-  pm.d1 = pm.t1; pm.d2 = pm.t2base; pm.stretch = m.stretch; pm.color = m.color;
-  if (L.sn_chi2mode == PMCB200_CHI2_no_sc) { pm.d1 = 0.0; pm.d2 = 0.0; pm.t1 = 0.0; pm.t2base = 0.0; }
-  if (L.sn_chi2mode == PMCB200_CHI2_Theta2_denom_fixed) { pm.d1 = L.Theta2_denom[1]; pm.d2 = L.Theta2_denom[2]; }
-  pm.base0 = pm.Theta0 - pm.t1 * pm.stretch - pm.t2base * pm.color;
-  pm.k1 = pm.d1 * pm.d1; pm.k2 = pm.d2 * pm.d2; pm.k3 = 2.0 * pm.d1; pm.k4 = 2.0 * pm.d2;
-  pm.k5 = 2.0 * pm.d1 * pm.d2;
+  double f1, f1s;
+  sn_setup(L, m, force_slow, ec, pm, f1, f1s);
   double chi2 = 0.0, logdet = 0.0;
   if (__any_sync(0xffffffffu, ec.slow)) sn_zloop<HASQ, FLAT, true, false>(L, ec, T, pm, f1, R_HUBBLE, chi2, logdet, e, nev);
   else if (__any_sync(0xffffffffu, ec.sgn != 0u))

@@ -43,10 +43,23 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
   // tests to validate the fast path against it)
   static const int force_slow = getenv("PMCB200_SN_FORCE_SLOW") ? atoi(getenv("PMCB200_SN_FORCE_SLOW")) : 0;
   // PMCB200_LIKE_V1=1: round-1 BAO / CMB kernels (A/B measurements, cross-check of the lean integrand); read per call
+  // crossover of the two SN layouts: the thread-per-sample kernel runs one wave (~0.1 ms at two resident blocks per SM)
+  // for up to 2 x 148 x 256 samples, the warp-per-sample kernel costs ~5.5 ns per sample
+  const char *evw = getenv("PMCB200_SN_WARP_MAX");
+  const int64_t sn_warp_max = evw && *evw ? atoll(evw) : 16384;
   const char *ev1 = getenv("PMCB200_LIKE_V1");
   const int like_v1 = ev1 && *ev1 && *ev1 != '0';
   switch (L.kind) {
     case PMCB200_LIKE_SNIa:
+      // small batches: one sample per warp (fills the machine from ~600 samples on); PMCB200_SN_WARP_MAX overrides
+      if (N <= sn_warp_max) {
+        const int gw = (int)((N + SN_BLOCK / 32 - 1) / (SN_BLOCK / 32));
+        if (L.sn_hasq && L.sn_flat) k_like_sn_warp<true, true><<<gw, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+        else if (L.sn_hasq) k_like_sn_warp<true, false><<<gw, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+        else if (L.sn_flat) k_like_sn_warp<false, true><<<gw, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+        else k_like_sn_warp<false, false><<<gw, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+        break;
+      }
       if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
       else if (L.sn_hasq) k_like_sn<true, false><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
       else if (L.sn_flat) k_like_sn<false, true><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);

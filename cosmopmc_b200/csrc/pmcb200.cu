@@ -9,6 +9,8 @@
 #include <vector>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>     // header-only; the ranges cost nothing unless a profiler injects itself
+
 #include "common.cuh"
 #include "cosmo_types.cuh"
 #include "pmc_kernels.cuh"
@@ -75,6 +77,12 @@ struct pmcb200_ctx {
   uint64_t seq = 0;
   DevBuf sFish, sLogpi, sErr, sBlock, sAll;
   DevBuf sPost, sPostTmp;                 // post-processing work space
+};
+
+// NVTX range per phase of the iteration (nsys / ncu --nvtx timelines: sample, likelihood, weights, EM, M-step, copies)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
 };
 
 static int fail(pmcb200_ctx *c, int code, const char *fmt, ...) {
@@ -631,6 +639,7 @@ static int reset_scal(pmcb200_ctx *c) {
 
 static int launch_simulate(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t iter, int64_t offset,
                            double *dX, int32_t *didx, int16_t *dflg) {
+  NvtxRange nvtx_("pmc:simulate");
   if (N <= 0) return 0;
   if (!c->d_box) return fail(c, PMCB200_ERR_STATE, "simulate needs the target's box (pmcb200_set_target)");
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.box = c->d_box; a.N = N; a.seed = seed; a.iter = iter;
@@ -642,6 +651,7 @@ static int launch_simulate(pmcb200_ctx *c, int64_t N, uint64_t seed, uint32_t it
 
 static int launch_posterior(pmcb200_ctx *c, int64_t N, const double *dX, const int16_t *dflg,
                             double *dlogpi, int32_t *derr) {
+  NvtxRange nvtx_("pmc:posterior");
   if (N <= 0) return 0;
   const int d = c->tgt.npar;
   for (int i = 0; i < c->tgt.ndata; i++) {
@@ -668,6 +678,7 @@ static int launch_posterior(pmcb200_ctx *c, int64_t N, const double *dX, const i
 
 static int launch_weights(pmcb200_ctx *c, int64_t N, const double *dX, const double *dlogpi,
                           const int32_t *derr, double beta, int16_t *dflg, double *dlogw) {
+  NvtxRange nvtx_("pmc:weights");
   if (N <= 0) return 0;
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.logpic = dlogpi; a.errc = derr; a.beta = beta;
   a.flg = dflg; a.logw = dlogw; a.scal = c->d_scal;
@@ -692,6 +703,7 @@ static int launch_weights(pmcb200_ctx *c, int64_t N, const double *dX, const dou
 
 static int launch_em_local(pmcb200_ctx *c, int64_t N, const double *dX, const int32_t *didx,
                            const int16_t *dflg, const double *dlogw, double *dblock, int linear = 0) {
+  NvtxRange nvtx_("pmc:em_local");
   const int K = c->h.K, d = c->h.d;
   const int64_t len = stat_len(K, d);
   int64_t ntiles = (N + PMC_BLOCK - 1) / PMC_BLOCK;
@@ -875,6 +887,7 @@ extern "C" int pmcb200_em_finish(pmcb200_ctx *c, int nranks, const double *dall,
   int rc = need(c, true, false);
   if (rc) return rc;
   if (nranks < 1 || nranks > 64 || !dall || N_global < 1) return fail(c, PMCB200_ERR_ARG, "em_finish: bad arguments");
+  NvtxRange nvtx_("pmc:em_finish");
   const int K = c->h.K, d = c->h.d;
   pmc_launch_em_finish(c->d_mix, c->h, nranks, dall, N_global, c->d_work, c->d_result, c->d_fin_cnt, c->stream);
   LAUNCH_OK(c);
@@ -976,6 +989,7 @@ extern "C" int pmcb200_iteration_shard_host(pmcb200_ctx *c, int64_t N, uint64_t 
 extern "C" int pmcb200_shard_weights_host_begin(pmcb200_ctx *c, int64_t N, double *hw) {
   int rc = need(c, true, false);
   if (rc) return rc;
+  NvtxRange nvtx_("pmc:weights_to_host");
   pmcb200_ctx::ScratchSet &t = c->set[c->cur];
   if (N < 0 || (hw && (size_t)N * sizeof(double) > t.Logw.cap)) return fail(c, PMCB200_ERR_ARG, "shard_weights_host: bad arguments");
   if (N > 0 && hw) {

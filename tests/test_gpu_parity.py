@@ -134,6 +134,7 @@ def box_samples(spec, N, seed, shrink=0.0):
 
 
 def check_posterior(oracle, pmc, spec, X):
+    import os
     ref, eref = oracle.posterior_log_pdf(spec, X)
     got, egot = pmc.posterior_log_pdf(dev(X))
     got, egot = got.cpu().numpy(), egot.cpu().numpy()
@@ -142,6 +143,22 @@ def check_posterior(oracle, pmc, spec, X):
     assert ok.sum() > 0.5 * len(X)
     r = rel(got[ok], ref[ok])
     assert r < RTOL_LOG, r
+    if any(spec.t.like[i].kind == 3 for i in range(spec.t.ndata)):
+        # the SN likelihood has two layouts (one sample per thread for large batches, one sample per warp for small
+        # ones, switched at PMCB200_SN_WARP_MAX): this batch through the OTHER one as well
+        old = os.environ.get("PMCB200_SN_WARP_MAX")
+        os.environ["PMCB200_SN_WARP_MAX"] = "0" if len(X) <= 16384 else "1000000000"
+        try:
+            got2, egot2 = pmc.posterior_log_pdf(dev(X))
+        finally:
+            if old is None:
+                del os.environ["PMCB200_SN_WARP_MAX"]
+            else:
+                os.environ["PMCB200_SN_WARP_MAX"] = old
+        got2, egot2 = got2.cpu().numpy(), egot2.cpu().numpy()
+        assert np.array_equal(egot2 != 0, eref != 0)
+        assert rel(got2[ok], ref[ok]) < RTOL_LOG
+        assert rel(got2[ok], got[ok]) < 1e-12
     return r
 
 
