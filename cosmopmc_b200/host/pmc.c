@@ -195,6 +195,30 @@ void pmc_b200_mirror_traffic(long *uploaded_bytes, long *skipped_bytes)
    if (skipped_bytes) *skipped_bytes = g_mir_skipped_bytes;
 }
 
+/* ---- PMCB200_TIMING=1: wall-clock per pmclib-named entry point, printed to stderr when the process exits
+ * (how INTEGRATION.md's per-phase table of the unchanged driver at 10^6 - 10^7 samples was taken) ---------------- */
+#include <time.h>
+enum { TM_SIMULATE, TM_WEIGHTS, TM_NORMALIZE, TM_UPDATE, TM_STATS, TM_CLIP, TM_N };
+static const char *tm_name[TM_N] = { "simulate_mix_mvdens", "generic_get_importance_weight", "normalize_importance_weight",
+                                     "update_prop_rb", "perplexity/ess/evidence", "clip_weights" };
+static double tm_sec[TM_N]; static long tm_calls[TM_N]; static int tm_on = -1;
+static double tm_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+static void tm_report(void)
+{
+   long up = g_mir_uploaded_bytes, sk = g_mir_skipped_bytes;
+   fprintf(stderr, "[pmcb200 timing] %-32s %8s %12s\n", "entry point", "calls", "seconds");
+   for (int i = 0; i < TM_N; i++)
+      if (tm_calls[i]) fprintf(stderr, "[pmcb200 timing] %-32s %8ld %12.4f\n", tm_name[i], tm_calls[i], tm_sec[i]);
+   fprintf(stderr, "[pmcb200 timing] host->device sample traffic: %.1f MB uploaded, %.1f MB avoided by the mirror bookkeeping\n",
+           up / 1e6, sk / 1e6);
+}
+static double tm_begin(void)
+{
+   if (tm_on < 0) { const char *e = getenv("PMCB200_TIMING"); tm_on = e && *e && *e != '0'; if (tm_on) atexit(tm_report); }
+   return tm_on ? tm_now() : 0.0;
+}
+static void tm_end(int which, double t0) { if (tm_on > 0) { tm_sec[which] += tm_now() - t0; tm_calls[which]++; } }
+
 #define B200_OK(ctx, call, errcode, ret)                                                          \
    do { int rc__ = (call);                                                                        \
         if (rc__ != 0) { *err = addErrorVA((errcode), "%s (pmcb200 code %d)", *err, __LINE__,     \
@@ -484,6 +508,7 @@ double pmc_b200_single_loglike(const pmcb200_like_t *like, const double *x, erro
 /* ---- simulate_mix_mvdens (cosmo_pmc.c:320) -------------------------------------------- */
 size_t simulate_mix_mvdens(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, parabox *pb, error **err)
 {
+   const double tm0 = tm_begin();
    pmc_b200_context(err);
    forwardError(*err, __LINE__, 0);
    testErrorRetVA((size_t)psim->ndim != proposal->ndim, pmc_dimension, "psim ndim %d != proposal ndim %zu", *err,
@@ -519,6 +544,7 @@ size_t simulate_mix_mvdens(pmc_simu *psim, mix_mvdens *proposal, gsl_rng *r, par
    }
    for (long i = 0; i < n; i++) psim->indices[i] = (size_t)t[i];
    psim->isLog = 0;
+   tm_end(TM_SIMULATE, tm0);
    pmc_b200_invalidate_mirror(psim);
    mirror_mark(psim, MV_X | MV_IDX | MV_FLG);       /* the draw is identical on host and device; the weights are stale */
    return (size_t)nok;
@@ -530,6 +556,7 @@ size_t generic_get_importance_weight_and_deduced_verb(pmc_simu *psim, const void
           retrieve_ded_func *retrieve_ded, void *target_data, double beta, int quiet, error **err)
 {
    (void)retrieve_ded; (void)quiet;
+   const double tm0 = tm_begin();
    pmc_b200_context(err);
    forwardError(*err, __LINE__, 0);
    testErrorRet(proposal_log_pdf != mix_mvdens_log_pdf_void, pmc_undef,
@@ -562,6 +589,7 @@ size_t generic_get_importance_weight_and_deduced_verb(pmc_simu *psim, const void
    }
    psim->isLog = 1;
    psim->maxW = maxW;
+   tm_end(TM_WEIGHTS, tm0);
    mirror_mark(psim, MV_W | MV_FLG);                /* log weights and the cleared flags, both sides */
    return (size_t)nok;
 }
@@ -659,6 +687,7 @@ static void weight_stats_dev(long n, int is_log, double o[8], error **err)
 /* ---- normalize_importance_weight (cosmo_pmc.c:378) --------------------------------------- */
 double normalize_importance_weight(pmc_simu *psim, error **err)
 {
+   const double tm0 = tm_begin();
    pmc_b200_context(err);
    forwardError(*err, __LINE__, 0.0);
    testErrorRet(psim->isLog != 1, pmc_isLog, "Weights are not in log form", *err, __LINE__, 0.0);
@@ -678,6 +707,7 @@ double normalize_importance_weight(pmc_simu *psim, error **err)
    }
    sync_all(err);                                                  forwardError(*err, __LINE__, 0.0);
    psim->isLog = 0; psim->logSum = log(o[1]) + o[0]; psim->maxW = o[0];
+   tm_end(TM_NORMALIZE, tm0);
    mirror_mark(psim, MV_W);
    return o[1];
 }
@@ -685,6 +715,7 @@ double normalize_importance_weight(pmc_simu *psim, error **err)
 /* ---- update_prop_rb (cosmo_pmc.c:247) ------------------------------------------------------ */
 void update_prop_rb(mix_mvdens *proposal, pmc_simu *psim, error **err)
 {
+   const double tm0 = tm_begin();
    pmc_b200_context(err);
    forwardError(*err, __LINE__, );
    testErrorRet(psim->isLog != 0, pmc_isLog, "update_prop_rb needs normalised (non-log) weights", *err, __LINE__, );
@@ -713,6 +744,7 @@ void update_prop_rb(mix_mvdens *proposal, pmc_simu *psim, error **err)
       B200_OK(g_ctxs[s], rc, pmc_undef, );
    }
    pull_proposal(proposal, err);
+   tm_end(TM_UPDATE, tm0);
    forwardError(*err, __LINE__, );
 }
 void update_prop_rb_void(void *proposal, pmc_simu *psim, error **err) { update_prop_rb((mix_mvdens *)proposal, psim, err); }
@@ -720,12 +752,14 @@ void update_prop_rb_void(void *proposal, pmc_simu *psim, error **err) { update_p
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 static void weight_stats(pmc_simu *psim, double o[8], error **err)
 {
+   const double tm0 = tm_begin();
    pmc_b200_context(err);
    forwardError(*err, __LINE__, );
    long n = psim->nsamples;
    ensure_dev(n, psim->ndim, 0, err);                              forwardError(*err, __LINE__, );
    push_samples(psim, 0, 0, 1, err);                               forwardError(*err, __LINE__, );
    weight_stats_dev(n, psim->isLog, o, err);                       forwardError(*err, __LINE__, );
+   tm_end(TM_STATS, tm0);
 }
 
 /* perplexity = exp(-sum wbar log wbar)/N, ESS = 1/sum wbar^2 (manual.tex:555-590) */
@@ -762,6 +796,7 @@ double evidence(pmc_simu *psim, double *ln_evi, error **err)
 void clip_weights(pmc_simu *psim, int nclipw, FILE *OUT, error **err)
 {
    testErrorRet(psim->isLog != 0, pmc_isLog, "clip_weights needs normalised weights", *err, __LINE__, );
+   const double tm0 = tm_begin();
    for (int c = 0; c < nclipw; c++) {
       long imax = -1; double wmax = 0.0;
       for (long i = 0; i < psim->nsamples; i++)
@@ -776,6 +811,7 @@ void clip_weights(pmc_simu *psim, int nclipw, FILE *OUT, error **err)
    mirror_clear(psim, MV_W | MV_FLG);               /* host-side edit of weights and flags */
    for (long i = 0; i < psim->nsamples; i++) psim->weights[i] = psim->flg[i] ? psim->weights[i] / s : 0.0;
    psim->logSum += log(s);
+   tm_end(TM_CLIP, tm0);
 }
 
 double mean_from_psim(const double *X, const double *weights, const short *flg, long nsamples, int ndim, int a)
