@@ -158,7 +158,9 @@ def check_posterior(oracle, pmc, spec, X):
         got2, egot2 = got2.cpu().numpy(), egot2.cpu().numpy()
         assert np.array_equal(egot2 != 0, eref != 0)
         assert rel(got2[ok], ref[ok]) < RTOL_LOG
-        assert rel(got2[ok], got[ok]) < 1e-12
+        # same per-redshift arithmetic, the sum over redshifts associated differently; log pi = -chi2/2 + constants can
+        # come out near zero, which amplifies the last bits of chi2 in this relative measure
+        assert rel(got2[ok], got[ok]) < 1e-11
     return r
 
 
