@@ -26,15 +26,19 @@ METRIC = "pmc_samples_per_sec_full_iteration"
 UNIT = "samples/s"
 SEED = 20090903
 
-# algorithmic FLOPs of the SN likelihood = operation count of the REFERENCE algorithm as
-# restated in oracle/pmc_oracle.c (convention SURVEY.md 8d: + - * = 1, FMA = 2,
-# / sqrt exp log pow = 1 each); derivation in DESIGN.md section 6
+# FLOPs of the SN likelihood (convention SURVEY.md 8d: + - * = 1, FMA = 2, / sqrt exp log pow = 1 each); derivation in
+# DESIGN.md section 6.  Node-by-node path (the reference algorithm as restated in oracle/pmc_oracle.c):
 FLOP_PER_EVAL = 18.0       # int_for_w: a^4 E^2(a) incl. 1 pow + 1 exp (14), sqrt, 1/x, sum += (4)
 FLOP_PER_ZSTEP = 86.0      # per (sample, redshift): 5 trapzd combines (22), NR polint K=5 (54), test (4), D_L + modulus (6)
 FLOP_PER_SN = 29.0         # per (sample, supernova): mu_obs 7, sigma^2 18, chi^2 term 4
-# ncu evidence for the dominant kernel (profiles/sn_r01_v8_summary.txt), N = 2e6 capture
-NCU_SN = {"fp64_pipe_active_pct": 64.6, "dram_bytes_per_sample": 44.1,
-          "source": "profiles/sn_r01_v8_summary.txt"}
+# Spectral path (k_like_sn_spec): M integrand evaluations, the folded DCT (M^2/2 FMA + M adds), the two certificates
+# (~3 M), then per redshift an M-term dot product (M FMA) + D_L + modulus (8)
+SPEC_M = 32
+FLOP_SPEC_SAMPLE = SPEC_M * FLOP_PER_EVAL + SPEC_M * SPEC_M + 4 * SPEC_M
+FLOP_SPEC_ZSTEP = 2.0 * SPEC_M + 8.0
+# ncu evidence for the dominant kernel, per sample (filled from the capture named in "source")
+NCU_SN = {"fp64_pipe_active_pct": None, "dram_bytes_per_sample": None, "source": None}
+NCU_SN_EXACT = {"fp64_pipe_active_pct": 64.6, "dram_bytes_per_sample": 44.1, "source": "profiles/sn_r01_v8_summary.txt"}
 
 
 def parse():
@@ -44,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nsamples", type=int, default=10_000_000, help="samples per GPU per iteration")
-    ap.add_argument("--config", default="sn", choices=["sn", "banana", "sn_bao", "cmb_bao_sn"])
+    ap.add_argument("--config", default="sn", choices=["sn", "sn_curved", "banana", "sn_bao", "cmb_bao_sn"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -343,18 +347,34 @@ def main():
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
         c = pmc.counters()
-        n_sn = spec.t.like[0].sn_n
-        flops = (c["sn_evals"] * FLOP_PER_EVAL + c["sn_zsteps"] * FLOP_PER_ZSTEP
-                 + reps * n_loc * n_sn * FLOP_PER_SN) / reps
+        n_sn, n_z = spec.t.like[0].sn_n, c["sn_zsteps"] // max(1, c["sn_spec"] + c["sn_exact"])
+        spectral = c["sn_spec"] > 0
+        # the flops of the algorithm the kernels run: spectral samples by the spectral count, the rest node by node
+        ev_exact = c["sn_evals"] - SPEC_M * c["sn_spec"]
+        zs_exact = c["sn_zsteps"] - n_z * c["sn_spec"]
+        flops = (c["sn_spec"] * (FLOP_SPEC_SAMPLE + n_z * FLOP_SPEC_ZSTEP) + ev_exact * FLOP_PER_EVAL + zs_exact * FLOP_PER_ZSTEP
+                 + (c["sn_spec"] + c["sn_exact"]) * n_sn * FLOP_PER_SN) / reps
+        # what the reference's node-by-node algorithm would have spent on the same samples (17 evaluations per redshift
+        # when stage 5 converges, which the spectral kernel certifies for every sample it keeps)
+        flops_ref = (c["sn_spec"] * n_z * (17 * FLOP_PER_EVAL + FLOP_PER_ZSTEP) + ev_exact * FLOP_PER_EVAL + zs_exact * FLOP_PER_ZSTEP
+                     + (c["sn_spec"] + c["sn_exact"]) * n_sn * FLOP_PER_SN) / reps
         peak = pmc.fp64_peak_tflops()
         ach = flops / (k_ms * 1e-3) * 1e-12
-        roof = {"kernel": "k_like_sn", "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+        ncu = NCU_SN if spectral else NCU_SN_EXACT
+        roof = {"kernel": "k_like_sn_spec (+ k_like_sn_warp_list for the samples it hands over)" if spectral else "k_like_sn",
+                "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak if peak else None,
-                "traffic": NCU_SN["dram_bytes_per_sample"] * n_loc,
-                "traffic_source": "ncu dram__bytes_read+write per sample (%s) x samples per launch; algorithmic = %d B/sample" % (NCU_SN["source"], 8 * d + 12),
-                "fp64_pipe_active_pct_ncu": NCU_SN["fp64_pipe_active_pct"],
+                "traffic": ncu["dram_bytes_per_sample"] * n_loc if ncu["dram_bytes_per_sample"] else None,
+                "traffic_source": "ncu dram__bytes_read+write per sample (%s) x samples per launch; algorithmic = %d B/sample" % (ncu["source"], 8 * d + 12),
+                "fp64_pipe_active_pct_ncu": ncu["fp64_pipe_active_pct"],
                 "kernel_ms": k_ms, "flop_per_launch": flops,
+                "flop_convention": "flops of the algorithm the kernel runs: spectral samples %g + %d x %g + %d x %g per sample; "
+                                   "node-by-node samples 18 per evaluation + 86 per redshift + 29 per SN" % (FLOP_SPEC_SAMPLE, n_z, FLOP_SPEC_ZSTEP, n_sn, FLOP_PER_SN),
+                "samples_spectral": c["sn_spec"] / reps, "samples_node_by_node": c["sn_exact"] / reps,
                 "evals_per_sample": c["sn_evals"] / reps / n_loc,
+                "reference_algorithm": {"flop_per_launch": flops_ref, "equivalent_TFLOPs": flops_ref / (k_ms * 1e-3) * 1e-12,
+                                        "note": "work the reference's 17-node Romberg per redshift would need for the same result; "
+                                                "a speed-up measure, not a roofline fraction"},
                 "peak_source": "measured live: DFMA-only kernel (pmcb200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "hbm_algorithmic_GBs": n_loc * (8 * d + 8 + 4) / (k_ms * 1e-3) * 1e-9}
 

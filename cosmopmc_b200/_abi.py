@@ -123,6 +123,7 @@ SYMBOLS = {
     "pmcb200_normalize_log_weights": (_i, [_vp, _i64, _vp, _vp, C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),
     "pmcb200_em_local_linear": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "pmcb200_counters": (_i, [_vp, C.POINTER(C.c_int64 * 4)]),
+    "pmcb200_counters_ex": (_i, [_vp, C.POINTER(C.c_int64), _i]),
     "pmcb200_fp64_peak": (_i, [_vp, C.POINTER(C.c_double)]),
     "pmcb200_dev_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "pmcb200_dev_free": (_i, [_vp, _vp]),

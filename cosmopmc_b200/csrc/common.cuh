@@ -60,6 +60,8 @@ struct DevCount {
   unsigned long long sn_zsteps; // (sample, redshift) pairs integrated
   unsigned long long gen_evals;      // integrand evaluations of the BAO / CMB kernels (on-the-fly nodes)
   unsigned long long gen_integrals;  // their integrals
+  unsigned long long sn_spec;        // SN samples evaluated by the spectral kernel (k_like_sn_spec)
+  unsigned long long sn_exact;       // SN samples evaluated by the exact warp-per-sample kernel
 };
 
 __device__ __forceinline__ unsigned long long dkey(double x) {

@@ -907,18 +907,13 @@ __device__ __forceinline__ void sn_setup(const DevLike &L, const Model &m, int f
 // distance modulus and the chi^2 terms of the supernovae at that redshift are all lane-local (sn_zone); the
 // sample's chi^2 is one butterfly sum.  Same per-redshift arithmetic as k_like_sn; the sum over redshifts is
 // associated differently (per lane, then across lanes), an O(1e-16) relative difference.
+// one sample, evaluated by the calling warp (flg already checked by the caller)
 template <bool HASQ, bool FLAT>
-__global__ void __launch_bounds__(SN_BLOCK, 2)
-k_like_sn_warp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
-               const int16_t *__restrict__ flg, double *__restrict__ logpi,
-               int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow) {
-  __shared__ double T[96 + SN_EXP2_N];
-  load_fast_tables_sn(T);
+__device__ __forceinline__ void sn_warp_sample(const DevLike &L, const double *__restrict__ T, int64_t n,
+                                               const double *__restrict__ X, int d, double *__restrict__ logpi,
+                                               int32_t *__restrict__ err, int set, double add_const, DevCount *cnt,
+                                               int force_slow) {
   const int lane = threadIdx.x & 31;
-  const int64_t n = (int64_t)blockIdx.x * (SN_BLOCK / 32) + (threadIdx.x >> 5);     // this warp's sample
-  if (n >= N) return;
-  const bool active = !flg || flg[n];
-  if (!active) { if (lane == 0 && set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
   Model m;
   int e = apply_params(L, X + n * d, m);
   const bool cut = !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c);
@@ -950,8 +945,35 @@ k_like_sn_warp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
     if (lane == 0) {
       atomicAdd(&cnt->sn_evals, (unsigned long long)tot);
       atomicAdd(&cnt->sn_zsteps, (unsigned long long)L.sn_nz);
+      atomicAdd(&cnt->sn_exact, 1ull);
     }
   }
+}
+template <bool HASQ, bool FLAT>
+__global__ void __launch_bounds__(SN_BLOCK, 2)
+k_like_sn_warp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+               const int16_t *__restrict__ flg, double *__restrict__ logpi,
+               int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow) {
+  __shared__ double T[96 + SN_EXP2_N];
+  load_fast_tables_sn(T);
+  const int64_t n = (int64_t)blockIdx.x * (SN_BLOCK / 32) + (threadIdx.x >> 5);     // this warp's sample
+  if (n >= N) return;
+  if (flg && !flg[n]) { if ((threadIdx.x & 31) == 0 && set) { logpi[n] = 0.0; if (err) err[n] = 0; } return; }
+  sn_warp_sample<HASQ, FLAT>(L, T, n, X, d, logpi, err, set, add_const, cnt, force_slow);
+}
+// the same for a LIST of samples (the ones k_like_sn_spec could not certify): a fixed grid, warps stride over the list
+template <bool HASQ, bool FLAT>
+__global__ void __launch_bounds__(SN_BLOCK, 2)
+k_like_sn_warp_list(const DevLike L, const double *__restrict__ X, int d, double *__restrict__ logpi,
+                    int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int force_slow,
+                    const uint32_t *__restrict__ list, const unsigned *__restrict__ count) {
+  __shared__ double T[96 + SN_EXP2_N];
+  const unsigned cntv = *count;
+  if (cntv == 0u) return;
+  load_fast_tables_sn(T);
+  const unsigned nw = gridDim.x * (SN_BLOCK / 32);
+  for (unsigned i = blockIdx.x * (SN_BLOCK / 32) + (threadIdx.x >> 5); i < cntv; i += nw)
+    sn_warp_sample<HASQ, FLAT>(L, T, (int64_t)list[i], X, d, logpi, err, set, add_const, cnt, force_slow);
 }
 
 template <bool HASQ, bool FLAT>

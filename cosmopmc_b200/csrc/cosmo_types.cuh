@@ -21,6 +21,10 @@ struct DevLike {
   const int *first;       // [sn_nz+1] ranges of supernovae sharing a redshift
   const double *sn;       // [sn_n][SN_ROW]: m s | c z | Vmm+pv2+int2 Vss | Vcc Cms | Cmc Csc | - -
   int sn_hasq, sn_flat;   // launch-uniform specialisation flags (set by the host)
+  // spectral form (sn_spectral.cuh): Chebyshev points of [a(z_max), 1], the Romberg functional on T_m, its error bound
+  const double *cheb_nodes4;  // [SNS_M][4] {ln a_j, 1, a_j, -}
+  const double *cheb_W;       // [sn_nz][SNS_M]
+  const double *cheb_dmax;    // [SNS_M] max_z |D[z][m]| / h_z
   // Gaussian data (BAO, CMB distance priors): packed like a mixture component
   int bao_method, g_ndim;
   const double *g_z;

@@ -1,11 +1,13 @@
 // k_cosmo.cu -- the cosmology / analytic likelihood kernels and the small
 // non-templated kernels, with their host launch wrappers.
 #include "cosmo.cuh"
+#include "sn_spectral.cuh"
 #include "small_kernels.cuh"
 #include "launch.h"
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 
 // Fill the SN kernel's 2^(j/1024) table on the current device (pre-biased high words, cosmo.cuh).
 int pmc_init_sn_tables() {
@@ -29,14 +31,34 @@ int pmc_init_sn_tables() {
       ltab[2 * i] = rc;
       ltab[2 * i + 1] = (double)(-logl((long double)rc));
     }
+  // the spectral SN kernel's folded DCT: [m][j < M/2] = (2/M) cos(pi m (j + 1/2) / M), row 0 halved
+  static double dct[SNS_M * SNS_M / 2];
+  if (dct[0] == 0.0)
+    for (int m = 0; m < SNS_M; m++)
+      for (int j = 0; j < SNS_M / 2; j++)
+        dct[m * (SNS_M / 2) + j] = (double)((m == 0 ? 1.0L : 2.0L) / SNS_M * cosl(M_PIl * m * (j + 0.5L) / SNS_M));
+  if (cudaMemcpyToSymbol(SNS_DCT, dct, sizeof(dct)) != cudaSuccess) return 1;
   if (cudaMemcpyToSymbol(g_log1k, ltab, sizeof(ltab)) != cudaSuccess) return 1;
   return cudaMemcpyToSymbol(g_sn_exp2, tab, sizeof(tab)) == cudaSuccess ? 0 : 1;
 }
 
 static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK); }
 
+static int64_t sn_warp_max() {
+  const char *evw = getenv("PMCB200_SN_WARP_MAX");
+  return evw && *evw ? atoll(evw) : 16384;
+}
+// PMCB200_SN_EXACT=1: node-by-node kernels only (A/B measurements, cross-check of the spectral form); read per call
+bool pmc_sn_spectral_wanted(const DevLike &L, int64_t N) {
+  const char *ev = getenv("PMCB200_SN_EXACT");
+  if (ev && *ev && *ev != '0') return false;
+  return L.kind == PMCB200_LIKE_SNIa && L.cheb_W && N > sn_warp_max() && N < 4294967296ll;
+}
+int pmc_sn_spectral_M() { return SNS_M; }
+
 void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const int16_t *flg, double *logpi,
-                     int32_t *err, int set, double add, DevCount *cnt, cudaStream_t s) {
+                     int32_t *err, int set, double add, DevCount *cnt, uint32_t *fb_list, unsigned *fb_count,
+                     cudaStream_t s) {
   const int g = nblk(N);
   const int gs = (int)((N + SN_BLOCK - 1) / SN_BLOCK);
   // PMCB200_SN_FORCE_SLOW=1 routes every warp through libdevice exp (used by the
@@ -45,8 +67,7 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
   // PMCB200_LIKE_V1=1: round-1 BAO / CMB kernels (A/B measurements, cross-check of the lean integrand); read per call
   // crossover of the two SN layouts: the thread-per-sample kernel runs one wave (~0.1 ms at two resident blocks per SM)
   // for up to 2 x 148 x 256 samples, the warp-per-sample kernel costs ~5.5 ns per sample
-  const char *evw = getenv("PMCB200_SN_WARP_MAX");
-  const int64_t sn_warp_max = evw && *evw ? atoll(evw) : 16384;
+  const int64_t sn_warp_max = ::sn_warp_max();
   const char *ev1 = getenv("PMCB200_LIKE_V1");
   const int like_v1 = ev1 && *ev1 && *ev1 != '0';
   switch (L.kind) {
@@ -58,6 +79,23 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
         else if (L.sn_hasq) k_like_sn_warp<true, false><<<gw, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
         else if (L.sn_flat) k_like_sn_warp<false, true><<<gw, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
         else k_like_sn_warp<false, false><<<gw, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);
+        break;
+      }
+      // large batches: spectral form of the quadrature; the samples it cannot certify go to the exact kernel by list
+      if (fb_list && fb_count && pmc_sn_spectral_wanted(L, N)) {
+        const int gp = (int)((N + SNS_BLOCK - 1) / SNS_BLOCK);
+        const int gl = (int)std::min<int64_t>(148 * 8, (N + SN_BLOCK / 32 - 1) / (SN_BLOCK / 32));
+        cudaMemsetAsync(fb_count, 0, sizeof(unsigned), s);
+#define SPEC_LAUNCH(H, F)                                                                                          \
+        do {                                                                                                       \
+          k_like_sn_spec<H, F><<<gp, SNS_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count); \
+          k_like_sn_warp_list<H, F><<<gl, SN_BLOCK, 0, s>>>(L, X, d, logpi, err, set, add, cnt, force_slow, fb_list, fb_count); \
+        } while (0)
+        if (L.sn_hasq && L.sn_flat) SPEC_LAUNCH(true, true);
+        else if (L.sn_hasq) SPEC_LAUNCH(true, false);
+        else if (L.sn_flat) SPEC_LAUNCH(false, true);
+        else SPEC_LAUNCH(false, false);
+#undef SPEC_LAUNCH
         break;
       }
       if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);

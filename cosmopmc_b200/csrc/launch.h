@@ -42,8 +42,13 @@ static inline cudaError_t pmc_mix_launch(int op, const MixArgs &a, cudaStream_t 
 }
 
 // cosmology / analytic likelihood kernels (k_cosmo.cu)
+// fb_list [>= N] / fb_count: work list of the SN samples the spectral kernel hands to the exact kernel (both may be
+// null: the exact kernels run alone); pmc_sn_spectral_wanted says whether a launch of N samples would use them
 void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const int16_t *flg, double *logpi,
-                     int32_t *err, int set, double add_const, DevCount *cnt, cudaStream_t s);
+                     int32_t *err, int set, double add_const, DevCount *cnt, uint32_t *fb_list, unsigned *fb_count,
+                     cudaStream_t s);
+bool pmc_sn_spectral_wanted(const DevLike &L, int64_t N);
+int pmc_sn_spectral_M();
 void pmc_launch_map_params(const DevLike &L, int64_t N, const double *X, int d, double *out, int32_t *err, cudaStream_t s);
 // small kernels (k_cosmo.cu)
 void pmc_launch_normalize(int64_t N, const int16_t *flg, double *w, double M, double invS, cudaStream_t s);

@@ -76,6 +76,8 @@ struct pmcb200_ctx {
   int cur = 0;
   uint64_t seq = 0;
   DevBuf sFish, sLogpi, sErr, sBlock, sAll;
+  DevBuf sFb;                             // [N] uint32 work list + counter (at the end): SN samples for the exact kernel
+  unsigned *d_fb_cnt = nullptr;
   DevBuf sPost, sPostTmp;                 // post-processing work space
 };
 
@@ -241,6 +243,8 @@ static int create_impl(pmcb200_ctx *c, int device, void *stream) {
   if (pmc_init_sn_tables()) return fail(c, PMCB200_ERR_CUDA, "SN table upload failed");
   CUDA_OK(c, cudaMalloc((void **)&c->d_cnt, sizeof(DevCount)));
   CUDA_OK(c, cudaMemset(c->d_cnt, 0, sizeof(DevCount)));
+  CUDA_OK(c, cudaMalloc((void **)&c->d_fb_cnt, sizeof(unsigned)));
+  CUDA_OK(c, cudaMemset(c->d_fb_cnt, 0, sizeof(unsigned)));
   CUDA_OK(c, cudaMalloc((void **)&c->d_fin_cnt, sizeof(unsigned)));
   CUDA_OK(c, cudaMemset(c->d_fin_cnt, 0, sizeof(unsigned)));
   CUDA_OK(c, cudaMallocHost((void **)&c->h_result, sizeof(double) * (RES_HDR + PMCB200_MAX_COMP * (1 + PMCB200_MAX_DIM + PMCB200_MAX_DIM * PMCB200_MAX_DIM))));
@@ -279,8 +283,9 @@ extern "C" void pmcb200_destroy(pmcb200_ctx *c) {
     for (DevBuf *b : {&t.X, &t.Idx, &t.Flg, &t.Logw}) if (b->p) cudaFree(b->p);
     if (t.copied) cudaEventDestroy(t.copied);
   }
-  for (DevBuf *b : {&c->sFish, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll, &c->sPost, &c->sPostTmp, &c->sRho})
+  for (DevBuf *b : {&c->sFish, &c->sLogpi, &c->sErr, &c->sBlock, &c->sAll, &c->sPost, &c->sPostTmp, &c->sRho, &c->sFb})
     if (b->p) cudaFree(b->p);
+  if (c->d_fb_cnt) cudaFree(c->d_fb_cnt);
   if (c->d_mix) cudaFree(c->d_mix);
   if (c->d_scal) cudaFree(c->d_scal);
   if (c->d_cnt) cudaFree(c->d_cnt);
@@ -502,6 +507,51 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
   if ((rc = dev_copy<double>(c, nodes4.data(), nodes4.size(), &D.nodes4))) return rc;
   if ((rc = dev_copy<int>(c, first.data(), first.size(), &D.first))) return rc;
   if ((rc = dev_copy<double>(c, rows.data(), rows.size(), &D.sn))) return rc;
+  // Spectral form (sn_spectral.cuh).  Stage 5 of NR qromb at redshift z is ss = h sum_i w_i f(a_i), dss = h sum_i e_i
+  // f(a_i) over the 17 nodes tabulated above (+ the end point a = 1), f(a) = a^-1/2 q(a).  With q = sum_m c_m T_m(x(a))
+  // on [a(z_max), 1]:  ss = sum_m W[z][m] c_m,  dss = sum_m D[z][m] c_m.  Long double throughout.
+  {
+    const int M = pmc_sn_spectral_M(), nz = D.sn_nz;
+    static const long double RW[10] = {3937.0L / 103275.0L, 3062.0L / 80325.0L, 27728.0L / 722925.0L, 22016.0L / 722925.0L,
+                                       65536.0L / 722925.0L, -31.0L / 206550.0L, -73.0L / 481950.0L, -67.0L / 722925.0L,
+                                       -424.0L / 722925.0L, 256.0L / 722925.0L};      // = ROMBW (cosmo.cuh)
+    long double alo = 1.0L;
+    for (int z = 0; z < nz; z++) alo = std::min<long double>(alo, (long double)nodes_a[(size_t)z * SN_NODES]);
+    if (alo > 0.999L) alo = 0.999L;     // keep the map x(a) well conditioned for a sample of tiny redshifts
+    const long double mid = 0.5L * (1.0L + alo), half = 0.5L * (1.0L - alo);
+    std::vector<double> cn((size_t)M * 4, 0.0), W((size_t)nz * M), dmax(M, 0.0);
+    for (int j = 0; j < M; j++) {
+      const long double aj = mid + half * cosl(M_PIl * (j + 0.5L) / M);
+      cn[4 * j + 1] = 1.0; cn[4 * j + 2] = (double)aj;
+      cn[4 * j] = (double)logl((long double)cn[4 * j + 2]);      // ln of the ROUNDED node (what the kernel evaluates at)
+    }
+    std::vector<long double> Tm(M);
+    for (int z = 0; z < nz; z++) {
+      const size_t base = (size_t)z * SN_NODES;
+      const long double az = nodes_a[base], h = 1.0L - az;
+      std::vector<long double> w(M, 0.0L), dd(M, 0.0L);
+      for (int i = 0; i <= 16; i++) {       // i < 16: tabulated node i; i = 16: the end point a = 1
+        const long double a = (i < 16) ? (long double)nodes_a[base + i] : 1.0L;
+        int st = 0;                         // weight class: 0 = end points (half weight), j = new nodes of stage j + 1
+        if (i >= 1 && i < 16) { st = 1; while ((2 << (st - 1)) <= i) st++; }
+        const long double wi = (st == 0 ? 0.5L : 1.0L) * RW[st], ei = (st == 0 ? 0.5L : 1.0L) * RW[5 + st];
+        long double x = (a - mid) / half;
+        x = std::max<long double>(-1.0L, std::min<long double>(1.0L, x));
+        const long double th = acosl(x), rsa = 1.0L / sqrtl(a);
+        for (int m = 0; m < M; m++) {
+          const long double t = cosl(m * th) * rsa;
+          w[m] += wi * t; dd[m] += ei * t;
+        }
+      }
+      for (int m = 0; m < M; m++) {
+        W[(size_t)z * M + m] = (double)(h * w[m]);
+        dmax[m] = std::max(dmax[m], (double)fabsl(dd[m]));      // |D[z][m]| / h_z
+      }
+    }
+    if ((rc = dev_copy<double>(c, cn.data(), cn.size(), &D.cheb_nodes4))) return rc;
+    if ((rc = dev_copy<double>(c, W.data(), W.size(), &D.cheb_W))) return rc;
+    if ((rc = dev_copy<double>(c, dmax.data(), dmax.size(), &D.cheb_dmax))) return rc;
+  }
   return 0;
 }
 
@@ -665,7 +715,14 @@ static int launch_posterior(pmcb200_ctx *c, int64_t N, const double *dX, const i
       MIX_OK(c, OP_LIKE_MIX, a);
       continue;
     }
-    pmc_launch_like(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt, c->stream);
+    uint32_t *fb = nullptr;
+    if (pmc_sn_spectral_wanted(L, N)) {       // work list for the samples the spectral kernel hands to the exact one
+      int rc = ensure(c, c->sFb, (size_t)N * sizeof(uint32_t));
+      if (rc) return rc;
+      fb = (uint32_t *)c->sFb.p;
+    }
+    pmc_launch_like(L, N, dX, d, dflg, dlogpi, derr, set, add, c->d_cnt, fb, c->d_fb_cnt, c->stream);
+    if (fb) c->launches += 2;
     LAUNCH_OK(c);
   }
   if (c->d_prior) {
@@ -1358,6 +1415,18 @@ extern "C" int pmcb200_counters(pmcb200_ctx *c, int64_t out[4]) {
   CUDA_OK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCount), c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   out[0] = (int64_t)h.sn_evals; out[1] = (int64_t)h.sn_zsteps; out[2] = (int64_t)h.gen_evals; out[3] = (int64_t)h.gen_integrals;
+  return 0;
+}
+
+extern "C" int pmcb200_counters_ex(pmcb200_ctx *c, int64_t *out, int n) {
+  if (!c || !out || n < 1) return PMCB200_ERR_ARG;
+  DevCount h;
+  CUDA_OK(c, cudaMemcpyAsync(&h, c->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCount), c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  const int64_t v[6] = {(int64_t)h.sn_evals, (int64_t)h.sn_zsteps, (int64_t)h.gen_evals, (int64_t)h.gen_integrals,
+                        (int64_t)h.sn_spec, (int64_t)h.sn_exact};
+  for (int i = 0; i < n; i++) out[i] = i < 6 ? v[i] : 0;
   return 0;
 }
 

@@ -1,0 +1,179 @@
+// sn_spectral.cuh -- SN Ia likelihood, spectral form of the reference's quadrature (replaces nicaea SetDl + chi2_SN
+// behind wrappers/src/sn.c:138-281 for large batches; the node-by-node kernel k_like_sn / k_like_sn_warp of
+// cosmo.cuh stays the exact path).
+//
+// What the reference computes per (sample, redshift) is NR qromb on 1/sqrt(a^4 E^2) over [a_z, 1]: when it stops
+// at stage 5 -- it always does on a smooth integrand, see below -- the result ss_z and its error estimate dss_z
+// are two FIXED linear functionals of the integrand at 17 nodes (ROMBW, cosmo.cuh).  The 241 redshifts of the
+// Union sample therefore ask for 4097 evaluations of ONE smooth function of a per sample, all inside
+// [a(z_max), 1].  This kernel evaluates the sample-dependent factor q(a) = Q(a)^-1/2 (Q = a^3 E^2 / |Omega_de|)
+// at SNS_M Chebyshev points of that interval, turns the values into Chebyshev coefficients c_m (a 32-point DCT,
+// folded), and applies the reference's functional to the interpolant:
+//     ss_z = sum_m W[z][m] c_m,      W[z][m] = h_z sum_i w_i a_i^-1/2 T_m(x(a_i))   (host, long double)
+// i.e. the Romberg rule -- nodes, weights, truncation error and all -- acts on a polynomial that agrees with the
+// integrand to ~1e-15.  Per sample: 32 integrand evaluations + a 241 x 32 matrix-vector product instead of 4097
+// evaluations (13 FP64 instructions each).
+//
+// Guarantees (per sample, checked in the kernel; a sample that fails ANY of them is handed to the exact kernel
+// through a list, so the fast path never decides anything the reference would decide differently):
+//   * interpolation: |c_(M-1)| + |c_(M-2)| + |c_(M-3)| <= SNS_TAIL_TOL |c_0|  (measured: the error of ss_z is
+//     below 1e-13 relative whenever this holds, tools/proto/sn_spectral_proto.py)
+//   * stopping rule: sum_m dmax_m |c_m| <= 0.25e-6 min_j q_j, with dmax_m = max_z |D[z][m]| / h_z the error
+//     functional of stage 5 -- a sufficient condition for |dss_z| <= EPS |ss_z| at EVERY redshift, so the
+//     reference stops at stage 5 everywhere and ss_z above is what it returns
+//   * range: Omega_de > 0, exponent inside the table-based 2^s (the exact kernel has the general paths)
+#pragma once
+#include "cosmo.cuh"
+
+#define SNS_M 32
+#define SNS_TAIL_TOL 1.0e-12
+#ifndef SNS_BLOCK
+#define SNS_BLOCK 256
+#endif
+#ifndef SNS_MIN_BLOCKS
+#define SNS_MIN_BLOCKS 2
+#endif
+
+// [m][j < M/2]: (2/M) cos(pi m (j + 1/2) / M), row 0 halved (filled by pmc_init_sn_tables, long double)
+__constant__ double SNS_DCT[SNS_M * SNS_M / 2];
+
+// chi^2 terms of the supernovae at redshift iz (the body of sn_zloop's inner loop)
+__device__ __forceinline__ void sn_chi2_terms(const DevLike &L, const SNPer &m_, int mode, int iz, double mu_th,
+                                              double &chi2, double &logdet) {
+  const int i0 = __ldg(&L.first[iz]), i1 = __ldg(&L.first[iz + 1]);
+  for (int i = i0; i < i1; i++) {
+    const double2 *__restrict__ r = reinterpret_cast<const double2 *>(L.sn + (size_t)i * SN_ROW);
+    const double2 ms = __ldg(&r[0]), cz = __ldg(&r[1]), w01 = __ldg(&r[2]), w23 = __ldg(&r[3]), w45 = __ldg(&r[4]);
+    double mu_obs, sig2;
+    if (mode == PMCB200_CHI2_betaz) {
+      const double t2 = fma(m_.Theta3, cz.y, m_.t2base);
+      mu_obs = ms.x + m_.Theta0 + m_.t1 * (ms.y - m_.stretch) + t2 * (cz.x - m_.color);
+      sig2 = w01.x + m_.d1 * m_.d1 * w01.y + t2 * t2 * w23.x + 2.0 * (m_.d1 * w23.y + t2 * w45.x + m_.d1 * t2 * w45.y);
+    } else {
+      mu_obs = fma(m_.t1, ms.y, fma(m_.t2base, cz.x, ms.x + m_.base0));
+      sig2 = fma(m_.k1, w01.y, fma(m_.k2, w23.x, fma(m_.k3, w23.y, fma(m_.k4, w45.x, fma(m_.k5, w45.y, w01.x)))));
+    }
+    const double res = mu_obs - mu_th;
+    chi2 = fma(res * res, fast_rcp(sig2), chi2);
+    if (L.sn_add_logdetCov) logdet += log(sig2);
+  }
+}
+
+template <bool HASQ, bool FLAT>
+__global__ void __launch_bounds__(SNS_BLOCK, SNS_MIN_BLOCKS)
+k_like_sn_spec(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+               const int16_t *__restrict__ flg, double *__restrict__ logpi,
+               int32_t *__restrict__ err, int set, double add_const, DevCount *cnt,
+               uint32_t *__restrict__ fb_list, unsigned *__restrict__ fb_count) {
+  __shared__ double T[96 + SN_EXP2_N];     // general tables + pre-biased 2^(j/1024)
+  __shared__ double2 LT[LOG1K_N];          // lean_log's {1/c_i, -ln(1/c_i)}
+  for (int i = threadIdx.x; i < LOG1K_N; i += blockDim.x) LT[i] = g_log1k[i];
+  load_fast_tables_sn(T);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = (n < N) && (!flg || flg[n]);
+  Model m;
+  int e = 0;
+  if (active) e = apply_params(L, X + n * d, m);
+  const bool cut = active && !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c);
+  if (!active || e) {   // benign model: the lane walks the loops, its result is not used
+    m.c = L.model;
+#pragma unroll
+    for (int i = 0; i < 4; i++) m.Theta2[i] = L.Theta2[i];
+    m.stretch = 1.0; m.color = 0.0;
+  }
+  SNCoef ec;
+  SNPer pm;
+  double f1, f1s;
+  sn_setup(L, m, 0, ec, pm, f1, f1s);
+  bool ok = !(ec.slow || ec.sgn != 0u);
+
+  // --- Chebyshev coefficients of q(a) = Q(a)^-1/2 on [a(z_max), 1]
+  double c[SNS_M];
+  double qmin;
+  {
+    double q[SNS_M];
+#pragma unroll
+    for (int j = 0; j < SNS_M; j++) {
+      const Ld4 nd = ld256(L.cheb_nodes4 + 4 * j);      // {ln a_j, 1, a_j, -}
+      q[j] = sn_f<HASQ, FLAT, false, false>(ec, T, nd.x, 1.0, nd.z, 0.0);
+    }
+    qmin = q[0];
+#pragma unroll
+    for (int j = 1; j < SNS_M; j++) qmin = fmin(qmin, q[j]);
+    // even coefficients from u_j = q_j + q_(M-1-j), odd ones from v_j = q_j - q_(M-1-j)
+#pragma unroll
+    for (int j = 0; j < SNS_M / 2; j++) {
+      const double u = q[j] + q[SNS_M - 1 - j], v = q[j] - q[SNS_M - 1 - j];
+      q[j] = u; q[SNS_M - 1 - j] = v;
+    }
+#pragma unroll
+    for (int mm = 0; mm < SNS_M; mm += 2) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < SNS_M / 2; j += 2) {
+        s0 = fma(SNS_DCT[mm * (SNS_M / 2) + j], q[j], s0);
+        s1 = fma(SNS_DCT[mm * (SNS_M / 2) + j + 1], q[j + 1], s1);
+      }
+      c[mm] = s0 + s1;
+    }
+#pragma unroll
+    for (int mm = 1; mm < SNS_M; mm += 2) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < SNS_M / 2; j += 2) {
+        s0 = fma(SNS_DCT[mm * (SNS_M / 2) + j], q[SNS_M - 1 - j], s0);
+        s1 = fma(SNS_DCT[mm * (SNS_M / 2) + j + 1], q[SNS_M - 2 - j], s1);
+      }
+      c[mm] = s0 + s1;
+    }
+  }
+  {   // the two guarantees (a NaN anywhere fails them)
+    const double tail = fabs(c[SNS_M - 1]) + fabs(c[SNS_M - 2]) + fabs(c[SNS_M - 3]);
+    double B = 0.0;
+#pragma unroll
+    for (int mm = 0; mm < SNS_M; mm++) B = fma(__ldg(&L.cheb_dmax[mm]), fabs(c[mm]), B);
+    if (!(tail <= SNS_TAIL_TOL * fabs(c[0]))) ok = false;
+    if (!(B <= 0.25 * ROMB_EPS * qmin)) ok = false;
+  }
+
+  // --- redshift loop: ss_z = W[z] . c, then the distance modulus and the chi^2 terms as in sn_zloop
+  const double rh = R_HUBBLE * ec.scale;
+  const bool flat = fabs(ec.OK) < FLAT_EPS;
+  const int mode = L.sn_chi2mode;
+  double chi2 = 0.0, logdet = 0.0;
+  const int nz = L.sn_nz;
+  for (int iz = 0; iz < nz; iz++) {
+    const double *__restrict__ w = L.cheb_W + (size_t)iz * SNS_M;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int mm = 0; mm < SNS_M; mm += 4) {
+      const Ld4 ww4 = ld256(w + mm);
+      s0 = fma(ww4.x, c[mm], s0); s1 = fma(ww4.y, c[mm + 1], s1);
+      s2 = fma(ww4.z, c[mm + 2], s2); s3 = fma(ww4.w, c[mm + 3], s3);
+    }
+    const double ss = (s0 + s1) + (s2 + s3);
+    const double ww = rh * ss;
+    const double fk = (FLAT || flat) ? ww : f_K_from(ec.OK, ww);
+    if (!(fk > 0.0)) e = 1;
+    const double lnaz = __ldg(&L.nodes[(size_t)iz * SN_NODES]).x;
+    const double mu_th = fma(5.0 / M_LN10, lean_log(fk, LT) - lnaz, SN_MU0);
+    sn_chi2_terms(L, pm, mode, iz, mu_th, chi2, logdet);
+  }
+  double res = -0.5 * chi2;
+  if (L.sn_add_logdetCov) res -= 0.5 * logdet;
+  if (cut) res = 0.0;
+  else if (!isfinite(res)) e = 1;
+  if (active && ok) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  else if (active) fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)n;      // the exact kernel evaluates this sample
+  else if (n < N && set) { logpi[n] = 0.0; if (err) err[n] = 0; }
+  if (cnt) {
+    unsigned nsp = (active && ok) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsp += __shfl_xor_sync(0xffffffffu, nsp, o);
+    if ((threadIdx.x & 31) == 0 && nsp) {
+      atomicAdd(&cnt->sn_evals, (unsigned long long)nsp * SNS_M);
+      atomicAdd(&cnt->sn_zsteps, (unsigned long long)nsp * nz);
+      atomicAdd(&cnt->sn_spec, (unsigned long long)nsp);
+    }
+  }
+}

@@ -398,6 +398,10 @@ int64_t pmcb200_launch_count(const pmcb200_ctx *ctx);
  * measured vector-FP64 peak in TFLOP/s (the roofline denominator that
  * MEASURED_PEAKS.json does not carry). */
 int pmcb200_counters(pmcb200_ctx *ctx, int64_t out[4]);
+/* the same with the SN kernel split: out[4] = samples evaluated by the spectral SN kernel, out[5] = samples
+ * evaluated node by node by the warp-per-sample kernel (small batches, and the samples the spectral kernel could
+ * not certify); n <= 6 entries are written, further ones zeroed */
+int pmcb200_counters_ex(pmcb200_ctx *ctx, int64_t *out, int n);
 int pmcb200_fp64_peak(pmcb200_ctx *ctx, double *tflops);
 
 /* raw device helpers so C hosts need not link the CUDA runtime */

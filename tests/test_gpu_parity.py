@@ -133,8 +133,27 @@ def box_samples(spec, N, seed, shrink=0.0):
     return lo + (shrink + (1 - 2 * shrink) * rng.random((N, len(lo)))) * (hi - lo)
 
 
+class environ:
+    """set environment variables for the duration of a with block (the library reads its switches per call)"""
+
+    def __init__(self, kv):
+        self.kv = kv
+
+    def __enter__(self):
+        import os
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        import os
+        for k, v in self.old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
 def check_posterior(oracle, pmc, spec, X):
-    import os
     ref, eref = oracle.posterior_log_pdf(spec, X)
     got, egot = pmc.posterior_log_pdf(dev(X))
     got, egot = got.cpu().numpy(), egot.cpu().numpy()
@@ -144,23 +163,20 @@ def check_posterior(oracle, pmc, spec, X):
     r = rel(got[ok], ref[ok])
     assert r < RTOL_LOG, r
     if any(spec.t.like[i].kind == 3 for i in range(spec.t.ndata)):
-        # the SN likelihood has two layouts (one sample per thread for large batches, one sample per warp for small
-        # ones, switched at PMCB200_SN_WARP_MAX): this batch through the OTHER one as well
-        old = os.environ.get("PMCB200_SN_WARP_MAX")
-        os.environ["PMCB200_SN_WARP_MAX"] = "0" if len(X) <= 16384 else "1000000000"
-        try:
-            got2, egot2 = pmc.posterior_log_pdf(dev(X))
-        finally:
-            if old is None:
-                del os.environ["PMCB200_SN_WARP_MAX"]
-            else:
-                os.environ["PMCB200_SN_WARP_MAX"] = old
-        got2, egot2 = got2.cpu().numpy(), egot2.cpu().numpy()
-        assert np.array_equal(egot2 != 0, eref != 0)
-        assert rel(got2[ok], ref[ok]) < RTOL_LOG
-        # same per-redshift arithmetic, the sum over redshifts associated differently; log pi = -chi2/2 + constants can
-        # come out near zero, which amplifies the last bits of chi2 in this relative measure
-        assert rel(got2[ok], got[ok]) < 1e-11
+        # the SN likelihood has three kernels: spectral form of the quadrature (large batches; hands what it cannot
+        # certify to the warp kernel), one sample per warp (small batches, node by node), one sample per thread (node
+        # by node).  This batch through all three.
+        small = len(X) <= 16384
+        for env in ({"PMCB200_SN_WARP_MAX": "0" if small else "1000000000"},
+                    {"PMCB200_SN_WARP_MAX": "0", "PMCB200_SN_EXACT": "1"}):
+            with environ(env):
+                got2, egot2 = pmc.posterior_log_pdf(dev(X))
+            got2, egot2 = got2.cpu().numpy(), egot2.cpu().numpy()
+            assert np.array_equal(egot2 != 0, eref != 0), env
+            assert rel(got2[ok], ref[ok]) < RTOL_LOG, env
+            # same per-redshift result to ~1e-15, the sum over redshifts associated differently; log pi = -chi2/2 +
+            # constants can come out near zero, which amplifies the last bits of chi2 in this relative measure
+            assert rel(got2[ok], got[ok]) < 1e-11, env
     return r
 
 
@@ -618,6 +634,42 @@ def test_iteration_host_multi_on_two_devices(oracle):
         assert np.allclose(a, b, rtol=1e-10, atol=1e-14)
     for a, b in zip(p2[0], p2[1]):
         assert np.array_equal(a, b)
+
+
+def test_sn_spectral_large_batch(oracle, pmc_factory):
+    """The spectral SN kernel on a batch drawn from the benchmark proposal (the layout large batches take by default):
+    log-posteriors against the oracle's node-by-node Romberg, against the exact device kernel, and the split between
+    the spectral kernel and the samples it handed to the exact one."""
+    for spec, lo_frac in ((T.target_sn_demo(), 0.99), (T.target_sn_curved(), 0.5)):
+        pmc = pmc_factory()
+        pmc.set_target(spec)
+        w, m, cov = T.proposal_sn(10)
+        rng = np.random.default_rng(77)
+        N = 60000
+        k = rng.integers(0, 10, N)
+        X = m[k] + np.einsum("nij,nj->ni", np.linalg.cholesky(cov)[k], rng.normal(size=(N, 5)))
+        if spec.spar[1] == "Omega_de":
+            X[:, 1] = 0.7 + 0.35 * rng.normal(size=N)      # curved: Omega_de instead of w0
+        lo, hi = spec.box
+        X = X[((X >= lo) & (X <= hi)).all(axis=1)]
+        pmc.counters()
+        got, egot = pmc.posterior_log_pdf(dev(X))
+        cnt = pmc.counters()
+        assert cnt["sn_spec"] + cnt["sn_exact"] == len(X)
+        assert cnt["sn_spec"] >= lo_frac * len(X), cnt
+        with environ({"PMCB200_SN_EXACT": "1"}):
+            ex, eex = pmc.posterior_log_pdf(dev(X))
+            cnt2 = pmc.counters()
+        assert cnt2["sn_spec"] == 0
+        got, egot, ex, eex = got.cpu().numpy(), egot.cpu().numpy(), ex.cpu().numpy(), eex.cpu().numpy()
+        assert np.array_equal(egot != 0, eex != 0)
+        ok = eex == 0
+        assert rel(got[ok], ex[ok]) < 1e-11
+        sub = np.arange(0, len(X), 3)
+        ref, eref = oracle.posterior_log_pdf(spec, X[sub])
+        assert np.array_equal(egot[sub] != 0, eref != 0)
+        oks = eref == 0
+        assert rel(got[sub][oks], ref[oks]) < RTOL_LOG
 
 
 def test_sn_fast_path_matches_libdevice_path(oracle, pmc_factory, tmp_path):
