@@ -25,6 +25,8 @@ struct DevLike {
   const double *cheb_nodes4;  // [SNS_M][4] {ln a_j, 1, a_j, -}
   const double *cheb_W;       // [sn_nz][SNS_M]
   const double *cheb_dmax;    // [SNS_M] max_z |D[z][m]| / h_z
+  const double *cheb_Wf;      // [sn_ntile][SNS_M/4 + 3][32] B fragments of the tensor-core kernel (8 supernovae per tile)
+  int sn_ntile, pad1;
   // Gaussian data (BAO, CMB distance priors): packed like a mixture component
   int bao_method, g_ndim;
   const double *g_z;

@@ -56,6 +56,27 @@ bool pmc_sn_spectral_wanted(const DevLike &L, int64_t N) {
 }
 int pmc_sn_spectral_M() { return SNS_M; }
 
+// spectral SN kernel + the exact kernel over the list of samples it could not certify
+template <bool H, bool F>
+static void launch_sn_spectral(const DevLike &L, int64_t N, const double *X, int d, const int16_t *flg, double *logpi,
+                               int32_t *err, int set, double add, DevCount *cnt, uint32_t *fb_list, unsigned *fb_count,
+                               int force_slow, cudaStream_t s) {
+  // tensor-core form unless the chi^2 mode has redshift-dependent coefficients (chi2_betaz) or wants log sigma^2; PMCB200_SN_SPEC_V1=1
+  // keeps the one-sample-per-thread form (A/B measurements); read per call
+  const char *ev = getenv("PMCB200_SN_SPEC_V1");
+  const bool mma = L.sn_chi2mode != PMCB200_CHI2_betaz && !L.sn_add_logdetCov && !(ev && *ev && *ev != '0');
+  if (mma) {
+    cudaFuncSetAttribute(k_like_sn_spec_mma<H, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SNS2_SMEM);   // per device
+    k_like_sn_spec_mma<H, F><<<(int)((N + SNS2_BLOCK - 1) / SNS2_BLOCK), SNS2_BLOCK, SNS2_SMEM, s>>>(
+        L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);
+  } else {
+    k_like_sn_spec<H, F><<<(int)((N + SNS_BLOCK - 1) / SNS_BLOCK), SNS_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt,
+                                                                                     fb_list, fb_count);
+  }
+  const int gl = (int)std::min<int64_t>(148 * 8, (N + SN_BLOCK / 32 - 1) / (SN_BLOCK / 32));
+  k_like_sn_warp_list<H, F><<<gl, SN_BLOCK, 0, s>>>(L, X, d, logpi, err, set, add, cnt, force_slow, fb_list, fb_count);
+}
+
 void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const int16_t *flg, double *logpi,
                      int32_t *err, int set, double add, DevCount *cnt, uint32_t *fb_list, unsigned *fb_count,
                      cudaStream_t s) {
@@ -83,19 +104,11 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
       }
       // large batches: spectral form of the quadrature; the samples it cannot certify go to the exact kernel by list
       if (fb_list && fb_count && pmc_sn_spectral_wanted(L, N)) {
-        const int gp = (int)((N + SNS_BLOCK - 1) / SNS_BLOCK);
-        const int gl = (int)std::min<int64_t>(148 * 8, (N + SN_BLOCK / 32 - 1) / (SN_BLOCK / 32));
         cudaMemsetAsync(fb_count, 0, sizeof(unsigned), s);
-#define SPEC_LAUNCH(H, F)                                                                                          \
-        do {                                                                                                       \
-          k_like_sn_spec<H, F><<<gp, SNS_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count); \
-          k_like_sn_warp_list<H, F><<<gl, SN_BLOCK, 0, s>>>(L, X, d, logpi, err, set, add, cnt, force_slow, fb_list, fb_count); \
-        } while (0)
-        if (L.sn_hasq && L.sn_flat) SPEC_LAUNCH(true, true);
-        else if (L.sn_hasq) SPEC_LAUNCH(true, false);
-        else if (L.sn_flat) SPEC_LAUNCH(false, true);
-        else SPEC_LAUNCH(false, false);
-#undef SPEC_LAUNCH
+        if (L.sn_hasq && L.sn_flat) launch_sn_spectral<true, true>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count, force_slow, s);
+        else if (L.sn_hasq) launch_sn_spectral<true, false>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count, force_slow, s);
+        else if (L.sn_flat) launch_sn_spectral<false, true>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count, force_slow, s);
+        else launch_sn_spectral<false, false>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count, force_slow, s);
         break;
       }
       if (L.sn_hasq && L.sn_flat) k_like_sn<true, true><<<gs, SN_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, force_slow);

@@ -551,6 +551,30 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
     if ((rc = dev_copy<double>(c, cn.data(), cn.size(), &D.cheb_nodes4))) return rc;
     if ((rc = dev_copy<double>(c, W.data(), W.size(), &D.cheb_W))) return rc;
     if ((rc = dev_copy<double>(c, dmax.data(), dmax.size(), &D.cheb_dmax))) return rc;
+    // B fragments of the tensor-core kernel: tile t = supernovae 8 t .. 8 t + 7 (sorted by redshift), k-step ks, lane l
+    // holds B[k = l % 4][column = l / 4]: W of the supernova's redshift (ks < M / 4), then the chi^2 features
+    const int KS = M / 4 + 3, ntile = (n + 7) / 8;
+    std::vector<double> Wf((size_t)ntile * KS * 32, 0.0);
+    std::vector<int> zof(n);
+    for (int z = 0; z < nz; z++) for (int r = first[z]; r < first[z + 1]; r++) zof[r] = z;
+    for (int t = 0; t < ntile; t++)
+      for (int ks = 0; ks < KS; ks++)
+        for (int l = 0; l < 32; l++) {
+          const int r = std::min(8 * t + l / 4, n - 1), k = l % 4;
+          const bool padcol = 8 * t + l / 4 >= n;      // repeats the last supernova with sigma^2 = 1e300: its term vanishes
+          const double *row = rows.data() + (size_t)r * SN_ROW;      // m s | c z | V0 Vss | Vcc Cms | Cmc Csc
+          double v;
+          if (ks < M / 4) v = W[(size_t)zof[r] * M + 4 * ks + k];
+          else if (ks == M / 4) {
+            const double lnaz = nodes[(size_t)zof[r] * SN_NODES].x;
+            const double f[4] = {row[0] + (5.0 / M_LN10) * lnaz - SN_MU0, 1.0, row[1], row[2]};
+            v = f[k];
+          } else if (ks == M / 4 + 1) v = padcol ? (k == 0 ? 1.0e300 : 0.0) : row[4 + k];
+          else v = (k < 2 && !padcol) ? row[8 + k] : 0.0;
+          Wf[((size_t)t * KS + ks) * 32 + l] = v;
+        }
+    if ((rc = dev_copy<double>(c, Wf.data(), Wf.size(), &D.cheb_Wf))) return rc;
+    D.sn_ntile = ntile;
   }
   return 0;
 }

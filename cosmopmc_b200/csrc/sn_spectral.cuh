@@ -177,3 +177,224 @@ k_like_sn_spec(const DevLike L, int64_t N, const double *__restrict__ X, int d,
     }
   }
 }
+
+// ---- the same on the FP64 tensor cores ---------------------------------------------------------------------------
+// ncu on k_like_sn_spec (profiles/r02/sn_spec_v1_summary.txt): FP64 pipe 26 % busy, 9.5 long-scoreboard stall cycles
+// per issue, LSU write-back 63 % -- the warp-uniform 32-byte loads that feed W[z][m] (and the supernova rows) to
+// one-sample-per-thread DFMAs deliver 1 KB into the register file per instruction.  Here the three contractions of
+// the redshift loop are mma.sync.m8n8k4.f64 tiles (8 samples x 8 supernovae x 4 terms), whose B operands are ONE
+// double per lane from a fragment-ordered table (256 coalesced bytes per instruction, 8 DFMA-equivalents each, shared
+// by the warp's four 8-sample row tiles):
+//     ss[s][i]   = sum_m  c_s[m]              W[z(i)][m]                              (M/4 k-steps)
+//     mu'[s][i]  = (1, base0, t1, t2)_s     . (m_i + 5/ln10 ln a_i - mu0, 1, s_i, c_i)     (1 k-step)
+//     sig2[s][i] = (1, k1..k5, 0, 0)_s      . (V0, Vss, Vcc, Cms, Cmc, Csc, 0, 0)_i        (2 k-steps)
+// (chi2_betaz, whose coefficients depend on the redshift, and add_logdetCov stay with k_like_sn_spec.)
+// Columns are SUPERNOVAE (sorted by redshift; two supernovae at one redshift repeat its W row), so that ss, mu' and
+// sig2 of a (sample, supernova) pair land in the same accumulator slot of the same lane and the chi^2 term is formed
+// right there: res = mu' - 5/ln10 ln f_K(rh ss), chi2 += res^2 / sig2.  Phase 1 (one sample per lane: parameters,
+// integrand at the Chebyshev points, DCT, certificates) is k_like_sn_spec's; the coefficients and the per-sample
+// chi^2 constants reach the A fragments through a per-warp shared-memory transposition.
+#ifndef SNS2_BLOCK
+#define SNS2_BLOCK 256      // 2 warps per scheduler: the A fragments alone are 88 registers
+#endif
+#define SNS_KS (SNS_M / 4 + 3)        // k-steps per supernova tile: coefficients, mu', sig2 (2)
+#define SNS_TRS 12                    // row stride of the transposition buffer (12 r mod 16 distinct for 4 rows)
+#define SNS2_SMEM (sizeof(double2) * LOG1K_N + sizeof(double) * (96 + SN_EXP2_N + (SNS2_BLOCK / 32) * 32 * SNS_TRS))
+
+__device__ __forceinline__ void sn_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// 1/s, s > 0: MUFU.RCP64H seed y (rel. error e < 2^-20), y (1 + e + e^2): error e^3
+__device__ __forceinline__ double sn_rcp3(double s) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  const double e = fma(-s, y, 1.0);
+  return fma(y, fma(e, e, e), y);
+}
+
+template <bool HASQ, bool FLAT>
+__global__ void __launch_bounds__(SNS2_BLOCK, 1)
+k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int d,
+                   const int16_t *__restrict__ flg, double *__restrict__ logpi,
+                   int32_t *__restrict__ err, int set, double add_const, DevCount *cnt,
+                   uint32_t *__restrict__ fb_list, unsigned *__restrict__ fb_count) {
+  extern __shared__ double2 sns2_smem[];      // SNS2_SMEM bytes: LT | T | per-warp transposition buffers
+  double2 *LT = sns2_smem;
+  double *T = reinterpret_cast<double *>(sns2_smem + LOG1K_N);
+  for (int i = threadIdx.x; i < LOG1K_N; i += blockDim.x) LT[i] = g_log1k[i];
+  load_fast_tables_sn(T);
+  const int lane = threadIdx.x & 31;
+  double *__restrict__ tr = T + (96 + SN_EXP2_N) + (threadIdx.x >> 5) * (32 * SNS_TRS);
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = (n < N) && (!flg || flg[n]);
+  Model m;
+  int e = 0;
+  if (active) e = apply_params(L, X + n * d, m);
+  const bool cut = active && !e && L.special == PMCB200_SPECIAL_de_conservative && de_conservative_violated(m.c);
+  if (!active || e) {
+    m.c = L.model;
+#pragma unroll
+    for (int i = 0; i < 4; i++) m.Theta2[i] = L.Theta2[i];
+    m.stretch = 1.0; m.color = 0.0;
+  }
+  bool ok;
+  const int qrow = lane >> 2, qcol = lane & 3;
+  double A[4][SNS_KS];       // A fragments: [row tile][k-step] = value [sample 8 rt + lane/4][4 ks + lane%4]
+  double rhv[4], OKv[4];
+  {
+    SNCoef ec;
+    SNPer pm;
+    double f1, f1s;
+    sn_setup(L, m, 0, ec, pm, f1, f1s);
+    ok = !(ec.slow || ec.sgn != 0u);
+    double c[SNS_M];
+    double qmin;
+    {
+      double q[SNS_M];
+#pragma unroll
+      for (int j = 0; j < SNS_M; j++) {
+        const Ld4 nd = ld256(L.cheb_nodes4 + 4 * j);
+        q[j] = sn_f<HASQ, FLAT, false, false>(ec, T, nd.x, 1.0, nd.z, 0.0);
+      }
+      qmin = q[0];
+#pragma unroll
+      for (int j = 1; j < SNS_M; j++) qmin = fmin(qmin, q[j]);
+#pragma unroll
+      for (int j = 0; j < SNS_M / 2; j++) {
+        const double u = q[j] + q[SNS_M - 1 - j], v = q[j] - q[SNS_M - 1 - j];
+        q[j] = u; q[SNS_M - 1 - j] = v;
+      }
+#pragma unroll
+      for (int mm = 0; mm < SNS_M; mm += 2) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < SNS_M / 2; j += 2) {
+          s0 = fma(SNS_DCT[mm * (SNS_M / 2) + j], q[j], s0);
+          s1 = fma(SNS_DCT[mm * (SNS_M / 2) + j + 1], q[j + 1], s1);
+        }
+        c[mm] = s0 + s1;
+      }
+#pragma unroll
+      for (int mm = 1; mm < SNS_M; mm += 2) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < SNS_M / 2; j += 2) {
+          s0 = fma(SNS_DCT[mm * (SNS_M / 2) + j], q[SNS_M - 1 - j], s0);
+          s1 = fma(SNS_DCT[mm * (SNS_M / 2) + j + 1], q[SNS_M - 2 - j], s1);
+        }
+        c[mm] = s0 + s1;
+      }
+    }
+    {
+      const double tail = fabs(c[SNS_M - 1]) + fabs(c[SNS_M - 2]) + fabs(c[SNS_M - 3]);
+      double B = 0.0;
+#pragma unroll
+      for (int mm = 0; mm < SNS_M; mm++) B = fma(__ldg(&L.cheb_dmax[mm]), fabs(c[mm]), B);
+      if (!(tail <= SNS_TAIL_TOL * fabs(c[0]))) ok = false;
+      if (!(B <= 0.25 * ROMB_EPS * qmin)) ok = false;
+    }
+    // lane-owned values -> A fragments, eight values per trip through the warp's buffer
+#pragma unroll
+    for (int ch = 0; ch < SNS_M / 8; ch++) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; j++) tr[lane * SNS_TRS + j] = c[8 * ch + j];
+      __syncwarp();
+#pragma unroll
+      for (int rt = 0; rt < 4; rt++) {
+        A[rt][2 * ch] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
+        A[rt][2 * ch + 1] = tr[(8 * rt + qrow) * SNS_TRS + 4 + qcol];
+      }
+    }
+    __syncwarp();
+    // flat: ln f_K = ln rh + ln ss, the per-sample part joins the constant of mu'
+    tr[lane * SNS_TRS + 0] = 1.0;
+    tr[lane * SNS_TRS + 1] = FLAT ? fma(-5.0 / M_LN10, log(R_HUBBLE * ec.scale), pm.base0) : pm.base0;
+    tr[lane * SNS_TRS + 2] = pm.t1;
+    tr[lane * SNS_TRS + 3] = pm.t2base;
+    tr[lane * SNS_TRS + 4] = 1.0; tr[lane * SNS_TRS + 5] = pm.k1; tr[lane * SNS_TRS + 6] = pm.k2;
+    tr[lane * SNS_TRS + 7] = pm.k3;
+    __syncwarp();
+#pragma unroll
+    for (int rt = 0; rt < 4; rt++) {
+      A[rt][SNS_M / 4] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
+      A[rt][SNS_M / 4 + 1] = tr[(8 * rt + qrow) * SNS_TRS + 4 + qcol];
+    }
+    __syncwarp();
+    tr[lane * SNS_TRS + 0] = pm.k4; tr[lane * SNS_TRS + 1] = pm.k5; tr[lane * SNS_TRS + 2] = 0.0;
+    tr[lane * SNS_TRS + 3] = 0.0;
+    tr[lane * SNS_TRS + 4] = R_HUBBLE * ec.scale; tr[lane * SNS_TRS + 5] = ec.OK;
+    __syncwarp();
+#pragma unroll
+    for (int rt = 0; rt < 4; rt++) {
+      A[rt][SNS_M / 4 + 2] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
+      rhv[rt] = tr[(8 * rt + qrow) * SNS_TRS + 4];
+      OKv[rt] = tr[(8 * rt + qrow) * SNS_TRS + 5];
+    }
+  }
+
+  // --- supernova tiles (columns past the last supernova repeat it with sigma^2 = 1e300: their terms vanish)
+  const double *__restrict__ wf = L.cheb_Wf + lane;
+  const int ntile = L.sn_ntile;
+  double chi[4] = {0.0, 0.0, 0.0, 0.0};
+  unsigned ebits = 0u;
+  double b[SNS_KS], bn[SNS_KS];
+#pragma unroll
+  for (int ks = 0; ks < SNS_KS; ks++) bn[ks] = __ldg(wf + (size_t)ks * 32);
+  for (int t = 0; t < ntile; t++) {
+#pragma unroll
+    for (int ks = 0; ks < SNS_KS; ks++) b[ks] = bn[ks];
+    const int tn = min(t + 1, ntile - 1);       // next tile's fragments travel while this one computes
+#pragma unroll
+    for (int ks = 0; ks < SNS_KS; ks++) bn[ks] = __ldg(wf + ((size_t)tn * SNS_KS + ks) * 32);
+#pragma unroll
+    for (int rt = 0; rt < 4; rt++) {
+      double s0 = 0.0, s1 = 0.0, m0 = 0.0, m1 = 0.0, g0 = 0.0, g1 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < SNS_M / 4; ks++) sn_dmma(s0, s1, A[rt][ks], b[ks]);
+      sn_dmma(m0, m1, A[rt][SNS_M / 4], b[SNS_M / 4]);
+      sn_dmma(g0, g1, A[rt][SNS_M / 4 + 1], b[SNS_M / 4 + 1]);
+      sn_dmma(g0, g1, A[rt][SNS_M / 4 + 2], b[SNS_M / 4 + 2]);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const double ss = h ? s1 : s0, mu = h ? m1 : m0, sg = h ? g1 : g0;
+        const double fk = FLAT ? ss : f_K_from(OKv[rt], rhv[rt] * ss);
+        if (!(fk > 0.0)) ebits |= 1u << rt;
+        const double res = fma(-5.0 / M_LN10, lean_log(fk, LT), mu);
+        chi[rt] = fma(res * res, sn_rcp3(sg), chi[rt]);
+      }
+    }
+  }
+  // --- per-sample sums: the four lanes of a quad hold the columns of one sample row; then to the owner lane
+  double chi2 = 0.0;
+  ebits |= __shfl_xor_sync(0xffffffffu, ebits, 1);
+  ebits |= __shfl_xor_sync(0xffffffffu, ebits, 2);
+#pragma unroll
+  for (int rt = 0; rt < 4; rt++) {
+    double v = chi[rt];
+    v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+    const double vo = __shfl_sync(0xffffffffu, v, 4 * (lane & 7));
+    if ((lane >> 3) == rt) chi2 = vo;
+  }
+  {
+    const unsigned eo = __shfl_sync(0xffffffffu, ebits, 4 * (lane & 7));
+    if ((eo >> (lane >> 3)) & 1u) e = 1;
+  }
+  double res = -0.5 * chi2;
+  if (cut) res = 0.0;
+  else if (!isfinite(res)) e = 1;
+  if (active && ok) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
+  else if (active) fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)n;      // the exact kernel evaluates this sample
+  else if (n < N && set) { logpi[n] = 0.0; if (err) err[n] = 0; }
+  if (cnt) {
+    unsigned nsp = (active && ok) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsp += __shfl_xor_sync(0xffffffffu, nsp, o);
+    if (lane == 0 && nsp) {
+      atomicAdd(&cnt->sn_evals, (unsigned long long)nsp * SNS_M);
+      atomicAdd(&cnt->sn_zsteps, (unsigned long long)nsp * L.sn_nz);
+      atomicAdd(&cnt->sn_spec, (unsigned long long)nsp);
+    }
+  }
+}

@@ -163,11 +163,12 @@ def check_posterior(oracle, pmc, spec, X):
     r = rel(got[ok], ref[ok])
     assert r < RTOL_LOG, r
     if any(spec.t.like[i].kind == 3 for i in range(spec.t.ndata)):
-        # the SN likelihood has three kernels: spectral form of the quadrature (large batches; hands what it cannot
-        # certify to the warp kernel), one sample per warp (small batches, node by node), one sample per thread (node
-        # by node).  This batch through all three.
+        # the SN likelihood has four kernels: spectral form of the quadrature on the FP64 tensor cores (large batches;
+        # hands what it cannot certify to the warp kernel), the same one sample per thread (chi2_betaz, add_logdetCov),
+        # one sample per warp (small batches, node by node), one sample per thread (node by node).  This batch through all.
         small = len(X) <= 16384
         for env in ({"PMCB200_SN_WARP_MAX": "0" if small else "1000000000"},
+                    {"PMCB200_SN_WARP_MAX": "0", "PMCB200_SN_SPEC_V1": "1"},
                     {"PMCB200_SN_WARP_MAX": "0", "PMCB200_SN_EXACT": "1"}):
             with environ(env):
                 got2, egot2 = pmc.posterior_log_pdf(dev(X))
