@@ -59,6 +59,42 @@ __device__ __forceinline__ void sn_chi2_terms(const DevLike &L, const SNPer &m_,
   }
 }
 
+// Chebyshev coefficients c[0..M) of q(a) = Q(a)^-1/2 on [a(z_max), 1] and the smallest node value.  Four nodes from
+// each end per step (u_j = q_j + q_(M-1-j) feeds the even coefficients, v_j = q_j - q_(M-1-j) the odd ones), so that
+// only the 32 running sums and eight node values are live at a time.
+template <bool HASQ, bool FLAT>
+__device__ __forceinline__ void sn_cheb_coeffs(const DevLike &L, const SNCoef &ec, const double *__restrict__ T,
+                                               double (&c)[SNS_M], double &qmin) {
+#pragma unroll
+  for (int mm = 0; mm < SNS_M; mm++) c[mm] = 0.0;
+  qmin = INFINITY;
+#pragma unroll
+  for (int j0 = 0; j0 < SNS_M / 2; j0 += 4) {
+    double u[4], v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const Ld4 na = ld256(L.cheb_nodes4 + 4 * (j0 + i)), nb = ld256(L.cheb_nodes4 + 4 * (SNS_M - 1 - j0 - i));
+      const double qa = sn_f<HASQ, FLAT, false, false>(ec, T, na.x, 1.0, na.z, 0.0);
+      const double qb = sn_f<HASQ, FLAT, false, false>(ec, T, nb.x, 1.0, nb.z, 0.0);
+      qmin = fmin(qmin, fmin(qa, qb));
+      u[i] = qa + qb; v[i] = qa - qb;
+    }
+#pragma unroll
+    for (int mm = 0; mm < SNS_M; mm++) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) c[mm] = fma(SNS_DCT[mm * (SNS_M / 2) + j0 + i], (mm & 1) ? v[i] : u[i], c[mm]);
+    }
+  }
+}
+// the two certificates of the header (a NaN anywhere fails them)
+__device__ __forceinline__ bool sn_spec_certified(const DevLike &L, const double (&c)[SNS_M], double qmin) {
+  const double tail = fabs(c[SNS_M - 1]) + fabs(c[SNS_M - 2]) + fabs(c[SNS_M - 3]);
+  double B = 0.0;
+#pragma unroll
+  for (int mm = 0; mm < SNS_M; mm++) B = fma(__ldg(&L.cheb_dmax[mm]), fabs(c[mm]), B);
+  return (tail <= SNS_TAIL_TOL * fabs(c[0])) && (B <= 0.25 * ROMB_EPS * qmin);
+}
+
 template <bool HASQ, bool FLAT>
 __global__ void __launch_bounds__(SNS_BLOCK, SNS_MIN_BLOCKS)
 k_like_sn_spec(const DevLike L, int64_t N, const double *__restrict__ X, int d,
@@ -87,53 +123,12 @@ k_like_sn_spec(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   sn_setup(L, m, 0, ec, pm, f1, f1s);
   bool ok = !(ec.slow || ec.sgn != 0u);
 
-  // --- Chebyshev coefficients of q(a) = Q(a)^-1/2 on [a(z_max), 1]
+  // --- Chebyshev coefficients of q(a) = Q(a)^-1/2 on [a(z_max), 1], and the two guarantees
   double c[SNS_M];
-  double qmin;
   {
-    double q[SNS_M];
-#pragma unroll
-    for (int j = 0; j < SNS_M; j++) {
-      const Ld4 nd = ld256(L.cheb_nodes4 + 4 * j);      // {ln a_j, 1, a_j, -}
-      q[j] = sn_f<HASQ, FLAT, false, false>(ec, T, nd.x, 1.0, nd.z, 0.0);
-    }
-    qmin = q[0];
-#pragma unroll
-    for (int j = 1; j < SNS_M; j++) qmin = fmin(qmin, q[j]);
-    // even coefficients from u_j = q_j + q_(M-1-j), odd ones from v_j = q_j - q_(M-1-j)
-#pragma unroll
-    for (int j = 0; j < SNS_M / 2; j++) {
-      const double u = q[j] + q[SNS_M - 1 - j], v = q[j] - q[SNS_M - 1 - j];
-      q[j] = u; q[SNS_M - 1 - j] = v;
-    }
-#pragma unroll
-    for (int mm = 0; mm < SNS_M; mm += 2) {
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int j = 0; j < SNS_M / 2; j += 2) {
-        s0 = fma(SNS_DCT[mm * (SNS_M / 2) + j], q[j], s0);
-        s1 = fma(SNS_DCT[mm * (SNS_M / 2) + j + 1], q[j + 1], s1);
-      }
-      c[mm] = s0 + s1;
-    }
-#pragma unroll
-    for (int mm = 1; mm < SNS_M; mm += 2) {
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int j = 0; j < SNS_M / 2; j += 2) {
-        s0 = fma(SNS_DCT[mm * (SNS_M / 2) + j], q[SNS_M - 1 - j], s0);
-        s1 = fma(SNS_DCT[mm * (SNS_M / 2) + j + 1], q[SNS_M - 2 - j], s1);
-      }
-      c[mm] = s0 + s1;
-    }
-  }
-  {   // the two guarantees (a NaN anywhere fails them)
-    const double tail = fabs(c[SNS_M - 1]) + fabs(c[SNS_M - 2]) + fabs(c[SNS_M - 3]);
-    double B = 0.0;
-#pragma unroll
-    for (int mm = 0; mm < SNS_M; mm++) B = fma(__ldg(&L.cheb_dmax[mm]), fabs(c[mm]), B);
-    if (!(tail <= SNS_TAIL_TOL * fabs(c[0]))) ok = false;
-    if (!(B <= 0.25 * ROMB_EPS * qmin)) ok = false;
+    double qmin;
+    sn_cheb_coeffs<HASQ, FLAT>(L, ec, T, c, qmin);
+    if (!sn_spec_certified(L, c, qmin)) ok = false;
   }
 
   // --- redshift loop: ss_z = W[z] . c, then the distance modulus and the chi^2 terms as in sn_zloop
@@ -249,50 +244,10 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
     sn_setup(L, m, 0, ec, pm, f1, f1s);
     ok = !(ec.slow || ec.sgn != 0u);
     double c[SNS_M];
-    double qmin;
     {
-      double q[SNS_M];
-#pragma unroll
-      for (int j = 0; j < SNS_M; j++) {
-        const Ld4 nd = ld256(L.cheb_nodes4 + 4 * j);
-        q[j] = sn_f<HASQ, FLAT, false, false>(ec, T, nd.x, 1.0, nd.z, 0.0);
-      }
-      qmin = q[0];
-#pragma unroll
-      for (int j = 1; j < SNS_M; j++) qmin = fmin(qmin, q[j]);
-#pragma unroll
-      for (int j = 0; j < SNS_M / 2; j++) {
-        const double u = q[j] + q[SNS_M - 1 - j], v = q[j] - q[SNS_M - 1 - j];
-        q[j] = u; q[SNS_M - 1 - j] = v;
-      }
-#pragma unroll
-      for (int mm = 0; mm < SNS_M; mm += 2) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < SNS_M / 2; j += 2) {
-          s0 = fma(SNS_DCT[mm * (SNS_M / 2) + j], q[j], s0);
-          s1 = fma(SNS_DCT[mm * (SNS_M / 2) + j + 1], q[j + 1], s1);
-        }
-        c[mm] = s0 + s1;
-      }
-#pragma unroll
-      for (int mm = 1; mm < SNS_M; mm += 2) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < SNS_M / 2; j += 2) {
-          s0 = fma(SNS_DCT[mm * (SNS_M / 2) + j], q[SNS_M - 1 - j], s0);
-          s1 = fma(SNS_DCT[mm * (SNS_M / 2) + j + 1], q[SNS_M - 2 - j], s1);
-        }
-        c[mm] = s0 + s1;
-      }
-    }
-    {
-      const double tail = fabs(c[SNS_M - 1]) + fabs(c[SNS_M - 2]) + fabs(c[SNS_M - 3]);
-      double B = 0.0;
-#pragma unroll
-      for (int mm = 0; mm < SNS_M; mm++) B = fma(__ldg(&L.cheb_dmax[mm]), fabs(c[mm]), B);
-      if (!(tail <= SNS_TAIL_TOL * fabs(c[0]))) ok = false;
-      if (!(B <= 0.25 * ROMB_EPS * qmin)) ok = false;
+      double qmin;
+      sn_cheb_coeffs<HASQ, FLAT>(L, ec, T, c, qmin);
+      if (!sn_spec_certified(L, c, qmin)) ok = false;
     }
     // lane-owned values -> A fragments, eight values per trip through the warp's buffer
 #pragma unroll
