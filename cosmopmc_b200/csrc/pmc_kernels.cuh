@@ -4,38 +4,53 @@
 #pragma once
 #include "common.cuh"
 #include "stat_layout.cuh"
+#include "fastmath.cuh"
 
 // ---- K1: mixture sampler (replaces simulate_mix_mvdens, cosmo_pmc.c:320) ------
 // Philox counter = (g_lo, g_hi, call, iter), key = seed; g = global sample
 // index, so a shard's draws are independent of the number of ranks.
+// Box-Muller pair from one Philox call: rad = sqrt(-2 ln u1) with the table-based log (fastmath.cuh, T = the
+// block's shared fast tables), angle by sincospi(2 u2) (no reduction by pi).  The published Box-Muller transform;
+// against libm's log / cos / sin the variates agree to ~1e-16.
+__device__ __forceinline__ void box_muller(const uint32_t (&r)[4], const double *__restrict__ T, double &z0, double &z1) {
+  const double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
+  const double rad = sqrt(-2.0 * fast_log(u1, T));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  z0 = rad * cs; z1 = rad * sn;
+}
 template <int D>
 __device__ __forceinline__ void draw_normals(uint64_t seed, uint32_t iter, uint64_t g, int d, int df,
-                                             double &u, double (&z)[D], double &tscale) {
+                                             double &u, double (&z)[D], double &tscale, const double *__restrict__ T) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t g0 = (uint32_t)g, g1 = (uint32_t)(g >> 32), r[4];
   philox4x32_10(g0, g1, 0u, iter, k0, k1, r);
   u = (double)r[0] * (1.0 / 4294967296.0);
-  const int nz = d + (df > 0 ? df : 0);
-  double chi2 = 0.0;
+  // the d coordinates: pairs with compile-time indices (no selects over the register array)
 #pragma unroll
-  for (int i = 0; i < D; i++) z[i] = 0.0;
-  for (int p = 0; 2 * p < nz; p++) {
-    philox4x32_10(g0, g1, 1u + p, iter, k0, k1, r);
-    double u1 = u53(r[0], r[1]), u2 = u53(r[2], r[3]);
-    double rad = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincos(2.0 * M_PI * u2, &sn, &cs);
-    double zz0 = rad * cs, zz1 = rad * sn;
-    int i0 = 2 * p, i1 = 2 * p + 1;
-#pragma unroll
-    for (int i = 0; i < D; i++) {
-      if (i == i0 && i < d) z[i] = zz0;
-      if (i == i1 && i < d) z[i] = zz1;
+  for (int p = 0; 2 * p < D; p++) {
+    double zz0 = 0.0, zz1 = 0.0;
+    if (2 * p < d) {
+      philox4x32_10(g0, g1, 1u + p, iter, k0, k1, r);
+      box_muller(r, T, zz0, zz1);
     }
-    if (i0 >= d && i0 < nz) chi2 = fma(zz0, zz0, chi2);
-    if (i1 >= d && i1 < nz) chi2 = fma(zz1, zz1, chi2);
+    z[2 * p] = zz0;
+    if (2 * p + 1 < D) z[2 * p + 1] = (2 * p + 1 < d) ? zz1 : 0.0;
   }
-  tscale = (df > 0) ? sqrt((double)df / chi2) : 1.0;
+  tscale = 1.0;
+  if (df > 0) {      // Student-t: df further variates for the chi^2 (continuing the pair sequence)
+    double chi2 = 0.0;
+    const int nz = d + df;
+    for (int p = d / 2; 2 * p < nz; p++) {
+      philox4x32_10(g0, g1, 1u + p, iter, k0, k1, r);
+      double zz0, zz1;
+      box_muller(r, T, zz0, zz1);
+      const int i0 = 2 * p, i1 = 2 * p + 1;
+      if (i0 >= d && i0 < nz) chi2 = fma(zz0, zz0, chi2);
+      if (i1 >= d && i1 < nz) chi2 = fma(zz1, zz1, chi2);
+    }
+    tscale = sqrt((double)df / chi2);
+  }
 }
 
 template <int D>
@@ -66,11 +81,13 @@ k_simulate(const double *__restrict__ mix, const MixHdr h, const double *__restr
            int64_t N, uint64_t seed, uint32_t iter, int64_t offset,
            double *__restrict__ X, int32_t *__restrict__ idx, int16_t *__restrict__ flg,
            DevScal *scal) {
+  __shared__ double T[96];
+  load_fast_tables(T);
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int inbox = 0;
   if (n < N) {
     double u, z[D], ts;
-    draw_normals<D>(seed, iter, (uint64_t)(offset + n), h.d, h.df, u, z, ts);
+    draw_normals<D>(seed, iter, (uint64_t)(offset + n), h.d, h.df, u, z, ts, T);
     int k = select_component(mix, h, u);
     transform_store<D>(mix + (size_t)k * h.stride, h.d, z, ts, box, box + h.d, X + n * h.d, inbox);
     idx[n] = k;
@@ -99,13 +116,14 @@ k_simulate_staged(const double *__restrict__ mixg, const MixHdr h, const double 
     const int k = i / h.stride;
     s_mix[k * sstride + (i - k * h.stride)] = mixg[i];
   }
-  __syncthreads();
+  __shared__ double T[96];
+  load_fast_tables(T);      // ends with __syncthreads()
   const int64_t base = (int64_t)blockIdx.x * PMC_BLOCK;
   const int64_t n = base + threadIdx.x;
   int inbox = 0;
   if (n < N) {
     double u, z[D], ts;
-    draw_normals<D>(seed, iter, (uint64_t)(offset + n), h.d, h.df, u, z, ts);
+    draw_normals<D>(seed, iter, (uint64_t)(offset + n), h.d, h.df, u, z, ts, T);
     MixHdr hs = h; hs.stride = sstride;
     int k = select_component(s_mix, hs, u);
     transform_store<D>(s_mix + (size_t)k * sstride, h.d, z, ts, box, box + h.d, s_out + (size_t)threadIdx.x * xs, inbox);

@@ -25,7 +25,9 @@
 #pragma once
 #include "cosmo.cuh"
 
-#define SNS_M 32
+#ifndef SNS_M
+#define SNS_M 32       // Chebyshev points per sample (a multiple of 4)
+#endif
 #define SNS_TAIL_TOL 1.0e-12
 #ifndef SNS_BLOCK
 #define SNS_BLOCK 256
@@ -70,9 +72,10 @@ __device__ __forceinline__ void sn_cheb_coeffs(const DevLike &L, const SNCoef &e
   qmin = INFINITY;
 #pragma unroll
   for (int j0 = 0; j0 < SNS_M / 2; j0 += 4) {
-    double u[4], v[4];
+    double u[4] = {0.0, 0.0, 0.0, 0.0}, v[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
+      if (j0 + i >= SNS_M / 2) continue;
       const Ld4 na = ld256(L.cheb_nodes4 + 4 * (j0 + i)), nb = ld256(L.cheb_nodes4 + 4 * (SNS_M - 1 - j0 - i));
       const double qa = sn_f<HASQ, FLAT, false, false>(ec, T, na.x, 1.0, na.z, 0.0);
       const double qb = sn_f<HASQ, FLAT, false, false>(ec, T, nb.x, 1.0, nb.z, 0.0);
@@ -82,7 +85,8 @@ __device__ __forceinline__ void sn_cheb_coeffs(const DevLike &L, const SNCoef &e
 #pragma unroll
     for (int mm = 0; mm < SNS_M; mm++) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) c[mm] = fma(SNS_DCT[mm * (SNS_M / 2) + j0 + i], (mm & 1) ? v[i] : u[i], c[mm]);
+      for (int i = 0; i < 4; i++)
+        if (j0 + i < SNS_M / 2) c[mm] = fma(SNS_DCT[mm * (SNS_M / 2) + j0 + i], (mm & 1) ? v[i] : u[i], c[mm]);
     }
   }
 }
@@ -251,15 +255,15 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
     }
     // lane-owned values -> A fragments, eight values per trip through the warp's buffer
 #pragma unroll
-    for (int ch = 0; ch < SNS_M / 8; ch++) {
+    for (int ch = 0; ch < (SNS_M + 7) / 8; ch++) {
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; j++) tr[lane * SNS_TRS + j] = c[8 * ch + j];
+      for (int j = 0; j < 8; j++) if (8 * ch + j < SNS_M) tr[lane * SNS_TRS + j] = c[8 * ch + j];
       __syncwarp();
 #pragma unroll
       for (int rt = 0; rt < 4; rt++) {
         A[rt][2 * ch] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
-        A[rt][2 * ch + 1] = tr[(8 * rt + qrow) * SNS_TRS + 4 + qcol];
+        if (2 * ch + 1 < SNS_M / 4) A[rt][2 * ch + 1] = tr[(8 * rt + qrow) * SNS_TRS + 4 + qcol];
       }
     }
     __syncwarp();
@@ -293,7 +297,7 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
   const double *__restrict__ wf = L.cheb_Wf + lane;
   const int ntile = L.sn_ntile;
   double chi[4] = {0.0, 0.0, 0.0, 0.0};
-  unsigned ebits = 0u;
+  unsigned ebits = 0u, ubits = 0u;      // per row tile: distance error; curvature argument outside the series
   double b[SNS_KS], bn[SNS_KS];
 #pragma unroll
   for (int ks = 0; ks < SNS_KS; ks++) bn[ks] = __ldg(wf + (size_t)ks * 32);
@@ -314,7 +318,13 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const double ss = h ? s1 : s0, mu = h ? m1 : m0, sg = h ? g1 : g0;
-        const double fk = FLAT ? ss : f_K_from(OKv[rt], rhv[rt] * ss);
+        double fk;
+        if (FLAT) fk = ss;
+        else {      // f_K_from without branches: the series covers |u| < 1, beyond it the sample goes to the exact kernel
+          const double ww = rhv[rt] * ss, x = ww * (1.0 / R_HUBBLE), u = OKv[rt] * x * x;
+          fk = (fabs(OKv[rt]) < FLAT_EPS) ? ww : ww * sinhc_series(u);
+          if (!(fabs(u) < 1.0)) ubits |= 1u << rt;
+        }
         if (!(fk > 0.0)) ebits |= 1u << rt;
         const double res = fma(-5.0 / M_LN10, lean_log(fk, LT), mu);
         chi[rt] = fma(res * res, sn_rcp3(sg), chi[rt]);
@@ -335,6 +345,12 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
   {
     const unsigned eo = __shfl_sync(0xffffffffu, ebits, 4 * (lane & 7));
     if ((eo >> (lane >> 3)) & 1u) e = 1;
+  }
+  if (!FLAT) {
+    ubits |= __shfl_xor_sync(0xffffffffu, ubits, 1);
+    ubits |= __shfl_xor_sync(0xffffffffu, ubits, 2);
+    const unsigned uo = __shfl_sync(0xffffffffu, ubits, 4 * (lane & 7));
+    if ((uo >> (lane >> 3)) & 1u) ok = false;
   }
   double res = -0.5 * chi2;
   if (cut) res = 0.0;

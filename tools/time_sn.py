@@ -15,9 +15,12 @@ pmc.simulate_mix_mvdens(a.n, SEED, 0, 0, b["X"], b["idx"], b["flg"])
 for _ in range(2): pmc.posterior_log_pdf(b["X"])
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize(); e0.record()
+pmc.counters()
 for _ in range(5): lp, err = pmc.posterior_log_pdf(b["X"])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print("%s: %.3f ms for %d samples -> %.3f ns/sample, checksum %.10f" % (os.environ.get("PMCB200_LIB", "default"), ms, a.n, ms * 1e6 / a.n, lp.sum().item()))
+c = pmc.counters()
+print("%s: %.3f ms for %d samples -> %.3f ns/sample, checksum %.10f, SN spectral %d node-by-node %d per call" % (
+    os.environ.get("PMCB200_LIB", "default"), ms, a.n, ms * 1e6 / a.n, lp.sum().item(), c["sn_spec"] // 5, c["sn_exact"] // 5))
 if a.save:
     torch.save({"lp": lp.cpu(), "err": err.cpu()}, a.save)
