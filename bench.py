@@ -33,11 +33,12 @@ FLOP_PER_ZSTEP = 86.0      # per (sample, redshift): 5 trapzd combines (22), NR 
 FLOP_PER_SN = 29.0         # per (sample, supernova): mu_obs 7, sigma^2 18, chi^2 term 4
 # Spectral path (k_like_sn_spec): M integrand evaluations, the folded DCT (M^2/2 FMA + M adds), the two certificates
 # (~3 M), then per redshift an M-term dot product (M FMA) + D_L + modulus (8)
-SPEC_M = 32
+SPEC_M = 28
 FLOP_SPEC_SAMPLE = SPEC_M * FLOP_PER_EVAL + SPEC_M * SPEC_M + 4 * SPEC_M
 FLOP_SPEC_ZSTEP = 2.0 * SPEC_M + 8.0
-# ncu evidence for the dominant kernel, per sample (filled from the capture named in "source")
-NCU_SN = {"fp64_pipe_active_pct": None, "dram_bytes_per_sample": None, "source": None}
+# ncu evidence for the dominant kernel (one --set full capture, N = 4e6): FP64 pipe = DMMA sub-pipe 57.4 % + vector 21.7 %;
+# DRAM bytes (read + write) per sample
+NCU_SN = {"fp64_pipe_active_pct": 79.1, "dram_bytes_per_sample": 48.0, "source": "profiles/r02/sn_spec_mma_v2_summary.txt"}
 NCU_SN_EXACT = {"fp64_pipe_active_pct": 64.6, "dram_bytes_per_sample": 44.1, "source": "profiles/sn_r01_v8_summary.txt"}
 
 
@@ -361,7 +362,7 @@ def main():
         peak = pmc.fp64_peak_tflops()
         ach = flops / (k_ms * 1e-3) * 1e-12
         ncu = NCU_SN if spectral else NCU_SN_EXACT
-        roof = {"kernel": "k_like_sn_spec (+ k_like_sn_warp_list for the samples it hands over)" if spectral else "k_like_sn",
+        roof = {"kernel": "k_like_sn_spec_mma (+ k_like_sn_warp_list for the samples it hands over)" if spectral else "k_like_sn",
                 "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak if peak else None,
                 "traffic": ncu["dram_bytes_per_sample"] * n_loc if ncu["dram_bytes_per_sample"] else None,

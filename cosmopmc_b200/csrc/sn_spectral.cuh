@@ -7,11 +7,11 @@
 // are two FIXED linear functionals of the integrand at 17 nodes (ROMBW, cosmo.cuh).  The 241 redshifts of the
 // Union sample therefore ask for 4097 evaluations of ONE smooth function of a per sample, all inside
 // [a(z_max), 1].  This kernel evaluates the sample-dependent factor q(a) = Q(a)^-1/2 (Q = a^3 E^2 / |Omega_de|)
-// at SNS_M Chebyshev points of that interval, turns the values into Chebyshev coefficients c_m (a 32-point DCT,
+// at SNS_M Chebyshev points of that interval, turns the values into Chebyshev coefficients c_m (an SNS_M-point DCT,
 // folded), and applies the reference's functional to the interpolant:
 //     ss_z = sum_m W[z][m] c_m,      W[z][m] = h_z sum_i w_i a_i^-1/2 T_m(x(a_i))   (host, long double)
 // i.e. the Romberg rule -- nodes, weights, truncation error and all -- acts on a polynomial that agrees with the
-// integrand to ~1e-15.  Per sample: 32 integrand evaluations + a 241 x 32 matrix-vector product instead of 4097
+// integrand to ~1e-15.  Per sample: SNS_M = 28 integrand evaluations + a 241 x 28 matrix-vector product instead of 4097
 // evaluations (13 FP64 instructions each).
 //
 // Guarantees (per sample, checked in the kernel; a sample that fails ANY of them is handed to the exact kernel
@@ -26,7 +26,7 @@
 #include "cosmo.cuh"
 
 #ifndef SNS_M
-#define SNS_M 32       // Chebyshev points per sample (a multiple of 4)
+#define SNS_M 28       // Chebyshev points per sample (a multiple of 4)
 #endif
 #define SNS_TAIL_TOL 1.0e-12
 #ifndef SNS_BLOCK
@@ -283,7 +283,7 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
     __syncwarp();
     tr[lane * SNS_TRS + 0] = pm.k4; tr[lane * SNS_TRS + 1] = pm.k5; tr[lane * SNS_TRS + 2] = 0.0;
     tr[lane * SNS_TRS + 3] = 0.0;
-    tr[lane * SNS_TRS + 4] = R_HUBBLE * ec.scale; tr[lane * SNS_TRS + 5] = ec.OK;
+    tr[lane * SNS_TRS + 4] = R_HUBBLE * ec.scale; tr[lane * SNS_TRS + 5] = (fabs(ec.OK) < FLAT_EPS) ? 0.0 : ec.OK;
     __syncwarp();
 #pragma unroll
     for (int rt = 0; rt < 4; rt++) {
@@ -322,7 +322,7 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
         if (FLAT) fk = ss;
         else {      // f_K_from without branches: the series covers |u| < 1, beyond it the sample goes to the exact kernel
           const double ww = rhv[rt] * ss, x = ww * (1.0 / R_HUBBLE), u = OKv[rt] * x * x;
-          fk = (fabs(OKv[rt]) < FLAT_EPS) ? ww : ww * sinhc_series(u);
+          fk = ww * sinhc_series(u);      // OKv = 0 for |Omega_K| < FLAT_EPS: the series is exactly 1, f_K = w as in f_K_from
           if (!(fabs(u) < 1.0)) ubits |= 1u << rt;
         }
         if (!(fk > 0.0)) ebits |= 1u << rt;

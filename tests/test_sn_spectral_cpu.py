@@ -16,7 +16,7 @@ from cosmopmc_b200 import _abi as A
 from cosmopmc_b200 import targets as T
 from oracle import oracle_lib as O
 
-M = 32
+M = 28
 TAIL_TOL, EPS = 1.0e-12, 1.0e-6
 RW = [3937.0 / 103275.0, 3062.0 / 80325.0, 27728.0 / 722925.0, 22016.0 / 722925.0, 65536.0 / 722925.0]
 RD = [-31.0 / 206550.0, -73.0 / 481950.0, -67.0 / 722925.0, -424.0 / 722925.0, 256.0 / 722925.0]
