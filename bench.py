@@ -279,7 +279,22 @@ def main():
                 pmc.shard_weights_host_begin(nl, hw[:nl])
             pmc.host_wait(1)
             return st
-        return step_device, step_e2e
+
+        def step_e2e_nox(it):
+            """the same call with a NULL sample pointer: indices, flags and normalised weights reach the host every
+            iteration, the sample array X stays on the device (a driver that dumps / post-processes it on request)"""
+            _, hidx, hflg, hw = hsets[it % 2]
+            pmc.set_proposal(w_pin.numpy(), m_pin.numpy(), chol=ch_pin.numpy())
+            if world == 1:
+                st = pmc.iteration_host_begin(nl, SEED, it, 1.0, None, hidx[:nl], hflg[:nl], hw[:nl])
+            else:
+                pmc.iteration_shard_host(nl, SEED, it, of, 1.0, block, None, hidx[:nl], hflg[:nl])
+                dist.all_gather_into_tensor(allb, block)
+                st = pmc.update_prop_rb(world, allb, ng)
+                pmc.shard_weights_host_begin(nl, hw[:nl])
+            pmc.host_wait(1)
+            return st
+        return step_device, step_e2e, step_e2e_nox
 
     def timed(fn, steps, warmup, sampler=None, drain=False):
         for i in range(warmup):
@@ -308,9 +323,10 @@ def main():
         return ms.item(), st, pmc.launch_count() - l0, pmc.counters()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    step_device, step_e2e = make_steps(n_loc)
+    step_device, step_e2e, step_e2e_nox = make_steps(n_loc)
     ms, st, launches, cnt = timed(step_device, args.steps, args.warmup, sampler)
     ms_e2e, st_e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1), drain=True)
+    ms_nox, _, _, _ = timed(step_e2e_nox, args.steps, max(1, args.warmup - 1), drain=True)
     value = n_glob * args.steps / (ms * 1e-3)
     e2e = n_glob * args.steps / (ms_e2e * 1e-3)
 
@@ -319,7 +335,7 @@ def main():
     strong = None
     if args.scaling == "weak" and world > 1:
         nl_s = (args.nsamples + world - 1) // world
-        sd, se = make_steps(nl_s)
+        sd, se, _ = make_steps(nl_s)
         ms_s, _, _, _ = timed(sd, args.steps, args.warmup)
         ms_se, _, _, _ = timed(se, args.steps, max(1, args.warmup - 1), drain=True)
         strong = {"n_gpus": world, "samples_global": nl_s * world, "samples_per_gpu": nl_s, "ms_per_step": ms_s / args.steps,
@@ -394,7 +410,11 @@ def main():
                                "pmcb200_iteration_shard_host + NCCL all-gather + pmcb200_em_finish + pmcb200_shard_weights_host_begin "
                                "+ pmcb200_host_wait (pipelined host delivery)",
                         "h2d_bytes_per_step": int(w_pin.numel() + m_pin.numel() + ch_pin.numel()) * 8,
-                        "d2h_bytes_per_step": int(n_loc * (8 * d + 4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d)))},
+                        "d2h_bytes_per_step": int(n_loc * (8 * d + 4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d))),
+                        "without_X": {"value": n_glob * args.steps / (ms_nox * 1e-3), "ms_per_step": ms_nox / args.steps,
+                                      "d2h_bytes_per_step": int(n_loc * (4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d))),
+                                      "note": "same call with a NULL sample pointer: indices, flags and normalised weights to the "
+                                              "host every iteration, X stays in HBM"}},
                 "strong": strong,
                 "gpu_launches": launches, "clocks": clocks,
                 "counters_timed_region": cnt,
