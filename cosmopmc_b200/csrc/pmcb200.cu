@@ -1084,6 +1084,28 @@ extern "C" int pmcb200_shard_weights_host_begin(pmcb200_ctx *c, int64_t N, doubl
   return 0;
 }
 
+// The sample array of the most recent iteration that used the library's scratch (hX was NULL in the iteration call:
+// X and the component indices stay in HBM for the device post-processing) to the host, on request -- the reference needs it only for the pmcsim
+// dump (cosmo_pmc.c:392) and the host post-processing.  Queued on the copy stream like the other arrays.
+extern "C" int pmcb200_samples_host_begin(pmcb200_ctx *c, int64_t N, double *hX, int32_t *hidx) {
+  int rc = need(c, true, false);
+  if (rc) return rc;
+  NvtxRange nvtx_("pmc:samples_to_host");
+  pmcb200_ctx::ScratchSet &t = c->set[c->cur];
+  const size_t n = (size_t)std::max<int64_t>(N, 0), bytes = n * c->h.d * sizeof(double);
+  if (N < 0 || (!hX && !hidx) || (hX && (!t.X.p || bytes > t.X.cap)) || (hidx && (!t.Idx.p || n * sizeof(int32_t) > t.Idx.cap)))
+    return fail(c, PMCB200_ERR_ARG, "samples_host: no such sample array in the scratch set");
+  if (N > 0) {
+    CUDA_OK(c, cudaEventRecord(c->ev_a, c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_a, 0));
+    if (hX) CUDA_OK(c, cudaMemcpyAsync(hX, t.X.p, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (hidx) CUDA_OK(c, cudaMemcpyAsync(hidx, t.Idx.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  CUDA_OK(c, cudaEventRecord(t.copied, c->copy_stream));
+  t.busy = true;
+  return 0;
+}
+
 // wait for the host arrays: lag = 0 all iterations begun so far, lag = 1 all but the most recent one
 extern "C" int pmcb200_host_wait(pmcb200_ctx *c, int lag) {
   if (!c || lag < 0) return PMCB200_ERR_ARG;

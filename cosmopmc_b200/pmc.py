@@ -179,6 +179,13 @@ class PMC:
         p = C.c_void_p(hw.data_ptr() if isinstance(hw, torch.Tensor) else hw.ctypes.data)
         self._ck(self.lib.pmcb200_shard_weights_host_begin(self.h, N, p))
 
+    def samples_host_begin(self, N, hX=None, hidx=None):
+        """sample array / component indices of the most recent iteration (left on the device by hX=None, hidx=None)
+        to the host, on request"""
+        def hp(a):
+            return None if a is None else C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+        self._ck(self.lib.pmcb200_samples_host_begin(self.h, N, hp(hX), hp(hidx)))
+
     def host_wait(self, lag=0):
         self._ck(self.lib.pmcb200_host_wait(self.h, lag))
 

@@ -313,6 +313,13 @@ int pmcb200_iteration_host_begin(pmcb200_ctx *ctx, int64_t N, uint64_t seed,
                                  pmcb200_stats_t *stats);
 int pmcb200_shard_weights_host_begin(pmcb200_ctx *ctx, int64_t N, double *hw);
 int pmcb200_host_wait(pmcb200_ctx *ctx, int lag);
+/* Lazy sample delivery: any of hX / hidx / hflg may be NULL in the iteration calls above, the array then stays on
+ * the device (the weighted post-processing of section "post" works there).  The reference touches psim->X on the
+ * host only to dump it together with the component indices (out_pmc_simu_cosmo_pmc, cosmo_pmc.c:392) and to
+ * post-process the final sample; this call copies the sample array (N x ndim doubles) and / or the component indices
+ * of the most recent iteration to hX / hidx on request (either may be NULL), queued like the other host arrays
+ * (complete after pmcb200_host_wait(ctx, 0)). */
+int pmcb200_samples_host_begin(pmcb200_ctx *ctx, int64_t N, double *hX, int32_t *hidx);
 
 /* ---- several GPUs in ONE process (the reference shards the sample
  * over MPI ranks, cosmo_pmc.c:323-376: send_simulation / receive_importance_weight)

@@ -516,6 +516,29 @@ def test_pipelined_host_delivery_matches_blocking_call(oracle, pmc_factory):
         assert np.array_equal(x, y)
 
 
+def test_lazy_sample_delivery(oracle, pmc_factory):
+    """hX = NULL in the iteration call leaves the sample array on the device; pmcb200_samples_host_begin fetches it on
+    request: same statistics, same weights / flags / indices, and the fetched X equals the delivered one."""
+    spec = T.target_sn_demo()
+    w, m, cov = T.proposal_sn(10)
+    ch = oracle.cholesky_stack(cov)
+    N = 30000
+    def host():
+        return (torch.empty((N, 5), dtype=torch.float64).pin_memory(), torch.empty(N, dtype=torch.int32).pin_memory(),
+                torch.empty(N, dtype=torch.int16).pin_memory(), torch.empty(N, dtype=torch.float64).pin_memory())
+    a = pmc_factory(); a.set_target(spec); a.set_proposal(w, m, chol=ch)
+    b = pmc_factory(); b.set_target(spec); b.set_proposal(w, m, chol=ch)
+    for it in range(2):
+        ha, hb = host(), host()
+        sa = a.iteration_host(N, 5, it, 1.0, *ha)
+        sb = b.iteration_host_begin(N, 5, it, 1.0, None, None, hb[2], hb[3])
+        b.samples_host_begin(N, hb[0], hb[1])
+        b.host_wait(0)
+        assert sa == sb
+        for x, y in zip(ha, hb):
+            assert torch.equal(x, y)
+
+
 def test_multi_iteration_convergence_gauss2d(pmc_factory):
     """Statistical known answer of the reference: Demo/tempering/README.md:11-36,
     2-D Gaussian on the unit square => evidence consistent with 1 and the
