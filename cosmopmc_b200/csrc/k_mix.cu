@@ -48,7 +48,7 @@ static cudaError_t run_em_mma(const MixArgs &a, cudaStream_t s) {
     const int mt = em_mma_mt(a.h.K);
     const bool st = a.h.df > 0;
 #define EMM(MTV) if (mt == MTV) { if constexpr (MTV * (((1 + DD + DD * (DD + 1) / 2 + 7) / 8 + 7) / 8) <= EM_MMA_MAXACC) \
-      { if constexpr (DD >= 10) { if (a.rho_in && !st) return launch_em_mma<DD, MTV, false, true>(a, s); } \
+      { if (a.rho_in && !st) return launch_em_mma<DD, MTV, false, true>(a, s); \
         return st ? launch_em_mma<DD, MTV, true, false>(a, s) : launch_em_mma<DD, MTV, false, false>(a, s); } }
     EMM(1) EMM(2) EMM(3) EMM(4)
 #undef EMM

@@ -64,6 +64,7 @@ struct pmcb200_ctx {
   DevBuf sRho;
   const double *rho_X = nullptr; int64_t rho_N = 0; uint64_t rho_ver = 0, prop_ver = 0; bool rho_valid = false;
   int em_no_rho = 0;
+  int rho_min_dim = 10;     // smallest padded dimension that uses the cache (PMCB200_RHO_MIN_DIM)
   // scratch for the host-buffer API.  The sample arrays exist twice so that the device-to-host copies of one
   // iteration can drain while the next one computes (pmcb200_iteration_host_begin / pmcb200_host_wait); the
   // second set is only allocated if a caller actually leaves copies in flight.
@@ -364,6 +365,7 @@ static int install_proposal(pmcb200_ctx *c, int K, int d, int df, const double *
   int64_t len = stat_len(K, d);
   { const char *ev = getenv("PMCB200_EM_NO_MMA"); c->em_no_mma = ev && *ev && *ev != '0'; }
   { const char *ev = getenv("PMCB200_EM_NO_RHO"); c->em_no_rho = ev && *ev && *ev != '0'; }
+  { const char *ev = getenv("PMCB200_RHO_MIN_DIM"); if (ev && *ev) c->rho_min_dim = atoi(ev); }
   c->prop_ver++; c->rho_valid = false;
   c->em_blocks = 4 * c->sm_count;     // capacity of the partials buffer; the launch uses the resident count
   size_t need = (size_t)c->em_blocks * len;
@@ -767,7 +769,7 @@ static int launch_weights(pmcb200_ctx *c, int64_t N, const double *dX, const dou
   c->rho_valid = false;
   int written = 0;
   const int K = c->h.K, d = c->h.d;
-  if (!c->em_no_rho && !c->em_no_mma && pmc_pad_dim(d) >= 10 && c->h.df <= 0 && em_mma_ok(K, d, 0)) {
+  if (!c->em_no_rho && !c->em_no_mma && pmc_pad_dim(d) >= c->rho_min_dim && c->h.df <= 0 && em_mma_ok(K, d, 0)) {
     const size_t bytes = (size_t)N * K * sizeof(double);
     if (c->sRho.cap < bytes) {        // soft: without the buffer the EM kernel simply recomputes
       if (c->sRho.p) cudaFree(c->sRho.p);
