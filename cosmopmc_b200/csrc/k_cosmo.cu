@@ -46,7 +46,7 @@ static inline int nblk(int64_t N) { return (int)((N + PMC_BLOCK - 1) / PMC_BLOCK
 
 static int64_t sn_warp_max() {
   const char *evw = getenv("PMCB200_SN_WARP_MAX");
-  return evw && *evw ? atoll(evw) : 16384;
+  return evw && *evw ? atoll(evw) : 4096;
 }
 // PMCB200_SN_EXACT=1: node-by-node kernels only (A/B measurements, cross-check of the spectral form); read per call
 bool pmc_sn_spectral_wanted(const DevLike &L, int64_t N) {
@@ -86,8 +86,8 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
   // tests to validate the fast path against it)
   static const int force_slow = getenv("PMCB200_SN_FORCE_SLOW") ? atoi(getenv("PMCB200_SN_FORCE_SLOW")) : 0;
   // PMCB200_LIKE_V1=1: round-1 BAO / CMB kernels (A/B measurements, cross-check of the lean integrand); read per call
-  // crossover of the two SN layouts: the thread-per-sample kernel runs one wave (~0.1 ms at two resident blocks per SM)
-  // for up to 2 x 148 x 256 samples, the warp-per-sample kernel costs ~5.5 ns per sample
+  // crossover of the SN kernels (measured, 1e4 samples: warp-per-sample node-by-node 0.20 ms, spectral tensor-core kernel
+  // 0.105 ms; 5e4: 0.74 / 0.16 ms): the spectral kernel from 4096 samples (one block per SM on 16 SMs) on
   const int64_t sn_warp_max = ::sn_warp_max();
   const char *ev1 = getenv("PMCB200_LIKE_V1");
   const int like_v1 = ev1 && *ev1 && *ev1 != '0';

@@ -58,13 +58,15 @@ struct pmcb200_ctx {
   int em_blocks = 0;
   int em_no_mma = 0;        // PMCB200_EM_NO_MMA=1: keep the shared-memory EM kernel for d >= 10 (A/B measurements)
   int sm_count = 148;
-  // E-step cache (d >= 10, Gaussian proposal): the weight kernel leaves alpha_k phi_k(x_n) here and the EM statistics
+  // E-step cache (d >= 5, Gaussian proposal): the weight kernel leaves alpha_k phi_k(x_n) here and the EM statistics
   // kernel of the same iteration reads it back instead of repeating the K whitenings per sample.  Valid for exactly
   // one (sample array, N, proposal version); consumed by the next em_local.  PMCB200_EM_NO_RHO=1 disables it.
   DevBuf sRho;
   const double *rho_X = nullptr; int64_t rho_N = 0; uint64_t rho_ver = 0, prop_ver = 0; bool rho_valid = false;
   int em_no_rho = 0;
-  int rho_min_dim = 10;     // smallest padded dimension that uses the cache (PMCB200_RHO_MIN_DIM)
+  int rho_min_dim = 5;      // smallest padded dimension that uses the cache (PMCB200_RHO_MIN_DIM; the multi-sample weight
+                            // kernel that fills it exists from d = 5).  Measured per 1e7 samples, cache from d = 10 / from d = 5:
+                            // C2 14.86 / 14.56 ms, C4 23.68 / 23.19, C5 (K = 30, d = 8) 44.19 / 42.46
   // scratch for the host-buffer API.  The sample arrays exist twice so that the device-to-host copies of one
   // iteration can drain while the next one computes (pmcb200_iteration_host_begin / pmcb200_host_wait); the
   // second set is only allocated if a caller actually leaves copies in flight.
@@ -765,7 +767,7 @@ static int launch_weights(pmcb200_ctx *c, int64_t N, const double *dX, const dou
   if (N <= 0) return 0;
   MixArgs a; a.mix = c->d_mix; a.h = c->h; a.N = N; a.Xc = dX; a.logpic = dlogpi; a.errc = derr; a.beta = beta;
   a.flg = dflg; a.logw = dlogw; a.scal = c->d_scal;
-  // E-step cache: worth its 16 K bytes of HBM traffic per sample where the K whitenings cost more (d >= 10)
+  // E-step cache: 16 K bytes of HBM traffic per sample instead of the K whitenings + exps of the EM kernel's phase 1
   c->rho_valid = false;
   int written = 0;
   const int K = c->h.K, d = c->h.d;

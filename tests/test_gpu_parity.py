@@ -166,7 +166,7 @@ def check_posterior(oracle, pmc, spec, X):
         # the SN likelihood has four kernels: spectral form of the quadrature on the FP64 tensor cores (large batches;
         # hands what it cannot certify to the warp kernel), the same one sample per thread (chi2_betaz, add_logdetCov),
         # one sample per warp (small batches, node by node), one sample per thread (node by node).  This batch through all.
-        small = len(X) <= 16384
+        small = len(X) <= 4096
         for env in ({"PMCB200_SN_WARP_MAX": "0" if small else "1000000000"},
                     {"PMCB200_SN_WARP_MAX": "0", "PMCB200_SN_SPEC_V1": "1"},
                     {"PMCB200_SN_WARP_MAX": "0", "PMCB200_SN_EXACT": "1"}):
