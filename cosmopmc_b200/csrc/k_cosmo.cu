@@ -66,9 +66,17 @@ static void launch_sn_spectral(const DevLike &L, int64_t N, const double *X, int
   const char *ev = getenv("PMCB200_SN_SPEC_V1");
   const bool mma = L.sn_chi2mode != PMCB200_CHI2_betaz && !L.sn_add_logdetCov && !(ev && *ev && *ev != '0');
   if (mma) {
-    cudaFuncSetAttribute(k_like_sn_spec_mma<H, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SNS2_SMEM);   // per device
-    k_like_sn_spec_mma<H, F><<<(int)((N + SNS2_BLOCK - 1) / SNS2_BLOCK), SNS2_BLOCK, SNS2_SMEM, s>>>(
-        L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);
+    // PMCB200_SN_TAIL32=0: every coefficient k-step on the FP64 tensor cores (A/B measurements; read per call)
+    const char *et = getenv("PMCB200_SN_TAIL32");
+    const bool t32 = !(et && *et == '0') && L.cheb_Wt;
+    const int gm = (int)((N + SNS2_BLOCK - 1) / SNS2_BLOCK);
+    if (t32) {
+      cudaFuncSetAttribute(k_like_sn_spec_mma<H, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SNS2_SMEM);   // per device
+      k_like_sn_spec_mma<H, F, true><<<gm, SNS2_BLOCK, SNS2_SMEM, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);
+    } else {
+      cudaFuncSetAttribute(k_like_sn_spec_mma<H, F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SNS2_SMEM);
+      k_like_sn_spec_mma<H, F, false><<<gm, SNS2_BLOCK, SNS2_SMEM, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);
+    }
   } else {
     k_like_sn_spec<H, F><<<(int)((N + SNS_BLOCK - 1) / SNS_BLOCK), SNS_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt,
                                                                                      fb_list, fb_count);

@@ -579,6 +579,28 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
         }
     if ((rc = dev_copy<double>(c, Wf.data(), Wf.size(), &D.cheb_Wf))) return rc;
     D.sn_ntile = ntile;
+    // TF32 tail of the coefficient contraction (m >= 16): W split into hi + lo TF32 numbers (cvt.rna: nearest, ties away),
+    // in the B-fragment order of mma.m16n8k8: lane l holds b0 = B[k = l % 4][column l / 4], b1 = B[k = l % 4 + 4][column l / 4]
+    // per k-step of 8 coefficients; per lane and tile: [k-step][hi b0, hi b1, lo b0, lo b1]
+    {
+      auto tf32 = [](float f) { uint32_t u; memcpy(&u, &f, 4); u = (u + 0x1000u) & 0xffffe000u; return u; };
+      auto asf = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+      const int M64 = 16, nk2 = (M - M64 + 7) / 8;
+      std::vector<uint32_t> Wt((size_t)ntile * 32 * 8, 0u);
+      for (int t = 0; t < ntile; t++)
+        for (int l = 0; l < 32; l++) {
+          const int r = std::min(8 * t + l / 4, n - 1);
+          for (int k2 = 0; k2 < nk2 && k2 < 2; k2++)
+            for (int j = 0; j < 2; j++) {
+              const int mm = M64 + 8 * k2 + l % 4 + 4 * j;
+              const double w = mm < M ? W[(size_t)zof[r] * M + mm] : 0.0;
+              const uint32_t hi = tf32((float)w), lo = tf32((float)(w - (double)asf(hi)));
+              Wt[((size_t)t * 32 + l) * 8 + 4 * k2 + j] = hi;
+              Wt[((size_t)t * 32 + l) * 8 + 4 * k2 + 2 + j] = lo;
+            }
+        }
+      if ((rc = dev_copy<uint32_t>(c, Wt.data(), Wt.size(), &D.cheb_Wt))) return rc;
+    }
   }
   return 0;
 }

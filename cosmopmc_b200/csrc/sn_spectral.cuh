@@ -212,7 +212,41 @@ __device__ __forceinline__ double sn_rcp3(double s) {
   return fma(y, fma(e, e, e), y);
 }
 
-template <bool HASQ, bool FLAT>
+// ---- mixed-precision tail (template flag T32) ----------------------------------------------------------------------
+// The Chebyshev coefficients of an analytic integrand decay geometrically: beyond m = SNS_M64 = 16 they are below
+// ~1e-8 |c_0| for every sample that passes certificate (i), so their contribution to ss needs 5-6 digits, not 16.  With
+// T32 the terms m >= 16 of ss = sum_m c_m W[z][m] leave the FP64 pipe: c_m and W are split into two TF32 numbers each
+// (hi + lo carries 22 bits) and the three leading products hi*hi + hi*lo + lo*hi are accumulated by
+// mma.sync.m16n8k8.tf32 with FP32 accumulators, whose accumulator layout (row lane/4 [+8], columns 2 (lane%4) [+1])
+// coincides with the FP64 tiles' -- the tail lands in the lane that owns the pair and seeds its FP64 accumulator.
+// 3 of the 7 coefficient k-steps (12 of 40 DMMA per tile) disappear.  Error: representation 3 * 2^-22 per product,
+// accumulation of 48 terms in FP32 <= 48 * 2^-23, together below 8e-6 of sum_m |c_m W_m|; with |W[z][m]| <= 0.62 h_z and
+// ss_z >= h_z min_j q_j the relative error of ss_z is below 5e-6 * S / min_j q_j, S = sum_(m>=16) |c_m|.
+// Certificate (iii): S <= SNS_T32_TOL * min_j q_j  =>  relative error of ss_z below 2.5e-13 (worst case; measured
+// against the node-by-node kernel over 1e7 samples: see DESIGN.md).  A sample that fails it goes to the exact kernel
+// like the others; in practice (iii) is implied by (i), which already demands the same decay rate.
+#define SNS_M64 16
+#define SNS_T32_TOL 5.0e-8
+__device__ __forceinline__ void sn_split_tf32(double v, uint32_t &hi, uint32_t &lo) {
+  const float f = (float)v;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(f));
+  const float r = (float)(v - (double)__uint_as_float(hi));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void sn_mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+struct Ld8u { uint32_t v[8]; };
+__device__ __forceinline__ Ld8u ld256u(const void *p) {
+  Ld8u r;
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+  return r;
+}
+
+template <bool HASQ, bool FLAT, bool T32>
 __global__ void __launch_bounds__(SNS2_BLOCK, 1)
 k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int d,
                    const int16_t *__restrict__ flg, double *__restrict__ logpi,
@@ -239,7 +273,12 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
   }
   bool ok;
   const int qrow = lane >> 2, qcol = lane & 3;
-  double A[4][SNS_KS];       // A fragments: [row tile][k-step] = value [sample 8 rt + lane/4][4 ks + lane%4]
+  // A fragments: [row tile][k-step] = value [sample 8 rt + lane/4][4 ks + lane%4]; k-steps: KC coefficient ones
+  // (all SNS_M / 4, or the first SNS_M64 / 4 with the TF32 tail), then mu', sig2, sig2
+  constexpr int KC = T32 ? SNS_M64 / 4 : SNS_M / 4;
+  constexpr int NT32 = (SNS_M - SNS_M64 + 7) / 8;      // TF32 k-steps of 8 coefficients
+  double A[4][KC + 3];
+  uint32_t A32[2][NT32 > 0 ? NT32 : 1][2][4];            // [16-sample tile][k-step][hi, lo][a0..a3]
   double rhv[4], OKv[4];
   {
     SNCoef ec;
@@ -252,18 +291,35 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
       double qmin;
       sn_cheb_coeffs<HASQ, FLAT>(L, ec, T, c, qmin);
       if (!sn_spec_certified(L, c, qmin)) ok = false;
+      if (T32) {      // certificate (iii)
+        double S = 0.0;
+#pragma unroll
+        for (int mm = SNS_M64; mm < SNS_M; mm++) S += fabs(c[mm]);
+        if (!(S <= SNS_T32_TOL * qmin)) ok = false;
+      }
     }
     // lane-owned values -> A fragments, eight values per trip through the warp's buffer
 #pragma unroll
     for (int ch = 0; ch < (SNS_M + 7) / 8; ch++) {
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; j++) if (8 * ch + j < SNS_M) tr[lane * SNS_TRS + j] = c[8 * ch + j];
+      for (int j = 0; j < 8; j++) tr[lane * SNS_TRS + j] = (8 * ch + j < SNS_M) ? c[8 * ch + j] : 0.0;
       __syncwarp();
+      if (!T32 || 8 * ch < SNS_M64) {
 #pragma unroll
-      for (int rt = 0; rt < 4; rt++) {
-        A[rt][2 * ch] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
-        if (2 * ch + 1 < SNS_M / 4) A[rt][2 * ch + 1] = tr[(8 * rt + qrow) * SNS_TRS + 4 + qcol];
+        for (int rt = 0; rt < 4; rt++) {
+          A[rt][2 * ch] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
+          if (2 * ch + 1 < KC) A[rt][2 * ch + 1] = tr[(8 * rt + qrow) * SNS_TRS + 4 + qcol];
+        }
+      } else {      // TF32 tail: m16n8k8 A fragment a0 (row g, col t), a1 (row g + 8, col t), a2 (row g, col t + 4), a3 (row g + 8, col t + 4)
+        const int k2 = (8 * ch - SNS_M64) / 8;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          const double v[4] = {tr[(16 * mt + qrow) * SNS_TRS + qcol], tr[(16 * mt + 8 + qrow) * SNS_TRS + qcol],
+                               tr[(16 * mt + qrow) * SNS_TRS + 4 + qcol], tr[(16 * mt + 8 + qrow) * SNS_TRS + 4 + qcol]};
+#pragma unroll
+          for (int i = 0; i < 4; i++) sn_split_tf32(v[i], A32[mt][k2][0][i], A32[mt][k2][1][i]);
+        }
       }
     }
     __syncwarp();
@@ -277,8 +333,8 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
     __syncwarp();
 #pragma unroll
     for (int rt = 0; rt < 4; rt++) {
-      A[rt][SNS_M / 4] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
-      A[rt][SNS_M / 4 + 1] = tr[(8 * rt + qrow) * SNS_TRS + 4 + qcol];
+      A[rt][KC] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
+      A[rt][KC + 1] = tr[(8 * rt + qrow) * SNS_TRS + 4 + qcol];
     }
     __syncwarp();
     tr[lane * SNS_TRS + 0] = pm.k4; tr[lane * SNS_TRS + 1] = pm.k5; tr[lane * SNS_TRS + 2] = 0.0;
@@ -287,7 +343,7 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
     __syncwarp();
 #pragma unroll
     for (int rt = 0; rt < 4; rt++) {
-      A[rt][SNS_M / 4 + 2] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
+      A[rt][KC + 2] = tr[(8 * rt + qrow) * SNS_TRS + qcol];
       rhv[rt] = tr[(8 * rt + qrow) * SNS_TRS + 4];
       OKv[rt] = tr[(8 * rt + qrow) * SNS_TRS + 5];
     }
@@ -298,23 +354,42 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
   const int ntile = L.sn_ntile;
   double chi[4] = {0.0, 0.0, 0.0, 0.0};
   unsigned ebits = 0u, ubits = 0u;      // per row tile: distance error; curvature argument outside the series
-  double b[SNS_KS], bn[SNS_KS];
+  // fragment table k-steps this kernel reads: the KC coefficient ones, then mu', sig2, sig2 (table positions M/4 ..)
+  double b[KC + 3], bn[KC + 3];
+  Ld8u bt, btn;      // TF32 tail fragments of the tile: [k-step][hi b0, hi b1, lo b0, lo b1]
+  const uint32_t *__restrict__ wt = L.cheb_Wt + (size_t)lane * 8;
 #pragma unroll
-  for (int ks = 0; ks < SNS_KS; ks++) bn[ks] = __ldg(wf + (size_t)ks * 32);
+  for (int ks = 0; ks < KC + 3; ks++) bn[ks] = __ldg(wf + (size_t)(ks < KC ? ks : ks - KC + SNS_M / 4) * 32);
+  if (T32) btn = ld256u(wt);
   for (int t = 0; t < ntile; t++) {
 #pragma unroll
-    for (int ks = 0; ks < SNS_KS; ks++) b[ks] = bn[ks];
+    for (int ks = 0; ks < KC + 3; ks++) b[ks] = bn[ks];
+    if (T32) bt = btn;
     const int tn = min(t + 1, ntile - 1);       // next tile's fragments travel while this one computes
 #pragma unroll
-    for (int ks = 0; ks < SNS_KS; ks++) bn[ks] = __ldg(wf + ((size_t)tn * SNS_KS + ks) * 32);
+    for (int ks = 0; ks < KC + 3; ks++) bn[ks] = __ldg(wf + ((size_t)tn * SNS_KS + (ks < KC ? ks : ks - KC + SNS_M / 4)) * 32);
+    if (T32) btn = ld256u(wt + (size_t)tn * 256);
+    float t32[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    if (T32) {
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int k2 = 0; k2 < NT32; k2++) {
+          sn_mma_tf32(t32[mt], A32[mt][k2][1], bt.v[4 * k2], bt.v[4 * k2 + 1]);          // lo * hi
+          sn_mma_tf32(t32[mt], A32[mt][k2][0], bt.v[4 * k2 + 2], bt.v[4 * k2 + 3]);      // hi * lo
+          sn_mma_tf32(t32[mt], A32[mt][k2][0], bt.v[4 * k2], bt.v[4 * k2 + 1]);          // hi * hi
+        }
+    }
 #pragma unroll
     for (int rt = 0; rt < 4; rt++) {
-      double s0 = 0.0, s1 = 0.0, m0 = 0.0, m1 = 0.0, g0 = 0.0, g1 = 0.0;
+      // the tail (accumulator rows lane/4 and lane/4 + 8 of the 16-sample tile = row tiles 2 mt and 2 mt + 1) seeds ss
+      double s0 = T32 ? (double)t32[rt >> 1][2 * (rt & 1)] : 0.0, s1 = T32 ? (double)t32[rt >> 1][2 * (rt & 1) + 1] : 0.0;
+      double m0 = 0.0, m1 = 0.0, g0 = 0.0, g1 = 0.0;
 #pragma unroll
-      for (int ks = 0; ks < SNS_M / 4; ks++) sn_dmma(s0, s1, A[rt][ks], b[ks]);
-      sn_dmma(m0, m1, A[rt][SNS_M / 4], b[SNS_M / 4]);
-      sn_dmma(g0, g1, A[rt][SNS_M / 4 + 1], b[SNS_M / 4 + 1]);
-      sn_dmma(g0, g1, A[rt][SNS_M / 4 + 2], b[SNS_M / 4 + 2]);
+      for (int ks = 0; ks < KC; ks++) sn_dmma(s0, s1, A[rt][ks], b[ks]);
+      sn_dmma(m0, m1, A[rt][KC], b[KC]);
+      sn_dmma(g0, g1, A[rt][KC + 1], b[KC + 1]);
+      sn_dmma(g0, g1, A[rt][KC + 2], b[KC + 2]);
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const double ss = h ? s1 : s0, mu = h ? m1 : m0, sg = h ? g1 : g0;
