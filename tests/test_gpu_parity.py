@@ -603,11 +603,13 @@ def test_iteration_host_multi_contexts(oracle, pmc_factory):
     X2 = np.empty((N, 5)); i2 = np.empty(N, np.int32); f2 = np.empty(N, np.int16); w2 = np.empty(N)
     s2 = iteration_host_multi(many, N, seed, 2, 0.8, X2, i2, f2, w2)
     assert np.array_equal(X1, X2) and np.array_equal(i1, i2) and np.array_equal(f1, f2)
-    assert np.allclose(w1, w2, rtol=1e-12, atol=0)
+    # the SN kernel is chosen by shard size (10001 samples: spectral tensor-core kernel, 3334: one sample per
+    # warp, node by node); the two agree to ~2e-14 of log L ~ -180, i.e. ~4e-12 of a weight: parity tolerance
+    assert np.allclose(w1, w2, rtol=1e-10, atol=0)
     for k in ("nok", "nok_box", "ndead", "nsamples"):
         assert s1[k] == s2[k]
     for k in ("maxW", "logSum", "perplexity", "ess", "enc", "ln_evidence"):
-        assert abs(s1[k] - s2[k]) <= 1e-12 * abs(s1[k]), k
+        assert abs(s1[k] - s2[k]) <= 1e-10 * abs(s1[k]), k
     ref = one.get_proposal()
     props = [p.get_proposal() for p in many]
     for a, b in zip(ref, props[0]):
