@@ -42,8 +42,38 @@ static cudaError_t launch_em_mma(const MixArgs &a, cudaStream_t s) {
                                        a.rho_in);
   return cudaGetLastError();
 }
+// warp-sliced form (d <= 10: few feature tiles): samples sliced over the warps, up to 4 resident blocks per SM
+template <int DD, int MT, bool STUDENT, bool RHO>
+static cudaError_t launch_em_ws(const MixArgs &a, cudaStream_t s) {
+  auto kern = k_em_stats_mma_ws<DD, MT, STUDENT, RHO>;
+  const size_t smem = em_ws_smem_bytes(a.h.K, a.h.d, STUDENT);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 1, dev = 0, sms = 148;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PMC_BLOCK, smem);
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t nsteps = (a.N + 31) / 32, want = (nsteps + PMC_BLOCK / 32 - 1) / (PMC_BLOCK / 32);
+  int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(a.blocks, want), (int64_t)std::max(1, per_sm) * sms));
+  if (a.nblocks_out) *a.nblocks_out = blocks;
+  kern<<<blocks, PMC_BLOCK, smem, s>>>(a.mix, a.h, a.N, a.Xc, a.idxc, a.flgc, a.logwc, a.scal, a.partials, a.linear,
+                                       a.rho_in);
+  return cudaGetLastError();
+}
 template <int DD>
 static cudaError_t run_em_mma(const MixArgs &a, cudaStream_t s) {
+  if constexpr (em_ws_nt(DD) <= 9) {
+    static const int no_ws = getenv("PMCB200_EM_NO_WS") ? atoi(getenv("PMCB200_EM_NO_WS")) : 0;
+    const int mt = em_mma_mt(a.h.K);
+    const bool st = a.h.df > 0;
+    if (!no_ws && em_ws_ok(a.h.K, a.h.d, st)) {
+#define EMW(MTV) if (mt == MTV) { if constexpr (MTV * em_ws_nt(DD) <= 24) \
+      { if (a.rho_in && !st) return launch_em_ws<DD, MTV, false, true>(a, s); \
+        return st ? launch_em_ws<DD, MTV, true, false>(a, s) : launch_em_ws<DD, MTV, false, false>(a, s); } }
+      EMW(1) EMW(2) EMW(3) EMW(4)
+#undef EMW
+    }
+  }
   {
     const int mt = em_mma_mt(a.h.K);
     const bool st = a.h.df > 0;

@@ -791,3 +791,198 @@ k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
     if (STUDENT && warp == 0 && t == 0) Pk[0] = accA[m][0];
   }
 }
+
+// ---- K5, FP64 tensor cores, warp-sliced (few feature tiles: d <= 10) ---------------------------------------------
+// ncu on k_em_stats_mma at C2 (d = 5, K = 10; profiles/r02/c2_k_em_stats_mma_summary.txt): 21 features are 3 tiles, so 3 of
+// the block's 8 warps own all of phase 2 (64 dependent k-steps each per 256-sample tile, two accumulator chains),
+// the other 5 walk an empty loop between two block barriers: 77 warp instructions per sample, DMMA sub-pipe 35 %, 1.6 ms
+// per 1e7 samples where the contraction itself is worth 0.2 ms.  Here the SAMPLES are sliced over the warps instead of
+// the feature tiles: a warp takes 32 samples per step, does phase 1 for them (one sample per lane, its own shared-memory
+// rows), and contracts them against ALL feature tiles (8 k-steps x MT x NT independent accumulator chains) -- no block
+// barrier inside the sample loop, every warp issues DMMA, every shared-memory row is read by the warp that wrote it.
+// The 8 warps' accumulators are summed in warp order at the end (fixed order => deterministic for a given grid).
+#define EM_WS_STRIDE 36                // row stride of the per-warp w rho rows (4 mod 16: the 8 rows of an A fragment on distinct banks)
+__host__ __device__ constexpr int em_ws_nt(int D) { return (1 + D + D * (D + 1) / 2 + 7) / 8; }
+__host__ __device__ constexpr int em_ws_perwarp(int D, int MT, bool student) {
+  const int work = 8 * MT * EM_WS_STRIDE * (student ? 2 : 1) + 32 * ((D + 1) | 1), accn = MT * em_ws_nt(D) * 64;
+  return work > accn ? work : accn;
+}
+__host__ __device__ inline size_t em_ws_smem_bytes(int K, int d, int student) {
+  const int D = pmc_pad_dim(d);
+  return ((size_t)(PMC_BLOCK / 32) * em_ws_perwarp(D, em_mma_mt(K), student != 0) + (size_t)K * mix_stride(d) + D) * sizeof(double) +
+         (size_t)K * sizeof(unsigned long long);
+}
+__host__ __device__ inline bool em_ws_ok(int K, int d, int student) {
+  const int D = pmc_pad_dim(d);
+  return K <= 32 && em_ws_nt(D) <= 9 && em_mma_mt(K) * em_ws_nt(D) <= 24 && em_ws_smem_bytes(K, d, student) <= 100 * 1024;
+}
+
+template <int D, int MT, bool STUDENT, bool RHO>
+__global__ void __launch_bounds__(PMC_BLOCK, (MT * em_ws_nt(D) > 12) ? 1 : (MT * em_ws_nt(D) <= 6 ? 3 : 2))
+k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
+                  const double *__restrict__ X, const int32_t *__restrict__ idx,
+                  const int16_t *__restrict__ flg, const double *__restrict__ logw,
+                  const DevScal *__restrict__ scal, double *__restrict__ partials, int linear,
+                  const double *__restrict__ rho) {
+  static_assert(!(RHO && STUDENT), "the E-step cache holds no Mahalanobis distances (Student-t gamma)");
+  extern __shared__ double sm[];
+  constexpr int XS = (D + 1) | 1;           // odd row stride; column D holds the constant 1
+  constexpr int NT = em_ws_nt(D);
+  constexpr int KP = 8 * MT;
+  constexpr int WS = EM_WS_STRIDE;
+  constexpr int PERW = em_ws_perwarp(D, MT, STUDENT);
+  constexpr int NW = PMC_BLOCK / 32;
+  const int K = h.K, d = h.d, M = stat_cs(d);
+  const int nfeat = 1 + d + mix_tri(d);       // G, B[d], C[tri] (stat block position: f = 0 -> 1, f >= 1 -> f + 2)
+  const int ntv = (nfeat + 7) / 8;            // feature tiles in use (d < D leaves the last ones empty)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  double *s_wr = sm + (size_t)warp * PERW;                                  // [KP][WS] w rho of this warp's 32 samples
+  double *s_wg = STUDENT ? s_wr + KP * WS : s_wr;                           // w rho gamma
+  double *s_x = s_wg + KP * WS;                                             // [32][XS] x - pivot | 1
+  unsigned long long *s_cnt = (unsigned long long *)(sm + (size_t)NW * PERW);   // [K]
+  double *s_mix = (double *)(s_cnt + K);
+  __shared__ double red[32];
+  for (int i = tid; i < K * h.stride + D; i += PMC_BLOCK) s_mix[i] = mix[i];
+  const double *pivot = s_mix + (size_t)K * h.stride;
+  const double M0 = linear ? 0.0 : dunkey(scal->max_key);
+  double tS = 0.0, tS2 = 0.0, tT = 0.0, tN = 0.0;
+  int oi[NT], oj[NT];      // this lane's B-fragment column (feature 8 q + g) as staged-row offsets
+#pragma unroll
+  for (int q = 0; q < NT; q++) {
+    const int f = q * 8 + g;
+    int a = D, b = D;
+    if (f >= 1 && f < 1 + d) a = f - 1;
+    else if (f >= 1 + d && f < nfeat) {
+      const int qq = f - 1 - d;
+      int i = 0;
+      while ((i + 1) * (i + 2) / 2 <= qq) i++;
+      a = i; b = qq - i * (i + 1) / 2;
+    }
+    oi[q] = a; oj[q] = b;
+  }
+  double acc[MT][NT][2], accA[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    accA[m][0] = 0.0; accA[m][1] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NT; q++) { acc[m][q][0] = 0.0; acc[m][q][1] = 0.0; }
+  }
+  for (int k = K; k < KP; k++) { s_wr[k * WS + lane] = 0.0; if (STUDENT) s_wg[k * WS + lane] = 0.0; }
+  if (tid < K) s_cnt[tid] = 0ull;
+  __syncthreads();
+  const int64_t nsteps = (N + 31) / 32;
+
+  for (int64_t st = (int64_t)blockIdx.x * NW + warp; st < nsteps; st += (int64_t)gridDim.x * NW) {
+    const int64_t n = st * 32 + lane;
+    __syncwarp();
+    // ---- phase 1: weight and responsibilities of this lane's sample (the arithmetic of k_em_stats_mma)
+    const bool fl = (n < N) && flg[n];
+    const bool ok = fl && (!linear || logw[n] > 0.0);
+    double *xrow = s_x + lane * XS;
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < D; i++) xrow[i] = (i < d) ? X[n * d + i] : 0.0;
+      double lw, w;
+      if (linear) { w = logw[n]; lw = log(w); }
+      else { lw = logw[n] - M0; w = exp(lw); }
+      tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT); tN += 1.0;
+      double rt = 0.0;
+#pragma unroll 5
+      for (int k = 0; k < K; k++) {
+        const double *comp = s_mix + (size_t)k * h.stride;
+        double r = 0.0, gam = 1.0;
+        if (RHO) r = rho[(size_t)k * N + n];      // alpha_k phi_k(x_n) left by the weight kernel of this iteration
+        else if (comp[0] != 0.0) {
+          double tt[1][D], m1[1];
+#pragma unroll
+          for (int i = 0; i < D; i++) tt[0][i] = xrow[i];
+          comp_maha_cols<D, 1>(comp, tt, m1);
+          const double m = m1[0];
+          r = comp[0] * exp(comp_logpdf_from_maha(comp, d, h.df, m));
+          if (STUDENT) gam = (double)(h.df + d) / ((double)h.df + m);
+        }
+        rt += r;
+        s_wr[k * WS + lane] = r;
+        if (STUDENT) s_wg[k * WS + lane] = gam;
+      }
+      const double sc = w / rt;
+#pragma unroll 5
+      for (int k = 0; k < K; k++) {
+        const double r = s_wr[k * WS + lane] * sc;
+        s_wr[k * WS + lane] = r;
+        if (STUDENT) s_wg[k * WS + lane] *= r;
+      }
+#pragma unroll
+      for (int i = 0; i < D; i++) xrow[i] -= pivot[i];      // padded: 0 - 0
+    } else {
+      for (int k = 0; k < K; k++) { s_wr[k * WS + lane] = 0.0; if (STUDENT) s_wg[k * WS + lane] = 0.0; }
+#pragma unroll
+      for (int i = 0; i < D; i++) xrow[i] = 0.0;
+    }
+    xrow[D] = 1.0;
+    if (fl) { const int c = idx[n]; if (c >= 0 && c < K) atomicAdd(&s_cnt[c], 1ull); }
+    __syncwarp();
+    // ---- phase 2: K x 32 x nfeat on the FP64 tensor cores, 4 samples per k-step, all feature tiles
+    const double *wa = s_wg + g * WS + t;
+    const double *wr = s_wr + g * WS + t;
+    const double *xr = s_x + t * XS;
+#pragma unroll
+    for (int s0 = 0; s0 < 32; s0 += 4) {
+      double a[MT];
+#pragma unroll
+      for (int m = 0; m < MT; m++) a[m] = wa[m * 8 * WS + s0];
+      double b0 = 0.0;
+#pragma unroll
+      for (int q = 0; q < NT; q++) {
+        if (q < ntv) {
+          const double b = xr[s0 * XS + oi[q]] * xr[s0 * XS + oj[q]];
+          if (q == 0) b0 = b;
+#pragma unroll
+          for (int m = 0; m < MT; m++) dmma884(acc[m][q][0], acc[m][q][1], a[m], b);
+        }
+      }
+      if (STUDENT) {
+#pragma unroll
+        for (int m = 0; m < MT; m++) dmma884(accA[m][0], accA[m][1], wr[m * 8 * WS + s0], b0);
+      }
+    }
+  }
+  // ---- this block's partial: the warps' accumulators summed in warp order
+  __syncwarp();
+  double *s_acc = sm + (size_t)warp * PERW;      // [(m NT + q) 2 + c][lane], over this warp's own (now idle) rows
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int q = 0; q < NT; q++) {
+      s_acc[((m * NT + q) * 2 + 0) * 32 + lane] = acc[m][q][0];
+      s_acc[((m * NT + q) * 2 + 1) * 32 + lane] = acc[m][q][1];
+    }
+  __syncthreads();
+  double *P0 = partials + (size_t)blockIdx.x * stat_len(K, d);
+  for (int slot = tid; slot < MT * NT * 64; slot += PMC_BLOCK) {
+    const int ln = slot & 31, c = (slot >> 5) & 1, mq = slot >> 6, m = mq / NT, q = mq - m * NT;
+    const int k = m * 8 + (ln >> 2), f = q * 8 + 2 * (ln & 3) + c;
+    if (k >= K || f >= nfeat) continue;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) v += sm[(size_t)w * PERW + slot];
+    double *Pk = P0 + STAT_HDR + (size_t)k * M;
+    if (f == 0) { Pk[1] = v; if (!STUDENT) Pk[0] = v; }
+    else Pk[f + 2] = v;
+  }
+  if (STUDENT) {      // A = sum w rho (without gamma): column 0 of the ones tile, rows 8 m + g, held by the lanes t = 0
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MT; m++) if (t == 0) s_acc[m * 8 + g] = accA[m][0];
+    __syncthreads();
+    if (tid < K) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) v += sm[(size_t)w * PERW + tid];
+      P0[STAT_HDR + (size_t)tid * M] = v;
+    }
+  }
+  double bS = block_sum(tS, red), bS2 = block_sum(tS2, red), bT = block_sum(tT, red), bN = block_sum(tN, red);
+  if (tid == 0) { P0[0] = M0; P0[1] = bS; P0[2] = bS2; P0[3] = bT; P0[4] = bN; P0[5] = 0; P0[6] = 0; P0[7] = 0; }
+  if (tid < K) P0[STAT_HDR + (size_t)tid * M + 2] = (double)s_cnt[tid];
+}
