@@ -26,6 +26,8 @@ struct DevLike {
   const double *cheb_W;       // [sn_nz][SNS_M]
   const double *cheb_dmax;    // [SNS_M] max_z |D[z][m]| / h_z
   const double *cheb_Wf;      // [sn_ntile][SNS_M/4 + 3][32] B fragments of the tensor-core kernel (8 supernovae per tile)
+  const int *sn_tile_sec;     // [sn_ntile] 0 = primary tile (8 distinct redshifts), 1 = secondary (further supernovae at the
+                              // redshifts of the primary tile before it, same columns)
   const uint32_t *cheb_Wt;    // [sn_ntile][32][8] TF32 hi / lo B fragments of the coefficient tail m >= 16 (m16n8k8)
   int sn_ntile, pad1;
   // Gaussian data (BAO, CMB distance priors): packed like a mixture component

@@ -814,11 +814,16 @@ __host__ __device__ inline size_t em_ws_smem_bytes(int K, int d, int student) {
 }
 __host__ __device__ inline bool em_ws_ok(int K, int d, int student) {
   const int D = pmc_pad_dim(d);
-  return K <= 32 && em_ws_nt(D) <= 9 && em_mma_mt(K) * em_ws_nt(D) <= 24 && em_ws_smem_bytes(K, d, student) <= 100 * 1024;
+  return K <= 32 && em_ws_nt(D) <= 9 && em_mma_mt(K) * em_ws_nt(D) <= 24 && em_ws_smem_bytes(K, d, student) <= 200 * 1024;
 }
 
+// resident blocks per SM the register budget allows: accumulators + prefetch registers (+ ~50 for the rest)
+__host__ __device__ constexpr int em_ws_minb(int D, int MT, bool rho) {
+  const int est = 2 * (2 * MT * em_ws_nt(D) + (rho ? 8 * MT : 0) + D) + 50, b = 65536 / (PMC_BLOCK * est);
+  return b < 1 ? 1 : (b > 3 ? 3 : b);
+}
 template <int D, int MT, bool STUDENT, bool RHO>
-__global__ void __launch_bounds__(PMC_BLOCK, (MT * em_ws_nt(D) > 12) ? 1 : (MT * em_ws_nt(D) <= 6 ? 3 : 2))
+__global__ void __launch_bounds__(PMC_BLOCK, em_ws_minb(D, MT, RHO))
 k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
                   const double *__restrict__ X, const int32_t *__restrict__ idx,
                   const int16_t *__restrict__ flg, const double *__restrict__ logw,
@@ -870,47 +875,72 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
   for (int k = K; k < KP; k++) { s_wr[k * WS + lane] = 0.0; if (STUDENT) s_wg[k * WS + lane] = 0.0; }
   if (tid < K) s_cnt[tid] = 0ull;
   __syncthreads();
-  const int64_t nsteps = (N + 31) / 32;
+  const int64_t nsteps = (N + 31) / 32, stride = (int64_t)gridDim.x * NW;
+  // this lane's sample of the NEXT step travels while the tensor cores work on the current one (ncu on the first version:
+  // 8.9 long-scoreboard stall cycles per issue, 0.35 of the HBM peak -- load, compute, load without overlap)
+  double px[D], plw = 0.0, prh[RHO ? KP : 1];
+  int pfl = 0, pix = 0;
+  auto fetch = [&](int64_t stf) {
+    const int64_t nf = stf * 32 + lane;
+    pfl = 0;
+    if (nf < N) {
+      pfl = flg[nf]; plw = logw[nf]; pix = idx[nf];
+#pragma unroll
+      for (int i = 0; i < D; i++) px[i] = (i < d) ? X[nf * d + i] : 0.0;
+      if (RHO) {
+#pragma unroll
+        for (int k = 0; k < KP; k++) if (k < K) prh[k] = rho[(size_t)k * N + nf];      // alpha_k phi_k(x_n) left by the weight kernel
+      }
+    }
+  };
+  int64_t st = (int64_t)blockIdx.x * NW + warp;
+  if (st < nsteps) fetch(st);
 
-  for (int64_t st = (int64_t)blockIdx.x * NW + warp; st < nsteps; st += (int64_t)gridDim.x * NW) {
-    const int64_t n = st * 32 + lane;
+  for (; st < nsteps; st += stride) {
     __syncwarp();
     // ---- phase 1: weight and responsibilities of this lane's sample (the arithmetic of k_em_stats_mma)
-    const bool fl = (n < N) && flg[n];
-    const bool ok = fl && (!linear || logw[n] > 0.0);
+    const bool fl = pfl != 0;
+    const bool ok = fl && (!linear || plw > 0.0);
     double *xrow = s_x + lane * XS;
     if (ok) {
 #pragma unroll
-      for (int i = 0; i < D; i++) xrow[i] = (i < d) ? X[n * d + i] : 0.0;
+      for (int i = 0; i < D; i++) xrow[i] = px[i];
       double lw, w;
-      if (linear) { w = logw[n]; lw = log(w); }
-      else { lw = logw[n] - M0; w = exp(lw); }
+      if (linear) { w = plw; lw = log(w); }
+      else { lw = plw - M0; w = exp(lw); }
       tS += w; tS2 = fma(w, w, tS2); tT = fma(w, lw, tT); tN += 1.0;
       double rt = 0.0;
-#pragma unroll 5
-      for (int k = 0; k < K; k++) {
-        const double *comp = s_mix + (size_t)k * h.stride;
-        double r = 0.0, gam = 1.0;
-        if (RHO) r = rho[(size_t)k * N + n];      // alpha_k phi_k(x_n) left by the weight kernel of this iteration
-        else if (comp[0] != 0.0) {
-          double tt[1][D], m1[1];
+      if (RHO) {
 #pragma unroll
-          for (int i = 0; i < D; i++) tt[0][i] = xrow[i];
-          comp_maha_cols<D, 1>(comp, tt, m1);
-          const double m = m1[0];
-          r = comp[0] * exp(comp_logpdf_from_maha(comp, d, h.df, m));
-          if (STUDENT) gam = (double)(h.df + d) / ((double)h.df + m);
-        }
-        rt += r;
-        s_wr[k * WS + lane] = r;
-        if (STUDENT) s_wg[k * WS + lane] = gam;
-      }
-      const double sc = w / rt;
+        for (int k = 0; k < KP; k++) if (k < K) rt += prh[k];
+        const double sc = w / rt;
+#pragma unroll
+        for (int k = 0; k < KP; k++) if (k < K) s_wr[k * WS + lane] = prh[k] * sc;
+      } else {
 #pragma unroll 5
-      for (int k = 0; k < K; k++) {
-        const double r = s_wr[k * WS + lane] * sc;
-        s_wr[k * WS + lane] = r;
-        if (STUDENT) s_wg[k * WS + lane] *= r;
+        for (int k = 0; k < K; k++) {
+          const double *comp = s_mix + (size_t)k * h.stride;
+          double r = 0.0, gam = 1.0;
+          if (comp[0] != 0.0) {
+            double tt[1][D], m1[1];
+#pragma unroll
+            for (int i = 0; i < D; i++) tt[0][i] = xrow[i];
+            comp_maha_cols<D, 1>(comp, tt, m1);
+            const double m = m1[0];
+            r = comp[0] * exp(comp_logpdf_from_maha(comp, d, h.df, m));
+            if (STUDENT) gam = (double)(h.df + d) / ((double)h.df + m);
+          }
+          rt += r;
+          s_wr[k * WS + lane] = r;
+          if (STUDENT) s_wg[k * WS + lane] = gam;
+        }
+        const double sc = w / rt;
+#pragma unroll 5
+        for (int k = 0; k < K; k++) {
+          const double r = s_wr[k * WS + lane] * sc;
+          s_wr[k * WS + lane] = r;
+          if (STUDENT) s_wg[k * WS + lane] *= r;
+        }
       }
 #pragma unroll
       for (int i = 0; i < D; i++) xrow[i] -= pivot[i];      // padded: 0 - 0
@@ -920,7 +950,8 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
       for (int i = 0; i < D; i++) xrow[i] = 0.0;
     }
     xrow[D] = 1.0;
-    if (fl) { const int c = idx[n]; if (c >= 0 && c < K) atomicAdd(&s_cnt[c], 1ull); }
+    if (fl) { const int c = pix; if (c >= 0 && c < K) atomicAdd(&s_cnt[c], 1ull); }
+    if (st + stride < nsteps) fetch(st + stride);
     __syncwarp();
     // ---- phase 2: K x 32 x nfeat on the FP64 tensor cores, 4 samples per k-step, all feature tiles
     const double *wa = s_wg + g * WS + t;

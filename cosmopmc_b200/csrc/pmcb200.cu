@@ -555,22 +555,44 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
     if ((rc = dev_copy<double>(c, cn.data(), cn.size(), &D.cheb_nodes4))) return rc;
     if ((rc = dev_copy<double>(c, W.data(), W.size(), &D.cheb_W))) return rc;
     if ((rc = dev_copy<double>(c, dmax.data(), dmax.size(), &D.cheb_dmax))) return rc;
-    // B fragments of the tensor-core kernel: tile t = supernovae 8 t .. 8 t + 7 (sorted by redshift), k-step ks, lane l
-    // holds B[k = l % 4][column = l / 4]: W of the supernova's redshift (ks < M / 4), then the chi^2 features
-    const int KS = M / 4 + 3, ntile = (n + 7) / 8;
+    // B fragments of the tensor-core kernel.  Columns are supernovae; a PRIMARY tile holds the first supernova of 8 distinct
+    // redshifts, the further supernovae of those redshifts sit in the same column of the SECONDARY tiles that follow it
+    // (they reuse the primary column's ss: only the chi^2 k-steps are read).  Redshifts ordered by multiplicity so that the
+    // repeated ones share primary tiles (Union: 241 redshifts, 307 supernovae -> 31 primary + 12 secondary tiles).
+    // Lane l of k-step ks holds B[k = l % 4][column = l / 4]: W of the column's redshift (ks < M / 4), then the chi^2
+    // features.  An empty column repeats a supernova with sigma^2 = 1e300: its term vanishes.
+    const int KS = M / 4 + 3;
+    std::vector<int> zord(nz);
+    for (int z = 0; z < nz; z++) zord[z] = z;
+    std::stable_sort(zord.begin(), zord.end(), [&](int a, int b) { return first[a + 1] - first[a] > first[b + 1] - first[b]; });
+    std::vector<int> tcol, tsec;      // per tile: 8 x {supernova row, or -(row) - 1 for an empty column}; secondary flag
+    std::vector<int> tz;              // per tile column: redshift index (the W row)
+    for (int p0 = 0; p0 < nz; p0 += 8) {
+      int maxm = 1;
+      for (int j = 0; j < 8 && p0 + j < nz; j++) maxm = std::max(maxm, first[zord[p0 + j] + 1] - first[zord[p0 + j]]);
+      for (int sidx = 0; sidx < maxm; sidx++) {
+        tsec.push_back(sidx > 0);
+        for (int j = 0; j < 8; j++) {
+          const int z = zord[std::min(p0 + j, nz - 1)], mult = first[z + 1] - first[z];
+          const bool real = p0 + j < nz && sidx < mult;
+          tz.push_back(z);
+          tcol.push_back(real ? first[z] + sidx : -first[z] - 1);
+        }
+      }
+    }
+    const int ntile = (int)tsec.size();
     std::vector<double> Wf((size_t)ntile * KS * 32, 0.0);
-    std::vector<int> zof(n);
-    for (int z = 0; z < nz; z++) for (int r = first[z]; r < first[z + 1]; r++) zof[r] = z;
     for (int t = 0; t < ntile; t++)
       for (int ks = 0; ks < KS; ks++)
         for (int l = 0; l < 32; l++) {
-          const int r = std::min(8 * t + l / 4, n - 1), k = l % 4;
-          const bool padcol = 8 * t + l / 4 >= n;      // repeats the last supernova with sigma^2 = 1e300: its term vanishes
+          const int col = tcol[(size_t)t * 8 + l / 4], k = l % 4, z = tz[(size_t)t * 8 + l / 4];
+          const bool padcol = col < 0;
+          const int r = padcol ? -col - 1 : col;
           const double *row = rows.data() + (size_t)r * SN_ROW;      // m s | c z | V0 Vss | Vcc Cms | Cmc Csc
           double v;
-          if (ks < M / 4) v = W[(size_t)zof[r] * M + 4 * ks + k];
+          if (ks < M / 4) v = W[(size_t)z * M + 4 * ks + k];
           else if (ks == M / 4) {
-            const double lnaz = nodes[(size_t)zof[r] * SN_NODES].x;
+            const double lnaz = nodes[(size_t)z * SN_NODES].x;
             const double f[4] = {row[0] + (5.0 / M_LN10) * lnaz - SN_MU0, 1.0, row[1], row[2]};
             v = f[k];
           } else if (ks == M / 4 + 1) v = padcol ? (k == 0 ? 1.0e300 : 0.0) : row[4 + k];
@@ -578,6 +600,7 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
           Wf[((size_t)t * KS + ks) * 32 + l] = v;
         }
     if ((rc = dev_copy<double>(c, Wf.data(), Wf.size(), &D.cheb_Wf))) return rc;
+    if ((rc = dev_copy<int>(c, tsec.data(), tsec.size(), &D.sn_tile_sec))) return rc;
     D.sn_ntile = ntile;
     // TF32 tail of the coefficient contraction (m >= 16): W split into hi + lo TF32 numbers (cvt.rna: nearest, ties away),
     // in the B-fragment order of mma.m16n8k8: lane l holds b0 = B[k = l % 4][column l / 4], b1 = B[k = l % 4 + 4][column l / 4]
@@ -589,11 +612,11 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
       std::vector<uint32_t> Wt((size_t)ntile * 32 * 8, 0u);
       for (int t = 0; t < ntile; t++)
         for (int l = 0; l < 32; l++) {
-          const int r = std::min(8 * t + l / 4, n - 1);
+          const int zc = tz[(size_t)t * 8 + l / 4];
           for (int k2 = 0; k2 < nk2 && k2 < 2; k2++)
             for (int j = 0; j < 2; j++) {
               const int mm = M64 + 8 * k2 + l % 4 + 4 * j;
-              const double w = mm < M ? W[(size_t)zof[r] * M + mm] : 0.0;
+              const double w = mm < M ? W[(size_t)zc * M + mm] : 0.0;
               const uint32_t hi = tf32((float)w), lo = tf32((float)(w - (double)asf(hi)));
               Wt[((size_t)t * 32 + l) * 8 + 4 * k2 + j] = hi;
               Wt[((size_t)t * 32 + l) * 8 + 4 * k2 + 2 + j] = lo;

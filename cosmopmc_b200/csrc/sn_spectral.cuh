@@ -349,10 +349,16 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
     }
   }
 
-  // --- supernova tiles (columns past the last supernova repeat it with sigma^2 = 1e300: their terms vanish)
+  // --- supernova tiles.  A PRIMARY tile holds 8 distinct redshifts (its columns = the first supernova at each): all k-steps,
+  // ln f_K per pair.  The Union sample has 307 supernovae at 241 redshifts; the further supernovae of a redshift sit in the
+  // SAME column of a SECONDARY tile that follows its primary tile directly: ss, hence ln f_K, is the primary column's (same
+  // lane, same accumulator slot, kept in lnf), so a secondary tile only runs the mu' and sig2 k-steps (3 of 10) and no
+  // logarithm.  Empty columns carry sigma^2 = 1e300: their terms vanish.  31 primary + 12 secondary tiles instead of 39 full ones.
   const double *__restrict__ wf = L.cheb_Wf + lane;
+  const int *__restrict__ tsec = L.sn_tile_sec;
   const int ntile = L.sn_ntile;
   double chi[4] = {0.0, 0.0, 0.0, 0.0};
+  double lnf[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
   unsigned ebits = 0u, ubits = 0u;      // per row tile: distance error; curvature argument outside the series
   // fragment table k-steps this kernel reads: the KC coefficient ones, then mu', sig2, sig2 (table positions M/4 ..)
   double b[KC + 3], bn[KC + 3];
@@ -361,14 +367,33 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
 #pragma unroll
   for (int ks = 0; ks < KC + 3; ks++) bn[ks] = __ldg(wf + (size_t)(ks < KC ? ks : ks - KC + SNS_M / 4) * 32);
   if (T32) btn = ld256u(wt);
+  int secn = 0;      // tile 0 is a primary tile
   for (int t = 0; t < ntile; t++) {
 #pragma unroll
     for (int ks = 0; ks < KC + 3; ks++) b[ks] = bn[ks];
     if (T32) bt = btn;
+    const int sec = secn;
     const int tn = min(t + 1, ntile - 1);       // next tile's fragments travel while this one computes
 #pragma unroll
     for (int ks = 0; ks < KC + 3; ks++) bn[ks] = __ldg(wf + ((size_t)tn * SNS_KS + (ks < KC ? ks : ks - KC + SNS_M / 4)) * 32);
     if (T32) btn = ld256u(wt + (size_t)tn * 256);
+    secn = __ldg(tsec + tn);
+    if (sec) {      // further supernovae at the primary tile's redshifts: mu', sig2, and the stored ln f_K
+#pragma unroll
+      for (int rt = 0; rt < 4; rt++) {
+        double m0 = 0.0, m1 = 0.0, g0 = 0.0, g1 = 0.0;
+        sn_dmma(m0, m1, A[rt][KC], b[KC]);
+        sn_dmma(g0, g1, A[rt][KC + 1], b[KC + 1]);
+        sn_dmma(g0, g1, A[rt][KC + 2], b[KC + 2]);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const double mu = h ? m1 : m0, sg = h ? g1 : g0;
+          const double res = fma(-5.0 / M_LN10, lnf[rt][h], mu);
+          chi[rt] = fma(res * res, sn_rcp3(sg), chi[rt]);
+        }
+      }
+      continue;
+    }
     float t32[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     if (T32) {
 #pragma unroll
@@ -401,7 +426,9 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
           if (!(fabs(u) < 1.0)) ubits |= 1u << rt;
         }
         if (!(fk > 0.0)) ebits |= 1u << rt;
-        const double res = fma(-5.0 / M_LN10, lean_log(fk, LT), mu);
+        const double lg = lean_log(fk, LT);
+        lnf[rt][h] = lg;
+        const double res = fma(-5.0 / M_LN10, lg, mu);
         chi[rt] = fma(res * res, sn_rcp3(sg), chi[rt]);
       }
     }

@@ -169,6 +169,7 @@ def check_posterior(oracle, pmc, spec, X):
         small = len(X) <= 4096
         for env in ({"PMCB200_SN_WARP_MAX": "0" if small else "1000000000"},
                     {"PMCB200_SN_WARP_MAX": "0", "PMCB200_SN_SPEC_V1": "1"},
+                    {"PMCB200_SN_WARP_MAX": "0", "PMCB200_SN_TAIL32": "1"},      # opt-in TF32 coefficient tail
                     {"PMCB200_SN_WARP_MAX": "0", "PMCB200_SN_EXACT": "1"}):
             with environ(env):
                 got2, egot2 = pmc.posterior_log_pdf(dev(X))
