@@ -70,7 +70,11 @@ static void launch_sn_spectral(const DevLike &L, int64_t N, const double *X, int
     // 12.22 ms per 1e7 samples -- the legacy HMMA path shares the dispatch with the FP64 pipe -- so not the default; read per call)
     const char *et = getenv("PMCB200_SN_TAIL32");
     const bool t32 = (et && *et == '1') && L.cheb_Wt;
-    const int gm = (int)((N + SNS2_BLOCK - 1) / SNS2_BLOCK);
+    // persistent: one block per SM (register-bound), each warp walks its own 32-sample tasks
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int gm = (int)std::min<int64_t>((N + SNS2_BLOCK - 1) / SNS2_BLOCK, sms);
     if (t32) {
       cudaFuncSetAttribute(k_like_sn_spec_mma<H, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SNS2_SMEM);   // per device
       k_like_sn_spec_mma<H, F, true><<<gm, SNS2_BLOCK, SNS2_SMEM, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);

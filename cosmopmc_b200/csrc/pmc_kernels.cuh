@@ -804,7 +804,7 @@ k_em_stats_mma(const double *__restrict__ mix, const MixHdr h, int64_t N,
 #define EM_WS_STRIDE 36                // row stride of the per-warp w rho rows (4 mod 16: the 8 rows of an A fragment on distinct banks)
 __host__ __device__ constexpr int em_ws_nt(int D) { return (1 + D + D * (D + 1) / 2 + 7) / 8; }
 __host__ __device__ constexpr int em_ws_perwarp(int D, int MT, bool student) {
-  const int work = 8 * MT * EM_WS_STRIDE * (student ? 2 : 1) + 32 * ((D + 1) | 1), accn = MT * em_ws_nt(D) * 64;
+  const int work = 8 * MT * EM_WS_STRIDE * (student ? 2 : 1) + 8 * em_ws_nt(D) * EM_WS_STRIDE, accn = MT * em_ws_nt(D) * 64;
   return work > accn ? work : accn;
 }
 __host__ __device__ inline size_t em_ws_smem_bytes(int K, int d, int student) {
@@ -831,7 +831,6 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
                   const double *__restrict__ rho) {
   static_assert(!(RHO && STUDENT), "the E-step cache holds no Mahalanobis distances (Student-t gamma)");
   extern __shared__ double sm[];
-  constexpr int XS = (D + 1) | 1;           // odd row stride; column D holds the constant 1
   constexpr int NT = em_ws_nt(D);
   constexpr int KP = 8 * MT;
   constexpr int WS = EM_WS_STRIDE;
@@ -843,7 +842,7 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   double *s_wr = sm + (size_t)warp * PERW;                                  // [KP][WS] w rho of this warp's 32 samples
   double *s_wg = STUDENT ? s_wr + KP * WS : s_wr;                           // w rho gamma
-  double *s_x = s_wg + KP * WS;                                             // [32][XS] x - pivot | 1
+  double *s_f = s_wg + KP * WS;                                             // [8 NT][WS] features 1, x_i, x_i x_j (x - pivot) of the 32 samples
   unsigned long long *s_cnt = (unsigned long long *)(sm + (size_t)NW * PERW);   // [K]
   double *s_mix = (double *)(s_cnt + K);
   __shared__ double red[32];
@@ -851,20 +850,6 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
   const double *pivot = s_mix + (size_t)K * h.stride;
   const double M0 = linear ? 0.0 : dunkey(scal->max_key);
   double tS = 0.0, tS2 = 0.0, tT = 0.0, tN = 0.0;
-  int oi[NT], oj[NT];      // this lane's B-fragment column (feature 8 q + g) as staged-row offsets
-#pragma unroll
-  for (int q = 0; q < NT; q++) {
-    const int f = q * 8 + g;
-    int a = D, b = D;
-    if (f >= 1 && f < 1 + d) a = f - 1;
-    else if (f >= 1 + d && f < nfeat) {
-      const int qq = f - 1 - d;
-      int i = 0;
-      while ((i + 1) * (i + 2) / 2 <= qq) i++;
-      a = i; b = qq - i * (i + 1) / 2;
-    }
-    oi[q] = a; oj[q] = b;
-  }
   double acc[MT][NT][2], accA[MT][2];
 #pragma unroll
   for (int m = 0; m < MT; m++) {
@@ -873,6 +858,7 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
     for (int q = 0; q < NT; q++) { acc[m][q][0] = 0.0; acc[m][q][1] = 0.0; }
   }
   for (int k = K; k < KP; k++) { s_wr[k * WS + lane] = 0.0; if (STUDENT) s_wg[k * WS + lane] = 0.0; }
+  for (int f = 0; f < 8 * NT; f++) s_f[f * WS + lane] = 0.0;      // a sample without weight keeps the previous (finite) features
   if (tid < K) s_cnt[tid] = 0ull;
   __syncthreads();
   const int64_t nsteps = (N + 31) / 32, stride = (int64_t)gridDim.x * NW;
@@ -901,10 +887,7 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
     // ---- phase 1: weight and responsibilities of this lane's sample (the arithmetic of k_em_stats_mma)
     const bool fl = pfl != 0;
     const bool ok = fl && (!linear || plw > 0.0);
-    double *xrow = s_x + lane * XS;
     if (ok) {
-#pragma unroll
-      for (int i = 0; i < D; i++) xrow[i] = px[i];
       double lw, w;
       if (linear) { w = plw; lw = log(w); }
       else { lw = plw - M0; w = exp(lw); }
@@ -924,7 +907,7 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
           if (comp[0] != 0.0) {
             double tt[1][D], m1[1];
 #pragma unroll
-            for (int i = 0; i < D; i++) tt[0][i] = xrow[i];
+            for (int i = 0; i < D; i++) tt[0][i] = px[i];
             comp_maha_cols<D, 1>(comp, tt, m1);
             const double m = m1[0];
             r = comp[0] * exp(comp_logpdf_from_maha(comp, d, h.df, m));
@@ -942,21 +925,28 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
           if (STUDENT) s_wg[k * WS + lane] *= r;
         }
       }
+      // this sample's feature column: 1, x_i, x_i x_j about the pivot (the lane holds x in registers; the warp's B fragments
+      // are then ONE conflict-free load each -- the gather x[oi] * x[oj] from staged rows kept the LSU wavefronts at 70 %)
+      double xc[D];
 #pragma unroll
-      for (int i = 0; i < D; i++) xrow[i] -= pivot[i];      // padded: 0 - 0
+      for (int i = 0; i < D; i++) xc[i] = px[i] - pivot[i];      // padded: 0 - 0
+      s_f[lane] = 1.0;
+#pragma unroll
+      for (int i = 0; i < D; i++) if (i < d) s_f[(1 + i) * WS + lane] = xc[i];
+#pragma unroll
+      for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) if (i < d) s_f[(1 + d + i * (i + 1) / 2 + j) * WS + lane] = xc[i] * xc[j];
     } else {
       for (int k = 0; k < K; k++) { s_wr[k * WS + lane] = 0.0; if (STUDENT) s_wg[k * WS + lane] = 0.0; }
-#pragma unroll
-      for (int i = 0; i < D; i++) xrow[i] = 0.0;
     }
-    xrow[D] = 1.0;
     if (fl) { const int c = pix; if (c >= 0 && c < K) atomicAdd(&s_cnt[c], 1ull); }
     if (st + stride < nsteps) fetch(st + stride);
     __syncwarp();
     // ---- phase 2: K x 32 x nfeat on the FP64 tensor cores, 4 samples per k-step, all feature tiles
     const double *wa = s_wg + g * WS + t;
     const double *wr = s_wr + g * WS + t;
-    const double *xr = s_x + t * XS;
+    const double *fb = s_f + g * WS + t;
 #pragma unroll
     for (int s0 = 0; s0 < 32; s0 += 4) {
       double a[MT];
@@ -966,7 +956,7 @@ k_em_stats_mma_ws(const double *__restrict__ mix, const MixHdr h, int64_t N,
 #pragma unroll
       for (int q = 0; q < NT; q++) {
         if (q < ntv) {
-          const double b = xr[s0 * XS + oi[q]] * xr[s0 * XS + oj[q]];
+          const double b = fb[q * 8 * WS + s0];
           if (q == 0) b0 = b;
 #pragma unroll
           for (int m = 0; m < MT; m++) dmma884(acc[m][q][0], acc[m][q][1], a[m], b);

@@ -259,7 +259,16 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
   load_fast_tables_sn(T);
   const int lane = threadIdx.x & 31;
   double *__restrict__ tr = T + (96 + SN_EXP2_N) + (threadIdx.x >> 5) * (32 * SNS_TRS);
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // Persistent block (one per SM: the tables are staged once), every warp walks its own sequence of 32-sample tasks;
+  // nothing below is block-wide.  11.93 -> 11.5 ms per 1e7 samples.  (Measured and not adopted, session O / P: the second
+  // warp of each scheduler started half a task late -- 11.56 / 11.45 / 11.42 ms for 0 / 20 / 40 us; phase 1 as a kernel of
+  // its own at 12 warps per SM with the A fragments through HBM, tools/micro/sn_two_kernel_split_experiment.patch -- 0.29 +
+  // 2.11 ms per 2e6 samples = 12.0 ms: the tile loop alone keeps the FP64 pipe 78 % busy with two warps per scheduler.)
+  const int64_t ntask = (N + 31) / 32;
+  for (int64_t task = (int64_t)blockIdx.x * (SNS2_BLOCK / 32) + (threadIdx.x >> 5); task < ntask;
+       task += (int64_t)gridDim.x * (SNS2_BLOCK / 32)) {
+  __syncwarp();
+  const int64_t n = task * 32 + lane;
   const bool active = (n < N) && (!flg || flg[n]);
   Model m;
   int e = 0;
@@ -470,4 +479,5 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
       atomicAdd(&cnt->sn_spec, (unsigned long long)nsp);
     }
   }
+  }      // task loop
 }
