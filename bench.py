@@ -36,9 +36,9 @@ FLOP_PER_SN = 29.0         # per (sample, supernova): mu_obs 7, sigma^2 18, chi^
 SPEC_M = 28
 FLOP_SPEC_SAMPLE = SPEC_M * FLOP_PER_EVAL + SPEC_M * SPEC_M + 4 * SPEC_M
 FLOP_SPEC_ZSTEP = 2.0 * SPEC_M + 8.0
-# ncu evidence for the dominant kernel (one --set full capture, N = 4e6): FP64 pipe = DMMA sub-pipe 57.4 % + vector 21.7 %;
+# ncu evidence for the dominant kernel (one --set full capture, N = 4e6): FP64 pipe = DMMA sub-pipe 53.8 % + vector 23.1 %;
 # DRAM bytes (read + write) per sample
-NCU_SN = {"fp64_pipe_active_pct": 79.1, "dram_bytes_per_sample": 48.0, "source": "profiles/r02/sn_spec_mma_v2_summary.txt"}
+NCU_SN = {"fp64_pipe_active_pct": 76.8, "dram_bytes_per_sample": 48.4, "source": "profiles/r02/sn_spec_mma_v6_summary.txt"}
 NCU_SN_EXACT = {"fp64_pipe_active_pct": 64.6, "dram_bytes_per_sample": 44.1, "source": "profiles/sn_r01_v8_summary.txt"}
 
 
@@ -357,7 +357,7 @@ def main():
 
     # dominant kernel alone (SN likelihood), CUDA events on the launching stream
     roof = None
-    if args.config == "sn":
+    if args.config in ("sn", "sn_curved", "sn_bao", "cmb_bao_sn"):
         pmc.set_proposal(w, m, chol=ch)
         pmc.simulate_mix_mvdens(n_loc, SEED, 0, off, bufs["X"], bufs["idx"], bufs["flg"])
         for _ in range(2):
@@ -373,31 +373,43 @@ def main():
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
         c = pmc.counters()
-        n_sn, n_z = spec.t.like[0].sn_n, c["sn_zsteps"] // max(1, c["sn_spec"] + c["sn_exact"])
+        sn_like = [spec.t.like[i] for i in range(spec.t.ndata) if spec.t.like[i].kind == 3][0]      # PMCB200_LIKE_SNIa
+        n_sn, n_z = sn_like.sn_n, c["sn_zsteps"] // max(1, c["sn_spec"] + c["sn_exact"])
         spectral = c["sn_spec"] > 0
         # the flops of the algorithm the kernels run: spectral samples by the spectral count, the rest node by node
         ev_exact = c["sn_evals"] - SPEC_M * c["sn_spec"]
         zs_exact = c["sn_zsteps"] - n_z * c["sn_spec"]
         flops = (c["sn_spec"] * (FLOP_SPEC_SAMPLE + n_z * FLOP_SPEC_ZSTEP) + ev_exact * FLOP_PER_EVAL + zs_exact * FLOP_PER_ZSTEP
                  + (c["sn_spec"] + c["sn_exact"]) * n_sn * FLOP_PER_SN) / reps
+        # BAO / CMB distance-prior kernels of the joint configurations: their Romberg integrals by the in-kernel counters
+        flops_gen = (c["gen_evals"] * FLOP_PER_EVAL + c["gen_integrals"] * FLOP_PER_ZSTEP) / reps
+        flops += flops_gen
         # what the reference's node-by-node algorithm would have spent on the same samples (17 evaluations per redshift
         # when stage 5 converges, which the spectral kernel certifies for every sample it keeps)
         flops_ref = (c["sn_spec"] * n_z * (17 * FLOP_PER_EVAL + FLOP_PER_ZSTEP) + ev_exact * FLOP_PER_EVAL + zs_exact * FLOP_PER_ZSTEP
-                     + (c["sn_spec"] + c["sn_exact"]) * n_sn * FLOP_PER_SN) / reps
+                     + (c["sn_spec"] + c["sn_exact"]) * n_sn * FLOP_PER_SN) / reps + flops_gen
         peak = pmc.fp64_peak_tflops()
         ach = flops / (k_ms * 1e-3) * 1e-12
         ncu = NCU_SN if spectral else NCU_SN_EXACT
-        roof = {"kernel": "k_like_sn_spec_mma (+ k_like_sn_warp_list for the samples it hands over)" if spectral else "k_like_sn",
+        kern = "k_like_sn_spec_mma (+ k_like_sn_warp_list for the samples it hands over)" if spectral else "k_like_sn"
+        if args.config == "sn_bao":
+            kern = "likelihood stage: " + kern + " + k_like_bao"
+        elif args.config == "cmb_bao_sn":
+            kern = "likelihood stage: k_like_cmbdp + " + kern + " + k_like_bao"
+        roof = {"kernel": kern,
                 "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak if peak else None,
-                "traffic": ncu["dram_bytes_per_sample"] * n_loc if ncu["dram_bytes_per_sample"] else None,
+                "traffic": ncu["dram_bytes_per_sample"] * n_loc if (ncu["dram_bytes_per_sample"] and args.config == "sn") else None,
                 "traffic_source": "ncu dram__bytes_read+write per sample (%s) x samples per launch; algorithmic = %d B/sample" % (ncu["source"], 8 * d + 12),
-                "fp64_pipe_active_pct_ncu": ncu["fp64_pipe_active_pct"],
+                "fp64_pipe_active_pct_ncu": ncu["fp64_pipe_active_pct"] if args.config == "sn" else None,
                 "kernel_ms": k_ms, "flop_per_launch": flops,
                 "flop_convention": "flops of the algorithm the kernel runs: spectral samples %g + %d x %g + %d x %g per sample; "
                                    "node-by-node samples 18 per evaluation + 86 per redshift + 29 per SN" % (FLOP_SPEC_SAMPLE, n_z, FLOP_SPEC_ZSTEP, n_sn, FLOP_PER_SN),
                 "samples_spectral": c["sn_spec"] / reps, "samples_node_by_node": c["sn_exact"] / reps,
                 "evals_per_sample": c["sn_evals"] / reps / n_loc,
+                "generic_integrals": {"evals_per_sample": c["gen_evals"] / reps / n_loc, "integrals_per_sample": c["gen_integrals"] / reps / n_loc,
+                                      "flop_per_launch": flops_gen,
+                                      "convention": "BAO / CMB distance-prior Romberg integrals: 18 per evaluation + 86 per integral"},
                 "reference_algorithm": {"flop_per_launch": flops_ref, "equivalent_TFLOPs": flops_ref / (k_ms * 1e-3) * 1e-12,
                                         "note": "work the reference's 17-node Romberg per redshift would need for the same result; "
                                                 "a speed-up measure, not a roofline fraction"},

@@ -352,6 +352,9 @@ __device__ __forceinline__ GInt gint_from_lane(const GInt &q, int src) {
 // l, l + 32, ... and a butterfly sum hands the stage sum back (the same bits in every lane, and a function of
 // the owner's sample alone: results do not depend on the warp's other samples).
 #define ROMB_COOP_MIN 1024
+#ifndef ROMB_COOP_MIN_RS
+#define ROMB_COOP_MIN_RS ROMB_COOP_MIN      // the same threshold for the sound-horizon integral (build switch for A/B measurements)
+#endif
 template <bool HASQ, bool RS>
 __device__ double romberg_warp(const GInt &q, const double2 *__restrict__ LT, const double *__restrict__ ET, double fa,
                                double fb, double a, double b, bool active, int &err, unsigned &nev) {
@@ -368,7 +371,7 @@ __device__ double romberg_warp(const GInt &q, const double2 *__restrict__ LT, co
     const int it = 1 << (j - 1);
     const double tnm = (double)it, del = h / tnm;
     double sum = 0.0;
-    if (it < ROMB_COOP_MIN) {
+    if (it < (RS ? ROMB_COOP_MIN_RS : ROMB_COOP_MIN)) {
       if (!done) {
         if (it < 4) {
           for (int i = 0; i < it; i++) sum = gint_acc<HASQ, RS>(q, LT, ET, fma((double)i + 0.5, del, a), sum);

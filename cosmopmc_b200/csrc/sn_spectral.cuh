@@ -420,7 +420,7 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
       double s0 = T32 ? (double)t32[rt >> 1][2 * (rt & 1)] : 0.0, s1 = T32 ? (double)t32[rt >> 1][2 * (rt & 1) + 1] : 0.0;
       double m0 = 0.0, m1 = 0.0, g0 = 0.0, g1 = 0.0;
 #pragma unroll
-      for (int ks = 0; ks < KC; ks++) sn_dmma(s0, s1, A[rt][ks], b[ks]);
+      for (int ks = 0; ks < KC; ks++) sn_dmma(s0, s1, A[rt][ks], b[ks]);      // (two independent half chains: 11.73 against 11.34 ms)
       sn_dmma(m0, m1, A[rt][KC], b[KC]);
       sn_dmma(g0, g1, A[rt][KC + 1], b[KC + 1]);
       sn_dmma(g0, g1, A[rt][KC + 2], b[KC + 2]);
