@@ -63,7 +63,8 @@ static cudaError_t launch_em_ws(const MixArgs &a, cudaStream_t s) {
 template <int DD>
 static cudaError_t run_em_mma(const MixArgs &a, cudaStream_t s) {
   if constexpr (em_ws_nt(DD) <= 9) {
-    static const int no_ws = getenv("PMCB200_EM_NO_WS") ? atoi(getenv("PMCB200_EM_NO_WS")) : 0;
+    const char *ew = getenv("PMCB200_EM_NO_WS");      // A/B measurements, cross-check in the tests; read per call
+    const int no_ws = ew && *ew && *ew != '0';
     const int mt = em_mma_mt(a.h.K);
     const bool st = a.h.df > 0;
     if (!no_ws && em_ws_ok(a.h.K, a.h.d, st)) {

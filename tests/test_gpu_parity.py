@@ -426,12 +426,15 @@ def test_iteration_banana(oracle, pmc_factory):
 @pytest.mark.parametrize("K,d,df,N", [(10, 20, -1, 30011), (20, 12, 5, 20000), (32, 11, -1, 25000),
                                        (3, 18, 4, 9000), (8, 10, -1, 4096), (4, 32, 7, 12000),
                                        (10, 5, -1, 20011), (30, 8, -1, 15000), (6, 5, 3, 9000), (9, 2, -1, 7000),
-                                       (5, 3, 6, 5000), (12, 7, 4, 8000), (17, 1, -1, 6000), (16, 32, 5, 6000)])
+                                       (5, 3, 6, 5000), (12, 7, 4, 8000), (17, 1, -1, 6000), (16, 32, 5, 6000),
+                                       (8, 9, -1, 7000), (24, 6, -1, 9000), (11, 4, 3, 5000)])
 def test_iteration_em_tensor_core_shapes(oracle, pmc_factory, K, d, df, N, monkeypatch):
-    """K <= 32 runs the EM statistics on the FP64 tensor cores (k_em_stats_mma): every component-tile
-    count MT = 1..4, every padded dimension class (odd, even, 11 -> 12, 18 -> 20), Gaussian and Student-t, ragged
-    last tile (and K = 16, d = 32 Student-t, whose staging exceeds the shared-memory budget: shared-memory kernel);
-    against the oracle, and against the shared-memory kernel (PMCB200_EM_NO_MMA=1) on the same sample."""
+    """K <= 32 runs the EM statistics on the FP64 tensor cores (d <= 10: k_em_stats_mma_ws, samples sliced over the warps;
+    else k_em_stats_mma, feature tiles over the warps): every component-tile count MT = 1..4, every padded dimension class
+    (odd, even, 9 -> 10, 11 -> 12, 18 -> 20), Gaussian and Student-t, with and without the E-step cache, ragged last tile
+    (and K = 16, d = 32 Student-t, whose staging exceeds the shared-memory budget: shared-memory kernel); against the
+    oracle, against the shared-memory kernel (PMCB200_EM_NO_MMA=1) and, for d <= 10, against the tile-sliced tensor-core
+    kernel (PMCB200_EM_NO_WS=1) on the same sample."""
     pmc = pmc_factory()
     rng = np.random.default_rng(100 * K + d)
     lo, hi = -6.0 * np.ones(d), 6.0 * np.ones(d)
@@ -455,6 +458,14 @@ def test_iteration_em_tensor_core_shapes(oracle, pmc_factory, K, d, df, N, monke
     assert rel(wg, w2) < 1e-11 and rel(mg, m2, 1e-3) < 1e-10
     assert np.max(np.abs(covg - cov2)) < 1e-10 * np.max(np.abs(cov2))
     assert abs(st["perplexity"] - st2["perplexity"]) < 1e-12 * st2["perplexity"]
+    if d <= 10:
+        monkeypatch.delenv("PMCB200_EM_NO_MMA")
+        monkeypatch.setenv("PMCB200_EM_NO_WS", "1")
+        pmc.set_proposal(w, mean, chol=ch, df=df)
+        o3, st3, *h3 = run_both(oracle, pmc, spec, w, mean, ch, N, seed=11, df=df)
+        w3, m3, ch3, cov3 = pmc.get_proposal()
+        assert rel(wg, w3) < 1e-11 and rel(mg, m3, 1e-3) < 1e-10
+        assert np.max(np.abs(covg - cov3)) < 1e-10 * np.max(np.abs(cov3))
 
 
 def test_iteration_cmb_bao_sn(oracle, pmc_factory):
