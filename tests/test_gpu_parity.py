@@ -710,6 +710,48 @@ def test_sn_spectral_large_batch(oracle, pmc_factory):
         assert rel(got[sub][oks], ref[oks]) < RTOL_LOG
 
 
+@pytest.mark.parametrize("zs", [[0.5], [0.3] * 9, [0.02, 0.02, 0.4, 0.4, 0.4, 0.9, 1.4],
+                                [0.05 + 0.06 * i for i in range(17)] + [0.11, 0.11, 0.65, 0.65, 0.65, 0.65]])
+def test_sn_tile_layouts_synthetic_tables(oracle, pmc_factory, tmp_path, zs):
+    """Primary / secondary supernova tiles of the tensor-core SN kernel on synthetic tables: one supernova; nine at one
+    redshift (one primary tile, eight secondary ones with a single live column); multiplicities 2, 3, 1, 1; 19 redshifts
+    (three primary tiles, the last one ragged) with multiplicities up to 5.  Spectral tensor-core kernel (forced for any
+    batch size) against the oracle and the node-by-node device kernel."""
+    rng = np.random.default_rng(len(zs))
+    path = tmp_path / "sn.txt"
+    with open(path, "w") as f:
+        f.write("@sig_int 0.15\n@v_pec 300\n")
+        for z in zs:
+            mu = 5.0 * np.log10((1 + z) * z * 4283.0) + 25.0 - 19.3 + 0.15 * rng.normal()      # roughly the Hubble diagram
+            s_, c_ = 1.0 + 0.1 * rng.normal(), 0.1 * rng.normal()
+            v = [0.01 + 0.01 * rng.random(), 0.002 + 0.002 * rng.random(), 0.003 + 0.002 * rng.random(), 5e-4, 4e-4, 1e-3]
+            f.write(" ".join("%.17g" % t for t in [z, mu, s_, c_] + v) + "\n")
+    spec = T.TargetSpec(["Omega_m", "w_0_de", "M", "alpha", "beta"], [0.0, -3.5, 19.1, 0.5, -3.5],
+                        [1.2, 0.5, 19.8, 2.6, -0.8]).add_snia(table=str(path))
+    pmc = pmc_factory()
+    pmc.set_target(spec)
+    w, m, cov = T.proposal_sn(10)
+    N = 6000
+    k = rng.integers(0, 10, N)
+    X = m[k] + np.einsum("nij,nj->ni", np.linalg.cholesky(cov)[k], rng.normal(size=(N, 5)))
+    lo, hi = spec.box
+    X = X[((X >= lo) & (X <= hi)).all(axis=1)]
+    ref, eref = oracle.posterior_log_pdf(spec, X)
+    with environ({"PMCB200_SN_WARP_MAX": "0"}):
+        pmc.counters()
+        got, egot = pmc.posterior_log_pdf(dev(X))
+        cnt = pmc.counters()
+    assert cnt["sn_spec"] > 0.9 * len(X), cnt
+    with environ({"PMCB200_SN_EXACT": "1", "PMCB200_SN_WARP_MAX": "0"}):
+        ex, eex = pmc.posterior_log_pdf(dev(X))
+    got, egot, ex, eex = got.cpu().numpy(), egot.cpu().numpy(), ex.cpu().numpy(), eex.cpu().numpy()
+    assert np.array_equal(egot != 0, eref != 0) and np.array_equal(eex != 0, eref != 0)
+    ok = eref == 0
+    # log pi = -chi2 / 2 + constants of a handful of supernovae can come out near zero: absolute floor of 1e-12 on top
+    assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-2)) < RTOL_LOG
+    assert np.max(np.abs(got[ok] - ex[ok]) / np.maximum(np.abs(ex[ok]), 1e-2)) < 1e-11
+
+
 def test_sn_fast_path_matches_libdevice_path(oracle, pmc_factory, tmp_path):
     """The SN kernel's table-based exp2 / MUFU-seeded rsqrt path against the same
     kernel forced through libdevice exp (PMCB200_SN_FORCE_SLOW=1, separate
