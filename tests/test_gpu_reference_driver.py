@@ -34,7 +34,7 @@ def write_fisher(path):
 
 @pytest.mark.skipif(not (os.path.exists(EXE) and os.path.isdir(DEMO)),
                     reason="build_ref/cosmo_pmc not built (tools/build_ref_cosmo_pmc.py, container only)")
-def test_unchanged_reference_driver_runs_sn_demo(tmp_path):
+def test_unchanged_reference_driver_runs_sn_demo(tmp_path, oracle):
     run = tmp_path / "run"
     shutil.copytree(DEMO, run, ignore=shutil.ignore_patterns("iter_*", "perplexity", "enc", "evidence*", "log_pmc",
                                                              "temperature", "proposal_fin", "run.log"))
@@ -82,6 +82,14 @@ def test_unchanged_reference_driver_runs_sn_demo(tmp_path):
         # log w_new - log w_old = log posterior: spot-check one row against the stored sample
         old = np.loadtxt(run / "sub.pmcsim")
         assert np.array_equal(old[:, 2:], ref[:, 2:]) and np.all(np.isfinite(ref[:, 0]))
+        # ... and against the CPU oracle, so that this row is not only the device path against itself: the tool replaces
+        # the weights by the log-posterior at the stored (9-digit) parameters, adds the previous log-weights and
+        # normalises (importance_sample.c:75-77,273-290, exec_helper.c:408-420), i.e. new - old - log posterior is one
+        # constant over the sample
+        lp, elp = oracle.posterior_log_pdf(T.target_sn_demo(), np.ascontiguousarray(ref[:, 2:]))
+        assert not elp.any()
+        dlt = ref[:, 0] - old[:, 0] - lp
+        assert np.max(np.abs(dlt - np.median(dlt))) < 5e-6, np.max(np.abs(dlt - np.median(dlt)))      # two %16.9g of ~ -180
 
 
 @pytest.mark.skipif(not (os.path.exists(EXE) and os.path.isdir(DEMO)),
