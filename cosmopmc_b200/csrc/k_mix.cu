@@ -93,7 +93,8 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
     case OP_SIMULATE: {
       // staged kernel where the Cholesky-factor gather weighs (measured per 1e7 samples: d = 20 2.56 -> 2.22 ms,
       // d = 5 0.47 -> 0.55 ms, where the Philox / Box-Muller arithmetic dominates); PMCB200_SIM_STAGED=0/1 forces
-      static const int staged_env = getenv("PMCB200_SIM_STAGED") ? atoi(getenv("PMCB200_SIM_STAGED")) : -1;
+      const char *es = getenv("PMCB200_SIM_STAGED");      // read per call
+      const int staged_env = es && *es ? atoi(es) : -1;
       const int staged = staged_env >= 0 ? staged_env : (DD >= 10);
       const size_t sm = ((size_t)PMC_BLOCK * (a.h.d | 1) + (size_t)a.h.K * (a.h.stride | 1)) * sizeof(double);
       if (staged && sm <= 100 * 1024) {
@@ -122,7 +123,8 @@ static cudaError_t run(int op, const MixArgs &a, cudaStream_t s) {
         // PMCB200_ESTEP: 0 = one sample per thread, row-oriented, mixture through L1 (k_weights);
         // 1, 3 = k_weights_multi with that many samples per thread; 2 (default) = 4 samples for d <= 8, else 2
         // (measured, C3 d = 20 K = 10, 1e7 samples: 5.78 / 3.89 / 3.00 / 3.33 ms for modes 0 / 1 / 2 / 3)
-        static const int mode = getenv("PMCB200_ESTEP") ? atoi(getenv("PMCB200_ESTEP")) : ESTEP_DEFAULT;
+        const char *em = getenv("PMCB200_ESTEP");      // read per call
+        const int mode = em && *em ? atoi(em) : ESTEP_DEFAULT;
         const size_t mixbytes = (size_t)a.h.K * a.h.stride * sizeof(double);
 #define WM(SV) { auto kern = k_weights_multi<DD, SV>; const size_t sm = mixbytes + (size_t)DD * SV * PMC_BLOCK * sizeof(double); \
           if (sm <= 200 * 1024) { \

@@ -468,6 +468,44 @@ def test_iteration_em_tensor_core_shapes(oracle, pmc_factory, K, d, df, N, monke
         assert np.max(np.abs(covg - cov3)) < 1e-10 * np.max(np.abs(cov3))
 
 
+@pytest.mark.parametrize("cfg", ["sn", "banana", "student"])
+def test_build_variants_behind_switches_agree(oracle, pmc_factory, cfg):
+    """Every kernel variant the library keeps behind a run-time switch (A/B measurements) must deliver what the default
+    path delivers: weight-kernel variants PMCB200_ESTEP = 0 (one sample per thread), 1, 3 (samples per thread), 4
+    (column-packed staging); sampler PMCB200_SIM_STAGED = 0 / 1; no E-step cache (PMCB200_EM_NO_RHO); tile-sliced
+    tensor-core EM kernel (PMCB200_EM_NO_WS).  Same seed => same samples, flags, indices bit for bit; weights and the updated
+    proposal to 1e-12 (the variants re-associate nothing in a sample's own arithmetic; the EM variants sum in another order)."""
+    pmc = pmc_factory()
+    if cfg == "sn":
+        spec = T.target_sn_demo(); w, m, cov = T.proposal_sn(10); df = -1
+    elif cfg == "banana":
+        spec = T.target_banana(20); w, m, cov = T.proposal_banana(10, 20); df = -1
+    else:
+        spec = T.target_banana(8); w, m, cov = T.proposal_banana(12, 8); df = 4
+    ch = oracle.cholesky_stack(cov)
+    N, d = 24001, len(m[0])
+    pmc.set_target(spec)
+
+    def run(env):
+        with environ(env):
+            pmc.set_proposal(w, m, chol=ch, df=df)
+            hX = np.empty((N, d)); hidx = np.empty(N, np.int32); hflg = np.empty(N, np.int16); hw = np.empty(N)
+            st = pmc.iteration_host(N, 5, 1, 1.0, hX, hidx, hflg, hw)
+            return st, hX, hidx, hflg, hw, pmc.get_proposal()
+    st0, X0, i0, f0, w0, p0 = run({})
+    for env in ({"PMCB200_ESTEP": "0"}, {"PMCB200_ESTEP": "1"}, {"PMCB200_ESTEP": "3"}, {"PMCB200_ESTEP": "4"},
+                {"PMCB200_SIM_STAGED": "0"}, {"PMCB200_SIM_STAGED": "1"}, {"PMCB200_EM_NO_RHO": "1"},
+                {"PMCB200_EM_NO_WS": "1"}, {"PMCB200_EM_NO_MMA": "1"}):
+        st, X, i_, f_, w_, p = run(env)
+        assert np.array_equal(i_, i0) and np.array_equal(f_, f0), env
+        assert rel(X, X0, 1e-2) < 1e-13, env
+        assert st["nok"] == st0["nok"] and abs(st["perplexity"] - st0["perplexity"]) <= 1e-11 * st0["perplexity"], env
+        big = w0 > 1e-12 * w0.max()
+        assert rel(w_[big], w0[big]) < 1e-11, env
+        assert rel(p[0], p0[0], 1e-300) < 1e-10 and rel(p[1], p0[1], 1e-3) < 1e-10, env
+        assert np.max(np.abs(p[3] - p0[3])) < 1e-10 * np.max(np.abs(p0[3])), env
+
+
 def test_iteration_cmb_bao_sn(oracle, pmc_factory):
     pmc = pmc_factory()
     spec = T.target_cmb_bao_sn()
