@@ -162,6 +162,14 @@ def check_posterior(oracle, pmc, spec, X):
     assert ok.sum() > 0.5 * len(X)
     r = rel(got[ok], ref[ok])
     assert r < RTOL_LOG, r
+    if any(spec.t.like[i].kind in (6, 7) for i in range(spec.t.ndata)):
+        # BAO / CMB distance priors: the round-1 kernels (libdevice integrand, one lane per integral) are kept behind
+        # PMCB200_LIKE_V1 for A/B measurements -- same integrals, same error flags
+        with environ({"PMCB200_LIKE_V1": "1"}):
+            got1, egot1 = pmc.posterior_log_pdf(dev(X))
+        got1, egot1 = got1.cpu().numpy(), egot1.cpu().numpy()
+        assert np.array_equal(egot1 != 0, eref != 0)
+        assert rel(got1[ok], ref[ok]) < RTOL_LOG
     if any(spec.t.like[i].kind == 3 for i in range(spec.t.ndata)):
         # the SN likelihood has four kernels: spectral form of the quadrature on the FP64 tensor cores (large batches;
         # hands what it cannot certify to the warp kernel), the same one sample per thread (chi2_betaz, add_logdetCov),
