@@ -99,8 +99,7 @@ __device__ __forceinline__ double fast_rcp(double s) {
 
 // load the shared table [32 exp2 | 32 log reciprocals | 32 log offsets]; blockDim.x >= 96
 __device__ __forceinline__ void load_fast_tables(double *T) {
-  if (threadIdx.x < 32) T[threadIdx.x] = EXP2T[threadIdx.x];
-  else if (threadIdx.x < 64) T[threadIdx.x] = LOGRC[threadIdx.x - 32];
-  else if (threadIdx.x < 96) T[threadIdx.x] = LOGLC[threadIdx.x - 64];
+  for (int i = threadIdx.x; i < 96; i += blockDim.x)      // any block size (the SN tensor-core kernel launches 32 .. 256 threads)
+    T[i] = i < 32 ? EXP2T[i] : (i < 64 ? LOGRC[i - 32] : LOGLC[i - 64]);
   __syncthreads();
 }

@@ -74,13 +74,17 @@ static void launch_sn_spectral(const DevLike &L, int64_t N, const double *X, int
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int gm = (int)std::min<int64_t>((N + SNS2_BLOCK - 1) / SNS2_BLOCK, sms);
+    // small batches: fewer warps per block, so that the 32-sample tasks spread over all SMs (1e4 samples = 313 tasks: 40 blocks
+    // of 8 warps would leave 108 SMs idle and put two warps on every busy scheduler)
+    const int64_t ntask = (N + 31) / 32;
+    const int wpb = (int)std::max<int64_t>(1, std::min<int64_t>(SNS2_BLOCK / 32, (ntask + sms - 1) / sms));
+    const int gm = (int)std::min<int64_t>((ntask + wpb - 1) / wpb, sms);
     if (t32) {
       cudaFuncSetAttribute(k_like_sn_spec_mma<H, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SNS2_SMEM);   // per device
-      k_like_sn_spec_mma<H, F, true><<<gm, SNS2_BLOCK, SNS2_SMEM, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);
+      k_like_sn_spec_mma<H, F, true><<<gm, 32 * wpb, SNS2_SMEM, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);
     } else {
       cudaFuncSetAttribute(k_like_sn_spec_mma<H, F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SNS2_SMEM);
-      k_like_sn_spec_mma<H, F, false><<<gm, SNS2_BLOCK, SNS2_SMEM, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);
+      k_like_sn_spec_mma<H, F, false><<<gm, 32 * wpb, SNS2_SMEM, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, fb_list, fb_count);
     }
   } else {
     k_like_sn_spec<H, F><<<(int)((N + SNS_BLOCK - 1) / SNS_BLOCK), SNS_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt,

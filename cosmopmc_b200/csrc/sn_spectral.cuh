@@ -265,8 +265,8 @@ k_like_sn_spec_mma(const DevLike L, int64_t N, const double *__restrict__ X, int
   // its own at 12 warps per SM with the A fragments through HBM, tools/micro/sn_two_kernel_split_experiment.patch -- 0.29 +
   // 2.11 ms per 2e6 samples = 12.0 ms: the tile loop alone keeps the FP64 pipe 78 % busy with two warps per scheduler.)
   const int64_t ntask = (N + 31) / 32;
-  for (int64_t task = (int64_t)blockIdx.x * (SNS2_BLOCK / 32) + (threadIdx.x >> 5); task < ntask;
-       task += (int64_t)gridDim.x * (SNS2_BLOCK / 32)) {
+  for (int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); task < ntask;      // blockDim <= SNS2_BLOCK:
+       task += (int64_t)gridDim.x * (blockDim.x >> 5)) {                                                 // small batches launch fewer warps per block
   __syncwarp();
   const int64_t n = task * 32 + lane;
   const bool active = (n < N) && (!flg || flg[n]);
