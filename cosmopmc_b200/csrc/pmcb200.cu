@@ -133,6 +133,58 @@ static int ensure(pmcb200_ctx *c, DevBuf &b, size_t bytes) {
   return 0;
 }
 
+// ---- supernova tiles of the tensor-core SN kernel (sn_spectral.cuh) ------------------------------------------------
+// nz redshifts, the supernovae sorted by redshift: first[z] .. first[z + 1] are the rows at redshift z.  Per tile 8 columns:
+// tcol = supernova row, or -(row) - 1 for an empty column (repeats that row with sigma^2 = 1e300); tz = redshift index of
+// the column (its W row); tsec = 1 for a secondary tile.  A primary tile takes the first supernova of 8 redshifts
+// (ordered by multiplicity, so that the repeated ones share tiles), the s-th further supernova of each sits in the same
+// column of the s-th secondary tile behind it.
+static void sn_tile_plan(int nz, const std::vector<int> &first, std::vector<int> &tcol, std::vector<int> &tsec,
+                         std::vector<int> &tz) {
+  std::vector<int> zord(nz);
+  for (int z = 0; z < nz; z++) zord[z] = z;
+  std::stable_sort(zord.begin(), zord.end(), [&](int a, int b) { return first[a + 1] - first[a] > first[b + 1] - first[b]; });
+  tcol.clear(); tsec.clear(); tz.clear();
+  for (int p0 = 0; p0 < nz; p0 += 8) {
+    int maxm = 1;
+    for (int j = 0; j < 8 && p0 + j < nz; j++) maxm = std::max(maxm, first[zord[p0 + j] + 1] - first[zord[p0 + j]]);
+    for (int sidx = 0; sidx < maxm; sidx++) {
+      tsec.push_back(sidx > 0);
+      for (int j = 0; j < 8; j++) {
+        const int z = zord[std::min(p0 + j, nz - 1)], mult = first[z + 1] - first[z];
+        const bool real = p0 + j < nz && sidx < mult;
+        tz.push_back(z);
+        tcol.push_back(real ? first[z] + sidx : -first[z] - 1);
+      }
+    }
+  }
+}
+// the plan for a list of redshifts (host only, no device needed: diagnostics and the CPU tests).  tile_col[8 t + j] = index
+// into z[] of the supernova in column j of tile t, or -1 - index for an empty column; returns the number of tiles, or
+// a negative error code (cap too small: -needed)
+extern "C" int pmcb200_sn_tile_plan(int n, const double *z, int cap, int *tile_sec, int *tile_col) {
+  if (n < 1 || !z || cap < 0 || (cap > 0 && (!tile_sec || !tile_col))) return PMCB200_ERR_ARG;
+  std::vector<int> ord(n);
+  for (int i = 0; i < n; i++) ord[i] = i;
+  std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return z[a] < z[b]; });
+  std::vector<int> first;
+  for (int r = 0; r < n; r++) if (r == 0 || z[ord[r]] != z[ord[r - 1]]) first.push_back(r);
+  const int nz = (int)first.size();
+  first.push_back(n);
+  std::vector<int> tcol, tsec, tz;
+  sn_tile_plan(nz, first, tcol, tsec, tz);
+  const int ntile = (int)tsec.size();
+  if (ntile > cap) return -ntile;
+  for (int t = 0; t < ntile; t++) {
+    tile_sec[t] = tsec[t];
+    for (int j = 0; j < 8; j++) {
+      const int col = tcol[(size_t)t * 8 + j];
+      tile_col[t * 8 + j] = col >= 0 ? ord[col] : -1 - ord[-col - 1];
+    }
+  }
+  return ntile;
+}
+
 // ---- host-side packing ---------------------------------------------------------
 static int host_cholesky(int d, double *A) {
   for (int j = 0; j < d; j++) {
@@ -562,24 +614,8 @@ static int build_sn(pmcb200_ctx *c, const pmcb200_like_t &L, DevLike &D) {
     // Lane l of k-step ks holds B[k = l % 4][column = l / 4]: W of the column's redshift (ks < M / 4), then the chi^2
     // features.  An empty column repeats a supernova with sigma^2 = 1e300: its term vanishes.
     const int KS = M / 4 + 3;
-    std::vector<int> zord(nz);
-    for (int z = 0; z < nz; z++) zord[z] = z;
-    std::stable_sort(zord.begin(), zord.end(), [&](int a, int b) { return first[a + 1] - first[a] > first[b + 1] - first[b]; });
-    std::vector<int> tcol, tsec;      // per tile: 8 x {supernova row, or -(row) - 1 for an empty column}; secondary flag
-    std::vector<int> tz;              // per tile column: redshift index (the W row)
-    for (int p0 = 0; p0 < nz; p0 += 8) {
-      int maxm = 1;
-      for (int j = 0; j < 8 && p0 + j < nz; j++) maxm = std::max(maxm, first[zord[p0 + j] + 1] - first[zord[p0 + j]]);
-      for (int sidx = 0; sidx < maxm; sidx++) {
-        tsec.push_back(sidx > 0);
-        for (int j = 0; j < 8; j++) {
-          const int z = zord[std::min(p0 + j, nz - 1)], mult = first[z + 1] - first[z];
-          const bool real = p0 + j < nz && sidx < mult;
-          tz.push_back(z);
-          tcol.push_back(real ? first[z] + sidx : -first[z] - 1);
-        }
-      }
-    }
+    std::vector<int> tcol, tsec, tz;
+    sn_tile_plan(nz, first, tcol, tsec, tz);
     const int ntile = (int)tsec.size();
     std::vector<double> Wf((size_t)ntile * KS * 32, 0.0);
     for (int t = 0; t < ntile; t++)

@@ -396,6 +396,14 @@ int pmcb200_fisher_host(pmcb200_ctx *ctx, const double *pos, const double *h, in
 
 /* number of kernels launched by this context since creation (bench's
  * gpu_launches claim) */
+/* Column plan of the tensor-core SN kernel for a list of redshifts (host only: diagnostics, CPU tests).  Replaces nothing
+ * in the reference: nicaea's chi2_SN (called at wrappers/src/sn.c:262-275) loops over the supernovae one by one; here 8 of
+ * them are the columns of a tile, a PRIMARY tile holds the first supernova of 8 distinct redshifts and the s-th further
+ * supernova of a redshift sits in the same column of the s-th SECONDARY tile behind it (it reuses the primary column's
+ * distance).  tile_col[8 t + j] = index into z[] of the supernova in column j of tile t, or -1 - index for an empty
+ * column; tile_sec[t] = 1 for a secondary tile.  Returns the number of tiles (-needed if cap is too small). */
+int pmcb200_sn_tile_plan(int n, const double *z, int cap, int *tile_sec, int *tile_col);
+
 int64_t pmcb200_launch_count(const pmcb200_ctx *ctx);
 /* measurement helpers (not part of the reference's API):
  * counters[0] = SN integrand evaluations summed over all posterior launches

@@ -163,3 +163,49 @@ def test_device_math_helpers_on_host(tmp_path):
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "device math host check ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_sn_tile_plan_of_the_tensor_core_kernel():
+    """Column plan of the tensor-core SN kernel (pmcb200_sn_tile_plan: host only).  Every supernova sits in exactly one
+    column; a primary tile holds distinct redshifts; the supernova in column j of a secondary tile has the redshift of
+    column j of the primary tile before it; the Union sample (307 supernovae, 241 redshifts) takes 31 + 12 tiles."""
+    import ctypes as C
+    lib = A.load_library()
+
+    def plan(z):
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        need = -lib.pmcb200_sn_tile_plan(len(z), z.ctypes.data, 0, None, None)
+        assert need > 0
+        sec = np.zeros(need, np.int32); col = np.zeros(8 * need, np.int32)
+        nt = lib.pmcb200_sn_tile_plan(len(z), z.ctypes.data, need, sec.ctypes.data, col.ctypes.data)
+        assert nt == need
+        return sec, col.reshape(nt, 8)
+
+    def check(z):
+        z = np.asarray(z, dtype=np.float64)
+        sec, col = plan(z)
+        live = col[col >= 0]
+        assert sorted(live.tolist()) == list(range(len(z)))            # every supernova exactly once
+        assert sec[0] == 0
+        prim = None
+        for t in range(len(sec)):
+            zc = np.where(col[t] >= 0, z[np.maximum(col[t], 0)], z[-1 - np.minimum(col[t], -1)])     # redshift of every column
+            if not sec[t]:
+                prim = zc
+                lz = zc[col[t] >= 0]
+                assert len(set(lz.tolist())) == len(lz) and len(lz) >= 1   # distinct redshifts, first supernova of each
+            else:
+                assert np.array_equal(zc, prim)                            # same column = same redshift as in the primary tile
+                assert (col[t] >= 0).any()                                 # no empty secondary tile
+        return sec, col
+
+    rng = np.random.default_rng(3)
+    sec, col = check([0.5]); assert len(sec) == 1 and (col[0] >= 0).sum() == 1
+    sec, col = check([0.3] * 9); assert sec.tolist() == [0] + [1] * 8
+    check([0.02, 0.02, 0.4, 0.4, 0.4, 0.9, 1.4])
+    check(np.round(rng.random(100) * 1.5 + 0.01, 2))        # many repeated redshifts
+    check(rng.random(64) + 0.01)                            # none repeated: 8 primary tiles
+    from cosmopmc_b200 import targets as T
+    tab, _, _ = T.load_sn_table(T.SN_FIXTURE)
+    sec, col = check(tab[:, 0])
+    assert (sec == 0).sum() == 31 and (sec == 1).sum() == 12
