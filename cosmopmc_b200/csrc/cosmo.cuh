@@ -225,17 +225,23 @@ __device__ inline double D_V(const pmcb200_cosmo_t &c, double z, int &err, const
   if (!(EE > 0.0)) { err = 1; return NAN; }
   return cbrt(fK * fK * R_HUBBLE * z / sqrt(EE));
 }
+// The fitting formulae take eleven powers of two bases: x^c = 2^(c log2 x) with ONE logarithm per base (the powers were
+// 20 % of k_like_bao's instructions as libdevice pow calls: profiles/r02/c4_k_like_bao_summary.txt).  |c log2 x| < 8, so
+// the result carries a few ulp; the callers have checked omega_m > 0 (omega_b = 0: 2^(-inf) = 0 = pow(0, c > 0)).
+__device__ __forceinline__ double pow2l(double l2x, double c) { return exp2(c * l2x); }
 __device__ inline double z_drag(const pmcb200_cosmo_t &c) {
-  double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
-  double b1 = 0.313 * pow(omm, -0.419) * (1.0 + 0.607 * pow(omm, 0.674));
-  double b2 = 0.238 * pow(omm, 0.223);
-  return 1291.0 * pow(omm, 0.251) / (1.0 + 0.659 * pow(omm, 0.828)) * (1.0 + b1 * pow(omb, b2));
+  const double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
+  const double lm = log2(omm), lb = log2(omb);
+  const double b1 = 0.313 * pow2l(lm, -0.419) * (1.0 + 0.607 * pow2l(lm, 0.674));
+  const double b2 = 0.238 * pow2l(lm, 0.223);
+  return 1291.0 * pow2l(lm, 0.251) / (1.0 + 0.659 * pow2l(lm, 0.828)) * (1.0 + b1 * pow2l(lb, b2));
 }
 __device__ inline double z_star(const pmcb200_cosmo_t &c) {
-  double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
-  double g1 = 0.0783 * pow(omb, -0.238) / (1.0 + 39.5 * pow(omb, 0.763));
-  double g2 = 0.560 / (1.0 + 21.1 * pow(omb, 1.81));
-  return 1048.0 * (1.0 + 0.00124 * pow(omb, -0.738)) * (1.0 + g1 * pow(omm, g2));
+  const double omm = c.Omega_m * c.h_100 * c.h_100, omb = c.Omega_b * c.h_100 * c.h_100;
+  const double lm = log2(omm), lb = log2(omb);
+  const double g1 = 0.0783 * pow2l(lb, -0.238) / (1.0 + 39.5 * pow2l(lb, 0.763));
+  const double g2 = 0.560 / (1.0 + 21.1 * pow2l(lb, 1.81));
+  return 1048.0 * (1.0 + 0.00124 * pow2l(lb, -0.738)) * (1.0 + g1 * pow2l(lm, g2));
 }
 // Gaussian log-pdf of a model vector against data packed as a component
 __device__ inline double gauss_comp_logpdf(const double *__restrict__ comp, int n, const double *model) {
