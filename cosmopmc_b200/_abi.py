@@ -119,6 +119,7 @@ SYMBOLS = {
     "pmcb200_samples_host_begin": (_i, [_vp, _i64, _vp, _vp]),
     "pmcb200_launch_count": (_i64, [_vp]),
     "pmcb200_sn_tile_plan": (_i, [_i, _vp, _i, _vp, _vp]),
+    "pmcb200_cmb_spectral_tables": (_i, [_vp, _vp, _vp]),
     "pmcb200_set_box": (_i, [_vp, _i, _vp, _vp]),
     "pmcb200_read_counts": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "pmcb200_weight_stats": (_i, [_vp, _i64, _vp, _vp, _i, C.POINTER(C.c_double * 8)]),

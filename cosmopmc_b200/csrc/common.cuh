@@ -62,6 +62,7 @@ struct DevCount {
   unsigned long long gen_integrals;  // their integrals
   unsigned long long sn_spec;        // SN samples evaluated by the spectral kernel (k_like_sn_spec)
   unsigned long long sn_exact;       // SN samples evaluated by the exact warp-per-sample kernel
+  unsigned long long cmb_spec;       // CMB samples whose distance to a* came from the spectral form (cmb_spec_w)
 };
 
 __device__ __forceinline__ unsigned long long dkey(double x) {

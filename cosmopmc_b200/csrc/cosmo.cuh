@@ -363,7 +363,8 @@ __device__ __forceinline__ GInt gint_from_lane(const GInt &q, int src) {
 #endif
 template <bool HASQ, bool RS>
 __device__ double romberg_warp(const GInt &q, const double2 *__restrict__ LT, const double *__restrict__ ET, double fa,
-                               double fb, double a, double b, bool active, int &err, unsigned &nev) {
+                               double fb, double a, double b, bool active, int &err, unsigned &nev,
+                               int coop_min = (RS ? ROMB_COOP_MIN_RS : ROMB_COOP_MIN)) {      // >= 128, warp-uniform
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   double y[5];
@@ -377,7 +378,7 @@ __device__ double romberg_warp(const GInt &q, const double2 *__restrict__ LT, co
     const int it = 1 << (j - 1);
     const double tnm = (double)it, del = h / tnm;
     double sum = 0.0;
-    if (it < (RS ? ROMB_COOP_MIN_RS : ROMB_COOP_MIN)) {
+    if (it < coop_min) {
       if (!done) {
         if (it < 4) {
           for (int i = 0; i < it; i++) sum = gint_acc<HASQ, RS>(q, LT, ET, fma((double)i + 0.5, del, a), sum);
@@ -433,14 +434,14 @@ struct LeanTabs { const double *T; const double2 *LT; const double *ET; };
 // comoving distance [Mpc/h], a .. 1.  Warp-synchronous: all lanes call it; act = this lane wants the value.
 template <bool HASQ>
 __device__ __forceinline__ double w_lean(const pmcb200_cosmo_t &c, double a, int wOmegar, bool act, int &err,
-                                         const LeanTabs &tb, unsigned &nev) {
+                                         const LeanTabs &tb, unsigned &nev, int coop_min = ROMB_COOP_MIN) {
   const ECoefF f = make_ecoef_fast(c, wOmegar);
   GInt q;
   q.g = make_glean(f); q.R3 = 0.0;
   const bool fast = act && (a > 0.0) && glean_in_range(q.g, a);
   double fa = 0.0, fb = 0.0;
   if (fast) { fa = rsqrt_acc(a4E2_fast(f, a, tb.T), 0.0); fb = rsqrt_acc(a4E2_fast(f, 1.0, tb.T), 0.0); }
-  double r = R_HUBBLE * romberg_warp<HASQ, false>(q, tb.LT, tb.ET, fa, fb, a, 1.0, fast, err, nev);
+  double r = R_HUBBLE * romberg_warp<HASQ, false>(q, tb.LT, tb.ET, fa, fb, a, 1.0, fast, err, nev, coop_min);
   if (act && !fast) r = w_generic(c, a, wOmegar, err, tb.T);      // outside the table-based exp2's range: general path
   return r;
 }
@@ -997,11 +998,56 @@ k_like_bao(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   count_gen(cnt, nev, nint);
 }
 
+// ---- comoving distance to a*: the reference's 11-stage Romberg value as a linear functional (round 2, session AC) ---
+// likeli_CMBDistPrior (wmap.c:945-1049) needs w(a*) = R_H int_(a*)^1 da / sqrt(a^4 E^2), and NR qromb takes 11 stages = 1025
+// equidistant nodes in a for it (the integrand varies over three decades of a): 95 % of k_like_cmbdp's evaluations.  The value
+// it returns is NOT the integral -- its truncation error is 2e-5, measured against Gauss-Legendre in ln a
+// (tools/proto/cmb_spectral_proto.py) -- so the rule itself has to be reproduced.  But when the stopping test fails at
+// stages 5..10 and holds at stage 11, what qromb returns is a FIXED linear functional of the integrand at the nodes
+// a_i = a* + (1 - a*) i / 1024: ss_11 = h sum_i omega_i f(a_i) (trapezoid stages 7..11 combined by the Neville weights), and
+// so is every stage's error estimate dss_j.  With t = (a - a*) / (1 - a*) in [0, 1] and the FIXED variable v = ln(t + tau)
+// (tau = a*_fid / (1 - a*_fid): v is ln a up to 1 % distortion at the lower end) the integrand is smooth in v, and the
+// functionals applied to its Chebyshev interpolant on CMB_M fixed points v_k become fixed weights on the node VALUES:
+//     ss_j = h sum_k Theta_j[k] f(a* + h t_k),   dss_j likewise          (tables: pmc_init_sn_tables, long double)
+// 56 evaluations + 18 x 56 FMA instead of 1025 evaluations; measured on the CPU: |ss_11 / orc_w - 1| <= 2.4e-15.
+// Certificates per sample (all from the same 56 values): the interpolant's last three coefficients <= CMB_TAIL_TOL |c_0|; the
+// stopping test FAILS at stages 5..10 and HOLDS at stage 11, each with a 1e-4 margin (the reference's |dss_11| / |ss_11| sits at
+// 0.77 .. 0.99 of EPS: the test is evaluated, not assumed).  A sample that fails any of them takes the node-by-node path.
+#define CMB_M 56
+#define CMB_NROW 18          // ss_11, dss_11, ss_5..10, dss_5..10, c_0, c_(M-3), c_(M-2), c_(M-1)
+#define CMB_TAIL_TOL 5.0e-12
+#define CMB_TAU (1.0 / 1090.0)      // (1/1091) / (1 - 1/1091)
+__constant__ double CMB_T[CMB_M];                 // t_k = exp(v_k) - tau
+__constant__ double CMB_TH[CMB_NROW * CMB_M];
+template <bool HASQ>
+__device__ __forceinline__ bool cmb_spec_w(const pmcb200_cosmo_t &c, double as, const LeanTabs &tb, double &w) {
+  const ECoefF f = make_ecoef_fast(c, 1);
+  GInt q;
+  q.g = make_glean(f); q.R3 = 0.0;
+  if (!((as > 0.0) && (as < 1.0) && glean_in_range(q.g, as))) return false;
+  const double h = 1.0 - as;
+  double acc[CMB_NROW];
+#pragma unroll
+  for (int r = 0; r < CMB_NROW; r++) acc[r] = 0.0;
+#pragma unroll
+  for (int k = 0; k < CMB_M; k++) {
+    const double fv = gint_acc<HASQ, false>(q, tb.LT, tb.ET, fma(h, CMB_T[k], as), 0.0);
+#pragma unroll
+    for (int r = 0; r < CMB_NROW; r++) acc[r] = fma(CMB_TH[r * CMB_M + k], fv, acc[r]);
+  }
+  bool ok = (fabs(acc[15]) + fabs(acc[16]) + fabs(acc[17]) <= CMB_TAIL_TOL * fabs(acc[14])) && (acc[0] > 0.0);
+  ok = ok && (fabs(acc[1]) <= (1.0 - 1.0e-4) * ROMB_EPS * fabs(acc[0]));
+#pragma unroll
+  for (int j = 0; j < 6; j++) ok = ok && (fabs(acc[8 + j]) > (1.0 + 1.0e-4) * ROMB_EPS * fabs(acc[2 + j]));
+  w = R_HUBBLE * h * acc[0];
+  return ok;      // a NaN anywhere fails the comparisons
+}
+
 template <bool HASQ>
 __global__ void __launch_bounds__(PMC_BLOCK)
 k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
              const int16_t *__restrict__ flg, double *__restrict__ logpi,
-             int32_t *__restrict__ err, int set, double add_const, DevCount *cnt) {
+             int32_t *__restrict__ err, int set, double add_const, DevCount *cnt, int spectral) {
   __shared__ double T[96];
   __shared__ double2 LT[LOG1K_N];
   __shared__ double ET[SN_EXP2_N];
@@ -1020,7 +1066,15 @@ k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   if (!act) m.c = L.model;
   const pmcb200_cosmo_t &c = m.c;
   const double zs = z_star(c), as = 1.0 / (1.0 + zs);
-  const double ww = w_lean<HASQ>(c, as, 1, act, e, tb, nev);
+  // distance to a*: spectral form where it is certified; the warp-synchronous Romberg runs for the other lanes only (and
+  // returns at once when no lane of the warp needs it)
+  double wsp = 0.0;
+  const bool cert = spectral && act && cmb_spec_w<HASQ>(c, as, tb, wsp);
+  if (cert) nev += CMB_M;
+  // (with the spectral form on, the few lanes left share their stages from 128 new nodes on with the whole warp: the warp would
+  // otherwise wait for one lane's 1025 or 2049 serial evaluations)
+  const double wex = w_lean<HASQ>(c, as, 1, act && !cert, e, tb, nev, spectral ? 128 : ROMB_COOP_MIN);
+  const double ww = cert ? wsp : wex;
   const double rs = r_sound_lean<HASQ>(c, as, act, e, tb, nev);
   nint += 2 * act;
   double res = 0.0;
@@ -1037,6 +1091,10 @@ k_like_cmbdp(const DevLike L, int64_t N, const double *__restrict__ X, int d,
   if (live) put_loglike(logpi, err, n, set, add_const, e ? 0.0 : res, e);
   else if (n < N && set) { logpi[n] = 0.0; if (err) err[n] = 0; }
   count_gen(cnt, nev, nint);
+  if (cnt) {
+    const unsigned nc = __popc(__ballot_sync(0xffffffffu, cert));
+    if ((threadIdx.x & 31) == 0 && nc) atomicAdd(&cnt->cmb_spec, (unsigned long long)nc);
+  }
 }
 
 // round-1 versions (general integrand with per-node checks, sequential sums): kept for A/B measurements

@@ -8,6 +8,81 @@
 #include <cstring>
 #include <cmath>
 #include <algorithm>
+#include <vector>
+
+// Tables of cmb_spec_w (cosmo.cuh), long double.  NR qromb with K = 5 (pmclib sm2_qromberg): stage j's value
+// is the degree-4 extrapolation to h^2 -> 0 of the trapezoid sums s_(j-4..j) (abscissae 4^-q), its error estimate the
+// difference to the degree-3 extrapolation of s_(j-3..j) (the last Neville correction on polint's path); s_k is the
+// trapezoid sum over 2^(k-1) intervals, whose nodes are every (1024 / 2^(k-1))-th of the 1025 stage-11 nodes t_i = i / 1024.
+// Node i in the Chebyshev variable: x_i = affine(ln(t_i + tau)); cardinal functions of the CMB_M Chebyshev points
+// l_k(x) = sum'_m (2/M) T_m(x_k) T_m(x).  Row r of the table: sum_i weight_r[i] l_k(x_i).
+void pmc_cmb_spectral_tables(double *tk, double *th) {
+  typedef long double ld;
+  const int M = CMB_M, NN = 1024, K = 5;
+  ld lam5[K], lam4[K], xq[K];
+  for (int q = 0; q < K; q++) xq[q] = powl(4.0L, -(ld)q);
+  for (int k = 0; k < K; k++) {
+    lam5[k] = 1.0L; lam4[k] = (k == 0) ? 0.0L : 1.0L;
+    for (int m = 0; m < K; m++) {
+      if (m == k) continue;
+      lam5[k] *= (0.0L - xq[m]) / (xq[k] - xq[m]);
+      if (k > 0 && m > 0) lam4[k] *= (0.0L - xq[m]) / (xq[k] - xq[m]);
+    }
+  }
+  const ld tau = (ld)CMB_TAU, vlo = logl(tau), vhi = logl(1.0L + tau);
+  std::vector<ld> xk(M), Tk((size_t)M * M);
+  for (int k = 0; k < M; k++) {
+    const ld th_k = M_PIl * (k + 0.5L) / M;
+    xk[k] = cosl(th_k);
+    tk[k] = (double)(expl((vhi - vlo) / 2 * xk[k] + (vhi + vlo) / 2) - tau);
+    for (int m = 0; m < M; m++) Tk[(size_t)k * M + m] = cosl(m * th_k);
+  }
+  // cardinal values card[i][k] at the 1025 nodes
+  std::vector<ld> card((size_t)(NN + 1) * M);
+  std::vector<ld> B(M);
+  for (int i = 0; i <= NN; i++) {
+    ld x = (2.0L * logl((ld)i / NN + tau) - (vhi + vlo)) / (vhi - vlo);
+    x = std::max<ld>(-1.0L, std::min<ld>(1.0L, x));
+    const ld thx = acosl(x);
+    for (int m = 0; m < M; m++) B[m] = cosl(m * thx) * ((m == 0 ? 1.0L : 2.0L) / M);
+    for (int k = 0; k < M; k++) {
+      ld v = 0.0L;
+      for (int m = 0; m < M; m++) v += B[m] * Tk[(size_t)k * M + m];
+      card[(size_t)i * M + k] = v;
+    }
+  }
+  auto stage_row = [&](int j, const ld *lam, double *out) {      // out[k] = sum_i weight[i] card[i][k]
+    std::vector<ld> wgt(NN + 1, 0.0L);
+    for (int q = 0; q < K; q++) {
+      const int kk = j - 4 + q, nk = 1 << (kk - 1), step = NN / nk;
+      for (int i = 0; i <= NN; i += step) wgt[i] += lam[q] * ((i == 0 || i == NN) ? 0.5L : 1.0L) / nk;
+    }
+    for (int k = 0; k < M; k++) {
+      ld v = 0.0L;
+      for (int i = 0; i <= NN; i++) v += wgt[i] * card[(size_t)i * M + k];
+      out[k] = (double)v;
+    }
+  };
+  ld mu5[K];
+  for (int q = 0; q < K; q++) mu5[q] = lam5[q] - lam4[q];
+  stage_row(11, lam5, th + 0 * M);
+  stage_row(11, mu5, th + 1 * M);
+  for (int j = 5; j <= 10; j++) { stage_row(j, lam5, th + (2 + j - 5) * M); stage_row(j, mu5, th + (8 + j - 5) * M); }
+  const int cm[4] = {0, M - 3, M - 2, M - 1};
+  for (int r = 0; r < 4; r++)
+    for (int k = 0; k < M; k++) th[(14 + r) * M + k] = (double)((cm[r] == 0 ? 1.0L : 2.0L) / M * Tk[(size_t)k * M + cm[r]]);
+}
+
+// nodes t_k [m] and value-space functionals [nrow][m] of the spectral form of the distance to a* (host only: the CPU tests check
+// them against a node-by-node Romberg); returns m, *nrow = rows; a null pointer skips that table
+extern "C" int pmcb200_cmb_spectral_tables(double *tk, double *theta, int *nrow) {
+  std::vector<double> t(CMB_M), th((size_t)CMB_NROW * CMB_M);
+  pmc_cmb_spectral_tables(t.data(), th.data());
+  if (tk) memcpy(tk, t.data(), sizeof(double) * CMB_M);
+  if (theta) memcpy(theta, th.data(), sizeof(double) * CMB_NROW * CMB_M);
+  if (nrow) *nrow = CMB_NROW;
+  return CMB_M;
+}
 
 // Fill the SN kernel's 2^(j/1024) table on the current device (pre-biased high words, cosmo.cuh).
 int pmc_init_sn_tables() {
@@ -37,6 +112,11 @@ int pmc_init_sn_tables() {
     for (int m = 0; m < SNS_M; m++)
       for (int j = 0; j < SNS_M / 2; j++)
         dct[m * (SNS_M / 2) + j] = (double)((m == 0 ? 1.0L : 2.0L) / SNS_M * cosl(M_PIl * m * (j + 0.5L) / SNS_M));
+  // spectral form of the distance to a* (cmb_spec_w): nodes and value-space functionals
+  static double cmb_t[CMB_M], cmb_th[CMB_NROW * CMB_M];
+  if (cmb_th[0] == 0.0) pmc_cmb_spectral_tables(cmb_t, cmb_th);
+  if (cudaMemcpyToSymbol(CMB_T, cmb_t, sizeof(cmb_t)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(CMB_TH, cmb_th, sizeof(cmb_th)) != cudaSuccess) return 1;
   if (cudaMemcpyToSymbol(SNS_DCT, dct, sizeof(dct)) != cudaSuccess) return 1;
   if (cudaMemcpyToSymbol(g_log1k, ltab, sizeof(ltab)) != cudaSuccess) return 1;
   return cudaMemcpyToSymbol(g_sn_exp2, tab, sizeof(tab)) == cudaSuccess ? 0 : 1;
@@ -140,8 +220,13 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
       break;
     case PMCB200_LIKE_CMBDistPrior:
       if (like_v1) k_like_cmbdp_v1<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);
-      else if (L.sn_hasq) k_like_cmbdp<true><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt);
-      else k_like_cmbdp<false><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt);
+      else {
+        // PMCB200_CMB_EXACT=1: the distance to a* node by node for every sample (A/B measurements, cross-check); read per call
+        const char *ec = getenv("PMCB200_CMB_EXACT");
+        const int spec = !(ec && *ec && *ec != '0');
+        if (L.sn_hasq) k_like_cmbdp<true><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, spec);
+        else k_like_cmbdp<false><<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add, cnt, spec);
+      }
       break;
     case PMCB200_LIKE_BANANA:
       k_like_banana<<<g, PMC_BLOCK, 0, s>>>(L, N, X, d, flg, logpi, err, set, add);

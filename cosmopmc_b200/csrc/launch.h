@@ -49,6 +49,7 @@ void pmc_launch_like(const DevLike &L, int64_t N, const double *X, int d, const 
                      cudaStream_t s);
 bool pmc_sn_spectral_wanted(const DevLike &L, int64_t N);
 int pmc_sn_spectral_M();
+void pmc_cmb_spectral_tables(double *tk, double *th);      // [CMB_M], [CMB_NROW][CMB_M] (cosmo.cuh); host only
 void pmc_launch_map_params(const DevLike &L, int64_t N, const double *X, int d, double *out, int32_t *err, cudaStream_t s);
 // small kernels (k_cosmo.cu)
 void pmc_launch_normalize(int64_t N, const int16_t *flg, double *w, double M, double invS, cudaStream_t s);

@@ -1555,9 +1555,9 @@ extern "C" int pmcb200_counters_ex(pmcb200_ctx *c, int64_t *out, int n) {
   CUDA_OK(c, cudaMemcpyAsync(&h, c->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(DevCount), c->stream));
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  const int64_t v[6] = {(int64_t)h.sn_evals, (int64_t)h.sn_zsteps, (int64_t)h.gen_evals, (int64_t)h.gen_integrals,
-                        (int64_t)h.sn_spec, (int64_t)h.sn_exact};
-  for (int i = 0; i < n; i++) out[i] = i < 6 ? v[i] : 0;
+  const int64_t v[7] = {(int64_t)h.sn_evals, (int64_t)h.sn_zsteps, (int64_t)h.gen_evals, (int64_t)h.gen_integrals,
+                        (int64_t)h.sn_spec, (int64_t)h.sn_exact, (int64_t)h.cmb_spec};
+  for (int i = 0; i < n; i++) out[i] = i < 7 ? v[i] : 0;
   return 0;
 }
 

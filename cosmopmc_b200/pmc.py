@@ -243,10 +243,10 @@ class PMC:
         return int(self.lib.pmcb200_launch_count(self.h))
 
     def counters(self):
-        out = (C.c_int64 * 6)()
-        self._ck(self.lib.pmcb200_counters_ex(self.h, out, 6))
+        out = (C.c_int64 * 7)()
+        self._ck(self.lib.pmcb200_counters_ex(self.h, out, 7))
         return dict(sn_evals=int(out[0]), sn_zsteps=int(out[1]), gen_evals=int(out[2]), gen_integrals=int(out[3]),
-                    sn_spec=int(out[4]), sn_exact=int(out[5]))
+                    sn_spec=int(out[4]), sn_exact=int(out[5]), cmb_spec=int(out[6]))
 
     def fp64_peak_tflops(self):
         v = C.c_double()

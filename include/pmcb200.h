@@ -415,8 +415,15 @@ int64_t pmcb200_launch_count(const pmcb200_ctx *ctx);
 int pmcb200_counters(pmcb200_ctx *ctx, int64_t out[4]);
 /* the same with the SN kernel split: out[4] = samples evaluated by the spectral SN kernel, out[5] = samples
  * evaluated node by node by the warp-per-sample kernel (small batches, and the samples the spectral kernel could
- * not certify); n <= 6 entries are written, further ones zeroed */
+ * not certify); out[6] = CMB samples whose distance to a* came from the spectral form; n <= 7 entries are written,
+ * further ones zeroed */
 int pmcb200_counters_ex(pmcb200_ctx *ctx, int64_t *out, int n);
+/* Tables of the spectral form of the comoving distance to a* in likeli_CMBDistPrior (wrappers/src/wmap.c:1027-1035 ->
+ * nicaea w(a*) -> pmclib sm2_qromberg: 11 stages, 1025 equidistant nodes): m fixed nodes t_k in [0, 1] (a = a* + (1 - a*) t)
+ * and nrow rows of m weights on the integrand's values there: row 0 = the stage-11 Romberg value, row 1 = its error
+ * estimate, rows 2..7 / 8..13 = the same for stages 5..10, rows 14..17 = Chebyshev coefficients 0, m-3, m-2, m-1 of the
+ * interpolant (host only; returns m). */
+int pmcb200_cmb_spectral_tables(double *tk, double *theta, int *nrow);
 int pmcb200_fp64_peak(pmcb200_ctx *ctx, double *tflops);
 
 /* raw device helpers so C hosts need not link the CUDA runtime */

@@ -162,6 +162,17 @@ def check_posterior(oracle, pmc, spec, X):
     assert ok.sum() > 0.5 * len(X)
     r = rel(got[ok], ref[ok])
     assert r < RTOL_LOG, r
+    if any(spec.t.like[i].kind == 6 for i in range(spec.t.ndata)):
+        # CMB distance priors: the distance to a* comes from the spectral form of the 11-stage Romberg rule where it is
+        # certified (cosmo.cuh cmb_spec_w), node by node elsewhere; PMCB200_CMB_EXACT=1 takes every sample node by node
+        with environ({"PMCB200_CMB_EXACT": "1"}):
+            pmc.counters()
+            gotx, egotx = pmc.posterior_log_pdf(dev(X))
+            assert pmc.counters()["cmb_spec"] == 0
+        gotx, egotx = gotx.cpu().numpy(), egotx.cpu().numpy()
+        assert np.array_equal(egotx != 0, eref != 0)
+        assert rel(gotx[ok], ref[ok]) < RTOL_LOG
+        assert rel(got[ok], gotx[ok]) < 1e-11
     if any(spec.t.like[i].kind in (6, 7) for i in range(spec.t.ndata)):
         # BAO / CMB distance priors: the round-1 kernels (libdevice integrand, one lane per integral) are kept behind
         # PMCB200_LIKE_V1 for A/B measurements -- same integrals, same error flags
@@ -523,8 +534,11 @@ def test_iteration_cmb_bao_sn(oracle, pmc_factory):
     ch = oracle.cholesky_stack(cov)
     pmc.set_target(spec)
     pmc.set_proposal(w, m, chol=ch)
+    pmc.counters()
     o, st, *h = run_both(oracle, pmc, spec, w, m, ch, 6000, seed=4)
     check_iteration(o, st, pmc, *h)
+    cnt = pmc.counters()
+    assert cnt["cmb_spec"] > 0.9 * st["nok_box"], cnt      # on this proposal nearly every sample is certified for the spectral form
 
 
 def test_iteration_sn_bao_w0wa(oracle, pmc_factory):
