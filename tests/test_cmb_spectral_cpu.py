@@ -101,3 +101,61 @@ def test_the_rule_is_reproduced_not_the_integral(oracle):
     w_ref = L.orc_w(C.byref(cc), a0, 1, C.byref(ns), C.byref(er)) / R_H
     assert abs(ss11 / w_ref - 1.0) < 1e-13
     assert 5e-6 < abs(w_ref / exact - 1.0) < 1e-4        # the reference's own truncation error, reproduced
+
+
+def _polint0(xa, ya):
+    """Numerical Recipes polint at x = 0 (as oracle/pmc_oracle.c polint0): value and last correction"""
+    n = len(xa)
+    c, d = list(ya), list(ya)
+    ns = int(np.argmin(np.abs(xa)))
+    y = ya[ns]; ns -= 1
+    dy = 0.0
+    for m in range(1, n):
+        for i in range(n - m):
+            ho, hp = xa[i], xa[i + m]
+            w = c[i + 1] - d[i]
+            den = w / (ho - hp)
+            d[i] = hp * den
+            c[i] = ho * den
+        if 2 * (ns + 1) < n - m:
+            dy = c[ns + 1]
+        else:
+            dy = d[ns]; ns -= 1
+        y += dy
+    return y, dy
+
+
+def test_every_stage_functional_against_a_node_by_node_tableau(oracle):
+    """Rows 0..13 of the table (value and error estimate of stages 5..11) against NR's trapzd / polint tableau run node
+    by node in numpy on the same integrand: the stage values to 1e-13, the error estimates to 1e-7 of themselves (they are
+    differences six orders below the value)."""
+    L = oracle.lib()
+    L.orc_z_star.restype = C.c_double; L.orc_z_star.argtypes = [C.POINTER(A.Cosmo)]
+    tk, th = tables()
+    spec = T.target_cmb_bao_sn()
+    cc = A.Cosmo.from_buffer_copy(bytes(spec.t.like[0].model))
+    cc.Omega_m, cc.w0_de = 0.29, -0.93
+    a0 = 1.0 / (1.0 + L.orc_z_star(C.byref(cc)))
+    f = lambda a: 1.0 / np.sqrt(a ** 4 * L.orc_Esqr(C.byref(cc), float(a), 1))
+    h = 1.0 - a0
+    # NR trapzd stages 1..11
+    s, hh = [], [1.0]
+    st = 0.5 * h * (f(a0) + f(1.0))
+    s.append(st)
+    for j in range(1, 11):
+        it = 1 << (j - 1)
+        dl = h / it
+        x = a0 + 0.5 * dl
+        tot = 0.0
+        for _ in range(it):
+            tot += f(x); x += dl
+        st = 0.5 * (st + h * tot / it)
+        s.append(st); hh.append(0.25 * hh[-1])
+    fk = np.array([f(a) for a in a0 + h * tk])
+    acc = h * (th @ fk)
+    for j in range(5, 12):            # stage j uses s[j-5 .. j-1]
+        ss, dss = _polint0(np.array(hh[j - 5:j]), s[j - 5:j])
+        row_s = 0 if j == 11 else 2 + (j - 5)
+        row_d = 1 if j == 11 else 8 + (j - 5)
+        assert abs(acc[row_s] / ss - 1.0) < 1e-13, (j, acc[row_s], ss)
+        assert abs(acc[row_d] / dss - 1.0) < 1e-7, (j, acc[row_d], dss)
